@@ -1,0 +1,633 @@
+// mmvq.cu — streaming decode GEMV (batch 1..8) over ggml quant blocks for sm_100a.
+//
+// Drop-in for the reference's `launch_mmvq_gguf_*` C ABI
+// (REF: mistralrs-quant/kernels/mmvq_gguf/mmvq_gguf.cu:1322-1641, declared in
+// mistralrs-quant/src/gguf/ffi.rs and called from src/gguf/fast_mmvq.rs:299,472,682).
+//
+// Design (B200-first, not a port of the dp4a kernel):
+//  * The weight matrix is a flat byte stream.  Each CTA owns a contiguous range of rows and a
+//    dedicated producer warp streams it HBM -> shared memory with cp.async.bulk (TMA engine)
+//    into a multi-stage mbarrier ring: one 16-byte-aligned bulk copy per (row, 1024-element K
+//    segment).  The byte phase (address mod 16) is preserved in shared memory, so ggml types
+//    whose blocks are not 16-byte multiples (Q6_K 210 B, Q8_0 34 B, ...) need no re-tiling.
+//  * 8 consumer warps; warp w owns two rows of the pass, lane l owns the l-th 32-weight unit
+//    of the current K segment.  Activations are Q8_1-quantised (the reference's decode
+//    numerics) and pre-permuted into unit order in shared memory once per CTA.
+//  * Partial sums stay in registers across K segments; one butterfly reduction per row.
+//  * Optional fused prologue (RMSNorm + Q8_1 quantisation of raw activations) and epilogue
+//    (GLU, residual add) — the `mrs_*` entry points; the reference-shaped launchers use the
+//    plain prologue (pre-quantised Q8_1 input).
+//  * PDL: the producer starts streaming weights before griddepcontrol.wait, so under
+//    programmatic stream serialisation the next GEMV's weights are already in flight while the
+//    previous kernel drains.
+#include "mmvq_types.cuh"
+
+#include <stdio.h>
+
+namespace mrs {
+
+constexpr int NCW = 8;                    // consumer warps
+constexpr int NTHREADS = (NCW + 1) * 32;  // + producer warp
+constexpr int SLOTS = 2 * NCW;            // row-segments per stage (2 per consumer warp)
+constexpr int SEG_UNITS = 32;             // 32-weight units per K segment (1024 weights)
+constexpr int MAX_STAGES = 12;
+
+enum { MODE_PLAIN = 0, MODE_GLU = 1, MODE_QKV = 2 };
+enum { X_Q8_1 = 0, X_RAW = 1 };
+
+struct MmvqParams {
+  const uint8_t *w[3];
+  void *dst[3];
+  int nrows[3];
+  const void *x;         // X_Q8_1: block_q8_1[ncols][stride_col_y]; X_RAW: act[ncols][K]
+  const void *norm_w;    // optional RMSNorm weight (X_RAW only)
+  const void *residual;  // optional residual added in the epilogue (MODE_PLAIN only)
+  float eps;
+  int xkind, xdtype;
+  int K, stride_col_y, stride_col_dst, ncols;
+  int mode, activation, dst_dtype;
+  int nstages, vrows, pdl;
+};
+
+template <int T> struct Geo {
+  using Q = QT<T>;
+  static constexpr int SEG_BLOCKS = SEG_UNITS / Q::UPB;      // weight blocks per segment
+  static constexpr int SEG_BYTES = SEG_BLOCKS * Q::BYTES;    // bytes per row-segment
+  static constexpr int SLOT_BYTES = (SEG_BYTES + 30 + 15) & ~15;
+  static constexpr int STAGE_BYTES = SLOTS * SLOT_BYTES;
+  static constexpr int XU_BYTES = 32 + 4 * Q::AUX;           // smem bytes per unit per column
+};
+
+__device__ __forceinline__ void resolve_row(const MmvqParams &p, int vrow, int which, int &m, int &row) {
+  if (p.mode == MODE_QKV) {
+    if (vrow < p.nrows[0]) { m = 0; row = vrow; }
+    else if (vrow < p.nrows[0] + p.nrows[1]) { m = 1; row = vrow - p.nrows[0]; }
+    else { m = 2; row = vrow - p.nrows[0] - p.nrows[1]; }
+  } else if (p.mode == MODE_GLU) {
+    m = which; row = vrow;
+  } else {
+    m = 0; row = vrow;
+  }
+}
+
+// accessor handed to QT::aux — d8/s8 of q8_1 block j relative to the weight block
+struct YGlobal {
+  const block_q8_1 *y;
+  __device__ __forceinline__ float d(int j) const { return __low2float(y[j].ds); }
+  __device__ __forceinline__ float s(int j) const { return __high2float(y[j].ds); }
+};
+struct YSmem {
+  const float2 *ds;  // (d, s) per q8 block, already widened
+  __device__ __forceinline__ float d(int j) const { return ds[j].x; }
+  __device__ __forceinline__ float s(int j) const { return ds[j].y; }
+};
+
+// Q8_1 quantisation of one 32-element block held by one thread (values already f32).
+// Same arithmetic as REF mmvq_gguf.cu:1235-1251 incl. the butterfly summation order and the
+// approximate divisions the reference gets from --use_fast_math.
+__device__ __forceinline__ void quantize_block_q8_1(const float *v, int8_t *q, float &d_out, float &s_out) {
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(v[i]));
+  // butterfly order: masks 16,8,4,2,1
+  float s[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) s[i] = v[i];
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+#pragma unroll
+    for (int i = 0; i < m; i++) s[i] = s[i] + s[i + m];
+  }
+  const float d = __fdividef(amax, 127.0f);
+#pragma unroll
+  for (int i = 0; i < 32; i++) q[i] = (amax == 0.0f) ? (int8_t)0 : (int8_t)roundf(__fdividef(v[i], d));
+  d_out = __half2float(__float2half_rn(d));
+  s_out = __half2float(__float2half_rn(s[0]));
+}
+
+template <int T, int NCOLS, bool FAST>
+__global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqParams p) {
+  using Q = QT<T>;
+  using G = Geo<T>;
+  extern __shared__ __align__(128) uint8_t smem[];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nunits = p.K / 32;
+  const int nseg = (nunits + SEG_UNITS - 1) / SEG_UNITS;
+  const int row_bytes = (p.K / Q::QK) * Q::BYTES;
+  const int nst = p.nstages;
+
+  // smem carve-up: [barriers][x: q lo | q hi | aux][ring]
+  uint64_t *full = (uint64_t *)smem;
+  uint64_t *empty = full + MAX_STAGES;
+  uint8_t *xbase = smem + 256;
+  int4 *xq0 = (int4 *)xbase;                           // [NCOLS][nunits]
+  int4 *xq1 = xq0 + (size_t)NCOLS * nunits;            // [NCOLS][nunits]
+  float *xa = (float *)(xq1 + (size_t)NCOLS * nunits); // [NCOLS][nunits][AUX]
+  uint8_t *ring = (uint8_t *)(((uintptr_t)(xa + (size_t)NCOLS * nunits * Q::AUX) + 127) & ~(uintptr_t)127);
+
+  if (tid == 0) {
+    for (int i = 0; i < nst; i++) { mbar_init(&full[i], 32); mbar_init(&empty[i], NCW); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  // contiguous virtual-row range of this CTA
+  const int vr0 = (int)((long long)p.vrows * blockIdx.x / gridDim.x);
+  const int vr1 = (int)((long long)p.vrows * (blockIdx.x + 1) / gridDim.x);
+  const int P = (p.mode == MODE_GLU) ? NCW : SLOTS;  // virtual rows per pass
+
+  if (warp == NCW) {
+    // =========================== producer warp: lane == slot ===========================
+    // Weights are immutable, so streaming may start before the upstream kernel finished.
+    int stage = 0, phase = 0;
+    const int slot = lane;
+    if (slot < SLOTS) {
+      for (int base = vr0; base < vr1; base += P) {
+        const int vrow = (p.mode == MODE_GLU) ? base + (slot >> 1) : base + slot;
+        const uint8_t *rowp = nullptr;
+        if (vrow < vr1) {
+          int m, row;
+          resolve_row(p, vrow, slot & 1, m, row);
+          rowp = p.w[m] + (size_t)row * row_bytes;
+        }
+        for (int s = 0; s < nseg; s++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (rowp != nullptr) {
+            const int off = s * G::SEG_BYTES;
+            const int len = min(G::SEG_BYTES, row_bytes - off);
+            const uintptr_t a = (uintptr_t)(rowp + off);
+            const uintptr_t a0 = a & ~(uintptr_t)15;
+            const uint32_t bytes = (uint32_t)(((a + len + 15) & ~(uintptr_t)15) - a0);
+            mbar_arrive_expect_tx(&full[stage], bytes);
+            bulk_g2s(ring + (size_t)stage * G::STAGE_BYTES + (size_t)slot * G::SLOT_BYTES, (const void *)a0, bytes, &full[stage]);
+          } else {
+            mbar_arrive(&full[stage]);
+          }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
+      // lanes without a slot still owe their arrival on every stage use
+      for (int base = vr0; base < vr1; base += P)
+        for (int s = 0; s < nseg; s++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive(&full[stage]);
+          if (++stage == nst) { stage = 0; phase ^= 1; }
+        }
+    }
+    if (p.pdl) pdl_launch_dependents();
+    return;
+  }
+
+  // ============================= consumer warps =============================
+  if (p.pdl) pdl_wait();  // activations come from the upstream kernel
+
+  const int ctid = tid;  // 0 .. NCW*32-1
+  constexpr int NCT = NCW * 32;
+  if (p.xkind == X_Q8_1) {
+    // gather pre-quantised Q8_1 blocks straight into unit order
+    const block_q8_1 *y = (const block_q8_1 *)p.x;
+    for (int idx = ctid; idx < NCOLS * nunits; idx += NCT) {
+      const int col = idx / nunits, u = idx - col * nunits;
+      const int blk = u / Q::UPB, c = u - blk * Q::UPB;
+      int q[8];
+      float a[Q::AUX];
+      if (col < p.ncols) {
+        const block_q8_1 *yb = y + (size_t)col * p.stride_col_y + (size_t)blk * (Q::QK / 32);
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+          const int e = Q::x_elem(c, w);
+          q[w] = *(const int *)(yb[e >> 5].qs + (e & 31));
+        }
+        Q::aux(q, c, YGlobal{yb}, a);
+      } else {
+#pragma unroll
+        for (int w = 0; w < 8; w++) q[w] = 0;
+#pragma unroll
+        for (int i = 0; i < Q::AUX; i++) a[i] = 0.f;
+      }
+      xq0[idx] = make_int4(q[0], q[1], q[2], q[3]);
+      xq1[idx] = make_int4(q[4], q[5], q[6], q[7]);
+#pragma unroll
+      for (int i = 0; i < Q::AUX; i++) xa[(size_t)idx * Q::AUX + i] = a[i];
+    }
+  } else {
+    // fused prologue: (optional RMSNorm) -> round to activation dtype -> Q8_1 -> unit order.
+    // Staging area = start of the ring?  No: the ring is live (producer is streaming), so the
+    // natural-order q8 data is staged in the x region itself, column by column, via registers.
+    float *red = (float *)(smem + 128 + 64);  // 8 floats of scratch inside the header page
+    for (int col = 0; col < NCOLS; col++) {
+      float inv_rms = 1.0f;
+      if (p.norm_w != nullptr && col < p.ncols) {
+        float ss = 0.f;
+        for (int i = ctid; i < p.K; i += NCT) {
+          const float v = load_act(p.x, (int64_t)col * p.K + i, p.xdtype);
+          ss += v * v;
+        }
+        ss = warp_sum(ss);
+        asm volatile("bar.sync 1, %0;" ::"n"(NCT));
+        if (lane == 0) red[warp] = ss;
+        asm volatile("bar.sync 1, %0;" ::"n"(NCT));
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < NCW; i++) tot += red[i];
+        inv_rms = rsqrtf(tot / (float)p.K + p.eps);
+      }
+      // thread per q8 block: quantise, scatter bytes into unit order
+      int8_t *xq0b = (int8_t *)(xq0 + (size_t)col * nunits);
+      int8_t *xq1b = (int8_t *)(xq1 + (size_t)col * nunits);
+      float2 *ds = (float2 *)(xa + (size_t)col * nunits * Q::AUX);  // temp (d,s) per q8 block lives in aux space
+      // pass 1: quantise into natural order staged in xq0/xq1 (32 B per q8 block: first 16 B in
+      // xq0[blk], last 16 B in xq1[blk]) and (d,s) into a scratch strip at the ring's tail.
+      float2 *dsbuf = (float2 *)(ring + (size_t)nst * G::STAGE_BYTES) + (size_t)col * nunits;
+      (void)ds;
+      for (int b = ctid; b < nunits; b += NCT) {
+        float v[32];
+        int8_t q[32];
+        if (col < p.ncols) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            float t = load_act(p.x, (int64_t)col * p.K + b * 32 + i, p.xdtype);
+            if (p.norm_w != nullptr) t = round_act(t * inv_rms * load_act(p.norm_w, b * 32 + i, p.xdtype), p.xdtype);
+            v[i] = t;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = 0.f;
+        }
+        float d, s;
+        quantize_block_q8_1(v, q, d, s);
+        dsbuf[b] = make_float2(d, s);
+        int4 lo, hi;
+        memcpy(&lo, q, 16);
+        memcpy(&hi, q + 16, 16);
+        ((int4 *)xq0b)[b] = lo;
+        ((int4 *)xq1b)[b] = hi;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NCT));
+    // pass 2: permute natural order -> unit order in registers, barrier, write back
+    {
+      constexpr int MAXU = 4;  // units per thread per column supported: K <= 4*256*32
+      for (int col = 0; col < NCOLS; col++) {
+        int q[MAXU][8];
+        float a[MAXU][Q::AUX];
+        const int8_t *n0 = (const int8_t *)(xq0 + (size_t)col * nunits);
+        const int8_t *n1 = (const int8_t *)(xq1 + (size_t)col * nunits);
+        const float2 *dsbuf = (const float2 *)(ring + (size_t)nst * G::STAGE_BYTES) + (size_t)col * nunits;
+#pragma unroll
+        for (int k = 0; k < MAXU; k++) {
+          const int u = ctid + k * NCT;
+          if (u < nunits) {
+            const int blk = u / Q::UPB, c = u - blk * Q::UPB;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+              const int e = Q::x_elem(c, w) + blk * Q::QK;  // element index along K
+              const int b32 = e >> 5, o = e & 31;
+              q[k][w] = (o < 16) ? *(const int *)(n0 + b32 * 16 + o) : *(const int *)(n1 + b32 * 16 + (o - 16));
+            }
+            Q::aux(q[k], c, YSmem{dsbuf + (size_t)blk * (Q::QK / 32)}, a[k]);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NCT));
+#pragma unroll
+        for (int k = 0; k < MAXU; k++) {
+          const int u = ctid + k * NCT;
+          if (u < nunits) {
+            const size_t idx = (size_t)col * nunits + u;
+            xq0[idx] = make_int4(q[k][0], q[k][1], q[k][2], q[k][3]);
+            xq1[idx] = make_int4(q[k][4], q[k][5], q[k][6], q[k][7]);
+#pragma unroll
+            for (int i = 0; i < Q::AUX; i++) xa[idx * Q::AUX + i] = a[k][i];
+          }
+        }
+      }
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(NCT));
+
+  // ----------------------------- main streaming loop -----------------------------
+  int stage = 0, phase = 0;
+  for (int base = vr0; base < vr1; base += P) {
+    // the two slots of this warp
+    const uint8_t *rowp[2] = {nullptr, nullptr};
+    int mm[2] = {0, 0}, rr[2] = {0, 0};
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int slot = 2 * warp + r;
+      const int vrow = (p.mode == MODE_GLU) ? base + warp : base + slot;
+      if (vrow < vr1) {
+        resolve_row(p, vrow, r, mm[r], rr[r]);
+        rowp[r] = p.w[mm[r]] + (size_t)rr[r] * row_bytes;
+      }
+    }
+    float acc[2][NCOLS];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int j = 0; j < NCOLS; j++) acc[r][j] = 0.f;
+
+    for (int s = 0; s < nseg; s++) {
+      mbar_wait(&full[stage], phase);
+      const int u = s * SEG_UNITS + lane;
+      if (u < nunits) {
+        const int bis = lane / Q::UPB, c = lane - bis * Q::UPB;
+        typename Q::W w[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          if (rowp[r] != nullptr) {
+            const uint8_t *slotp = ring + (size_t)stage * G::STAGE_BYTES + (size_t)(2 * warp + r) * G::SLOT_BYTES;
+            const uint32_t ph = (uint32_t)((uintptr_t)(rowp[r] + (size_t)s * G::SEG_BYTES) & 15);
+            Q::template load<FAST>(slotp + ph + bis * Q::BYTES, c, w[r]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NCOLS; j++) {
+          const size_t idx = (size_t)j * nunits + u;
+          const int4 q0 = xq0[idx], q1 = xq1[idx];
+          const int xq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+          float a[Q::AUX];
+          if constexpr (Q::AUX == 4) {
+            const float4 t = *(const float4 *)(xa + idx * 4);
+            a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+          } else if constexpr (Q::AUX == 2) {
+            const float2 t = *(const float2 *)(xa + idx * 2);
+            a[0] = t.x; a[1] = t.y;
+          } else if constexpr (Q::AUX == 8) {
+            const float4 t0 = *(const float4 *)(xa + idx * 8), t1 = *(const float4 *)(xa + idx * 8 + 4);
+            a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < Q::AUX; i++) a[i] = xa[idx * Q::AUX + i];
+          }
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+            if (rowp[r] != nullptr) acc[r][j] += Q::dot(w[r], xq, a, c);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == nst) { stage = 0; phase ^= 1; }
+    }
+
+    // ----------------------------- reduce + epilogue -----------------------------
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int j = 0; j < NCOLS; j++) acc[r][j] = warp_sum(acc[r][j]);
+
+    if (lane == 0) {
+      if (p.mode == MODE_GLU) {
+        if (rowp[0] != nullptr) {
+#pragma unroll
+          for (int j = 0; j < NCOLS; j++) {
+            if (j < p.ncols) {
+              // cast gate and up to the output dtype first, activation in f32, product in
+              // dtype — REF mmvq_gguf.cu:866-870
+              const float g = round_act(acc[0][j], p.dst_dtype);
+              const float up = round_act(acc[1][j], p.dst_dtype);
+              const float act = round_act(glu_activation(g, p.activation), p.dst_dtype);
+              store_act(p.dst[0], (int64_t)j * p.stride_col_dst + rr[0], act * up, p.dst_dtype);
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          if (rowp[r] == nullptr) continue;
+          const int nr = p.nrows[mm[r]];
+          const int64_t cs = (p.mode == MODE_QKV) ? nr : p.stride_col_dst;
+#pragma unroll
+          for (int j = 0; j < NCOLS; j++) {
+            if (j < p.ncols) {
+              float v = acc[r][j];
+              if (p.residual != nullptr) {
+                // y materialised in dtype, then residual add rounded again (candle `+`)
+                v = round_act(v, p.dst_dtype) + load_act(p.residual, (int64_t)j * cs + rr[r], p.dst_dtype);
+              }
+              store_act(p.dst[mm[r]], (int64_t)j * cs + rr[r], v, p.dst_dtype);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static int g_num_sms = 0;
+static int g_max_smem = 0;
+
+static void query_device() {
+  if (g_num_sms) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (g_num_sms <= 0) g_num_sms = 148;
+  if (g_max_smem <= 0) g_max_smem = 227 * 1024;
+}
+
+template <int T, int NCOLS, bool FAST>
+static cudaError_t launch_one(MmvqParams p, cudaStream_t stream) {
+  using G = Geo<T>;
+  query_device();
+  const int nunits = p.K / 32;
+  const size_t xbytes = 256 + (size_t)NCOLS * nunits * G::XU_BYTES + 128;
+  const size_t scratch = (p.xkind == X_RAW) ? (size_t)NCOLS * nunits * 8 : 0;
+  // two CTAs per SM by design: keep each under half of the SM's shared memory
+  const size_t budget = (size_t)g_max_smem / 2 - 1024;
+  int nst = MAX_STAGES;
+  while (nst > 2 && xbytes + scratch + (size_t)nst * G::STAGE_BYTES > budget) nst--;
+  size_t smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
+  if (smem > (size_t)g_max_smem) return cudaErrorInvalidConfiguration;
+  p.nstages = nst;
+  const int P = (p.mode == MODE_GLU) ? NCW : SLOTS;
+  int grid = (p.vrows + P - 1) / P;
+  const int max_grid = 2 * g_num_sms;
+  if (grid > max_grid) grid = max_grid;
+  if (grid < 1) grid = 1;
+  auto kern = mmvq_stream_kernel<T, NCOLS, FAST>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <int T>
+static cudaError_t launch_type(MmvqParams p, cudaStream_t stream) {
+  using Q = QT<T>;
+  // FAST: every block start is aligned to the type's natural alignment
+  const int row_bytes = (p.K / Q::QK) * Q::BYTES;
+  bool fast = (row_bytes % Q::WALIGN) == 0;
+  for (int m = 0; m < 3; m++)
+    if (p.w[m] != nullptr && ((uintptr_t)p.w[m] % Q::WALIGN) != 0) fast = false;
+  const int b = p.ncols;
+#define MRS_DISPATCH(NC)                                                        \
+  return fast ? launch_one<T, NC, true>(p, stream) : launch_one<T, NC, false>(p, stream)
+  if (b == 1) { MRS_DISPATCH(1); }
+  if (b == 2) { MRS_DISPATCH(2); }
+  if (b <= 4) { MRS_DISPATCH(4); }
+  MRS_DISPATCH(8);
+#undef MRS_DISPATCH
+}
+
+cudaError_t mmvq_dispatch(int type, const MmvqParams &p, cudaStream_t stream) {
+  if (p.ncols < 1 || p.ncols > 8) return cudaErrorInvalidValue;
+  switch (type) {
+  case MRS_Q4_0: return launch_type<MRS_Q4_0>(p, stream);
+  case MRS_Q4_1: return launch_type<MRS_Q4_1>(p, stream);
+  case MRS_Q5_0: return launch_type<MRS_Q5_0>(p, stream);
+  case MRS_Q5_1: return launch_type<MRS_Q5_1>(p, stream);
+  case MRS_Q8_0: return launch_type<MRS_Q8_0>(p, stream);
+  case MRS_Q2_K: return launch_type<MRS_Q2_K>(p, stream);
+  case MRS_Q3_K: return launch_type<MRS_Q3_K>(p, stream);
+  case MRS_Q4_K: return launch_type<MRS_Q4_K>(p, stream);
+  case MRS_Q5_K: return launch_type<MRS_Q5_K>(p, stream);
+  case MRS_Q6_K: return launch_type<MRS_Q6_K>(p, stream);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---------------------------------------------------------------- standalone Q8_1 quantiser
+// REF: mmvq_gguf.cu:1220-1318 (kernel) and :1606-1641 (launchers): grid (ceil(kx_padded/256),
+// rows), one warp per 32-element block, zero padding to kx_padded.
+template <typename T>
+__global__ void quantize_q8_1_kernel(const T *__restrict__ x, block_q8_1 *__restrict__ y, int kx, int kx_padded) {
+  const int ix = blockDim.x * blockIdx.x + threadIdx.x;
+  if (ix >= kx_padded) return;
+  const int iy = blockIdx.y;
+  const int64_t ip = (int64_t)iy * kx_padded + ix;
+  const int ib = (int)(ip >> 5), iqs = (int)(ip & 31);
+  const float xi = (ix < kx) ? (float)x[(int64_t)iy * kx + ix] : 0.0f;
+  const float amax = warp_max(fabsf(xi));
+  const float sum = warp_sum(xi);
+  const float d = __fdividef(amax, 127.0f);
+  const int8_t q = (amax == 0.0f) ? (int8_t)0 : (int8_t)roundf(__fdividef(xi, d));
+  y[ib].qs[iqs] = q;
+  if (iqs == 0) y[ib].ds = __halves2half2(__float2half_rn(d), __float2half_rn(sum));
+}
+
+}  // namespace mrs
+
+using namespace mrs;
+
+static int g_mrs_pdl = 0;  // PDL on reference-shaped launchers is opt-in (mrs_set_pdl)
+
+extern "C" void mrs_set_pdl(int enabled) { g_mrs_pdl = enabled; }
+
+static inline void report(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) fprintf(stderr, "mrs_b200: %s failed: %s\n", what, cudaGetErrorString(e));
+}
+
+// ---- reference-shaped launchers ------------------------------------------------------------
+#define MRS_Q8_1_LAUNCHER(tag, ctype)                                                          \
+  extern "C" void launch_mmvq_gguf_quantize_q8_1_##tag(const void *x, void *vy, int kx,        \
+                                                       int kx_padded, int num_rows,            \
+                                                       void *stream) {                         \
+    dim3 grid((kx_padded + 255) / 256, num_rows, 1);                                           \
+    quantize_q8_1_kernel<ctype><<<grid, 256, 0, (cudaStream_t)stream>>>(                       \
+        (const ctype *)x, (block_q8_1 *)vy, kx, kx_padded);                                    \
+  }
+MRS_Q8_1_LAUNCHER(bf16, __nv_bfloat16)
+MRS_Q8_1_LAUNCHER(f16, __half)
+MRS_Q8_1_LAUNCHER(f32, float)
+
+static void run_plain(int type, int dt, const void *vx, const void *vy, void *dst, int ncols_x, int nrows_x,
+                      int stride_col_y, int stride_col_dst, int b_size, void *stream) {
+  if (b_size < 1 || b_size > 8) return;  // REF launcher: `default: break`
+  MmvqParams p = {};
+  p.w[0] = (const uint8_t *)vx; p.dst[0] = dst; p.nrows[0] = nrows_x;
+  p.x = vy; p.xkind = X_Q8_1; p.K = ncols_x; p.stride_col_y = stride_col_y;
+  p.stride_col_dst = stride_col_dst; p.ncols = b_size; p.mode = MODE_PLAIN; p.dst_dtype = dt;
+  p.vrows = nrows_x; p.pdl = g_mrs_pdl;
+  report(mmvq_dispatch(type, p, (cudaStream_t)stream), "mmvq plain");
+}
+
+static void run_glu(int type, int dt, const void *vg, const void *vu, const void *vy, void *dst, int ncols_x,
+                    int nrows_x, int stride_col_y, int stride_col_dst, int b_size, int activation, void *stream) {
+  if (b_size < 1 || b_size > 8) return;
+  MmvqParams p = {};
+  p.w[0] = (const uint8_t *)vg; p.w[1] = (const uint8_t *)vu; p.dst[0] = dst; p.nrows[0] = nrows_x; p.nrows[1] = nrows_x;
+  p.x = vy; p.xkind = X_Q8_1; p.K = ncols_x; p.stride_col_y = stride_col_y;
+  p.stride_col_dst = stride_col_dst; p.ncols = b_size; p.mode = MODE_GLU; p.activation = activation;
+  p.dst_dtype = dt; p.vrows = nrows_x; p.pdl = g_mrs_pdl;
+  report(mmvq_dispatch(type, p, (cudaStream_t)stream), "mmvq fused_glu");
+}
+
+static void run_qkv(int type, int dt, const void *vq, const void *vk, const void *vv, const void *vy, void *qd,
+                    void *kd, void *vd, int ncols_x, int nq, int nk, int nv, int stride_col_y, int b_size,
+                    void *stream) {
+  if (b_size < 1 || b_size > 8) return;
+  MmvqParams p = {};
+  p.w[0] = (const uint8_t *)vq; p.w[1] = (const uint8_t *)vk; p.w[2] = (const uint8_t *)vv;
+  p.dst[0] = qd; p.dst[1] = kd; p.dst[2] = vd; p.nrows[0] = nq; p.nrows[1] = nk; p.nrows[2] = nv;
+  p.x = vy; p.xkind = X_Q8_1; p.K = ncols_x; p.stride_col_y = stride_col_y; p.ncols = b_size;
+  p.mode = MODE_QKV; p.dst_dtype = dt; p.vrows = nq + nk + nv; p.pdl = g_mrs_pdl;
+  report(mmvq_dispatch(type, p, (cudaStream_t)stream), "mmvq fused_qkv");
+}
+
+#define MRS_MMVQ_SET(tag, TYPE, dtag, DT)                                                              \
+  extern "C" void launch_mmvq_gguf_##tag##_##dtag##_plain(const void *vx, const void *vy, void *dst,   \
+      int ncols_x, int nrows_x, int stride_col_y, int stride_col_dst, int b_size, void *stream) {      \
+    run_plain(TYPE, DT, vx, vy, dst, ncols_x, nrows_x, stride_col_y, stride_col_dst, b_size, stream);  \
+  }                                                                                                    \
+  extern "C" void launch_mmvq_gguf_##tag##_##dtag##_fused_glu(const void *vx_gate, const void *vx_up,  \
+      const void *vy, void *dst, int ncols_x, int nrows_x, int stride_col_y, int stride_col_dst,       \
+      int b_size, int activation, void *stream) {                                                      \
+    run_glu(TYPE, DT, vx_gate, vx_up, vy, dst, ncols_x, nrows_x, stride_col_y, stride_col_dst, b_size, \
+            activation, stream);                                                                       \
+  }                                                                                                    \
+  extern "C" void launch_mmvq_gguf_##tag##_##dtag##_fused_qkv(const void *vx_q, const void *vx_k,      \
+      const void *vx_v, const void *vy, void *q_dst, void *k_dst, void *v_dst, int ncols_x,            \
+      int nrows_q, int nrows_k, int nrows_v, int stride_col_y, int b_size, void *stream) {             \
+    run_qkv(TYPE, DT, vx_q, vx_k, vx_v, vy, q_dst, k_dst, v_dst, ncols_x, nrows_q, nrows_k, nrows_v,   \
+            stride_col_y, b_size, stream);                                                             \
+  }
+#define MRS_MMVQ_TYPE(tag, TYPE)            \
+  MRS_MMVQ_SET(tag, TYPE, bf16, MRS_BF16)   \
+  MRS_MMVQ_SET(tag, TYPE, f16, MRS_F16)     \
+  MRS_MMVQ_SET(tag, TYPE, f32, MRS_F32)
+MRS_MMVQ_TYPE(q4_0, MRS_Q4_0)
+MRS_MMVQ_TYPE(q4_1, MRS_Q4_1)
+MRS_MMVQ_TYPE(q5_0, MRS_Q5_0)
+MRS_MMVQ_TYPE(q5_1, MRS_Q5_1)
+MRS_MMVQ_TYPE(q8_0, MRS_Q8_0)
+MRS_MMVQ_TYPE(q2_k, MRS_Q2_K)
+MRS_MMVQ_TYPE(q3_k, MRS_Q3_K)
+MRS_MMVQ_TYPE(q4_k, MRS_Q4_K)
+MRS_MMVQ_TYPE(q5_k, MRS_Q5_K)
+MRS_MMVQ_TYPE(q6_k, MRS_Q6_K)
+
+// ---- B200-native fused entry points (same arithmetic, fewer launches) ------------------------
+// y = W . q8_1( [rmsnorm_w *] x ) [+ residual]; mode 0 plain, 1 fused GLU, 2 fused QKV.
+// x is raw activations [b_size, K] of dtype `dt`; norm_w may be NULL; residual may be NULL.
+extern "C" int mrs_mmvq_fused(int ggml_type, int mode, int dt, const void *w0, const void *w1, const void *w2,
+                              const void *x, const void *norm_w, float eps, const void *residual,
+                              void *dst0, void *dst1, void *dst2, int K, int n0, int n1, int n2,
+                              int b_size, int activation, int pdl, void *stream) {
+  MmvqParams p = {};
+  p.w[0] = (const uint8_t *)w0; p.w[1] = (const uint8_t *)w1; p.w[2] = (const uint8_t *)w2;
+  p.dst[0] = dst0; p.dst[1] = dst1; p.dst[2] = dst2;
+  p.nrows[0] = n0; p.nrows[1] = n1; p.nrows[2] = n2;
+  p.x = x; p.xkind = X_RAW; p.xdtype = dt; p.norm_w = norm_w; p.eps = eps; p.residual = residual;
+  p.K = K; p.stride_col_dst = n0; p.ncols = b_size; p.mode = mode; p.activation = activation;
+  p.dst_dtype = dt; p.pdl = pdl;
+  p.vrows = (mode == MODE_QKV) ? n0 + n1 + n2 : n0;
+  if (K > 4 * NCW * 32 * 32) return (int)cudaErrorInvalidValue;  // fused prologue limit (MAXU)
+  return (int)mmvq_dispatch(ggml_type, p, (cudaStream_t)stream);
+}
