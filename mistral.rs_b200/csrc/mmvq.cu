@@ -29,7 +29,9 @@ namespace mrs {
 constexpr int NCW = 8;                    // consumer warps
 constexpr int NTHREADS = (NCW + 1) * 32;  // + producer warp
 constexpr int SLOTS = 2 * NCW;            // row-segments per stage (2 per consumer warp)
-constexpr int SEG_UNITS = 32;             // 32-weight units per K segment (1024 weights)
+#ifndef MRS_SEG_TARGET_BYTES
+#define MRS_SEG_TARGET_BYTES 2304         // bulk-copy size per (row, K segment): TMA issue cost is per copy
+#endif
 constexpr int MAX_STAGES = 12;
 
 enum { MODE_PLAIN = 0, MODE_GLU = 1, MODE_QKV = 2 };
@@ -51,6 +53,10 @@ struct MmvqParams {
 
 template <int T> struct Geo {
   using Q = QT<T>;
+  // units per lane per K segment, chosen so one row-segment is ~MRS_SEG_TARGET_BYTES
+  static constexpr int UPL_RAW = (MRS_SEG_TARGET_BYTES * Q::UPB + 16 * Q::BYTES) / (32 * Q::BYTES);
+  static constexpr int UPL = UPL_RAW < 1 ? 1 : (UPL_RAW > 8 ? 8 : UPL_RAW);
+  static constexpr int SEG_UNITS = 32 * UPL;                 // 32-weight units per K segment
   static constexpr int SEG_BLOCKS = SEG_UNITS / Q::UPB;      // weight blocks per segment
   static constexpr int SEG_BYTES = SEG_BLOCKS * Q::BYTES;    // bytes per row-segment
   static constexpr int SLOT_BYTES = (SEG_BYTES + 30 + 15) & ~15;
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int nunits = p.K / 32;
-  const int nseg = (nunits + SEG_UNITS - 1) / SEG_UNITS;
+  const int nseg = (nunits + G::SEG_UNITS - 1) / G::SEG_UNITS;
   const int row_bytes = (p.K / Q::QK) * Q::BYTES;
   const int nst = p.nstages;
 
@@ -331,9 +337,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 
     for (int s = 0; s < nseg; s++) {
       mbar_wait(&full[stage], phase);
-      const int u = s * SEG_UNITS + lane;
+#pragma unroll
+      for (int ui = 0; ui < G::UPL; ui++) {
+      const int us = ui * 32 + lane;           // unit within the segment
+      const int u = s * G::SEG_UNITS + us;
       if (u < nunits) {
-        const int bis = lane / Q::UPB, c = lane - bis * Q::UPB;
+        const int bis = us / Q::UPB, c = us - bis * Q::UPB;
         typename Q::W w[2];
 #pragma unroll
         for (int r = 0; r < 2; r++) {
@@ -366,6 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
           for (int r = 0; r < 2; r++)
             if (rowp[r] != nullptr) acc[r][j] += Q::dot(w[r], xq, a, c);
         }
+      }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);

@@ -17,12 +17,20 @@ try:
 except Exception:
     pass
 
+def cur():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
 def bench(fn, iters=20):
+    """Time `iters` back-to-back launches replayed from one CUDA graph (no CPU launch cost)."""
     for _ in range(3): fn(0)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters): fn(i)
+    g.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters): fn(i)
+    g.replay()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3  # us
 
@@ -38,19 +46,18 @@ def run(dtype, N, K, batch=1, mode="plain"):
     kp = (K + 511) // 512 * 512
     scratch = torch.empty(batch * kp // 32 * 36, dtype=torch.uint8, device=dev)
     out = torch.empty(batch, N, dtype=torch.bfloat16, device=dev)
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     res = {}
     for name, L in (("ours", lib()), ("ref", ref)):
         if L is None: continue
         qf = getattr(L, "launch_mmvq_gguf_quantize_q8_1_bf16")
-        qf(P(x), P(scratch), K, kp, batch, st)
+        qf(P(x), P(scratch), K, kp, batch, cur())
         if mode == "plain":
             f = getattr(L, f"launch_mmvq_gguf_{dtype}_bf16_plain")
-            fn = lambda i: f(P(ws[i % copies].data), P(scratch), P(out), K, N, kp // 32, N, batch, st)
+            fn = lambda i: f(P(ws[i % copies].data), P(scratch), P(out), K, N, kp // 32, N, batch, cur())
         else:
             f = getattr(L, f"launch_mmvq_gguf_{dtype}_bf16_fused_glu")
-            fn = lambda i: f(P(ws[2 * (i % copies)].data), P(ws[2 * (i % copies) + 1].data), P(scratch), P(out), K, N, kp // 32, N, batch, 0, st)
+            fn = lambda i: f(P(ws[2 * (i % copies)].data), P(ws[2 * (i % copies) + 1].data), P(scratch), P(out), K, N, kp // 32, N, batch, 0, cur())
         us = bench(fn)
         res[name] = (us, wbytes * nmats / us / 1e3, out.float().clone())
     line = f"{dtype:5s} {mode:5s} N={N:6d} K={K:6d} b={batch} bytes={wbytes*nmats/1e6:7.1f}MB"
@@ -61,6 +68,9 @@ def run(dtype, N, K, batch=1, mode="plain"):
         line += f" | maxdiff vs ref {d:.3g}"
     print(line, flush=True)
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "one":
+    run(sys.argv[2], int(sys.argv[3]), int(sys.argv[4]))
+    sys.exit(0)
 if __name__ == "__main__":
     shapes = [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336), (128256, 4096)]
     for dtype in ("q4_k", "q6_k", "q8_0"):
