@@ -29,9 +29,7 @@ namespace mrs {
 constexpr int NCW = 8;                    // consumer warps
 constexpr int NTHREADS = (NCW + 1) * 32;  // + producer warp
 constexpr int SLOTS = 2 * NCW;            // row-segments per stage (2 per consumer warp)
-#ifndef MRS_SEG_TARGET_BYTES
-#define MRS_SEG_TARGET_BYTES 2304         // bulk-copy size per (row, K segment): TMA issue cost is per copy
-#endif
+
 constexpr int MAX_STAGES = 12;
 
 enum { MODE_PLAIN = 0, MODE_GLU = 1, MODE_QKV = 2 };
@@ -53,16 +51,31 @@ struct MmvqParams {
 
 template <int T> struct Geo {
   using Q = QT<T>;
-  // units per lane per K segment, chosen so one row-segment is ~MRS_SEG_TARGET_BYTES
-  static constexpr int UPL_RAW = (MRS_SEG_TARGET_BYTES * Q::UPB + 16 * Q::BYTES) / (32 * Q::BYTES);
-  static constexpr int UPL = UPL_RAW < 1 ? 1 : (UPL_RAW > 8 ? 8 : UPL_RAW);
+  static constexpr int UPL = Q::UPL;                         // units per lane per K segment
   static constexpr int SEG_UNITS = 32 * UPL;                 // 32-weight units per K segment
-  static constexpr int SEG_BLOCKS = SEG_UNITS / Q::UPB;      // weight blocks per segment
-  static constexpr int SEG_BYTES = SEG_BLOCKS * Q::BYTES;    // bytes per row-segment
+  static constexpr int SEG_BLOCKS = SEG_UNITS / Q::UPB;      // weight blocks per segment (NB)
+  static constexpr int SEG_BYTES = SEG_BLOCKS * Q::BYTES;    // bytes per row-segment (~2-3.5 KB)
   static constexpr int SLOT_BYTES = (SEG_BYTES + 30 + 15) & ~15;
   static constexpr int STAGE_BYTES = SLOTS * SLOT_BYTES;
   static constexpr int XU_BYTES = 32 + 4 * Q::AUX;           // smem bytes per unit per column
+  // lane -> (block within segment, chunk): blk = lane % NBL, c = ui * CPS + lane / NBL
+  static constexpr int NBL = (Q::UPB == 1) ? 32 : (SEG_BLOCKS < 32 ? SEG_BLOCKS : 32);
+  static constexpr int CPS = (Q::UPB == 1) ? 1 : 32 / NBL;
+  static_assert(Q::UPB == 1 || (NBL * CPS == 32 && CPS * UPL == Q::UPB), "segment geometry");
 };
+
+// position p in the consumption-ordered activation array <-> (weight block, chunk)
+template <int T> __device__ __forceinline__ void pos_to_unit(int pos, int &blk, int &c) {
+  using G = Geo<T>;
+  if constexpr (QT<T>::UPB == 1) {
+    blk = pos; c = 0;
+  } else {
+    const int s = pos / G::SEG_UNITS, r = pos - s * G::SEG_UNITS;
+    const int ui = r >> 5, lane = r & 31;
+    blk = s * G::SEG_BLOCKS + (lane % G::NBL);
+    c = ui * G::CPS + lane / G::NBL;
+  }
+}
 
 __device__ __forceinline__ void resolve_row(const MmvqParams &p, int vrow, int which, int &m, int &row) {
   if (p.mode == MODE_QKV) {
@@ -95,12 +108,11 @@ __device__ __forceinline__ void quantize_block_q8_1(const float *v, int8_t *q, f
   float amax = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; i++) amax = fmaxf(amax, fabsf(v[i]));
-  // butterfly order: masks 16,8,4,2,1
-  float s[32];
+  float s[16];
 #pragma unroll
-  for (int i = 0; i < 32; i++) s[i] = v[i];
+  for (int i = 0; i < 16; i++) s[i] = v[i] + v[i + 16];
 #pragma unroll
-  for (int m = 16; m > 0; m >>= 1) {
+  for (int m = 8; m > 0; m >>= 1) {
 #pragma unroll
     for (int i = 0; i < m; i++) s[i] = s[i] + s[i + m];
   }
@@ -119,19 +131,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int nunits = p.K / 32;
-  const int nseg = (nunits + G::SEG_UNITS - 1) / G::SEG_UNITS;
-  const int row_bytes = (p.K / Q::QK) * Q::BYTES;
+  const int nblocks = p.K / Q::QK;
+  const int nseg = (nblocks + G::SEG_BLOCKS - 1) / G::SEG_BLOCKS;
+  const int npos = nseg * G::SEG_UNITS;  // padded unit count (consumption order)
+  const int row_bytes = nblocks * Q::BYTES;
   const int nst = p.nstages;
 
-  // smem carve-up: [barriers][x: q lo | q hi | aux][ring]
+  // smem carve-up (plain offsets so every access stays in the shared window):
+  // [barriers 256 B][xq0 | xq1 | xa][ring][(d,s) scratch for the fused prologue]
   uint64_t *full = (uint64_t *)smem;
   uint64_t *empty = full + MAX_STAGES;
-  uint8_t *xbase = smem + 256;
-  int4 *xq0 = (int4 *)xbase;                           // [NCOLS][nunits]
-  int4 *xq1 = xq0 + (size_t)NCOLS * nunits;            // [NCOLS][nunits]
-  float *xa = (float *)(xq1 + (size_t)NCOLS * nunits); // [NCOLS][nunits][AUX]
-  uint8_t *ring = (uint8_t *)(((uintptr_t)(xa + (size_t)NCOLS * nunits * Q::AUX) + 127) & ~(uintptr_t)127);
+  const uint32_t off_xq0 = 256;
+  const uint32_t off_xq1 = off_xq0 + (uint32_t)NCOLS * npos * 16;
+  const uint32_t off_xa = off_xq1 + (uint32_t)NCOLS * npos * 16;
+  const uint32_t off_ring = (off_xa + (uint32_t)NCOLS * npos * Q::AUX * 4 + 127u) & ~127u;
+  const uint32_t off_ds = off_ring + (uint32_t)nst * G::STAGE_BYTES;
+  int4 *xq0 = (int4 *)(smem + off_xq0);   // [NCOLS][npos]
+  int4 *xq1 = (int4 *)(smem + off_xq1);   // [NCOLS][npos]
+  float *xa = (float *)(smem + off_xa);   // [NCOLS][npos][AUX]
+  uint8_t *ring = smem + off_ring;
 
   if (tid == 0) {
     for (int i = 0; i < nst; i++) { mbar_init(&full[i], 32); mbar_init(&empty[i], NCW); }
@@ -149,39 +167,31 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
     // Weights are immutable, so streaming may start before the upstream kernel finished.
     int stage = 0, phase = 0;
     const int slot = lane;
-    if (slot < SLOTS) {
-      for (int base = vr0; base < vr1; base += P) {
+    for (int base = vr0; base < vr1; base += P) {
+      const uint8_t *rowp = nullptr;
+      if (slot < SLOTS) {
         const int vrow = (p.mode == MODE_GLU) ? base + (slot >> 1) : base + slot;
-        const uint8_t *rowp = nullptr;
         if (vrow < vr1) {
           int m, row;
           resolve_row(p, vrow, slot & 1, m, row);
           rowp = p.w[m] + (size_t)row * row_bytes;
         }
-        for (int s = 0; s < nseg; s++) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          if (rowp != nullptr) {
-            const int off = s * G::SEG_BYTES;
-            const int len = min(G::SEG_BYTES, row_bytes - off);
-            const uintptr_t a = (uintptr_t)(rowp + off);
-            const uintptr_t a0 = a & ~(uintptr_t)15;
-            const uint32_t bytes = (uint32_t)(((a + len + 15) & ~(uintptr_t)15) - a0);
-            mbar_arrive_expect_tx(&full[stage], bytes);
-            bulk_g2s(ring + (size_t)stage * G::STAGE_BYTES + (size_t)slot * G::SLOT_BYTES, (const void *)a0, bytes, &full[stage]);
-          } else {
-            mbar_arrive(&full[stage]);
-          }
-          if (++stage == nst) { stage = 0; phase ^= 1; }
-        }
       }
-    } else {
-      // lanes without a slot still owe their arrival on every stage use
-      for (int base = vr0; base < vr1; base += P)
-        for (int s = 0; s < nseg; s++) {
-          mbar_wait(&empty[stage], phase ^ 1);
+      for (int s = 0; s < nseg; s++) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (rowp != nullptr) {
+          const int off = s * G::SEG_BYTES;
+          const int len = min(G::SEG_BYTES, row_bytes - off);
+          const uintptr_t a = (uintptr_t)(rowp + off);
+          const uintptr_t a0 = a & ~(uintptr_t)15;
+          const uint32_t bytes = (uint32_t)(((a + len + 15) & ~(uintptr_t)15) - a0);
+          mbar_arrive_expect_tx(&full[stage], bytes);
+          bulk_g2s(ring + (uint32_t)stage * G::STAGE_BYTES + (uint32_t)slot * G::SLOT_BYTES, (const void *)a0, bytes, &full[stage]);
+        } else {
           mbar_arrive(&full[stage]);
-          if (++stage == nst) { stage = 0; phase ^= 1; }
         }
+        if (++stage == nst) { stage = 0; phase ^= 1; }
+      }
     }
     if (p.pdl) pdl_launch_dependents();
     return;
@@ -193,14 +203,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
   const int ctid = tid;  // 0 .. NCW*32-1
   constexpr int NCT = NCW * 32;
   if (p.xkind == X_Q8_1) {
-    // gather pre-quantised Q8_1 blocks straight into unit order
+    // gather pre-quantised Q8_1 blocks straight into consumption order
     const block_q8_1 *y = (const block_q8_1 *)p.x;
-    for (int idx = ctid; idx < NCOLS * nunits; idx += NCT) {
-      const int col = idx / nunits, u = idx - col * nunits;
-      const int blk = u / Q::UPB, c = u - blk * Q::UPB;
+    for (int idx = ctid; idx < NCOLS * npos; idx += NCT) {
+      const int col = idx / npos, pos = idx - col * npos;
+      int blk, c;
+      pos_to_unit<T>(pos, blk, c);
       int q[8];
       float a[Q::AUX];
-      if (col < p.ncols) {
+      if (col < p.ncols && blk < nblocks) {
         const block_q8_1 *yb = y + (size_t)col * p.stride_col_y + (size_t)blk * (Q::QK / 32);
 #pragma unroll
         for (int w = 0; w < 8; w++) {
@@ -220,10 +231,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
       for (int i = 0; i < Q::AUX; i++) xa[(size_t)idx * Q::AUX + i] = a[i];
     }
   } else {
-    // fused prologue: (optional RMSNorm) -> round to activation dtype -> Q8_1 -> unit order.
-    // Staging area = start of the ring?  No: the ring is live (producer is streaming), so the
-    // natural-order q8 data is staged in the x region itself, column by column, via registers.
-    float *red = (float *)(smem + 128 + 64);  // 8 floats of scratch inside the header page
+    // fused prologue: (optional RMSNorm) -> round to activation dtype -> Q8_1 -> consumption
+    // order.  Pass 1 stages natural-order q8 data in the x region itself (q8 block b: first
+    // 16 B in xq0[col][b], last 16 B in xq1[col][b]) and (d,s) in a strip behind the ring.
+    const int nq8 = p.K / 32;
+    float *red = (float *)(smem + 192);  // 8 floats of scratch inside the header page
+    float2 *dsall = (float2 *)(smem + off_ds);
     for (int col = 0; col < NCOLS; col++) {
       float inv_rms = 1.0f;
       if (p.norm_w != nullptr && col < p.ncols) {
@@ -241,17 +254,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
         for (int i = 0; i < NCW; i++) tot += red[i];
         inv_rms = rsqrtf(tot / (float)p.K + p.eps);
       }
-      // thread per q8 block: quantise, scatter bytes into unit order
-      int8_t *xq0b = (int8_t *)(xq0 + (size_t)col * nunits);
-      int8_t *xq1b = (int8_t *)(xq1 + (size_t)col * nunits);
-      float2 *ds = (float2 *)(xa + (size_t)col * nunits * Q::AUX);  // temp (d,s) per q8 block lives in aux space
-      // pass 1: quantise into natural order staged in xq0/xq1 (32 B per q8 block: first 16 B in
-      // xq0[blk], last 16 B in xq1[blk]) and (d,s) into a scratch strip at the ring's tail.
-      float2 *dsbuf = (float2 *)(ring + (size_t)nst * G::STAGE_BYTES) + (size_t)col * nunits;
-      (void)ds;
-      for (int b = ctid; b < nunits; b += NCT) {
+      int4 *n0 = xq0 + (size_t)col * npos, *n1 = xq1 + (size_t)col * npos;
+      float2 *dsbuf = dsall + (size_t)col * nq8;
+      for (int b = ctid; b < nq8; b += NCT) {
         float v[32];
-        int8_t q[32];
+        __align__(16) int8_t q[32];
         if (col < p.ncols) {
 #pragma unroll
           for (int i = 0; i < 32; i++) {
@@ -266,28 +273,26 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
         float d, s;
         quantize_block_q8_1(v, q, d, s);
         dsbuf[b] = make_float2(d, s);
-        int4 lo, hi;
-        memcpy(&lo, q, 16);
-        memcpy(&hi, q + 16, 16);
-        ((int4 *)xq0b)[b] = lo;
-        ((int4 *)xq1b)[b] = hi;
+        n0[b] = *(const int4 *)q;
+        n1[b] = *(const int4 *)(q + 16);
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NCT));
-    // pass 2: permute natural order -> unit order in registers, barrier, write back
+    // pass 2: natural order -> consumption order through registers
     {
-      constexpr int MAXU = 4;  // units per thread per column supported: K <= 4*256*32
+      constexpr int MAXU = 4;  // positions per thread per column: K <= MAXU * 256 * 32
       for (int col = 0; col < NCOLS; col++) {
         int q[MAXU][8];
         float a[MAXU][Q::AUX];
-        const int8_t *n0 = (const int8_t *)(xq0 + (size_t)col * nunits);
-        const int8_t *n1 = (const int8_t *)(xq1 + (size_t)col * nunits);
-        const float2 *dsbuf = (const float2 *)(ring + (size_t)nst * G::STAGE_BYTES) + (size_t)col * nunits;
+        const int8_t *n0 = (const int8_t *)(xq0 + (size_t)col * npos);
+        const int8_t *n1 = (const int8_t *)(xq1 + (size_t)col * npos);
+        const float2 *dsbuf = dsall + (size_t)col * nq8;
 #pragma unroll
         for (int k = 0; k < MAXU; k++) {
-          const int u = ctid + k * NCT;
-          if (u < nunits) {
-            const int blk = u / Q::UPB, c = u - blk * Q::UPB;
+          const int pos = ctid + k * NCT;
+          int blk = 0, c = 0;
+          if (pos < npos) pos_to_unit<T>(pos, blk, c);
+          if (pos < npos && blk < nblocks) {
 #pragma unroll
             for (int w = 0; w < 8; w++) {
               const int e = Q::x_elem(c, w) + blk * Q::QK;  // element index along K
@@ -295,14 +300,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
               q[k][w] = (o < 16) ? *(const int *)(n0 + b32 * 16 + o) : *(const int *)(n1 + b32 * 16 + (o - 16));
             }
             Q::aux(q[k], c, YSmem{dsbuf + (size_t)blk * (Q::QK / 32)}, a[k]);
+          } else {
+#pragma unroll
+            for (int w = 0; w < 8; w++) q[k][w] = 0;
+#pragma unroll
+            for (int i = 0; i < Q::AUX; i++) a[k][i] = 0.f;
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NCT));
 #pragma unroll
         for (int k = 0; k < MAXU; k++) {
-          const int u = ctid + k * NCT;
-          if (u < nunits) {
-            const size_t idx = (size_t)col * nunits + u;
+          const int pos = ctid + k * NCT;
+          if (pos < npos) {
+            const size_t idx = (size_t)col * npos + pos;
             xq0[idx] = make_int4(q[k][0], q[k][1], q[k][2], q[k][3]);
             xq1[idx] = make_int4(q[k][4], q[k][5], q[k][6], q[k][7]);
 #pragma unroll
@@ -316,18 +326,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 
   // ----------------------------- main streaming loop -----------------------------
   int stage = 0, phase = 0;
+  const int lblk = lane % G::NBL;   // block within the segment owned by this lane
+  const int lsub = lane / G::NBL;   // chunk offset within the step
   for (int base = vr0; base < vr1; base += P) {
-    // the two slots of this warp
-    const uint8_t *rowp[2] = {nullptr, nullptr};
-    int mm[2] = {0, 0}, rr[2] = {0, 0};
+    // the two slots of this warp; invalid slots are clamped to the last valid row (their
+    // results are computed on whatever the slot holds and discarded)
+    bool valid[2];
+    int mm[2], rr[2];
+    uint32_t ph[2];  // byte phase (address mod 16) of the row start, per slot
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-      const int slot = 2 * warp + r;
-      const int vrow = (p.mode == MODE_GLU) ? base + warp : base + slot;
-      if (vrow < vr1) {
-        resolve_row(p, vrow, r, mm[r], rr[r]);
-        rowp[r] = p.w[mm[r]] + (size_t)rr[r] * row_bytes;
-      }
+      int vrow = (p.mode == MODE_GLU) ? base + warp : base + 2 * warp + r;
+      valid[r] = vrow < vr1;
+      if (!valid[r]) vrow = vr1 - 1;
+      resolve_row(p, vrow, r, mm[r], rr[r]);
+      ph[r] = (uint32_t)((uintptr_t)(p.w[mm[r]] + (size_t)rr[r] * row_bytes) & 15);
     }
     float acc[2][NCOLS];
 #pragma unroll
@@ -337,45 +350,45 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 
     for (int s = 0; s < nseg; s++) {
       mbar_wait(&full[stage], phase);
+      const uint8_t *st = ring + (uint32_t)stage * G::STAGE_BYTES + (uint32_t)(2 * warp) * G::SLOT_BYTES;
+      // phase of this segment's start: (row phase + s * SEG_BYTES) mod 16
+      const uint32_t sp = (uint32_t)(s * G::SEG_BYTES) & 15u;
+      const uint8_t *wp0 = st + ((ph[0] + sp) & 15u) + lblk * Q::BYTES;
+      const uint8_t *wp1 = st + G::SLOT_BYTES + ((ph[1] + sp) & 15u) + lblk * Q::BYTES;
+      const bool live = (s * G::SEG_BLOCKS + lblk) < nblocks;  // ragged last segment
 #pragma unroll
       for (int ui = 0; ui < G::UPL; ui++) {
-      const int us = ui * 32 + lane;           // unit within the segment
-      const int u = s * G::SEG_UNITS + us;
-      if (u < nunits) {
-        const int bis = us / Q::UPB, c = us - bis * Q::UPB;
-        typename Q::W w[2];
+        const int c = (Q::UPB == 1) ? 0 : ui * G::CPS + lsub;
+        const uint32_t boff = (Q::UPB == 1) ? (uint32_t)(ui * 32 * Q::BYTES) : 0u;
+        const bool ulive = (Q::UPB == 1) ? (s * G::SEG_BLOCKS + ui * 32 + lblk) < nblocks : live;
+        if (ulive) {
+          typename Q::W w0, w1;
+          Q::template load<FAST>(wp0 + boff, c, w0);
+          Q::template load<FAST>(wp1 + boff, c, w1);
+          const int pos = s * G::SEG_UNITS + ui * 32 + lane;
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-          if (rowp[r] != nullptr) {
-            const uint8_t *slotp = ring + (size_t)stage * G::STAGE_BYTES + (size_t)(2 * warp + r) * G::SLOT_BYTES;
-            const uint32_t ph = (uint32_t)((uintptr_t)(rowp[r] + (size_t)s * G::SEG_BYTES) & 15);
-            Q::template load<FAST>(slotp + ph + bis * Q::BYTES, c, w[r]);
+          for (int j = 0; j < NCOLS; j++) {
+            const int idx = j * npos + pos;
+            const int4 q0 = xq0[idx], q1 = xq1[idx];
+            const int xq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            float a[Q::AUX];
+            if constexpr (Q::AUX == 4) {
+              const float4 t = *(const float4 *)(xa + (size_t)idx * 4);
+              a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+            } else if constexpr (Q::AUX == 2) {
+              const float2 t = *(const float2 *)(xa + (size_t)idx * 2);
+              a[0] = t.x; a[1] = t.y;
+            } else if constexpr (Q::AUX == 8) {
+              const float4 t0 = *(const float4 *)(xa + (size_t)idx * 8), t1 = *(const float4 *)(xa + (size_t)idx * 8 + 4);
+              a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < Q::AUX; i++) a[i] = xa[(size_t)idx * Q::AUX + i];
+            }
+            acc[0][j] += Q::dot(w0, xq, a, c);
+            acc[1][j] += Q::dot(w1, xq, a, c);
           }
         }
-#pragma unroll
-        for (int j = 0; j < NCOLS; j++) {
-          const size_t idx = (size_t)j * nunits + u;
-          const int4 q0 = xq0[idx], q1 = xq1[idx];
-          const int xq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-          float a[Q::AUX];
-          if constexpr (Q::AUX == 4) {
-            const float4 t = *(const float4 *)(xa + idx * 4);
-            a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
-          } else if constexpr (Q::AUX == 2) {
-            const float2 t = *(const float2 *)(xa + idx * 2);
-            a[0] = t.x; a[1] = t.y;
-          } else if constexpr (Q::AUX == 8) {
-            const float4 t0 = *(const float4 *)(xa + idx * 8), t1 = *(const float4 *)(xa + idx * 8 + 4);
-            a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < Q::AUX; i++) a[i] = xa[idx * Q::AUX + i];
-          }
-#pragma unroll
-          for (int r = 0; r < 2; r++)
-            if (rowp[r] != nullptr) acc[r][j] += Q::dot(w[r], xq, a, c);
-        }
-      }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
@@ -390,7 +403,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 
     if (lane == 0) {
       if (p.mode == MODE_GLU) {
-        if (rowp[0] != nullptr) {
+        if (valid[0]) {
 #pragma unroll
           for (int j = 0; j < NCOLS; j++) {
             if (j < p.ncols) {
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
       } else {
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-          if (rowp[r] == nullptr) continue;
+          if (!valid[r]) continue;
           const int nr = p.nrows[mm[r]];
           const int64_t cs = (p.mode == MODE_QKV) ? nr : p.stride_col_dst;
 #pragma unroll
@@ -444,9 +457,11 @@ template <int T, int NCOLS, bool FAST>
 static cudaError_t launch_one(MmvqParams p, cudaStream_t stream) {
   using G = Geo<T>;
   query_device();
-  const int nunits = p.K / 32;
-  const size_t xbytes = 256 + (size_t)NCOLS * nunits * G::XU_BYTES + 128;
-  const size_t scratch = (p.xkind == X_RAW) ? (size_t)NCOLS * nunits * 8 : 0;
+  const int nblocks = p.K / QT<T>::QK;
+  const int nseg = (nblocks + G::SEG_BLOCKS - 1) / G::SEG_BLOCKS;
+  const int npos = nseg * G::SEG_UNITS;
+  const size_t xbytes = 256 + (size_t)NCOLS * npos * G::XU_BYTES + 128;
+  const size_t scratch = (p.xkind == X_RAW) ? (size_t)NCOLS * (p.K / 32) * 8 : 0;
   // two CTAs per SM by design: keep each under half of the SM's shared memory
   const size_t budget = (size_t)g_max_smem / 2 - 1024;
   int nst = MAX_STAGES;

@@ -32,12 +32,19 @@ __device__ __forceinline__ void ld_words(const uint8_t *p, uint32_t (&out)[N]) {
   }
 }
 
+// unsigned-bytes x signed-bytes dot product (IDP.4A.U8.S8)
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 template <int TYPE> struct QT;
 
 // ------------------------------------------------------------------ Q4_K (144 B / 256)
 // layout: half2 dm | scales[12] | qs[128]   REF mmvq_gguf.cu:171-177; dot :386-407,:586-618
 template <> struct QT<MRS_Q4_K> {
-  static constexpr int BYTES = 144, QK = 256, UPB = 8, AUX = 4, WALIGN = 16;
+  static constexpr int BYTES = 144, QK = 256, UPB = 8, AUX = 4, WALIGN = 16, UPL = 4;
   // unit c: chunk c of qs; j = c>>1 (64-wide group), h = c&1 (16-byte half)
   __device__ static __forceinline__ int x_elem(int c, int w) {
     const int j = c >> 1, h = c & 1;
@@ -50,6 +57,7 @@ template <> struct QT<MRS_Q4_K> {
     const int s0 = __dp4a(q[0], 0x01010101, __dp4a(q[1], 0x01010101, __dp4a(q[2], 0x01010101, __dp4a(q[3], 0x01010101, 0))));
     const int s1 = __dp4a(q[4], 0x01010101, __dp4a(q[5], 0x01010101, __dp4a(q[6], 0x01010101, __dp4a(q[7], 0x01010101, 0))));
     a[2] = a[0] * (float)s0; a[3] = a[1] * (float)s1;
+    a[1] *= 0.0625f;  // the dot leaves the high nibbles in place (x16), exact power of two
   }
   struct W { uint32_t q[4]; uint32_t h[4]; };
   template <bool AL> __device__ static __forceinline__ void load(const uint8_t *blk, int c, W &w) {
@@ -75,11 +83,11 @@ template <> struct QT<MRS_Q4_K> {
   __device__ static __forceinline__ float dot(const W &w, const int *xq, const float *xa, int c) {
     int sc_lo, sc_hi, m_lo, m_hi;
     scales(w.h, c >> 1, sc_lo, sc_hi, m_lo, m_hi);
-    int dlo = 0, dhi = 0;
+    int dlo = 0, dhi = 0;  // dhi accumulates 16x the high-nibble dot (nibbles left in place)
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       dlo = __dp4a((int)(w.q[i] & 0x0F0F0F0Fu), xq[i], dlo);
-      dhi = __dp4a((int)((w.q[i] >> 4) & 0x0F0F0F0Fu), xq[4 + i], dhi);
+      dhi = dp4a_us(w.q[i] & 0xF0F0F0F0u, xq[4 + i], dhi);
     }
     const float2 dm = __half22float2(*(const __half2 *)&w.h[0]);
     const float sd = xa[0] * (float)(dlo * sc_lo) + xa[1] * (float)(dhi * sc_hi);
@@ -91,10 +99,11 @@ template <> struct QT<MRS_Q4_K> {
 // ------------------------------------------------------------------ Q5_K (176 B / 256)
 // layout: half2 dm | scales[12] | qh[32] | qs[128]  REF :179-186; dot :409-432,:620-660
 template <> struct QT<MRS_Q5_K> {
-  static constexpr int BYTES = 176, QK = 256, UPB = 8, AUX = 4, WALIGN = 16;
+  static constexpr int BYTES = 176, QK = 256, UPB = 8, AUX = 4, WALIGN = 16, UPL = 4;
   __device__ static __forceinline__ int x_elem(int c, int w) { return QT<MRS_Q4_K>::x_elem(c, w); }
   template <typename Y> __device__ static __forceinline__ void aux(const int *q, int c, Y y, float *a) {
     QT<MRS_Q4_K>::aux(q, c, y, a);
+    a[1] *= 16.0f;  // undo Q4_K's in-place-nibble folding
   }
   struct W { uint32_t q[4]; uint32_t qh[4]; uint32_t h[4]; };
   template <bool AL> __device__ static __forceinline__ void load(const uint8_t *blk, int c, W &w) {
@@ -127,7 +136,7 @@ template <> struct QT<MRS_Q5_K> {
 // unit c = 4n + t: ql chunk c; low nibbles -> elements 128n + 32(t>>1) + 16(t&1) + i,
 // high nibbles -> +64; qh[32n + 16(t&1) + i] bits 2(t>>1) (+4 for the high group).
 template <> struct QT<MRS_Q6_K> {
-  static constexpr int BYTES = 210, QK = 256, UPB = 8, AUX = 2, WALIGN = 2;
+  static constexpr int BYTES = 210, QK = 256, UPB = 8, AUX = 2, WALIGN = 2, UPL = 4;
   __device__ static __forceinline__ int x_elem(int c, int w) {
     const int n = c >> 2, t = c & 3;
     const int lo = 128 * n + 32 * (t >> 1) + 16 * (t & 1);
@@ -167,7 +176,7 @@ template <> struct QT<MRS_Q6_K> {
 // layout: scales[16] | qs[64] | half2 dm   REF :154-160; dot :348-366,:534-552
 // unit c = 4n + g: qs[32n + 8g .. +8); byte l holds elements 128n + 32j + 8g + l, j=0..3
 template <> struct QT<MRS_Q2_K> {
-  static constexpr int BYTES = 84, QK = 256, UPB = 8, AUX = 8, WALIGN = 4;
+  static constexpr int BYTES = 84, QK = 256, UPB = 8, AUX = 8, WALIGN = 4, UPL = 8;
   __device__ static __forceinline__ int x_elem(int c, int w) {
     const int n = c >> 2, g = c & 3;
     return 128 * n + 32 * (w >> 1) + 8 * g + 4 * (w & 1);
@@ -210,7 +219,7 @@ template <> struct QT<MRS_Q2_K> {
 // ------------------------------------------------------------------ Q3_K (110 B / 256)
 // layout: hmask[32] | qs[64] | scales[12] | half d   REF :162-169; dot :368-384,:554-584
 template <> struct QT<MRS_Q3_K> {
-  static constexpr int BYTES = 110, QK = 256, UPB = 8, AUX = 4, WALIGN = 2;
+  static constexpr int BYTES = 110, QK = 256, UPB = 8, AUX = 4, WALIGN = 2, UPL = 8;
   __device__ static __forceinline__ int x_elem(int c, int w) { return QT<MRS_Q2_K>::x_elem(c, w); }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int c, Y y, float *a) {
     const int n = c >> 2;
@@ -256,7 +265,7 @@ template <int AUXN> struct X32 {
 
 // Q8_0 (34 B): half d | int8 qs[32]   REF :136-141; dot :336-346
 template <> struct QT<MRS_Q8_0> {
-  static constexpr int BYTES = 34, QK = 32, UPB = 1, AUX = 1, WALIGN = 2;
+  static constexpr int BYTES = 34, QK = 32, UPB = 1, AUX = 1, WALIGN = 2, UPL = 2;
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); }
   struct W { uint32_t q[8]; float d; };
@@ -274,7 +283,7 @@ template <> struct QT<MRS_Q8_0> {
 
 // Q4_0 (18 B): half d | qs[16]   REF :197-202; dot :244-258
 template <> struct QT<MRS_Q4_0> {
-  static constexpr int BYTES = 18, QK = 32, UPB = 1, AUX = 2, WALIGN = 2;
+  static constexpr int BYTES = 18, QK = 32, UPB = 1, AUX = 2, WALIGN = 2, UPL = 4;
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); a[1] = y.s(0); }
   struct W { uint32_t q[4]; float d; };
@@ -295,7 +304,7 @@ template <> struct QT<MRS_Q4_0> {
 
 // Q4_1 (20 B): half2 dm | qs[16]   REF :204-209; dot :260-277
 template <> struct QT<MRS_Q4_1> {
-  static constexpr int BYTES = 20, QK = 32, UPB = 1, AUX = 2, WALIGN = 4;
+  static constexpr int BYTES = 20, QK = 32, UPB = 1, AUX = 2, WALIGN = 4, UPL = 4;
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); a[1] = y.s(0); }
   struct W { uint32_t q[4]; uint32_t dm; };
@@ -330,7 +339,7 @@ __device__ __forceinline__ uint32_t q5_hi_hi(uint32_t vh) {
 
 // Q5_0 (22 B): half d | qh[4] | qs[16]   REF :211-217; dot :279-306
 template <> struct QT<MRS_Q5_0> {
-  static constexpr int BYTES = 22, QK = 32, UPB = 1, AUX = 2, WALIGN = 2;
+  static constexpr int BYTES = 22, QK = 32, UPB = 1, AUX = 2, WALIGN = 2, UPL = 4;
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); a[1] = y.s(0); }
   struct W { uint32_t q[4]; uint32_t qh; float d; };
@@ -356,7 +365,7 @@ template <> struct QT<MRS_Q5_0> {
 
 // Q5_1 (24 B): half2 dm | qh[4] | qs[16]   REF :219-225; dot :308-334
 template <> struct QT<MRS_Q5_1> {
-  static constexpr int BYTES = 24, QK = 32, UPB = 1, AUX = 2, WALIGN = 8;
+  static constexpr int BYTES = 24, QK = 32, UPB = 1, AUX = 2, WALIGN = 8, UPL = 4;
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); a[1] = y.s(0); }
   struct W { uint32_t q[4]; uint32_t qh; uint32_t dm; };
