@@ -1,0 +1,474 @@
+// paged_attn.cu — decode attention over a paged KV cache for sm_100a, behind the reference's
+// C symbols:
+//   paged_attention_v1_{f16,bf16}, paged_attention_v2_{f16,bf16}   (vLLM cache layout)
+//        REF mistralrs-paged-attn/src/cuda/ffi.rs:269-438, pagedattention.cuh:110-485,549-665
+//   flashinfer_decode                                              (HND cache, CSR page table, split-KV tiles)
+//        REF mistralrs-paged-attn/src/cuda/ffi.rs:178-209, flashinfer_decode.cu:103-148,314-363
+//
+// Design: one CTA per (work tile, KV head).  A tile is a (sequence, KV chunk) pair.  The CTA
+// serves the whole GQA group of the KV head, so every K/V byte is read from HBM once (the
+// reference's vLLM kernel re-reads it per query head).  LPT = D/8 lanes own one token: each lane
+// holds a 16-byte (8-element) slice of the head dimension for q (all G heads), k and v; a token's
+// K and V rows are each one coalesced 16-byte-per-lane load.  Token groups walk the chunk with
+// 4-deep unrolled loads, run an online softmax privately (f32), and are merged once at the end
+// through shared memory.  Split-KV partials (normalised o + log-sum-exp) are merged by a second
+// tiny kernel.  Softcap, sliding window (window_left), ALiBi and attention sinks follow the
+// reference's formulas.
+#include "common.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace mrs {
+
+constexpr int PA_THREADS = 256;
+constexpr int PA_UNROLL = 4;
+
+struct PagedParams {
+  const void *q;       // [S, H, D] (+strides)
+  const void *kc, *vc; // caches
+  void *out;           // [S, H, D] contiguous
+  // split scratch (nullptr -> write final output directly)
+  void *tmp_o;         // [tiles, H, D] in T
+  float *tmp_lse;      // [tiles, H]
+  // work description
+  const int32_t *request_indices;  // [tiles] or nullptr (tile == seq, chunk 0)
+  const int32_t *kv_tile_indices;  // [tiles] or nullptr
+  const uint8_t *block_valid_mask; // [tiles] or nullptr
+  const int32_t *kv_chunk_size_ptr; // device scalar or nullptr
+  int kv_chunk_size;               // used when ptr is null; <=0 -> whole context
+  // page table: CSR (HND API) or dense block table (vLLM API)
+  const int32_t *kv_indptr, *kv_indices, *kv_last_page_len;
+  const int32_t *block_tables, *context_lens;
+  int max_blocks_per_seq;
+  int64_t kv_block_stride, kv_head_stride;  // elements
+  int num_heads, num_kv_heads, page_size;
+  int64_t q_stride_n, q_stride_h;
+  float sm_scale, softcap;  // softcap <= 0: disabled
+  int window_left;          // < 0: disabled
+  const float *alibi_slopes, *sinks;
+  int tiles_are_partitions; // vLLM v2: tile index = seq * num_partitions + partition
+  int num_partitions;
+};
+
+template <typename T> struct Vec8;
+template <> struct Vec8<__half> {
+  __device__ static __forceinline__ void load(const __half *p, float *f) {
+    const uint4 v = *(const uint4 *)p;
+    const __half2 *h = (const __half2 *)&v;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 t = __half22float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  __device__ static __forceinline__ float one(const __half *p) { return __half2float(*p); }
+  __device__ static __forceinline__ void store(__half *p, const float *f) {
+    uint4 v;
+    __half2 *h = (__half2 *)&v;
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    *(uint4 *)p = v;
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  __device__ static __forceinline__ void load(const __nv_bfloat16 *p, float *f) {
+    const uint4 v = *(const uint4 *)p;
+    const __nv_bfloat162 *h = (const __nv_bfloat162 *)&v;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  }
+  __device__ static __forceinline__ float one(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+  __device__ static __forceinline__ void store(__nv_bfloat16 *p, const float *f) {
+    uint4 v;
+    __nv_bfloat162 *h = (__nv_bfloat162 *)&v;
+#pragma unroll
+    for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *(uint4 *)p = v;
+  }
+};
+
+// LAYOUT 0: vLLM (K [NB,KVH,D/8,BS,8], V [NB,KVH,D,BS]); 1: HND ([NB,KVH,BS,D])
+template <typename T, int D, int G, int LAYOUT>
+__global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedParams p) {
+  constexpr int LPT = D / 8;               // lanes per token
+  constexpr int NGRP = PA_THREADS / LPT;   // token groups per CTA
+  const int tile = blockIdx.x, kvh = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int grp = tid / LPT, gl = tid % LPT;  // group, lane within group
+  const int d0 = gl * 8;
+
+  if (p.block_valid_mask != nullptr && p.block_valid_mask[tile] == 0) return;
+  int seq, chunk_idx;
+  if (p.tiles_are_partitions) { seq = tile / p.num_partitions; chunk_idx = tile % p.num_partitions; }
+  else if (p.request_indices != nullptr) { seq = p.request_indices[tile]; chunk_idx = p.kv_tile_indices[tile]; }
+  else { seq = tile; chunk_idx = 0; }
+
+  // context length and page list of this sequence
+  int kv_len;
+  const int32_t *pages;
+  if (p.kv_indptr != nullptr) {
+    const int p0 = p.kv_indptr[seq], p1 = p.kv_indptr[seq + 1];
+    pages = p.kv_indices + p0;
+    kv_len = (p1 > p0) ? (p1 - p0 - 1) * p.page_size + p.kv_last_page_len[seq] : 0;
+  } else {
+    pages = p.block_tables + (int64_t)seq * p.max_blocks_per_seq;
+    kv_len = p.context_lens[seq];
+  }
+  int chunk = p.kv_chunk_size_ptr ? *p.kv_chunk_size_ptr : p.kv_chunk_size;
+  if (chunk <= 0) chunk = kv_len > 0 ? kv_len : 1;
+  const int t_begin = chunk_idx * chunk;
+  const int t_end = min(kv_len, t_begin + chunk);
+  const bool partial = p.tmp_o != nullptr;
+
+  const int h0 = kvh * (p.num_heads / p.num_kv_heads);  // first query head of the group
+  const int gsize = p.num_heads / p.num_kv_heads;       // actual group size (<= G)
+
+  // q slice of this lane for all heads of the group, pre-scaled
+  float qf[G][8];
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    if (g < gsize) {
+      Vec8<T>::load((const T *)p.q + (int64_t)seq * p.q_stride_n + (int64_t)(h0 + g) * p.q_stride_h + d0, qf[g]);
+#pragma unroll
+      for (int i = 0; i < 8; i++) qf[g][i] *= p.sm_scale;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) qf[g][i] = 0.f;
+    }
+  }
+  float slope[G];
+#pragma unroll
+  for (int g = 0; g < G; g++) slope[g] = (p.alibi_slopes != nullptr && g < gsize) ? p.alibi_slopes[h0 + g] : 0.f;
+
+  float m[G], l[G], o[G][8];
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    m[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[g][i] = 0.f;
+  }
+
+  const T *kc = (const T *)p.kc, *vc = (const T *)p.vc;
+  const int win_lo = (p.window_left >= 0) ? max(0, kv_len - 1 - p.window_left) : 0;
+
+  for (int tb = t_begin + grp; tb < t_end; tb += NGRP * PA_UNROLL) {
+    float kf[PA_UNROLL][8], vf[PA_UNROLL][8];
+    bool ok[PA_UNROLL];
+#pragma unroll
+    for (int u = 0; u < PA_UNROLL; u++) {
+      const int t = tb + u * NGRP;
+      ok[u] = t < t_end;
+#pragma unroll
+      for (int i = 0; i < 8; i++) { kf[u][i] = 0.f; vf[u][i] = 0.f; }
+      if (ok[u]) {
+        const int64_t page = pages[t / p.page_size];
+        const int off = t % p.page_size;
+        const int64_t base = page * p.kv_block_stride + (int64_t)kvh * p.kv_head_stride;
+        if constexpr (LAYOUT == 1) {
+          Vec8<T>::load(kc + base + (int64_t)off * D + d0, kf[u]);
+          Vec8<T>::load(vc + base + (int64_t)off * D + d0, vf[u]);
+        } else {
+          Vec8<T>::load(kc + base + ((int64_t)gl * p.page_size + off) * 8, kf[u]);
+#pragma unroll
+          for (int i = 0; i < 8; i++) vf[u][i] = Vec8<T>::one(vc + base + (int64_t)(d0 + i) * p.page_size + off);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PA_UNROLL; u++) {
+      const int t = tb + u * NGRP;
+      float s[G];  // (all lanes take part in the shuffles; only live tokens update the state)
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) a = fmaf(qf[g][i], kf[u][i], a);
+        s[g] = a;
+      }
+      // reduce across the LPT lanes of the group (LPT is a power of two <= 32)
+#pragma unroll
+      for (int mask = LPT / 2; mask > 0; mask >>= 1)
+#pragma unroll
+        for (int g = 0; g < G; g++) s[g] += __shfl_xor_sync(0xffffffffu, s[g], mask);
+      const bool in_window = t >= win_lo && ok[u];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        float x = s[g];
+        if (p.softcap > 0.f) x = p.softcap * tanhf(x / p.softcap);
+        x += slope[g] * (float)(t - kv_len + 1);
+        if (!in_window) x = -INFINITY;
+        const float mn = fmaxf(m[g], x);
+        if (mn > -INFINITY) {
+          const float corr = __expf(m[g] - mn);
+          const float pv = __expf(x - mn);
+          l[g] = l[g] * corr + pv;
+#pragma unroll
+          for (int i = 0; i < 8; i++) o[g][i] = fmaf(pv, vf[u][i], o[g][i] * corr);
+          m[g] = mn;
+        }
+      }
+    }
+  }
+
+  // ---------------------------------------------------------------- merge the token groups
+  constexpr int NSTATE = PA_THREADS / 32;  // one softmax state per warp after the pre-merge
+  static_assert(LPT <= 16 || NGRP == NSTATE, "one token group per warp when LPT == 32");
+  __shared__ float sm_m[NSTATE][G], sm_l[NSTATE][G];
+  __shared__ float sm_o[NSTATE][G][D];
+  // pairwise pre-merge inside a warp when two groups share one (LPT == 16)
+  if constexpr (LPT <= 16) {
+#pragma unroll
+    for (int mask = LPT; mask < 32; mask <<= 1) {
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m[g], mask);
+        const float lo = __shfl_xor_sync(0xffffffffu, l[g], mask);
+        const float mn = fmaxf(m[g], mo);
+        const float ca = (mn > -INFINITY) ? __expf(m[g] - mn) : 0.f;
+        const float cb = (mn > -INFINITY) ? __expf(mo - mn) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float oo = __shfl_xor_sync(0xffffffffu, o[g][i], mask);
+          o[g][i] = o[g][i] * ca + oo * cb;
+        }
+        l[g] = l[g] * ca + lo * cb;
+        m[g] = mn;
+      }
+    }
+  }
+  constexpr int WG = NSTATE;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int sidx = warp;
+  const bool writer = lane < LPT;
+  if (writer) {
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (gl == 0) { sm_m[sidx][g] = m[g]; sm_l[sidx][g] = l[g]; }
+#pragma unroll
+      for (int i = 0; i < 8; i++) sm_o[sidx][g][d0 + i] = o[g][i];
+    }
+  }
+  __syncthreads();
+  // final: thread per (head, d)
+  for (int idx = tid; idx < G * D; idx += PA_THREADS) {
+    const int g = idx / D, d = idx % D;
+    if (g >= gsize) continue;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < WG; w++) M = fmaxf(M, sm_m[w][g]);
+    const bool use_sink = (p.sinks != nullptr) && !partial;
+    if (use_sink) M = fmaxf(M, p.sinks[h0 + g]);
+    float L = 0.f, acc = 0.f;
+    if (M > -INFINITY) {
+#pragma unroll
+      for (int w = 0; w < WG; w++) {
+        const float c = __expf(sm_m[w][g] - M);
+        L += sm_l[w][g] * c;
+        acc += sm_o[w][g][d] * c;
+      }
+    }
+    if (use_sink) L += __expf(p.sinks[h0 + g] - M);
+    const float val = (L > 0.f) ? acc / L : 0.f;
+    if (partial) {
+      ((T *)p.tmp_o)[((int64_t)tile * p.num_heads + h0 + g) * D + d] = (T)val;
+      if (d == 0) p.tmp_lse[(int64_t)tile * p.num_heads + h0 + g] = (L > 0.f) ? M + __logf(L) : -INFINITY;
+    } else {
+      ((T *)p.out)[((int64_t)seq * p.num_heads + h0 + g) * D + d] = (T)val;
+    }
+  }
+}
+
+// merge split-KV partials: out[s,h,:] = sum_p w_p o_p / sum_p w_p, w_p = exp(lse_p - max lse)
+// tiles of sequence s are [o_indptr[s], o_indptr[s+1]) (HND API) or s*P .. s*P+P-1 (vLLM v2)
+template <typename T>
+__global__ void merge_partials_kernel(const T *__restrict__ tmp_o, const float *__restrict__ tmp_lse,
+                                      T *__restrict__ out, const int32_t *__restrict__ o_indptr, int num_partitions,
+                                      int num_heads, int D, const float *__restrict__ sinks,
+                                      const int32_t *__restrict__ context_lens, int partition_size) {
+  const int s = blockIdx.x, h = blockIdx.y;
+  int t0, t1;
+  if (o_indptr != nullptr) { t0 = o_indptr[s]; t1 = o_indptr[s + 1]; }
+  else {
+    t0 = s * num_partitions;
+    const int np = (context_lens[s] + partition_size - 1) / partition_size;
+    t1 = t0 + max(np, 0);
+  }
+  float M = -INFINITY;
+  for (int t = t0; t < t1; t++) M = fmaxf(M, tmp_lse[(int64_t)t * num_heads + h]);
+  if (sinks != nullptr) M = fmaxf(M, sinks[h]);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float W = 0.f, acc = 0.f;
+    if (M > -INFINITY) {
+      for (int t = t0; t < t1; t++) {
+        const float w = __expf(tmp_lse[(int64_t)t * num_heads + h] - M);
+        W += w;
+        acc += w * (float)tmp_o[((int64_t)t * num_heads + h) * D + d];
+      }
+      if (sinks != nullptr) W += __expf(sinks[h] - M);
+    }
+    out[((int64_t)s * num_heads + h) * D + d] = (T)((W > 0.f) ? acc / W : 0.f);
+  }
+}
+
+template <typename T, int D, int LAYOUT>
+static cudaError_t launch_decode_g(const PagedParams &p, int tiles, cudaStream_t st) {
+  const int gsize = p.num_heads / p.num_kv_heads;
+  dim3 grid(tiles, p.num_kv_heads);
+  if (gsize <= 1) paged_decode_kernel<T, D, 1, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
+  else if (gsize <= 2) paged_decode_kernel<T, D, 2, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
+  else if (gsize <= 4) paged_decode_kernel<T, D, 4, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
+  else if (gsize <= 8) {
+    if constexpr (D <= 128) paged_decode_kernel<T, D, 8, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
+    else return cudaErrorInvalidValue;  // G=8 with D=256 exceeds the static smem budget
+  } else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+template <typename T, int LAYOUT>
+static cudaError_t launch_decode(const PagedParams &p, int head_size, int tiles, cudaStream_t st) {
+  if (tiles <= 0) return cudaSuccess;
+  if (p.num_heads % p.num_kv_heads) return cudaErrorInvalidValue;
+  switch (head_size) {
+  case 64: return launch_decode_g<T, 64, LAYOUT>(p, tiles, st);
+  case 128: return launch_decode_g<T, 128, LAYOUT>(p, tiles, st);
+  case 256: return launch_decode_g<T, 256, LAYOUT>(p, tiles, st);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace mrs
+
+using namespace mrs;
+
+// ---------------------------------------------------------------- flashinfer_decode (HND)
+extern "C" int32_t flashinfer_decode(void *q, void *key_cache, void *value_cache, const int32_t *kv_indptr,
+                                     const int32_t *kv_indices, const int32_t *kv_last_page_len,
+                                     const int32_t *request_indices, const int32_t *kv_tile_indices,
+                                     const int32_t *o_indptr, const int32_t *kv_chunk_size_ptr,
+                                     const bool *block_valid_mask, void *o, void *tmp_v, void *tmp_s,
+                                     int32_t batch_size, int32_t padded_batch_size, int32_t num_qo_heads,
+                                     int32_t num_kv_heads, int32_t head_size, int32_t page_size, int32_t q_stride_n,
+                                     int32_t q_stride_h, float sm_scale, int32_t window_left, float logits_soft_cap,
+                                     float k_scale, float v_scale, uint32_t dtype, uint32_t cache_dtype,
+                                     cudaStream_t stream) {
+  if (dtype != cache_dtype || (dtype != 0 && dtype != 1)) {
+    fprintf(stderr, "mrs_b200: flashinfer_decode supports f16/bf16 caches matching the query dtype (got %u/%u)\n", dtype, cache_dtype);
+    return (int32_t)cudaErrorInvalidValue;
+  }
+  (void)k_scale; (void)v_scale;
+  PagedParams p = {};
+  p.q = q; p.kc = key_cache; p.vc = value_cache; p.out = o;
+  const bool split = tmp_v != nullptr && padded_batch_size > batch_size;
+  p.tmp_o = split ? tmp_v : nullptr; p.tmp_lse = split ? (float *)tmp_s : nullptr;
+  p.request_indices = request_indices; p.kv_tile_indices = kv_tile_indices;
+  p.block_valid_mask = (const uint8_t *)block_valid_mask;
+  p.kv_chunk_size_ptr = split ? kv_chunk_size_ptr : nullptr;  // unsplit plans carry chunk = page_size
+  p.kv_chunk_size = 0;
+  p.kv_indptr = kv_indptr; p.kv_indices = kv_indices; p.kv_last_page_len = kv_last_page_len;
+  p.kv_block_stride = (int64_t)num_kv_heads * page_size * head_size; p.kv_head_stride = (int64_t)page_size * head_size;
+  p.num_heads = num_qo_heads; p.num_kv_heads = num_kv_heads; p.page_size = page_size;
+  p.q_stride_n = q_stride_n; p.q_stride_h = q_stride_h; p.sm_scale = sm_scale;
+  p.softcap = logits_soft_cap; p.window_left = window_left;
+  if (!split) {
+    // one tile per request, whole context (tile list may still be given: request i, tile 0)
+    p.request_indices = nullptr; p.kv_tile_indices = nullptr; p.block_valid_mask = nullptr;
+  }
+  const int tiles = split ? padded_batch_size : batch_size;
+  cudaError_t e = (dtype == 0) ? launch_decode<__half, 1>(p, head_size, tiles, stream)
+                               : launch_decode<__nv_bfloat16, 1>(p, head_size, tiles, stream);
+  if (e != cudaSuccess) { fprintf(stderr, "mrs_b200: flashinfer_decode failed: %s\n", cudaGetErrorString(e)); return (int32_t)e; }
+  if (split) {
+    dim3 grid(batch_size, num_qo_heads);
+    if (dtype == 0) merge_partials_kernel<__half><<<grid, 128, 0, stream>>>((const __half *)tmp_v, (const float *)tmp_s, (__half *)o, o_indptr, 0, num_qo_heads, head_size, nullptr, nullptr, 0);
+    else merge_partials_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16 *)tmp_v, (const float *)tmp_s, (__nv_bfloat16 *)o, o_indptr, 0, num_qo_heads, head_size, nullptr, nullptr, 0);
+    e = cudaGetLastError();
+  }
+  return (int32_t)e;
+}
+
+// ---------------------------------------------------------------- paged_attention v1 / v2 (vLLM)
+static void vllm_common(PagedParams &p, void *out, void *query, void *key_cache, void *value_cache, void *alibi,
+                        int num_kv_heads, float scale, float softcapping, const int32_t *block_tables,
+                        const int32_t *context_lens, int block_size, int num_heads, int head_size,
+                        int max_num_blocks_per_seq, int q_stride, int kv_block_stride, int kv_head_stride,
+                        const float *sinks) {
+  p.q = query; p.kc = key_cache; p.vc = value_cache; p.out = out;
+  p.block_tables = block_tables; p.context_lens = context_lens; p.max_blocks_per_seq = max_num_blocks_per_seq;
+  p.kv_block_stride = kv_block_stride; p.kv_head_stride = kv_head_stride;
+  p.num_heads = num_heads; p.num_kv_heads = num_kv_heads; p.page_size = block_size;
+  p.q_stride_n = q_stride; p.q_stride_h = head_size; p.sm_scale = scale;
+  p.softcap = (softcapping != 1.0f) ? softcapping : 0.f;  // REF pagedattention.cuh:276-279
+  p.window_left = -1; p.alibi_slopes = (const float *)alibi; p.sinks = sinks;
+}
+
+static void die_if(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) {  // REF pagedattention.cuh:46-56: report and exit
+    fprintf(stderr, "mrs_b200: %s failed: %s\n", what, cudaGetErrorString(e));
+    exit((int)e);
+  }
+}
+
+template <typename T>
+static void paged_v1(void *out, void *query, void *key_cache, void *value_cache, void *alibi, int num_kv_heads,
+                     float scale, float softcapping, const int32_t *block_tables, const int32_t *context_lens,
+                     int block_size, int num_seqs, int num_heads, int head_size, int max_num_blocks_per_seq,
+                     int q_stride, int kv_block_stride, int kv_head_stride, cudaStream_t stream, uint32_t cache_dtype,
+                     const float *sinks) {
+  if (cache_dtype == 3) die_if(cudaErrorInvalidValue, "paged_attention_v1 (FP8 cache not implemented)");
+  PagedParams p = {};
+  vllm_common(p, out, query, key_cache, value_cache, alibi, num_kv_heads, scale, softcapping, block_tables,
+              context_lens, block_size, num_heads, head_size, max_num_blocks_per_seq, q_stride, kv_block_stride,
+              kv_head_stride, sinks);
+  die_if(launch_decode<T, 0>(p, head_size, num_seqs, stream), "paged_attention_v1");
+}
+
+template <typename T>
+static void paged_v2(void *out, float *exp_sums, float *max_logits, void *tmp_out, void *query, void *key_cache,
+                     void *value_cache, void *alibi, int num_kv_heads, float scale, float softcapping,
+                     const int32_t *block_tables, const int32_t *context_lens, int block_size, int max_context_len,
+                     int num_seqs, int num_heads, int head_size, int max_num_blocks_per_seq, int q_stride,
+                     int kv_block_stride, int kv_head_stride, cudaStream_t stream, uint32_t cache_dtype,
+                     const float *sinks) {
+  if (cache_dtype == 3) die_if(cudaErrorInvalidValue, "paged_attention_v2 (FP8 cache not implemented)");
+  (void)exp_sums;
+  constexpr int PARTITION = 512;  // REF backend/paged_attention.rs:302
+  const int num_partitions = (max_context_len + PARTITION - 1) / PARTITION;
+  PagedParams p = {};
+  vllm_common(p, out, query, key_cache, value_cache, alibi, num_kv_heads, scale, softcapping, block_tables,
+              context_lens, block_size, num_heads, head_size, max_num_blocks_per_seq, q_stride, kv_block_stride,
+              kv_head_stride, nullptr);
+  p.tmp_o = tmp_out; p.tmp_lse = max_logits;  // scratch is opaque to the caller: lse lives in max_logits
+  p.kv_chunk_size = PARTITION; p.tiles_are_partitions = 1; p.num_partitions = num_partitions;
+  die_if(launch_decode<T, 0>(p, head_size, num_seqs * num_partitions, stream), "paged_attention_v2");
+  dim3 grid(num_seqs, num_heads);
+  merge_partials_kernel<T><<<grid, 128, 0, stream>>>((const T *)tmp_out, max_logits, (T *)out, nullptr,
+                                                     num_partitions, num_heads, head_size, sinks, context_lens,
+                                                     PARTITION);
+  die_if(cudaGetLastError(), "paged_attention_v2 reduce");
+}
+
+#define MRS_PAGED(tag, T)                                                                                       \
+  extern "C" void paged_attention_v1_##tag(void *out, void *query, void *key_cache, void *value_cache,          \
+      void *alibi_slopes, int32_t num_kv_heads, float scale, float softcapping, uint32_t *block_tables,         \
+      uint32_t *context_lens, int32_t block_size, int32_t max_context_len, int32_t num_seqs, int32_t num_heads, \
+      int32_t head_size, int32_t max_num_blocks_per_seq, int32_t q_stride, int32_t kv_block_stride,             \
+      int32_t kv_head_stride, cudaStream_t stream, uint32_t cache_dtype, float *k_scale, float *v_scale,        \
+      const float *sinks) {                                                                                     \
+    (void)max_context_len; (void)k_scale; (void)v_scale;                                                        \
+    paged_v1<T>(out, query, key_cache, value_cache, alibi_slopes, num_kv_heads, scale, softcapping,             \
+                (const int32_t *)block_tables, (const int32_t *)context_lens, block_size, num_seqs, num_heads,  \
+                head_size, max_num_blocks_per_seq, q_stride, kv_block_stride, kv_head_stride, stream,           \
+                cache_dtype, sinks);                                                                            \
+  }                                                                                                             \
+  extern "C" void paged_attention_v2_##tag(void *out, float *exp_sums, float *max_logits, void *tmp_out,        \
+      void *query, void *key_cache, void *value_cache, void *alibi_slopes, int32_t num_kv_heads, float scale,   \
+      float softcapping, uint32_t *block_tables, uint32_t *context_lens, int32_t block_size,                    \
+      int32_t max_context_len, int32_t num_seqs, int32_t num_heads, int32_t head_size,                          \
+      int32_t max_num_blocks_per_seq, int32_t q_stride, int32_t kv_block_stride, int32_t kv_head_stride,        \
+      cudaStream_t stream, uint32_t cache_dtype, float *k_scale, float *v_scale, const float *sinks) {          \
+    (void)k_scale; (void)v_scale;                                                                               \
+    paged_v2<T>(out, exp_sums, max_logits, tmp_out, query, key_cache, value_cache, alibi_slopes, num_kv_heads,  \
+                scale, softcapping, (const int32_t *)block_tables, (const int32_t *)context_lens, block_size,   \
+                max_context_len, num_seqs, num_heads, head_size, max_num_blocks_per_seq, q_stride,              \
+                kv_block_stride, kv_head_stride, stream, cache_dtype, sinks);                                   \
+  }
+MRS_PAGED(f16, __half)
+MRS_PAGED(bf16, __nv_bfloat16)

@@ -1,0 +1,127 @@
+"""ctypes front-end of the C++ host layer (host/kv_index.hpp): BlockPool, slot mapping, the
+FlashInfer CSR page table and the split-KV decode tile plan — the integer metadata the
+reference's scheduler side produces (REF: block_pool.rs, inputs_processor.rs:896-923,
+flashinfer/metadata.rs).  Pure host code; no GPU needed."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libmrs_b200_host.so")
+_lib = None
+PAD_SLOT_ID = -1
+
+
+def host_lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError(f"{HOST_LIB_PATH} missing: run __graft_entry__.build()")
+        L = ctypes.CDLL(HOST_LIB_PATH)
+        L.mrs_block_pool_new.restype = ctypes.c_void_p
+        for f in ("null_block_id", "num_free_blocks", "ref_cnt"):
+            getattr(L, f"mrs_block_pool_{f}").restype = ctypes.c_int64
+        L.mrs_decode_split_pages.restype = ctypes.c_int64
+        L.mrs_make_decode_tiles.restype = ctypes.c_int64
+        _lib = L
+    return _lib
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class BlockPool:
+    def __init__(self, num_gpu_blocks):
+        self._h = ctypes.c_void_p(host_lib().mrs_block_pool_new(ctypes.c_int64(num_gpu_blocks)))
+        if not self._h:
+            raise ValueError("Must have at least 1 GPU block")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            host_lib().mrs_block_pool_free(self._h)
+            self._h = None
+
+    def null_block_id(self):
+        return host_lib().mrs_block_pool_null_block_id(self._h)
+
+    def num_free_blocks(self):
+        return host_lib().mrs_block_pool_num_free_blocks(self._h)
+
+    def block_ref_cnt(self, block_id):
+        return host_lib().mrs_block_pool_ref_cnt(self._h, ctypes.c_int64(block_id))
+
+    def get_new_blocks(self, num):
+        out = np.empty(max(num, 1), dtype=np.int64)
+        ok = host_lib().mrs_block_pool_get_new_blocks(self._h, ctypes.c_int64(num), ctypes.c_void_p(out.ctypes.data))
+        return [int(v) for v in out[:num]] if ok else None
+
+    def free_blocks(self, ordered_block_ids):
+        a = _i64(ordered_block_ids)
+        host_lib().mrs_block_pool_free_blocks(self._h, ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(a.size))
+
+    def touch(self, block_ids):
+        a = _i64(block_ids)
+        host_lib().mrs_block_pool_touch(self._h, ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(a.size))
+
+
+def slot_mapping(table, block_size, start, end):
+    t = _i64(table)
+    out = np.empty(max(end - start, 0), dtype=np.int64)
+    rc = host_lib().mrs_slot_mapping(ctypes.c_void_p(t.ctypes.data), ctypes.c_int64(t.size), ctypes.c_int64(block_size),
+                                     ctypes.c_int64(start), ctypes.c_int64(end), ctypes.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise IndexError("Block table is too small (prompt)!")
+    return out
+
+
+def make_paged_kv_tensors(tables, context_lens, block_size, padded_indices_len):
+    batch = len(tables)
+    max_blocks = max((len(t) for t in tables), default=0)
+    dense = np.zeros((batch, max(max_blocks, 1)), dtype=np.int64)
+    for b, t in enumerate(tables):
+        dense[b, :len(t)] = t
+    cl = _i64(context_lens)
+    for b, t in enumerate(tables):
+        if -(-int(cl[b]) // block_size) > len(t):
+            raise IndexError("paged kv block table is too small")
+    indptr = np.empty(batch + 1, dtype=np.int32)
+    indices = np.empty(max(padded_indices_len, 1), dtype=np.int32)
+    last = np.empty(max(batch, 1), dtype=np.int32)
+    rc = host_lib().mrs_make_paged_kv(ctypes.c_void_p(dense.ctypes.data), ctypes.c_int64(batch),
+                                      ctypes.c_int64(dense.shape[1]), ctypes.c_void_p(cl.ctypes.data),
+                                      ctypes.c_int64(block_size), ctypes.c_int64(padded_indices_len),
+                                      ctypes.c_void_p(indptr.ctypes.data), ctypes.c_void_p(indices.ctypes.data),
+                                      ctypes.c_void_p(last.ctypes.data))
+    if rc != 0:
+        raise IndexError("paged kv indices exceed padded length")
+    return indptr, indices[:padded_indices_len], last[:batch]
+
+
+def decode_split_pages(block_size, batch_size, num_kv_heads, max_context_len, sm_count=148):
+    return int(host_lib().mrs_decode_split_pages(ctypes.c_int64(block_size), ctypes.c_int64(batch_size),
+                                                 ctypes.c_int64(num_kv_heads), ctypes.c_int64(sm_count),
+                                                 ctypes.c_int64(max_context_len)))
+
+
+def make_paged_kv_decode_tensors(tables, context_lens, block_size, split_pages, padded_tiles_len):
+    """split_pages None -> no split.  Returns (request_indices, kv_tile_indices, o_indptr,
+    kv_chunk_size, block_valid_mask) exactly like metadata.rs:152-216."""
+    batch = len(tables)
+    tl = _i64([len(t) for t in tables])
+    cl = _i64(context_lens)
+    req = np.empty(max(padded_tiles_len, 1), dtype=np.int32)
+    tile = np.empty(max(padded_tiles_len, 1), dtype=np.int32)
+    o_indptr = np.empty(batch + 1, dtype=np.int32)
+    chunk = np.empty(1, dtype=np.int32)
+    mask = np.empty(max(padded_tiles_len, 1), dtype=np.uint8)
+    n = host_lib().mrs_make_decode_tiles(ctypes.c_void_p(tl.ctypes.data), ctypes.c_void_p(cl.ctypes.data),
+                                         ctypes.c_int64(batch), ctypes.c_int64(block_size),
+                                         ctypes.c_int64(split_pages or 0), ctypes.c_int64(padded_tiles_len),
+                                         ctypes.c_void_p(req.ctypes.data), ctypes.c_void_p(tile.ctypes.data),
+                                         ctypes.c_void_p(o_indptr.ctypes.data), ctypes.c_void_p(chunk.ctypes.data),
+                                         ctypes.c_void_p(mask.ctypes.data))
+    if n < 0:
+        raise IndexError("paged kv decode tiles exceed padded length / table too small")
+    return req[:padded_tiles_len], tile[:padded_tiles_len], o_indptr, chunk, mask[:padded_tiles_len]

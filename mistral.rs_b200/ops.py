@@ -1,0 +1,89 @@
+"""Host-side mirror of the small fused ops the reference calls between the GEMMs:
+`fused_glu` (mistralrs-quant/src/utils/ops.rs, C: utils/ffi.rs:274-305), `apply_rotary_qk`
+(mistralrs-quant/src/rotary/mod.rs:851 -> rotary/ffi.rs), `RmsNorm::forward` /
+`forward_add_rms_norm` (mistralrs-core/src/layers.rs:328-413 -> core/src/cuda/ffi.rs)."""
+import ctypes
+
+import torch
+
+from . import lib
+
+_TAG = {torch.float16: "f16", torch.bfloat16: "bf16", torch.float32: "f32"}
+_DT_CODE = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def fused_glu(a, b, activation):
+    """out = act(a) * b over the last dim (rows may be strided)."""
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("fused_glu: shape/dtype mismatch")
+    cols = a.shape[-1]
+    rows = a.numel() // cols
+    a2, b2 = a.reshape(rows, cols), b.reshape(rows, cols)
+    if a2.stride(1) != 1 or b2.stride(1) != 1:
+        a2, b2 = a2.contiguous(), b2.contiguous()
+    out = torch.empty(a.shape, dtype=a.dtype, device=a.device)
+    getattr(lib(), f"fused_glu_{_TAG[a.dtype]}")(_p(a2), _p(b2), _p(out), ctypes.c_uint32(rows), ctypes.c_uint32(cols),
+                                                  ctypes.c_uint32(a2.stride(0)), ctypes.c_uint32(b2.stride(0)),
+                                                  ctypes.c_int(int(activation)), ctypes.c_void_p(_stream(a.device)))
+    return out
+
+
+def fused_split_glu(x, activation):
+    """x [..., 2*split]: act(x[..., :split]) * x[..., split:]."""
+    x = x.contiguous()
+    split = x.shape[-1] // 2
+    rows = x.numel() // (2 * split)
+    out = torch.empty(*x.shape[:-1], split, dtype=x.dtype, device=x.device)
+    getattr(lib(), f"fused_split_glu_{_TAG[x.dtype]}")(_p(x), _p(out), ctypes.c_uint32(rows), ctypes.c_uint32(split),
+                                                        ctypes.c_int(int(activation)), ctypes.c_void_p(_stream(x.device)))
+    return out
+
+
+def apply_rotary_qk(q, k, cos, sin, positions=None, is_neox=True):
+    """In-place RoPE on q [T, H, D] and k [T, KVH, D]; cos/sin [*, rot_half]."""
+    if q.dtype != k.dtype or cos.dtype != q.dtype or sin.dtype != q.dtype:
+        raise ValueError("apply_rotary_qk: dtype mismatch")
+    T, H, D = q.shape
+    KVH = k.shape[1]
+    rot_half = cos.shape[-1]
+    if positions is None:
+        lib().rotary_embedding(_p(q), _p(k), _p(cos), _p(sin), ctypes.c_int(int(is_neox)), ctypes.c_int(D),
+                               ctypes.c_int64(T), ctypes.c_int(rot_half), ctypes.c_int(H), ctypes.c_int(KVH),
+                               ctypes.c_int64(q.stride(0)), ctypes.c_int64(k.stride(0)),
+                               ctypes.c_uint32(_DT_CODE[q.dtype]), ctypes.c_int64(_stream(q.device)))
+    else:
+        if positions.dtype not in (torch.int32, torch.uint32):
+            raise ValueError("positions must be u32/i32")
+        lib().rotary_embedding_positions(_p(q), _p(k), _p(cos), _p(sin), _p(positions), ctypes.c_int(int(is_neox)),
+                                         ctypes.c_int(D), ctypes.c_int64(T), ctypes.c_int(rot_half),
+                                         ctypes.c_int(cos.shape[0]), ctypes.c_int(H), ctypes.c_int(KVH),
+                                         ctypes.c_int64(q.stride(0)), ctypes.c_int64(k.stride(0)),
+                                         ctypes.c_uint32(_DT_CODE[q.dtype]), ctypes.c_int64(_stream(q.device)))
+
+
+def rms_norm(x, weight, eps):
+    x = x.contiguous()
+    cols = x.shape[-1]
+    out = torch.empty_like(x)
+    getattr(lib(), f"mrs_rms_norm_{_TAG[x.dtype]}")(_p(x), _p(weight), _p(out), ctypes.c_int(x.numel() // cols),
+                                                     ctypes.c_int(cols), ctypes.c_float(eps), ctypes.c_int64(_stream(x.device)))
+    return out
+
+
+def add_rms_norm(x, residual, weight, eps):
+    """(sum, normed) = (x + residual, rmsnorm(x + residual)) — layers.rs:328 forward_add_rms_norm."""
+    x, residual = x.contiguous(), residual.contiguous()
+    cols = x.shape[-1]
+    s, n = torch.empty_like(x), torch.empty_like(x)
+    getattr(lib(), f"add_rms_norm_{_TAG[x.dtype]}")(_p(x), _p(residual), _p(weight), _p(s), _p(n),
+                                                     ctypes.c_int(x.numel() // cols), ctypes.c_int(cols),
+                                                     ctypes.c_float(eps), ctypes.c_int64(_stream(x.device)))
+    return s, n

@@ -1,0 +1,79 @@
+"""ORACLE (test infrastructure): pure-Python restatement of the reference's KV index producers,
+written independently of the C++ host layer so the two can be diffed on random traces.
+REF: mistralrs-core/src/paged_attention/block_pool.rs:60-170,290-442;
+     mistralrs-core/src/pipeline/inputs_processor.rs:896-923;
+     mistralrs-core/src/flashinfer/metadata.rs:61-216."""
+from collections import OrderedDict
+
+
+class BlockPool:
+    def __init__(self, num_gpu_blocks):
+        assert num_gpu_blocks > 0
+        self.free = OrderedDict((i, None) for i in range(num_gpu_blocks))  # FIFO free list
+        self.ref = [0] * num_gpu_blocks
+        self.null = self.free.popitem(last=False)[0]  # block 0 becomes the null block
+
+    def num_free_blocks(self):
+        return len(self.free)
+
+    def get_new_blocks(self, n):
+        if n > len(self.free):
+            return None
+        out = []
+        for _ in range(n):
+            b = self.free.popitem(last=False)[0]
+            self.ref[b] = 1
+            out.append(b)
+        return out
+
+    def free_blocks(self, ordered):
+        for b in ordered:
+            self.ref[b] = max(self.ref[b] - 1, 0)
+        for b in ordered:
+            if self.ref[b] == 0 and b != self.null and b not in self.free:
+                self.free[b] = None
+
+    def touch(self, ids):
+        for b in ids:
+            if self.ref[b] == 0 and b != self.null:
+                del self.free[b]
+            self.ref[b] += 1
+
+
+def slot_mapping(table, block_size, start, end):
+    return [table[i // block_size] * block_size + i % block_size for i in range(start, end)]
+
+
+def make_paged_kv(tables, context_lens, block_size, padded):
+    indptr, indices, last = [0], [], []
+    for t, c in zip(tables, context_lens):
+        nb = -(-c // block_size)
+        indptr.append(indptr[-1] + nb)
+        indices += list(t[:nb])
+        last.append(0 if nb == 0 else c - (nb - 1) * block_size)
+    return indptr, indices + [0] * (padded - len(indices)), last
+
+
+def decode_split_tokens(batch, kvh, sm_count, max_ctx):
+    unsplit = max(batch * kvh, 1)
+    chunks = max(-(-2 * sm_count // unsplit), 1)
+    tokens = min(max(max_ctx // chunks, 256), 2048)
+    return 1 << (tokens.bit_length() - 1)
+
+
+def decode_split_pages(block_size, batch, kvh, sm_count, max_ctx):
+    return max(-(-decode_split_tokens(batch, kvh, sm_count, max_ctx) // block_size), 1)
+
+
+def make_decode_tiles(tables, context_lens, block_size, split_pages, padded):
+    req, tile, o_indptr = [], [], [0]
+    for b, (t, c) in enumerate(zip(tables, context_lens)):
+        nb = -(-c // block_size)
+        chunks = 1 if not split_pages else -(-max(nb, 1) // split_pages)
+        for k in range(chunks):
+            req.append(b)
+            tile.append(k)
+        o_indptr.append(len(req))
+    valid = len(req)
+    mask = [1] * valid + [0] * (padded - valid)
+    return req + [0] * (padded - valid), tile + [0] * (padded - valid), o_indptr, (split_pages or 1) * block_size, mask
