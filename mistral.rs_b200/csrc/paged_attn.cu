@@ -49,6 +49,7 @@ struct PagedParams {
   const float *alibi_slopes, *sinks;
   int tiles_are_partitions; // vLLM v2: tile index = seq * num_partitions + partition
   int num_partitions;
+  int heads_per_cta;        // GQA group may be processed in sub-groups (blockIdx.z)
 };
 
 template <typename T> struct Vec8;
@@ -118,8 +119,9 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   const int t_end = min(kv_len, t_begin + chunk);
   const bool partial = p.tmp_o != nullptr;
 
-  const int h0 = kvh * (p.num_heads / p.num_kv_heads);  // first query head of the group
-  const int gsize = p.num_heads / p.num_kv_heads;       // actual group size (<= G)
+  const int group = p.num_heads / p.num_kv_heads;
+  const int h0 = kvh * group + blockIdx.z * p.heads_per_cta;      // first query head of this CTA
+  const int gsize = min(p.heads_per_cta, group - (int)blockIdx.z * p.heads_per_cta);  // heads here (<= G)
 
   // q slice of this lane for all heads of the group, pre-scaled
   float qf[G][8];
@@ -149,7 +151,9 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   const T *kc = (const T *)p.kc, *vc = (const T *)p.vc;
   const int win_lo = (p.window_left >= 0) ? max(0, kv_len - 1 - p.window_left) : 0;
 
-  for (int tb = t_begin + grp; tb < t_end; tb += NGRP * PA_UNROLL) {
+  // trip count is uniform across the CTA (the shuffles below need every lane of the warp)
+  for (int tb0 = t_begin; tb0 < t_end; tb0 += NGRP * PA_UNROLL) {
+    const int tb = tb0 + grp;
     float kf[PA_UNROLL][8], vf[PA_UNROLL][8];
     bool ok[PA_UNROLL];
 #pragma unroll
@@ -309,16 +313,20 @@ __global__ void merge_partials_kernel(const T *__restrict__ tmp_o, const float *
 }
 
 template <typename T, int D, int LAYOUT>
-static cudaError_t launch_decode_g(const PagedParams &p, int tiles, cudaStream_t st) {
-  const int gsize = p.num_heads / p.num_kv_heads;
-  dim3 grid(tiles, p.num_kv_heads);
-  if (gsize <= 1) paged_decode_kernel<T, D, 1, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
-  else if (gsize <= 2) paged_decode_kernel<T, D, 2, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
-  else if (gsize <= 4) paged_decode_kernel<T, D, 4, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
-  else if (gsize <= 8) {
+static cudaError_t launch_decode_g(PagedParams p, int tiles, cudaStream_t st) {
+  const int group = p.num_heads / p.num_kv_heads;
+  constexpr int GMAX = (D <= 128) ? 8 : 4;  // static smem budget: 8 states x G x D floats
+  const int nsub = (group + GMAX - 1) / GMAX;
+  const int per = (group + nsub - 1) / nsub;
+  p.heads_per_cta = per;
+  dim3 grid(tiles, p.num_kv_heads, nsub);
+  if (per <= 1) paged_decode_kernel<T, D, 1, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
+  else if (per <= 2) paged_decode_kernel<T, D, 2, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
+  else if (per <= 4) paged_decode_kernel<T, D, 4, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
+  else {
     if constexpr (D <= 128) paged_decode_kernel<T, D, 8, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
-    else return cudaErrorInvalidValue;  // G=8 with D=256 exceeds the static smem budget
-  } else return cudaErrorInvalidValue;
+    else return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

@@ -73,7 +73,7 @@ def test_flashinfer_hnd(cuda, dt, cfg, split):
     want = oracle.paged_attention(q, ku, vu, bt, ctx, KVH, D, BS, scale, 1, dt)
     indptr, indices, last = kv_index.make_paged_kv_tensors(tables, ctx, BS, bt.size)
     sp = kv_index.decode_split_pages(BS, S, KVH, max(ctx)) if split else None
-    ntiles = sum(max(-(-c // BS), 1) if not sp else -(-max(-(-c // BS), 1) // sp) for c in ctx)
+    ntiles = sum(1 if not sp else -(-max(-(-c // BS), 1) // sp) for c in ctx)
     padded = ntiles + (3 if split else 0)  # graph padding tiles with mask 0
     req, tile, o_indptr, chunk, mask = kv_index.make_paged_kv_decode_tensors(tables, ctx, BS, sp, padded)
     d = lambda a: to_dev(np.ascontiguousarray(a), cuda)
