@@ -1,0 +1,75 @@
+/* mrs_b200_model.h — C ABI of the B200-native Llama-family decode layer stack.
+ *
+ * This is the host-side caller of the hot path (the role of `Llama::forward` /
+ * `Block::forward` in the reference: mistralrs-core/src/models/llama.rs:243-260,475-…),
+ * restricted to what the benchmark needs: it owns no memory, takes raw device pointers, and
+ * enqueues the per-token kernel chain on the given stream (CUDA-graph capturable: no
+ * allocation, no host sync).  Per decoder layer it issues
+ *     [RMSNorm + Q8_1 + fused QKV GEMV] -> RoPE -> KV-cache write -> paged decode attention
+ *     -> [Q8_1 + o_proj GEMV + residual] -> [RMSNorm + Q8_1 + gate/up GEMV + SiLU*mul]
+ *     -> [Q8_1 + down GEMV + residual]
+ * with the bracketed groups being single `mrs_mmvq_fused` launches.
+ */
+#ifndef MRS_B200_MODEL_H
+#define MRS_B200_MODEL_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { const void *data; int32_t ggml_type; int32_t rows; int32_t cols; } mrs_qweight;
+
+typedef struct {
+  mrs_qweight wq, wk, wv, wo, w_gate, w_up, w_down; /* local (possibly TP-sharded) shapes */
+  const void *attn_norm, *ffn_norm;                  /* [hidden] in the activation dtype */
+  void *k_cache, *v_cache;                           /* HND [num_blocks, kv_heads, block_size, head_dim] */
+} mrs_llama_layer;
+
+typedef struct {
+  int32_t hidden, n_layers, n_heads, n_kv_heads, head_dim, vocab; /* heads are LOCAL counts under TP */
+  int32_t block_size, act_dtype;   /* act_dtype: 0 f16, 1 bf16 */
+  float rms_eps, sm_scale;
+  int32_t rope_neox, pdl;
+  const mrs_llama_layer *layers;   /* host array [n_layers] */
+  mrs_qweight tok_embd, lm_head;
+  const void *final_norm, *rope_cos, *rope_sin; /* rope tables [max_pos, head_dim/2] act dtype */
+  /* per-step device metadata (see mrs_decode_advance) */
+  int32_t batch, padded_tiles, max_blocks_per_seq;
+  int32_t *token_ids;        /* [batch] in: token to process; out_token may alias it */
+  int32_t *positions;        /* [batch] */
+  int64_t *slot_mapping;     /* [batch] */
+  int32_t *kv_indptr, *kv_indices, *kv_last_page_len;
+  int32_t *request_indices, *kv_tile_indices, *o_indptr, *kv_chunk_size;
+  uint8_t *block_valid_mask;
+  /* scratch (activation dtype unless noted) */
+  void *x, *x2, *q, *k, *v, *attn_out, *act, *logits; /* x, x2: [batch, hidden] residual stream ping-pong */
+  void *tmp_v; float *tmp_s;
+  int32_t *out_token;        /* [batch] argmax of the logits */
+  /* tensor parallel: called after the row-parallel projections when non-NULL */
+  void (*all_reduce)(void *buf, int64_t count, int32_t dtype, void *stream, void *user);
+  void *all_reduce_user;
+} mrs_llama_step;
+
+/* Enqueue one decode step (all layers + lm_head + argmax) on `stream`. Returns cudaError. */
+int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream);
+
+/* On-device restatement of the scheduler-side index producers for a running decode batch
+ * (REF inputs_processor.rs:896-923, flashinfer/metadata.rs:88-216): context_lens[b] += 1,
+ * positions, slot_mapping, the paged-KV CSR and the split-KV tile plan for the new lengths,
+ * all from the dense block table — so a whole generation replays as one CUDA graph. */
+int32_t mrs_decode_advance(const int32_t *block_tables, int32_t max_blocks_per_seq, int32_t *context_lens,
+                           int32_t batch, int32_t block_size, int32_t split_pages, int32_t padded_tiles,
+                           int32_t *positions, int64_t *slot_mapping, int32_t *kv_indptr, int32_t *kv_indices,
+                           int32_t *kv_last_page_len, int32_t *request_indices, int32_t *kv_tile_indices,
+                           int32_t *o_indptr, int32_t *kv_chunk_size, uint8_t *block_valid_mask, void *stream);
+
+/* rows of a quantised table -> activation dtype (embedding gather). ids on device. */
+int32_t mrs_embedding_gather(int32_t ggml_type, const void *table, int32_t cols, const int32_t *ids, int32_t n,
+                             void *out, int32_t act_dtype, void *stream);
+/* out[b] = argmax_v logits[b, v] (first maximum), logits in act dtype */
+int32_t mrs_argmax(const void *logits, int32_t rows, int32_t cols, int32_t act_dtype, int32_t *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,295 @@
+// decoder.cu — the caller of the hot path: a Llama-family decode layer stack over the kernels in
+// this library (see include/mrs_b200_model.h), plus the few glue kernels a token step needs
+// (quantised embedding gather, argmax, on-device KV index advance).
+//
+// REF structure being mirrored: mistralrs-core/src/models/llama.rs:68-135 (attention),
+// :243-260 (block), :475-… (model forward); embedding gather over ggml blocks:
+// mistralrs-quant/src/gguf/mod.rs:815-845; KV indices: see mrs_decode_advance in the header.
+#include "common.cuh"
+#include "mrs_b200_model.h"
+
+#include <stdio.h>
+
+extern "C" int mrs_mmvq_fused(int ggml_type, int mode, int dt, const void *w0, const void *w1, const void *w2,
+                              const void *x, const void *norm_w, float eps, const void *residual, void *dst0,
+                              void *dst1, void *dst2, int K, int n0, int n1, int n2, int b_size, int activation,
+                              int pdl, void *stream);
+extern "C" void rotary_embedding_positions(void *query, void *key, void *cos_cache, void *sin_cache, void *positions,
+                                           int32_t is_neox, int32_t head_size, int64_t num_tokens, int32_t rot_dim,
+                                           int32_t seq_len, int32_t num_heads, int32_t num_kv_heads,
+                                           int64_t query_stride, int64_t key_stride, uint32_t dtype, int64_t stream);
+extern "C" void reshape_and_cache_flashinfer(void *key, void *value, void *key_cache, void *value_cache,
+                                             int64_t *slot_mapping, int32_t num_tokens, int32_t num_heads,
+                                             int32_t head_size, int32_t block_size, int32_t key_stride,
+                                             int32_t value_stride, float k_scale, float v_scale, uint32_t dtype,
+                                             uint32_t cache_dtype, cudaStream_t stream);
+extern "C" int32_t flashinfer_decode(void *q, void *key_cache, void *value_cache, const int32_t *kv_indptr,
+                                     const int32_t *kv_indices, const int32_t *kv_last_page_len,
+                                     const int32_t *request_indices, const int32_t *kv_tile_indices,
+                                     const int32_t *o_indptr, const int32_t *kv_chunk_size_ptr,
+                                     const bool *block_valid_mask, void *o, void *tmp_v, void *tmp_s,
+                                     int32_t batch_size, int32_t padded_batch_size, int32_t num_qo_heads,
+                                     int32_t num_kv_heads, int32_t head_size, int32_t page_size, int32_t q_stride_n,
+                                     int32_t q_stride_h, float sm_scale, int32_t window_left, float logits_soft_cap,
+                                     float k_scale, float v_scale, uint32_t dtype, uint32_t cache_dtype,
+                                     cudaStream_t stream);
+
+namespace mrs {
+
+// ------------------------------------------------------------------ exact block decoders
+// (same formulas as oracle/mrs_oracle.c unpack_block; layouts REF mmvq_gguf.cu:134-225)
+__device__ __forceinline__ float h2f(const uint8_t *p) {
+  return __half2float(__ushort_as_half((unsigned short)(p[0] | (p[1] << 8))));
+}
+__device__ __forceinline__ void scale_min_k4(int j, const uint8_t *q, int &sc, int &m) {
+  if (j < 4) { sc = q[j] & 63; m = q[j + 4] & 63; }
+  else { sc = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4); m = (q[j + 4] >> 4) | ((q[j] >> 6) << 4); }
+}
+
+__device__ float dequant_elem(int type, const uint8_t *b, int e) {
+  switch (type) {
+  case MRS_Q4_0: { const int q = (e < 16) ? (b[2 + e] & 0xF) : (b[2 + e - 16] >> 4); return h2f(b) * (float)(q - 8); }
+  case MRS_Q4_1: { const int q = (e < 16) ? (b[4 + e] & 0xF) : (b[4 + e - 16] >> 4); return h2f(b) * (float)q + h2f(b + 2); }
+  case MRS_Q5_0: case MRS_Q5_1: {
+    const int o = (type == MRS_Q5_0) ? 2 : 4;
+    const uint32_t qh = b[o] | (b[o + 1] << 8) | (b[o + 2] << 16) | ((uint32_t)b[o + 3] << 24);
+    const int j = e & 15;
+    const int lo = (e < 16) ? (b[o + 4 + j] & 0xF) : (b[o + 4 + j] >> 4);
+    const int hi = (qh >> e) & 1;
+    const int q = lo | (hi << 4);
+    return (type == MRS_Q5_0) ? h2f(b) * (float)(q - 16) : h2f(b) * (float)q + h2f(b + 2);
+  }
+  case MRS_Q8_0: return h2f(b) * (float)(int8_t)b[2 + e];
+  case MRS_Q2_K: {
+    const int n = e / 128, j = (e % 128) / 32, l = e % 32, g = e / 16;
+    const int q = (b[16 + 32 * n + l] >> (2 * j)) & 3;
+    return h2f(b + 80) * (float)(b[g] & 0xF) * (float)q - h2f(b + 82) * (float)(b[g] >> 4);
+  }
+  case MRS_Q3_K: {
+    const int n = e / 128, j = (e % 128) / 32, l = e % 32, is = e / 16;
+    const int lo = (b[32 + 32 * n + l] >> (2 * j)) & 3;
+    const int hb = (b[l] >> (4 * n + j)) & 1;
+    const uint8_t *s = b + 96;
+    const int sc = (((s[is & 7] >> (4 * (is >> 3))) & 0xF) | (((s[8 + (is & 3)] >> (2 * (is >> 2))) & 3) << 4)) - 32;
+    return h2f(b + 108) * (float)sc * (float)(lo - (hb ? 0 : 4));
+  }
+  case MRS_Q4_K: case MRS_Q5_K: {
+    const int j = e / 64, hi = (e % 64) / 32, l = e % 32;
+    const uint8_t *qs = b + ((type == MRS_Q4_K) ? 16 : 48);
+    int v = hi ? (qs[32 * j + l] >> 4) : (qs[32 * j + l] & 0xF);
+    if (type == MRS_Q5_K) v |= ((b[16 + l] >> (2 * j + hi)) & 1) << 4;
+    int sc, m;
+    scale_min_k4(2 * j + hi, b + 4, sc, m);
+    return h2f(b) * (float)sc * (float)v - h2f(b + 2) * (float)m;
+  }
+  case MRS_Q6_K: {
+    const int n = e / 128, k = (e % 128) / 32, l = e % 32;
+    const uint8_t *ql = b + 64 * n, *qh = b + 128 + 32 * n;
+    int lo = (k & 1) ? ql[l + 32] : ql[l];
+    lo = (k & 2) ? (lo >> 4) : (lo & 0xF);
+    const int q = (lo | (((qh[l] >> (2 * k)) & 3) << 4)) - 32;
+    return h2f(b + 208) * (float)(int8_t)b[192 + e / 16] * (float)q;
+  }
+  default: return 0.f;
+  }
+}
+
+__host__ __device__ inline int blk_elems(int t) { return (t >= MRS_Q2_K) ? 256 : 32; }
+__host__ __device__ inline int blk_bytes(int t) {
+  switch (t) {
+  case MRS_Q4_0: return 18; case MRS_Q4_1: return 20; case MRS_Q5_0: return 22; case MRS_Q5_1: return 24;
+  case MRS_Q8_0: return 34; case MRS_Q2_K: return 84; case MRS_Q3_K: return 110; case MRS_Q4_K: return 144;
+  case MRS_Q5_K: return 176; case MRS_Q6_K: return 210; default: return 0;
+  }
+}
+
+__global__ void embedding_gather_kernel(int type, const uint8_t *__restrict__ table, int cols,
+                                        const int32_t *__restrict__ ids, void *__restrict__ out, int act_dtype) {
+  const int row = ids[blockIdx.x];
+  const int be = blk_elems(type), bb = blk_bytes(type);
+  const uint8_t *rp = table + (size_t)row * (cols / be) * bb;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x)
+    store_act(out, (int64_t)blockIdx.x * cols + i, dequant_elem(type, rp + (size_t)(i / be) * bb, i % be), act_dtype);
+}
+
+// first-maximum argmax of one row per CTA
+__global__ void argmax_kernel(const void *__restrict__ logits, int cols, int act_dtype, int32_t *__restrict__ out) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const int64_t base = (int64_t)blockIdx.x * cols;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    const float v = load_act(logits, base + i, act_dtype);
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, m);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sv[w] = best; si[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    best = (l < nw) ? sv[l] : -INFINITY;
+    bi = (l < nw) ? si[l] : 0x7fffffff;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, m);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (l == 0) out[blockIdx.x] = bi;
+  }
+}
+
+// dst = T(dst + res) — the residual add after a row-parallel all-reduce
+__global__ void add_residual_kernel(void *__restrict__ dst, const void *__restrict__ res, int64_t n, int dt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) store_act(dst, i, load_act(dst, i, dt) + load_act(res, i, dt), dt);
+}
+
+// one CTA, thread 0 walks the (tiny) batch: integers only, must match the host producers
+__global__ void decode_advance_kernel(const int32_t *__restrict__ block_tables, int max_blocks,
+                                      int32_t *__restrict__ context_lens, int batch, int bs, int split_pages,
+                                      int padded_tiles, int32_t *positions, int64_t *slot_mapping, int32_t *kv_indptr,
+                                      int32_t *kv_indices, int32_t *kv_last_page_len, int32_t *request_indices,
+                                      int32_t *kv_tile_indices, int32_t *o_indptr, int32_t *kv_chunk_size,
+                                      uint8_t *block_valid_mask) {
+  __shared__ int s_indptr[65], s_oind[65];
+  if (threadIdx.x == 0) {
+    int nnz = 0, tiles = 0;
+    s_indptr[0] = 0; s_oind[0] = 0;
+    for (int b = 0; b < batch; b++) {
+      const int pos = context_lens[b];       // position of the token being processed now
+      const int ctx = pos + 1;               // context length including it
+      context_lens[b] = ctx;
+      positions[b] = pos;
+      slot_mapping[b] = (int64_t)block_tables[(int64_t)b * max_blocks + pos / bs] * bs + pos % bs;
+      const int nb = (ctx + bs - 1) / bs;
+      nnz += nb;
+      s_indptr[b + 1] = nnz;
+      kv_last_page_len[b] = ctx - (nb - 1) * bs;
+      const int chunks = (split_pages > 0) ? ((nb < 1 ? 1 : nb) + split_pages - 1) / split_pages : 1;
+      for (int t = 0; t < chunks && tiles < padded_tiles; t++, tiles++) { request_indices[tiles] = b; kv_tile_indices[tiles] = t; }
+      s_oind[b + 1] = tiles;
+    }
+    for (int b = 0; b <= batch; b++) { kv_indptr[b] = s_indptr[b]; o_indptr[b] = s_oind[b]; }
+    for (int t = 0; t < padded_tiles; t++) {
+      block_valid_mask[t] = t < tiles ? 1 : 0;
+      if (t >= tiles) { request_indices[t] = 0; kv_tile_indices[t] = 0; }
+    }
+    kv_chunk_size[0] = (split_pages > 0 ? split_pages : 1) * bs;
+  }
+  __syncthreads();
+  // page indices: parallel over (b, i)
+  for (int b = 0; b < batch; b++) {
+    const int p0 = s_indptr[b], nb = s_indptr[b + 1] - p0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) kv_indices[p0 + i] = block_tables[(int64_t)b * max_blocks + i];
+  }
+}
+
+}  // namespace mrs
+
+using namespace mrs;
+
+extern "C" int32_t mrs_embedding_gather(int32_t ggml_type, const void *table, int32_t cols, const int32_t *ids,
+                                        int32_t n, void *out, int32_t act_dtype, void *stream) {
+  if (n <= 0) return 0;
+  if (blk_bytes(ggml_type) == 0 || cols % blk_elems(ggml_type)) return (int32_t)cudaErrorInvalidValue;
+  embedding_gather_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(ggml_type, (const uint8_t *)table, cols, ids, out, act_dtype);
+  return (int32_t)cudaGetLastError();
+}
+
+extern "C" int32_t mrs_argmax(const void *logits, int32_t rows, int32_t cols, int32_t act_dtype, int32_t *out, void *stream) {
+  if (rows <= 0) return 0;
+  argmax_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>(logits, cols, act_dtype, out);
+  return (int32_t)cudaGetLastError();
+}
+
+extern "C" int32_t mrs_decode_advance(const int32_t *block_tables, int32_t max_blocks_per_seq, int32_t *context_lens,
+                                      int32_t batch, int32_t block_size, int32_t split_pages, int32_t padded_tiles,
+                                      int32_t *positions, int64_t *slot_mapping, int32_t *kv_indptr,
+                                      int32_t *kv_indices, int32_t *kv_last_page_len, int32_t *request_indices,
+                                      int32_t *kv_tile_indices, int32_t *o_indptr, int32_t *kv_chunk_size,
+                                      uint8_t *block_valid_mask, void *stream) {
+  if (batch < 1 || batch > 64) return (int32_t)cudaErrorInvalidValue;
+  decode_advance_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(block_tables, max_blocks_per_seq, context_lens, batch,
+                                                             block_size, split_pages, padded_tiles, positions,
+                                                             slot_mapping, kv_indptr, kv_indices, kv_last_page_len,
+                                                             request_indices, kv_tile_indices, o_indptr, kv_chunk_size,
+                                                             block_valid_mask);
+  return (int32_t)cudaGetLastError();
+}
+
+#define MRS_TRY(expr)                                  \
+  do {                                                 \
+    const int _e = (int)(expr);                        \
+    if (_e != 0) {                                     \
+      fprintf(stderr, "mrs_b200: %s -> cudaError %d\n", #expr, _e); \
+      return _e;                                       \
+    }                                                  \
+  } while (0)
+
+extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) {
+  const int dt = s->act_dtype, B = s->batch, H = s->hidden, pdl = s->pdl;
+  const int nq = s->n_heads * s->head_dim, nkv = s->n_kv_heads * s->head_dim;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B < 1 || B > 8) return (int32_t)cudaErrorInvalidValue;
+
+  MRS_TRY(mrs_embedding_gather(s->tok_embd.ggml_type, s->tok_embd.data, H, s->token_ids, B, s->x, dt, stream));
+  void *hidden = s->x, *hidden2 = s->x2;
+  for (int l = 0; l < s->n_layers; l++) {
+    const mrs_llama_layer &L = s->layers[l];
+    // --- attention block: x = x + o_proj(attn(rope(qkv(norm(x)))))
+    if (L.wq.ggml_type == L.wk.ggml_type && L.wk.ggml_type == L.wv.ggml_type) {
+      MRS_TRY(mrs_mmvq_fused(L.wq.ggml_type, 2, dt, L.wq.data, L.wk.data, L.wv.data, hidden, L.attn_norm, s->rms_eps,
+                             nullptr, s->q, s->k, s->v, H, nq, nkv, nkv, B, 0, pdl, stream));
+    } else {  // Q4_K_M keeps attn_v in Q6_K on some layers: q∥k fused, v on its own
+      MRS_TRY(mrs_mmvq_fused(L.wq.ggml_type, 2, dt, L.wq.data, L.wk.data, nullptr, hidden, L.attn_norm, s->rms_eps,
+                             nullptr, s->q, s->k, nullptr, H, nq, nkv, 0, B, 0, pdl, stream));
+      MRS_TRY(mrs_mmvq_fused(L.wv.ggml_type, 0, dt, L.wv.data, nullptr, nullptr, hidden, L.attn_norm, s->rms_eps,
+                             nullptr, s->v, nullptr, nullptr, H, nkv, 0, 0, B, 0, pdl, stream));
+    }
+    rotary_embedding_positions(s->q, s->k, (void *)s->rope_cos, (void *)s->rope_sin, s->positions, s->rope_neox,
+                               s->head_dim, B, s->head_dim / 2, 0, s->n_heads, s->n_kv_heads, nq, nkv, (uint32_t)dt,
+                               (int64_t)stream);
+    reshape_and_cache_flashinfer(s->k, s->v, L.k_cache, L.v_cache, s->slot_mapping, B, s->n_kv_heads, s->head_dim,
+                                 s->block_size, nkv, nkv, 1.f, 1.f, (uint32_t)dt, (uint32_t)dt, st);
+    MRS_TRY(flashinfer_decode(s->q, L.k_cache, L.v_cache, s->kv_indptr, s->kv_indices, s->kv_last_page_len,
+                              s->request_indices, s->kv_tile_indices, s->o_indptr, s->kv_chunk_size,
+                              (const bool *)s->block_valid_mask, s->attn_out, s->padded_tiles > B ? s->tmp_v : nullptr,
+                              s->padded_tiles > B ? s->tmp_s : nullptr, B, s->padded_tiles, s->n_heads, s->n_kv_heads,
+                              s->head_dim, s->block_size, nq, s->head_dim, s->sm_scale, -1, 0.f, 1.f, 1.f,
+                              (uint32_t)dt, (uint32_t)dt, st));
+    if (s->all_reduce == nullptr) {
+      MRS_TRY(mrs_mmvq_fused(L.wo.ggml_type, 0, dt, L.wo.data, nullptr, nullptr, s->attn_out, nullptr, 0.f, hidden,
+                             hidden2, nullptr, nullptr, nq, H, 0, 0, B, 0, pdl, stream));
+    } else {  // row-parallel: partial sums -> all-reduce -> residual add (REF distributed/layers.rs:965-975)
+      MRS_TRY(mrs_mmvq_fused(L.wo.ggml_type, 0, dt, L.wo.data, nullptr, nullptr, s->attn_out, nullptr, 0.f, nullptr,
+                             hidden2, nullptr, nullptr, nq, H, 0, 0, B, 0, pdl, stream));
+      s->all_reduce(hidden2, (int64_t)B * H, dt, stream, s->all_reduce_user);
+      add_residual_kernel<<<(unsigned)(((int64_t)B * H + 255) / 256), 256, 0, st>>>(hidden2, hidden, (int64_t)B * H, dt);
+    }
+    // --- MLP block: x = x + down(silu(gate(norm(x))) * up(norm(x)))
+    MRS_TRY(mrs_mmvq_fused(L.w_gate.ggml_type, 1, dt, L.w_gate.data, L.w_up.data, nullptr, hidden2, L.ffn_norm,
+                           s->rms_eps, nullptr, s->act, nullptr, nullptr, H, L.w_gate.rows, L.w_gate.rows, 0, B, 0,
+                           pdl, stream));
+    if (s->all_reduce == nullptr) {
+      MRS_TRY(mrs_mmvq_fused(L.w_down.ggml_type, 0, dt, L.w_down.data, nullptr, nullptr, s->act, nullptr, 0.f, hidden2,
+                             hidden, nullptr, nullptr, L.w_down.cols, H, 0, 0, B, 0, pdl, stream));
+    } else {
+      MRS_TRY(mrs_mmvq_fused(L.w_down.ggml_type, 0, dt, L.w_down.data, nullptr, nullptr, s->act, nullptr, 0.f, nullptr,
+                             hidden, nullptr, nullptr, L.w_down.cols, H, 0, 0, B, 0, pdl, stream));
+      s->all_reduce(hidden, (int64_t)B * H, dt, stream, s->all_reduce_user);
+      add_residual_kernel<<<(unsigned)(((int64_t)B * H + 255) / 256), 256, 0, st>>>(hidden, hidden2, (int64_t)B * H, dt);
+    }
+  }
+  MRS_TRY(mrs_mmvq_fused(s->lm_head.ggml_type, 0, dt, s->lm_head.data, nullptr, nullptr, hidden, s->final_norm,
+                         s->rms_eps, nullptr, s->logits, nullptr, nullptr, H, s->vocab, 0, 0, B, 0, pdl, stream));
+  MRS_TRY(mrs_argmax(s->logits, B, s->vocab, dt, s->out_token, stream));
+  return 0;
+}

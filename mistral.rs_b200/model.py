@@ -1,0 +1,319 @@
+"""Llama-family decode runner over the C ABI (`mrs_llama_decode_step`, include/mrs_b200_model.h).
+
+Python here is only the harness: it allocates device memory with torch, fills the C structs with
+raw pointers and drives CUDA-graph capture/replay.  The layer stack itself (which kernels run, in
+which order) is C++ inside libmrs_b200.so.
+
+Synthetic weights follow SURVEY §8(d): ggml blocks with uniformly random quants over their full
+bit range, f16 scales d = 2^U(-9,-7), dmin = d*U(0,0.5); tensor-type map for Q4_K_M = the
+llama.cpp recipe (Q4_K everywhere; Q6_K for `output`, and for attn_v + ffn_down on layers
+i < n/8, i >= 7n/8 or (i - n/8) % 3 == 2).
+"""
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import BLOCK_BYTES, BLOCK_ELEMS, GGML, kv_index, lib
+
+F16_FIELDS = {"q4_0": [0], "q4_1": [0, 2], "q5_0": [0], "q5_1": [0, 2], "q8_0": [0],
+              "q2_k": [80, 82], "q3_k": [108], "q4_k": [0, 2], "q5_k": [0, 2], "q6_k": [208]}
+
+
+@dataclass
+class LlamaConfig:
+    hidden: int = 4096
+    inter: int = 14336
+    n_layers: int = 32
+    n_heads: int = 32
+    n_kv_heads: int = 8
+    head_dim: int = 128
+    vocab: int = 128256
+    rms_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    rope_scaling: dict = None
+    max_pos: int = 8192
+    quant: str = "q4_k_m"      # "q4_k_m" | any ggml type name for a uniform model
+    block_size: int = 16
+    name: str = "llama-3-8b"
+
+    @staticmethod
+    def llama3_8b(**kw):
+        return LlamaConfig(rope_scaling=None, **kw)
+
+    @staticmethod
+    def llama3_70b(**kw):
+        return LlamaConfig(hidden=8192, inter=28672, n_layers=80, n_heads=64, n_kv_heads=8, name="llama-3-70b", **kw)
+
+    @staticmethod
+    def tinyllama(**kw):
+        return LlamaConfig(hidden=2048, inter=5632, n_layers=22, n_heads=32, n_kv_heads=4, head_dim=64, vocab=32000,
+                           rope_theta=10000.0, name="tinyllama-1.1b", **kw)
+
+    @staticmethod
+    def tiny_test(**kw):
+        d = dict(hidden=512, inter=1024, n_layers=3, n_heads=8, n_kv_heads=2, head_dim=64, vocab=1024,
+                 rope_theta=10000.0, max_pos=512, name="tiny-test")
+        d.update(kw)
+        return LlamaConfig(**d)
+
+
+def tensor_type(cfg: LlamaConfig, name: str, layer: int = 0) -> str:
+    """ggml type of a tensor under cfg.quant (llama.cpp Q4_K_M recipe)."""
+    if cfg.quant != "q4_k_m":
+        return cfg.quant
+    if name == "output":
+        return "q6_k"
+    if name in ("attn_v", "ffn_down"):
+        n = cfg.n_layers
+        if layer < n // 8 or layer >= 7 * n // 8 or (layer - n // 8) % 3 == 2:
+            return "q6_k"
+    return "q4_k"
+
+
+TENSOR_IDS = {"attn_q": 0, "attn_k": 1, "attn_v": 2, "attn_output": 3, "ffn_gate": 4, "ffn_up": 5, "ffn_down": 6,
+              "attn_norm": 7, "ffn_norm": 8, "token_embd": 9, "output": 10, "output_norm": 11}
+
+
+def synth_blocks(dtype: str, nblocks: int, seed: int) -> np.ndarray:
+    """uint8 [nblocks, block_bytes] per SURVEY §8(d), numpy PCG64(seed)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    bb = BLOCK_BYTES[dtype]
+    raw = rng.integers(0, 256, size=(nblocks, bb), dtype=np.uint8)
+    f = F16_FIELDS[dtype]
+    d = np.exp2(rng.uniform(-9, -7, size=nblocks)).astype(np.float16)
+    raw[:, f[0]:f[0] + 2] = d.view(np.uint8).reshape(nblocks, 2)
+    if len(f) > 1:
+        m = (d.astype(np.float32) * rng.uniform(0, 0.5, size=nblocks)).astype(np.float16)
+        raw[:, f[1]:f[1] + 2] = m.view(np.uint8).reshape(nblocks, 2)
+    return raw
+
+
+def tensor_seed(layer: int, name: str) -> int:
+    return 0xB200 + layer * 16 + TENSOR_IDS[name]
+
+
+class _QW(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("ggml_type", ctypes.c_int32), ("rows", ctypes.c_int32),
+                ("cols", ctypes.c_int32)]
+
+
+class _Layer(ctypes.Structure):
+    _fields_ = [(n, _QW) for n in ("wq", "wk", "wv", "wo", "w_gate", "w_up", "w_down")] + \
+               [("attn_norm", ctypes.c_void_p), ("ffn_norm", ctypes.c_void_p),
+                ("k_cache", ctypes.c_void_p), ("v_cache", ctypes.c_void_p)]
+
+
+_AR_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p)
+
+
+class _Step(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("hidden", "n_layers", "n_heads", "n_kv_heads", "head_dim", "vocab",
+                                              "block_size", "act_dtype")] + \
+               [("rms_eps", ctypes.c_float), ("sm_scale", ctypes.c_float), ("rope_neox", ctypes.c_int32),
+                ("pdl", ctypes.c_int32), ("layers", ctypes.POINTER(_Layer)), ("tok_embd", _QW), ("lm_head", _QW),
+                ("final_norm", ctypes.c_void_p), ("rope_cos", ctypes.c_void_p), ("rope_sin", ctypes.c_void_p),
+                ("batch", ctypes.c_int32), ("padded_tiles", ctypes.c_int32), ("max_blocks_per_seq", ctypes.c_int32)] + \
+               [(n, ctypes.c_void_p) for n in ("token_ids", "positions", "slot_mapping", "kv_indptr", "kv_indices",
+                                               "kv_last_page_len", "request_indices", "kv_tile_indices", "o_indptr",
+                                               "kv_chunk_size", "block_valid_mask", "x", "x2", "q", "k", "v",
+                                               "attn_out", "act", "logits", "tmp_v", "tmp_s", "out_token")] + \
+               [("all_reduce", _AR_FN), ("all_reduce_user", ctypes.c_void_p)]
+
+
+def rope_tables(cfg: LlamaConfig):
+    """cos/sin [max_pos, head_dim/2] f32 — REF mistralrs-core/src/layers.rs:1071-1160."""
+    half = cfg.head_dim // 2
+    inv = (1.0 / np.power(np.float32(cfg.rope_theta), np.arange(0, cfg.head_dim, 2, dtype=np.float32) / np.float32(cfg.head_dim))).astype(np.float32)
+    sc = cfg.rope_scaling
+    if sc is not None:
+        low_wl = np.float32(sc["original_max_position_embeddings"]) / np.float32(sc["low_freq_factor"])
+        high_wl = np.float32(sc["original_max_position_embeddings"]) / np.float32(sc["high_freq_factor"])
+        out = []
+        for f in inv:
+            wl = np.float32(2 * np.pi) / f
+            if wl < high_wl:
+                out.append(f)
+            elif wl > low_wl:
+                out.append(f / np.float32(sc["factor"]))
+            else:
+                smooth = (np.float32(sc["original_max_position_embeddings"]) / wl - np.float32(sc["low_freq_factor"])) / \
+                         (np.float32(sc["high_freq_factor"]) - np.float32(sc["low_freq_factor"]))
+                out.append((1 - smooth) * f / np.float32(sc["factor"]) + smooth * f)
+        inv = np.array(out, dtype=np.float32)
+    freqs = np.arange(cfg.max_pos, dtype=np.float32)[:, None] * inv[None, :]
+    assert freqs.shape[1] == half
+    return np.cos(freqs).astype(np.float32), np.sin(freqs).astype(np.float32)
+
+
+class LlamaWeights:
+    """Synthetic device-resident weights (optionally one tensor-parallel shard)."""
+
+    def __init__(self, cfg: LlamaConfig, device, dtype=torch.bfloat16, tp_rank=0, tp_size=1, keep_host=False):
+        self.cfg, self.device, self.dtype = cfg, device, dtype
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+        self.host = {} if keep_host else None
+        H, I = cfg.hidden, cfg.inter
+        nq, nkv = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
+        assert cfg.n_heads % tp_size == 0 and cfg.n_kv_heads % tp_size == 0 and I % (tp_size * 256) == 0
+        self.layers = []
+        self.nbytes = 0
+        for l in range(cfg.n_layers):
+            L = {}
+            for name, rows, cols, kind in (("attn_q", nq, H, "col"), ("attn_k", nkv, H, "col"), ("attn_v", nkv, H, "col"),
+                                           ("attn_output", H, nq, "row"), ("ffn_gate", I, H, "col"),
+                                           ("ffn_up", I, H, "col"), ("ffn_down", H, I, "row")):
+                L[name] = self._qtensor(l, name, rows, cols, kind)
+            for name in ("attn_norm", "ffn_norm"):
+                L[name] = self._norm(l, name)
+            self.layers.append(L)
+        self.tok_embd = self._qtensor(0, "token_embd", cfg.vocab, H, "rep")
+        self.output = self._qtensor(0, "output", cfg.vocab, H, "rep")
+        self.output_norm = self._norm(0, "output_norm")
+        cos, sin = rope_tables(cfg)
+        self.rope_cos = torch.from_numpy(cos).to(device).to(dtype)
+        self.rope_sin = torch.from_numpy(sin).to(device).to(dtype)
+
+    def _norm(self, layer, name):
+        rng = np.random.Generator(np.random.PCG64(tensor_seed(layer, name)))
+        w = (1.0 + 0.1 * rng.standard_normal(self.cfg.hidden)).astype(np.float32)
+        t = torch.from_numpy(w).to(self.device).to(self.dtype)
+        if self.host is not None:
+            self.host[(layer, name)] = t.float().cpu().numpy()
+        return t
+
+    def _qtensor(self, layer, name, rows, cols, kind):
+        """kind: 'col' (rows sharded), 'row' (K sharded on block boundaries), 'rep' (replicated).
+        Sharding rules: REF mistralrs-quant/src/distributed/layers.rs:1167-1294 (column),
+        :695-975 (row), gguf/weight_source.rs:809-818 (block-aligned K slices)."""
+        dt = tensor_type(self.cfg, name, layer)
+        be, bb = BLOCK_ELEMS[dt], BLOCK_BYTES[dt]
+        full = synth_blocks(dt, rows * cols // be, tensor_seed(layer, name)).reshape(rows, cols // be, bb)
+        r, w = self.tp_rank, self.tp_size
+        if kind == "col" and w > 1:
+            full = full[r * rows // w:(r + 1) * rows // w]
+            rows //= w
+        elif kind == "row" and w > 1:
+            nb = cols // be
+            assert nb % w == 0
+            full = full[:, r * nb // w:(r + 1) * nb // w]
+            cols //= w
+        full = np.ascontiguousarray(full)
+        t = torch.from_numpy(full.reshape(-1)).to(self.device)
+        self.nbytes += t.numel()
+        if self.host is not None:
+            self.host[(layer, name)] = full.reshape(-1)
+        return (t, dt, rows, cols)
+
+
+class LlamaRunner:
+    """Owns KV cache + scratch + per-step metadata for a batch of sequences and drives
+    mrs_llama_decode_step / mrs_decode_advance (eagerly or as a captured CUDA graph)."""
+
+    def __init__(self, weights: LlamaWeights, batch=1, max_ctx=512, pdl=False, sm_count=148, comm=None):
+        cfg, dev, dt = weights.cfg, weights.device, weights.dtype
+        self.w, self.cfg, self.dev, self.dt, self.B = weights, cfg, dev, dt, batch
+        tp = weights.tp_size
+        self.n_heads, self.n_kv = cfg.n_heads // tp, cfg.n_kv_heads // tp
+        bs = cfg.block_size
+        self.max_blocks = -(-max_ctx // bs)
+        nb = batch * self.max_blocks + 1
+        self.pool = kv_index.BlockPool(nb)
+        self.tables = [self.pool.get_new_blocks(self.max_blocks) for _ in range(batch)]
+        self.block_tables = torch.tensor(self.tables, dtype=torch.int32, device=dev)
+        self.context_lens = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.split_pages = kv_index.decode_split_pages(bs, batch, self.n_kv, max_ctx, sm_count=sm_count)
+        self.padded_tiles = batch * -(-self.max_blocks // self.split_pages)
+        if self.padded_tiles <= batch:        # a single chunk per request: unsplit plan
+            self.split_pages, self.padded_tiles = 0, batch
+        z = lambda *s, d=torch.int32: torch.zeros(*s, dtype=d, device=dev)
+        self.meta = dict(token_ids=z(batch), positions=z(batch), slot_mapping=z(batch, d=torch.int64),
+                         kv_indptr=z(batch + 1), kv_indices=z(batch * self.max_blocks), kv_last_page_len=z(batch),
+                         request_indices=z(self.padded_tiles), kv_tile_indices=z(self.padded_tiles),
+                         o_indptr=z(batch + 1), kv_chunk_size=z(1), block_valid_mask=z(self.padded_tiles, d=torch.uint8))
+        a = lambda *s: torch.zeros(*s, dtype=dt, device=dev)
+        H = cfg.hidden
+        self.buf = dict(x=a(batch, H), x2=a(batch, H), q=a(batch, self.n_heads * cfg.head_dim),
+                        k=a(batch, self.n_kv * cfg.head_dim), v=a(batch, self.n_kv * cfg.head_dim),
+                        attn_out=a(batch, self.n_heads * cfg.head_dim), act=a(batch, cfg.inter // tp),
+                        logits=a(batch, cfg.vocab), tmp_v=a(self.padded_tiles, self.n_heads, cfg.head_dim),
+                        tmp_s=torch.zeros(self.padded_tiles, self.n_heads, dtype=torch.float32, device=dev),
+                        out_token=self.meta["token_ids"])  # argmax feeds the next step directly
+        self.k_cache = [a(nb, self.n_kv, bs, cfg.head_dim) for _ in range(cfg.n_layers)]
+        self.v_cache = [a(nb, self.n_kv, bs, cfg.head_dim) for _ in range(cfg.n_layers)]
+        self._layers = (_Layer * cfg.n_layers)()
+        for l, L in enumerate(weights.layers):
+            for field_, name in (("wq", "attn_q"), ("wk", "attn_k"), ("wv", "attn_v"), ("wo", "attn_output"),
+                                 ("w_gate", "ffn_gate"), ("w_up", "ffn_up"), ("w_down", "ffn_down")):
+                t, ty, rows, cols = L[name]
+                setattr(self._layers[l], field_, _QW(t.data_ptr(), GGML[ty], rows, cols))
+            self._layers[l].attn_norm = L["attn_norm"].data_ptr()
+            self._layers[l].ffn_norm = L["ffn_norm"].data_ptr()
+            self._layers[l].k_cache = self.k_cache[l].data_ptr()
+            self._layers[l].v_cache = self.v_cache[l].data_ptr()
+        s = _Step()
+        s.hidden, s.n_layers, s.n_heads, s.n_kv_heads, s.head_dim, s.vocab = H, cfg.n_layers, self.n_heads, self.n_kv, cfg.head_dim, cfg.vocab
+        s.block_size, s.act_dtype = bs, {torch.float16: 0, torch.bfloat16: 1}[dt]
+        s.rms_eps, s.sm_scale, s.rope_neox, s.pdl = cfg.rms_eps, 1.0 / float(np.sqrt(cfg.head_dim)), 1, int(pdl)
+        s.layers = ctypes.cast(self._layers, ctypes.POINTER(_Layer))
+        t, ty, rows, cols = weights.tok_embd
+        s.tok_embd = _QW(t.data_ptr(), GGML[ty], rows, cols)
+        t, ty, rows, cols = weights.output
+        s.lm_head = _QW(t.data_ptr(), GGML[ty], rows, cols)
+        s.final_norm, s.rope_cos, s.rope_sin = weights.output_norm.data_ptr(), weights.rope_cos.data_ptr(), weights.rope_sin.data_ptr()
+        s.batch, s.padded_tiles, s.max_blocks_per_seq = batch, self.padded_tiles, self.max_blocks
+        for n, t in self.meta.items():
+            setattr(s, n, t.data_ptr())
+        for n, t in self.buf.items():
+            setattr(s, n, t.data_ptr())
+        self._ar_cb = None
+        if comm is not None:
+            self._ar_cb = _AR_FN(comm)
+            s.all_reduce = self._ar_cb
+        self.step_struct = s
+        self.graph = None
+
+    # ---- eager pieces -------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def advance(self):
+        m = self.meta
+        rc = lib().mrs_decode_advance(ctypes.c_void_p(self.block_tables.data_ptr()), ctypes.c_int(self.max_blocks),
+                                      ctypes.c_void_p(self.context_lens.data_ptr()), ctypes.c_int(self.B),
+                                      ctypes.c_int(self.cfg.block_size), ctypes.c_int(self.split_pages),
+                                      ctypes.c_int(self.padded_tiles), *[ctypes.c_void_p(m[k].data_ptr()) for k in
+                                      ("positions", "slot_mapping", "kv_indptr", "kv_indices", "kv_last_page_len",
+                                       "request_indices", "kv_tile_indices", "o_indptr", "kv_chunk_size",
+                                       "block_valid_mask")], self._stream())
+        assert rc == 0, rc
+
+    def forward(self):
+        rc = lib().mrs_llama_decode_step(ctypes.byref(self.step_struct), self._stream())
+        if rc != 0:
+            raise RuntimeError(f"mrs_llama_decode_step failed: cudaError {rc}")
+
+    def step(self):
+        """advance the KV metadata for the token in `token_ids`, run the stack, argmax -> token_ids."""
+        self.advance()
+        self.forward()
+
+    def reset(self):
+        self.context_lens.zero_()
+
+    def capture(self):
+        self.step(); self.reset()  # warm-up outside capture (module load, attributes)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step()
+        self.reset()
+        self.graph = g
+        return g
+
+    def set_tokens(self, ids):
+        self.meta["token_ids"].copy_(torch.as_tensor(ids, dtype=torch.int32, device=self.dev))
+
+    def logits(self):
+        return self.buf["logits"]
