@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — decode tok/s of the quantized-linear + paged-attention hot path on B200.
+
+Workload (BASELINE.json configs[1]): Llama-3-8B, GGUF Q4_K_M tensor types, decode batch=1,
+128-token prompt -> +256 generated tokens, synthetic weights/prompts, paged KV
+cache block_size=16 in the FlashInfer HND layout.  Metric definitions follow the reference's
+`mistralrs bench` (mistralrs-cli/src/commands/bench.rs:269-296): decode tok/s =
+(gen_len - 1) / (t_last_token - t_first_token).
+
+A "step" is one full generation (prompt + 256 tokens); the timed region of a step is its decode
+phase, bracketed by CUDA events on the launching stream (max over ranks).  `value` replays the
+per-token CUDA graph with every input resident in HBM (the sampled token feeds the next step on
+the device); `e2e` drives the same graph the way a serving engine does: the token id is copied
+from pinned host memory before every step and the sampled id is read back after it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   (tensor parallel, NCCL)
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PROMPT_LEN, GEN_LEN = 128, 256
+
+
+def prompt_tokens(it, case=0, n=PROMPT_LEN):
+    # REF bench.rs:52-55,427-430: 1000 + ((131*(it+1) + 719*case + i) mod 2048)
+    return [1000 + ((131 * (it + 1) + 719 * case + i) % 2048) for i in range(n)]
+
+
+def algorithmic_bytes_per_token(cfg, M, tp=1):
+    """Quantized weight bytes touched once per token + KV bytes at the mean context."""
+    from mistralrs_b200 import BLOCK_BYTES, BLOCK_ELEMS
+    H, I = cfg.hidden, cfg.inter
+    nq, nkv = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
+    tot = 0
+    for l in range(cfg.n_layers):
+        for name, n in (("attn_q", nq * H), ("attn_k", nkv * H), ("attn_v", nkv * H), ("attn_output", H * nq),
+                        ("ffn_gate", I * H), ("ffn_up", I * H), ("ffn_down", H * I)):
+            t = M.tensor_type(cfg, name, l)
+            tot += n // tp * BLOCK_BYTES[t] // BLOCK_ELEMS[t]
+    t = M.tensor_type(cfg, "output", 0)
+    head = cfg.vocab * H * BLOCK_BYTES[t] // BLOCK_ELEMS[t]
+    mean_ctx = PROMPT_LEN + GEN_LEN // 2
+    kv = 2 * (nkv // tp) * 2 * cfg.n_layers * mean_ctx
+    return tot + head + kv, tot + head
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.lines, self.gpu = None, [], gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline_sample(cfg, M, threads, layers=2):
+    """The reference's CPU path restated (oracle/: Q8_K/Q8_0 activations + integer block dots,
+    candle QMatMul algorithm) timed on a bounded sample of the SAME workload: the seven GEMVs of
+    `layers` decoder layers + the lm_head of this model, batch 1; extrapolated to a full token."""
+    import numpy as np
+    import oracle
+    rng = np.random.default_rng(0)
+    H, I = cfg.hidden, cfg.inter
+    nq, nkv = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
+    shapes = [("attn_q", nq, H), ("attn_k", nkv, H), ("attn_v", nkv, H), ("attn_output", H, nq), ("ffn_gate", I, H),
+              ("ffn_up", I, H), ("ffn_down", H, I)]
+    ws = {}
+    for l in range(layers):
+        for name, rows, cols in shapes:
+            t = M.tensor_type(cfg, name, l)
+            ws[(l, name)] = (t, M.synth_blocks(t, rows * cols // oracle.BLOCK_ELEMS[t], M.tensor_seed(l, name)), rows, cols)
+    t = M.tensor_type(cfg, "output", 0)
+    head = (t, M.synth_blocks(t, cfg.vocab * H // oracle.BLOCK_ELEMS[t], M.tensor_seed(0, "output")), cfg.vocab, H)
+    xs = {c: rng.standard_normal((1, c)).astype(np.float32) for c in (H, I, nq)}
+
+    def once():
+        t0 = time.perf_counter()
+        for (l, name), (ty, w, rows, cols) in ws.items():
+            oracle.qmatmul_cpu(ty, w, xs[cols], cols, rows, threads)
+        t_layers = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oracle.qmatmul_cpu(head[0], head[1], xs[H], H, cfg.vocab, threads)
+        return t_layers, time.perf_counter() - t0
+
+    once()
+    reps, tl, th = 0, 0.0, 0.0
+    t_start = time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t_start < 8.0 and reps < 50):
+        a, b = once()
+        tl += a; th += b; reps += 1
+    per_token = tl / reps / layers * cfg.n_layers + th / reps
+    return 1.0 / per_token, f"{layers} of {cfg.n_layers} layers' GEMVs + lm_head, batch 1, x{reps} (GEMV-only: attention/norm/rope excluded)"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (candle QMatMul is not
+    buildable here: no Rust, candle un-vendored — so the C restatement in oracle/, kind 'port'),
+    all host threads, same metric/config; each step = one bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.load_package()
+    from mistralrs_b200 import model as M
+    cfg = M.LlamaConfig.llama3_8b()
+    threads = os.cpu_count() or 1
+    vals = []
+    for _ in range(max(args.warmup, 0)):
+        pass  # cpu_baseline_sample warms itself
+    sample = ""
+    t0 = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 3))):
+        v, sample = cpu_baseline_sample(cfg, M, threads)
+        vals.append(v)
+    value = sum(vals) / len(vals)
+    print(json.dumps({
+        "impl": "reference", "metric": "decode_tok_s", "value": value, "unit": "tok/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value * (GEN_LEN - 1), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4/6 block dots, f32 accumulate", "data": "synthetic",
+        "config": {"workload": "Llama-3-8B GGUF Q4_K_M decode batch=1 128->+256 (CPU sample)"},
+        "cpu_baseline": {"value": value, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=0, help="debug: truncate the model")
+    ap.add_argument("--pdl", type=int, default=int(os.environ.get("MRS_PDL", "1")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.load_package()
+    from mistralrs_b200 import lib, model as M
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib()  # fail loudly if the CUDA extension is missing
+
+    cfg = M.LlamaConfig.llama3_8b()
+    if args.layers:
+        cfg.n_layers = args.layers
+    weights = M.LlamaWeights(cfg, dev, tp_rank=rank, tp_size=world)
+    comm = None
+    if world > 1:
+        bufs = {}
+
+        def comm(buf, count, dtype, stream, user):  # row-parallel sum all-reduce (NCCL over NVLink)
+            t = bufs.get(buf)
+            if t is None:
+                raise RuntimeError("unknown all-reduce buffer")
+            dist.all_reduce(t)
+    runner = M.LlamaRunner(weights, batch=1, max_ctx=PROMPT_LEN + GEN_LEN + 16, pdl=bool(args.pdl), comm=comm)
+    if world > 1:
+        bufs[runner.buf["x"].data_ptr()] = runner.buf["x"]
+        bufs[runner.buf["x2"].data_ptr()] = runner.buf["x2"]
+    runner.capture()
+    graph = runner.graph
+    tok_dev = runner.meta["token_ids"]
+    pinned_in = torch.zeros(1, dtype=torch.int32).pin_memory()
+    pinned_out = torch.zeros(1, dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def generation(it, e2e):
+        """one step: prompt (token-by-token through the decode graph), then GEN_LEN tokens.
+        Returns device-timed seconds of the decode phase (first generated token -> last)."""
+        runner.reset()
+        for t in prompt_tokens(it):
+            pinned_in[0] = t
+            tok_dev.copy_(pinned_in, non_blocking=True)
+            graph.replay()
+        # the last prompt replay produced generated token #1 in tok_dev
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        if not e2e:
+            for _ in range(GEN_LEN - 1):
+                graph.replay()
+        else:
+            pinned_in.copy_(tok_dev)
+            for _ in range(GEN_LEN - 1):
+                tok_dev.copy_(pinned_in, non_blocking=True)      # H2D: this step's input token
+                graph.replay()
+                pinned_out.copy_(tok_dev, non_blocking=True)     # D2H: the sampled token
+                torch.cuda.current_stream().synchronize()
+                pinned_in[0] = pinned_out[0]
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / 1e3
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    for w in range(args.warmup):
+        generation(w, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    times = [max_over_ranks(generation(args.warmup + i, False)) for i in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_times = [max_over_ranks(generation(args.warmup + i, True)) for i in range(max(1, min(args.steps, 2)))]
+    ntok = GEN_LEN - 1
+    value = ntok * len(times) / sum(times)
+    e2e_value = ntok * len(e2e_times) / sum(e2e_times)
+
+    # ---- roofline of the dominant kernel (mmvq_stream_kernel: every quantized GEMV of a token) ----
+    # measured live: a CUDA graph of ONE token's GEMV chain only (attention-side kernels skipped),
+    # CUDA events on the launching stream; weights (4.6 GB) >> L2 so every launch streams from HBM.
+    runner.step_struct.skip_mask = 1
+    gg = torch.cuda.CUDAGraph()
+    runner.forward(); torch.cuda.synchronize()
+    with torch.cuda.graph(gg):
+        runner.forward()
+    for _ in range(3):
+        gg.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        gg.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    runner.step_struct.skip_mask = 0
+    gemv_s = e0.elapsed_time(e1) / 1e3 / reps
+    total_bytes, weight_bytes = algorithmic_bytes_per_token(cfg, M, world)
+    n_gemv = sum(4 if M.tensor_type(cfg, "attn_v", l) == M.tensor_type(cfg, "attn_q", l) else 5 for l in range(cfg.n_layers)) + 1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    achieved = weight_bytes / gemv_s / 1e9
+    per_layer_launches = [(5 if M.tensor_type(cfg, "attn_v", l) == M.tensor_type(cfg, "attn_q", l) else 6) +
+                          2 + (2 if runner.padded_tiles > 1 else 1) for l in range(cfg.n_layers)]
+    launches_per_token = 2 + sum(per_layer_launches) + 2  # advance+embed, layers, lm_head+argmax
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            v, sample = cpu_baseline_sample(cfg, M, threads)
+            cpu = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample}
+        out = {
+            "metric": "decode_tok_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int8 activations x 4/6-bit ggml blocks (dp4a), f32 accumulate, bf16 I/O",
+            "data": "synthetic",
+            "config": {"workload": "Llama-3-8B GGUF Q4_K_M decode batch=1, 128-token prompt -> +256 tokens, paged KV block_size=16 (HND)",
+                       "parallelism": f"tp{world}", "l2": "inputs larger than L2 (4.6 GB of weights streamed per token)",
+                       "layers": cfg.n_layers, "pdl": bool(args.pdl)},
+            "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": 4 * ntok, "d2h_bytes_per_step": 4 * ntok},
+            "gpu_launches": launches_per_token * ntok,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "mmvq_stream_kernel (all quantized GEMVs of one token)",
+                         "launches": n_gemv, "avg_launch_us": gemv_s / n_gemv * 1e6, "bytes_per_token": weight_bytes},
+            "step_hbm_frac": total_bytes * value / 1e9 / peak,
+            "clocks": clocks,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,7 @@ typedef struct {
   const void *final_norm, *rope_cos, *rope_sin; /* rope tables [max_pos, head_dim/2] act dtype */
   /* per-step device metadata (see mrs_decode_advance) */
   int32_t batch, padded_tiles, max_blocks_per_seq;
+  int32_t skip_mask;         /* measurement only: bit0 skip rope/cache/attention, bit1 skip the GEMVs */
   int32_t *token_ids;        /* [batch] in: token to process; out_token may alias it */
   int32_t *positions;        /* [batch] */
   int64_t *slot_mapping;     /* [batch] */

@@ -239,13 +239,15 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
   const int nq = s->n_heads * s->head_dim, nkv = s->n_kv_heads * s->head_dim;
   cudaStream_t st = (cudaStream_t)stream;
   if (B < 1 || B > 8) return (int32_t)cudaErrorInvalidValue;
+  const bool do_attn = !(s->skip_mask & 1), do_gemv = !(s->skip_mask & 2);
 
   MRS_TRY(mrs_embedding_gather(s->tok_embd.ggml_type, s->tok_embd.data, H, s->token_ids, B, s->x, dt, stream));
   void *hidden = s->x, *hidden2 = s->x2;
   for (int l = 0; l < s->n_layers; l++) {
     const mrs_llama_layer &L = s->layers[l];
     // --- attention block: x = x + o_proj(attn(rope(qkv(norm(x)))))
-    if (L.wq.ggml_type == L.wk.ggml_type && L.wk.ggml_type == L.wv.ggml_type) {
+    if (!do_gemv) {
+    } else if (L.wq.ggml_type == L.wk.ggml_type && L.wk.ggml_type == L.wv.ggml_type) {
       MRS_TRY(mrs_mmvq_fused(L.wq.ggml_type, 2, dt, L.wq.data, L.wk.data, L.wv.data, hidden, L.attn_norm, s->rms_eps,
                              nullptr, s->q, s->k, s->v, H, nq, nkv, nkv, B, 0, pdl, stream));
     } else {  // Q4_K_M keeps attn_v in Q6_K on some layers: q∥k fused, v on its own
@@ -254,6 +256,7 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
       MRS_TRY(mrs_mmvq_fused(L.wv.ggml_type, 0, dt, L.wv.data, nullptr, nullptr, hidden, L.attn_norm, s->rms_eps,
                              nullptr, s->v, nullptr, nullptr, H, nkv, 0, 0, B, 0, pdl, stream));
     }
+    if (do_attn) {
     rotary_embedding_positions(s->q, s->k, (void *)s->rope_cos, (void *)s->rope_sin, s->positions, s->rope_neox,
                                s->head_dim, B, s->head_dim / 2, 0, s->n_heads, s->n_kv_heads, nq, nkv, (uint32_t)dt,
                                (int64_t)stream);
@@ -265,6 +268,8 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
                               s->padded_tiles > B ? s->tmp_s : nullptr, B, s->padded_tiles, s->n_heads, s->n_kv_heads,
                               s->head_dim, s->block_size, nq, s->head_dim, s->sm_scale, -1, 0.f, 1.f, 1.f,
                               (uint32_t)dt, (uint32_t)dt, st));
+    }
+    if (!do_gemv) continue;
     if (s->all_reduce == nullptr) {
       MRS_TRY(mrs_mmvq_fused(L.wo.ggml_type, 0, dt, L.wo.data, nullptr, nullptr, s->attn_out, nullptr, 0.f, hidden,
                              hidden2, nullptr, nullptr, nq, H, 0, 0, B, 0, pdl, stream));
@@ -288,6 +293,7 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
       add_residual_kernel<<<(unsigned)(((int64_t)B * H + 255) / 256), 256, 0, st>>>(hidden, hidden2, (int64_t)B * H, dt);
     }
   }
+  if (do_gemv)
   MRS_TRY(mrs_mmvq_fused(s->lm_head.ggml_type, 0, dt, s->lm_head.data, nullptr, nullptr, hidden, s->final_norm,
                          s->rms_eps, nullptr, s->logits, nullptr, nullptr, H, s->vocab, 0, 0, B, 0, pdl, stream));
   MRS_TRY(mrs_argmax(s->logits, B, s->vocab, dt, s->out_token, stream));

@@ -39,8 +39,11 @@ class BlockPool:
             raise ValueError("Must have at least 1 GPU block")
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            host_lib().mrs_block_pool_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            try:
+                _lib.mrs_block_pool_free(self._h)
+            except Exception:
+                pass
             self._h = None
 
     def null_block_id(self):

@@ -114,7 +114,8 @@ class _Step(ctypes.Structure):
                [("rms_eps", ctypes.c_float), ("sm_scale", ctypes.c_float), ("rope_neox", ctypes.c_int32),
                 ("pdl", ctypes.c_int32), ("layers", ctypes.POINTER(_Layer)), ("tok_embd", _QW), ("lm_head", _QW),
                 ("final_norm", ctypes.c_void_p), ("rope_cos", ctypes.c_void_p), ("rope_sin", ctypes.c_void_p),
-                ("batch", ctypes.c_int32), ("padded_tiles", ctypes.c_int32), ("max_blocks_per_seq", ctypes.c_int32)] + \
+                ("batch", ctypes.c_int32), ("padded_tiles", ctypes.c_int32), ("max_blocks_per_seq", ctypes.c_int32),
+                ("skip_mask", ctypes.c_int32)] + \
                [(n, ctypes.c_void_p) for n in ("token_ids", "positions", "slot_mapping", "kv_indptr", "kv_indices",
                                                "kv_last_page_len", "request_indices", "kv_tile_indices", "o_indptr",
                                                "kv_chunk_size", "block_valid_mask", "x", "x2", "q", "k", "v",
