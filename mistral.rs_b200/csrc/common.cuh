@@ -54,6 +54,23 @@ __device__ __forceinline__ void store_act(void *p, int64_t i, float v, int dtype
   else if (dtype == MRS_F16) ((__half *)p)[i] = __float2half_rn(v);
   else ((float *)p)[i] = v;
 }
+// 8 consecutive activations (index multiple of 8): one 16-byte load for the 16-bit dtypes
+__device__ __forceinline__ void load_act8(const void *p, int64_t i, int dtype, float *out) {
+  if (dtype == MRS_BF16) {
+    const uint4 v = *(const uint4 *)((const __nv_bfloat16 *)p + i);
+    const __nv_bfloat162 *h = (const __nv_bfloat162 *)&v;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const float2 t = __bfloat1622float2(h[k]); out[2 * k] = t.x; out[2 * k + 1] = t.y; }
+  } else if (dtype == MRS_F16) {
+    const uint4 v = *(const uint4 *)((const __half *)p + i);
+    const __half2 *h = (const __half2 *)&v;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const float2 t = __half22float2(h[k]); out[2 * k] = t.x; out[2 * k + 1] = t.y; }
+  } else {
+    const float4 a = *(const float4 *)((const float *)p + i), b = *(const float4 *)((const float *)p + i + 4);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+  }
+}
 // round an f32 through the activation dtype (what materialising a tensor would do)
 __device__ __forceinline__ float round_act(float v, int dtype) {
   if (dtype == MRS_BF16) return __bfloat162float(__float2bfloat16_rn(v));

@@ -240,10 +240,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
     for (int col = 0; col < NCOLS; col++) {
       float inv_rms = 1.0f;
       if (p.norm_w != nullptr && col < p.ncols) {
+        // pass 0: sum of squares, 8 elements (16 B for 16-bit dtypes) per thread per trip
         float ss = 0.f;
-        for (int i = ctid; i < p.K; i += NCT) {
-          const float v = load_act(p.x, (int64_t)col * p.K + i, p.xdtype);
-          ss += v * v;
+        for (int i = ctid * 8; i < p.K; i += NCT * 8) {
+          float v[8];
+          load_act8(p.x, (int64_t)col * p.K + i, p.xdtype, v);
+#pragma unroll
+          for (int k = 0; k < 8; k++) ss = fmaf(v[k], v[k], ss);
         }
         ss = warp_sum(ss);
         asm volatile("bar.sync 1, %0;" ::"n"(NCT));
@@ -256,15 +259,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
       }
       int4 *n0 = xq0 + (size_t)col * npos, *n1 = xq1 + (size_t)col * npos;
       float2 *dsbuf = dsall + (size_t)col * nq8;
+      // pass 1: one thread per 32-element Q8_1 block, vector loads
       for (int b = ctid; b < nq8; b += NCT) {
         float v[32];
         __align__(16) int8_t q[32];
         if (col < p.ncols) {
 #pragma unroll
-          for (int i = 0; i < 32; i++) {
-            float t = load_act(p.x, (int64_t)col * p.K + b * 32 + i, p.xdtype);
-            if (p.norm_w != nullptr) t = round_act(t * inv_rms * load_act(p.norm_w, b * 32 + i, p.xdtype), p.xdtype);
-            v[i] = t;
+          for (int k = 0; k < 4; k++) load_act8(p.x, (int64_t)col * p.K + b * 32 + 8 * k, p.xdtype, v + 8 * k);
+          if (p.norm_w != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              float wv[8];
+              load_act8(p.norm_w, b * 32 + 8 * k, p.xdtype, wv);
+#pragma unroll
+              for (int i = 0; i < 8; i++) v[8 * k + i] = round_act(v[8 * k + i] * inv_rms * wv[i], p.xdtype);
+            }
           }
         } else {
 #pragma unroll
