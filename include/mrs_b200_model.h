@@ -36,6 +36,8 @@ typedef struct {
   /* per-step device metadata (see mrs_decode_advance) */
   int32_t batch, padded_tiles, max_blocks_per_seq;
   int32_t skip_mask;         /* measurement only: bit0 skip rope/cache/attention, bit1 skip the GEMVs */
+  int32_t fused_attention;   /* 1: mrs_paged_decode_fused; 0: rotary + reshape_and_cache + flashinfer_decode */
+  int32_t reserved0;
   int32_t *token_ids;        /* [batch] in: token to process; out_token may alias it */
   int32_t *positions;        /* [batch] */
   int64_t *slot_mapping;     /* [batch] */
@@ -46,6 +48,8 @@ typedef struct {
   void *x, *x2, *q, *k, *v, *attn_out, *act, *logits; /* x, x2: [batch, hidden] residual stream ping-pong */
   void *tmp_v; float *tmp_s;
   int32_t *out_token;        /* [batch] argmax of the logits */
+  int32_t *attn_counters;    /* zeroed int32 [batch * n_kv_heads * 2] (fused attention merge) */
+  void *argmax_scratch;      /* zeroed, >= 16 * batch + 16 bytes */
   /* tensor parallel: called after the row-parallel projections when non-NULL */
   void (*all_reduce)(void *buf, int64_t count, int32_t dtype, void *stream, void *user);
   void *all_reduce_user;
@@ -68,7 +72,8 @@ int32_t mrs_decode_advance(const int32_t *block_tables, int32_t max_blocks_per_s
 int32_t mrs_embedding_gather(int32_t ggml_type, const void *table, int32_t cols, const int32_t *ids, int32_t n,
                              void *out, int32_t act_dtype, void *stream);
 /* out[b] = argmax_v logits[b, v] (first maximum), logits in act dtype */
-int32_t mrs_argmax(const void *logits, int32_t rows, int32_t cols, int32_t act_dtype, int32_t *out, void *stream);
+int32_t mrs_argmax(const void *logits, int32_t rows, int32_t cols, int32_t act_dtype, int32_t *out, void *scratch,
+                   int32_t pdl, void *stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,17 @@ extern "C" void reshape_and_cache_flashinfer(void *key, void *value, void *key_c
                                              int32_t head_size, int32_t block_size, int32_t key_stride,
                                              int32_t value_stride, float k_scale, float v_scale, uint32_t dtype,
                                              uint32_t cache_dtype, cudaStream_t stream);
+extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, void *key_cache, void *value_cache,
+                                          const void *rope_cos, const void *rope_sin, const int32_t *positions,
+                                          const int64_t *slot_mapping, const int32_t *kv_indptr,
+                                          const int32_t *kv_indices, const int32_t *kv_last_page_len,
+                                          const int32_t *request_indices, const int32_t *kv_tile_indices,
+                                          const int32_t *o_indptr, const int32_t *kv_chunk_size_ptr,
+                                          const uint8_t *block_valid_mask, void *o, void *tmp_v, float *tmp_s,
+                                          int32_t *counters, int32_t batch_size, int32_t padded_batch_size,
+                                          int32_t num_qo_heads, int32_t num_kv_heads, int32_t head_size,
+                                          int32_t page_size, float sm_scale, uint32_t dtype, int32_t pdl,
+                                          void *stream);
 extern "C" int32_t flashinfer_decode(void *q, void *key_cache, void *value_cache, const int32_t *kv_indptr,
                                      const int32_t *kv_indices, const int32_t *kv_last_page_len,
                                      const int32_t *request_indices, const int32_t *kv_tile_indices,
@@ -112,37 +123,51 @@ __global__ void embedding_gather_kernel(int type, const uint8_t *__restrict__ ta
     store_act(out, (int64_t)blockIdx.x * cols + i, dequant_elem(type, rp + (size_t)(i / be) * bb, i % be), act_dtype);
 }
 
-// first-maximum argmax of one row per CTA
-__global__ void argmax_kernel(const void *__restrict__ logits, int cols, int act_dtype, int32_t *__restrict__ out) {
-  __shared__ float sv[32];
-  __shared__ int si[32];
-  const int64_t base = (int64_t)blockIdx.x * cols;
-  float best = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
-    const float v = load_act(logits, base + i, act_dtype);
-    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+// first-maximum argmax: grid (chunks, rows); each CTA reduces a chunk and folds it into a packed
+// 64-bit key (order-preserving float bits << 32 | ~index) with atomicMax; the last CTA of a row
+// publishes the index and re-zeroes the scratch (scratch: u64 key[rows] then u32 count[rows]).
+__device__ __forceinline__ unsigned long long pack_key(float v, int idx) {
+  unsigned int b = __float_as_uint(v);
+  b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)b << 32) | (unsigned int)(0xFFFFFFFFu - (unsigned int)idx);
+}
+__global__ void argmax_kernel(const void *__restrict__ logits, int cols, int act_dtype, int32_t *__restrict__ out,
+                              unsigned long long *__restrict__ keys, unsigned int *__restrict__ counts, int pdl) {
+  __shared__ unsigned long long sk[32];
+  if (pdl) pdl_wait();
+  const int row = blockIdx.y;
+  const int64_t base = (int64_t)row * cols;
+  unsigned long long best = 0ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += gridDim.x * blockDim.x) {
+    const unsigned long long k = pack_key(load_act(logits, base + i, act_dtype), i);
+    best = k > best ? k : best;
   }
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, m);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, m);
+    best = o > best ? o : best;
   }
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { sv[w] = best; si[w] = bi; }
+  if (l == 0) sk[w] = best;
   __syncthreads();
   if (w == 0) {
-    const int nw = blockDim.x >> 5;
-    best = (l < nw) ? sv[l] : -INFINITY;
-    bi = (l < nw) ? si[l] : 0x7fffffff;
+    best = (l < (blockDim.x >> 5)) ? sk[l] : 0ull;
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, m);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, m);
+      best = o > best ? o : best;
     }
-    if (l == 0) out[blockIdx.x] = bi;
+    if (l == 0) {
+      atomicMax(&keys[row], best);
+      __threadfence();
+      const unsigned int done = atomicAdd(&counts[row], 1u);
+      if (done == gridDim.x - 1) {
+        __threadfence();
+        const unsigned long long k = atomicExch(&keys[row], 0ull);
+        out[row] = (int32_t)(0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull));
+        counts[row] = 0u;
+      }
+    }
   }
 }
 
@@ -204,10 +229,21 @@ extern "C" int32_t mrs_embedding_gather(int32_t ggml_type, const void *table, in
   return (int32_t)cudaGetLastError();
 }
 
-extern "C" int32_t mrs_argmax(const void *logits, int32_t rows, int32_t cols, int32_t act_dtype, int32_t *out, void *stream) {
+extern "C" int32_t mrs_argmax(const void *logits, int32_t rows, int32_t cols, int32_t act_dtype, int32_t *out,
+                              void *scratch, int32_t pdl, void *stream) {
   if (rows <= 0) return 0;
-  argmax_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>(logits, cols, act_dtype, out);
-  return (int32_t)cudaGetLastError();
+  if (scratch == nullptr) return (int32_t)cudaErrorInvalidValue;
+  unsigned long long *keys = (unsigned long long *)scratch;
+  unsigned int *counts = (unsigned int *)(keys + rows);
+  int chunks = (cols + 4095) / 4096;
+  if (chunks > 64) chunks = 64;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(chunks, rows); cfg.blockDim = dim3(256); cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return (int32_t)cudaLaunchKernelEx(&cfg, argmax_kernel, logits, (int)cols, (int)act_dtype, out, keys, counts, (int)pdl);
 }
 
 extern "C" int32_t mrs_decode_advance(const int32_t *block_tables, int32_t max_blocks_per_seq, int32_t *context_lens,
@@ -256,7 +292,15 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
       MRS_TRY(mrs_mmvq_fused(L.wv.ggml_type, 0, dt, L.wv.data, nullptr, nullptr, hidden, L.attn_norm, s->rms_eps,
                              nullptr, s->v, nullptr, nullptr, H, nkv, 0, 0, B, 0, pdl, stream));
     }
-    if (do_attn) {
+    if (do_attn && s->fused_attention) {
+      MRS_TRY(mrs_paged_decode_fused(s->q, s->k, s->v, L.k_cache, L.v_cache, s->rope_cos, s->rope_sin, s->positions,
+                                     s->slot_mapping, s->kv_indptr, s->kv_indices, s->kv_last_page_len,
+                                     s->request_indices, s->kv_tile_indices, s->o_indptr, s->kv_chunk_size,
+                                     s->block_valid_mask, s->attn_out, s->padded_tiles > B ? s->tmp_v : nullptr,
+                                     s->padded_tiles > B ? s->tmp_s : nullptr, s->attn_counters, B, s->padded_tiles,
+                                     s->n_heads, s->n_kv_heads, s->head_dim, s->block_size, s->sm_scale, (uint32_t)dt,
+                                     pdl, stream));
+    } else if (do_attn) {
     rotary_embedding_positions(s->q, s->k, (void *)s->rope_cos, (void *)s->rope_sin, s->positions, s->rope_neox,
                                s->head_dim, B, s->head_dim / 2, 0, s->n_heads, s->n_kv_heads, nq, nkv, (uint32_t)dt,
                                (int64_t)stream);
@@ -296,6 +340,6 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
   if (do_gemv)
   MRS_TRY(mrs_mmvq_fused(s->lm_head.ggml_type, 0, dt, s->lm_head.data, nullptr, nullptr, hidden, s->final_norm,
                          s->rms_eps, nullptr, s->logits, nullptr, nullptr, H, s->vocab, 0, 0, B, 0, pdl, stream));
-  MRS_TRY(mrs_argmax(s->logits, B, s->vocab, dt, s->out_token, stream));
+  MRS_TRY(mrs_argmax(s->logits, B, s->vocab, dt, s->out_token, s->argmax_scratch, pdl, stream));
   return 0;
 }

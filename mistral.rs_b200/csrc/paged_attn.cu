@@ -50,6 +50,15 @@ struct PagedParams {
   int tiles_are_partitions; // vLLM v2: tile index = seq * num_partitions + partition
   int num_partitions;
   int heads_per_cta;        // GQA group may be processed in sub-groups (blockIdx.z)
+  int pdl;                  // launched with programmatic stream serialisation
+  // FUSED (mrs_paged_decode_fused): un-rotated new-token K/V, RoPE tables, slots, merge counters
+  const void *k_new, *v_new;
+  int64_t kv_new_stride;
+  const void *rope_cos, *rope_sin;
+  const int32_t *positions;
+  const int64_t *slot_mapping;
+  const int32_t *o_indptr;
+  int *counters;
 };
 
 template <typename T> struct Vec8;
@@ -86,8 +95,36 @@ template <> struct Vec8<__nv_bfloat16> {
   }
 };
 
+// round through T (what storing a tensor of dtype T would do)
+template <typename T> __device__ __forceinline__ float rnd(float v);
+template <> __device__ __forceinline__ float rnd<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <> __device__ __forceinline__ float rnd<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// NeoX RoPE of the 8-element slice held by lane `gl` (elements d0..d0+7 of a head), with the
+// reference kernel's per-operation rounding in T (rotary.cu:10-34).  The partner slice
+// (d +- D/2) lives in lane gl ^ (LPT/2).
+template <typename T, int D>
+__device__ __forceinline__ void rope_slice(float *x, const T *cosp, const T *sinp, int gl) {
+  constexpr int LPT = D / 8;
+  const bool upper = gl >= LPT / 2;
+  const int o0 = (upper ? gl - LPT / 2 : gl) * 8;  // rot offset of this slice
+  float c[8], sn[8];
+  Vec8<T>::load(cosp + o0, c);
+  Vec8<T>::load(sinp + o0, sn);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float other = __shfl_xor_sync(0xffffffffu, x[i], LPT / 2);
+    const float a = rnd<T>(x[i] * c[i]);       // x*cos (lower) / y*cos (upper)
+    const float b = rnd<T>(other * sn[i]);     // y*sin (lower) / x*sin (upper)
+    x[i] = upper ? rnd<T>(a + b) : rnd<T>(a - b);
+  }
+}
+
 // LAYOUT 0: vLLM (K [NB,KVH,D/8,BS,8], V [NB,KVH,D,BS]); 1: HND ([NB,KVH,BS,D])
-template <typename T, int D, int G, int LAYOUT>
+// FUSED: q/k/v of the new token arrive un-rotated; the kernel applies RoPE, writes the new K/V
+// row into the cache (the tile that owns the last position) and merges split-KV partials itself
+// ("last tile done" counter) — one launch instead of rope + reshape_and_cache + decode + merge.
+template <typename T, int D, int G, int LAYOUT, bool FUSED>
 __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedParams p) {
   constexpr int LPT = D / 8;               // lanes per token
   constexpr int NGRP = PA_THREADS / LPT;   // token groups per CTA
@@ -96,6 +133,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   const int grp = tid / LPT, gl = tid % LPT;  // group, lane within group
   const int d0 = gl * 8;
 
+  if (p.pdl) pdl_wait();
   if (p.block_valid_mask != nullptr && p.block_valid_mask[tile] == 0) return;
   int seq, chunk_idx;
   if (p.tiles_are_partitions) { seq = tile / p.num_partitions; chunk_idx = tile % p.num_partitions; }
@@ -116,25 +154,33 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   int chunk = p.kv_chunk_size_ptr ? *p.kv_chunk_size_ptr : p.kv_chunk_size;
   if (chunk <= 0) chunk = kv_len > 0 ? kv_len : 1;
   const int t_begin = chunk_idx * chunk;
-  const int t_end = min(kv_len, t_begin + chunk);
+  int t_end = min(kv_len, t_begin + chunk);
   const bool partial = p.tmp_o != nullptr;
 
   const int group = p.num_heads / p.num_kv_heads;
   const int h0 = kvh * group + blockIdx.z * p.heads_per_cta;      // first query head of this CTA
   const int gsize = min(p.heads_per_cta, group - (int)blockIdx.z * p.heads_per_cta);  // heads here (<= G)
 
-  // q slice of this lane for all heads of the group, pre-scaled
+  const T *cosp = nullptr, *sinp = nullptr;
+  if constexpr (FUSED) {
+    const int64_t pos = p.positions[seq];
+    cosp = (const T *)p.rope_cos + pos * (D / 2);
+    sinp = (const T *)p.rope_sin + pos * (D / 2);
+  }
+
+  // q slice of this lane for all heads of the group, (rotated,) pre-scaled
   float qf[G][8];
 #pragma unroll
   for (int g = 0; g < G; g++) {
     if (g < gsize) {
       Vec8<T>::load((const T *)p.q + (int64_t)seq * p.q_stride_n + (int64_t)(h0 + g) * p.q_stride_h + d0, qf[g]);
-#pragma unroll
-      for (int i = 0; i < 8; i++) qf[g][i] *= p.sm_scale;
     } else {
 #pragma unroll
       for (int i = 0; i < 8; i++) qf[g][i] = 0.f;
     }
+    if constexpr (FUSED) rope_slice<T, D>(qf[g], cosp, sinp, gl);
+#pragma unroll
+    for (int i = 0; i < 8; i++) qf[g][i] *= p.sm_scale;
   }
   float slope[G];
 #pragma unroll
@@ -151,7 +197,47 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   const T *kc = (const T *)p.kc, *vc = (const T *)p.vc;
   const int win_lo = (p.window_left >= 0) ? max(0, kv_len - 1 - p.window_left) : 0;
 
-  // trip count is uniform across the CTA (the shuffles below need every lane of the warp)
+  // one token's contribution to the running softmax state of this token group
+  auto update = [&](const float *kf, const float *vf, int t, bool live) {
+    float s[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; i++) a = fmaf(qf[g][i], kf[i], a);
+      s[g] = a;
+    }
+#pragma unroll
+    for (int mask = LPT / 2; mask > 0; mask >>= 1)
+#pragma unroll
+      for (int g = 0; g < G; g++) s[g] += __shfl_xor_sync(0xffffffffu, s[g], mask);
+    const bool in_window = t >= win_lo && live;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      float x = s[g];
+      if (p.softcap > 0.f) x = p.softcap * tanhf(x / p.softcap);
+      x += slope[g] * (float)(t - kv_len + 1);
+      if (!in_window) x = -INFINITY;
+      const float mn = fmaxf(m[g], x);
+      if (mn > -INFINITY) {
+        const float corr = __expf(m[g] - mn);
+        const float pv = __expf(x - mn);
+        l[g] = l[g] * corr + pv;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[g][i] = fmaf(pv, vf[i], o[g][i] * corr);
+        m[g] = mn;
+      }
+    }
+  };
+
+  // FUSED: the tile that owns the last position takes the new token from registers
+  bool owns_new = false;
+  if constexpr (FUSED) {
+    owns_new = kv_len > 0 && (kv_len - 1) >= t_begin && (kv_len - 1) < t_end;
+    if (owns_new) t_end = kv_len - 1;  // the cache loop stops before the new token
+  }
+
+  // trip count is uniform across the CTA (the shuffles need every lane of the warp)
   for (int tb0 = t_begin; tb0 < t_end; tb0 += NGRP * PA_UNROLL) {
     const int tb = tb0 + grp;
     float kf[PA_UNROLL][8], vf[PA_UNROLL][8];
@@ -177,36 +263,31 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
       }
     }
 #pragma unroll
-    for (int u = 0; u < PA_UNROLL; u++) {
-      const int t = tb + u * NGRP;
-      float s[G];  // (all lanes take part in the shuffles; only live tokens update the state)
+    for (int u = 0; u < PA_UNROLL; u++) update(kf[u], vf[u], tb + u * NGRP, ok[u]);
+  }
+
+  if constexpr (FUSED) {
+    if (owns_new) {  // CTA-uniform
+      // every token group computes the rotated key (cheap) so the shuffles stay warp-uniform;
+      // group 0 contributes it to the softmax and (sub-group 0 only) writes the cache row
+      float kn[8], vn[8];
+      Vec8<T>::load((const T *)p.k_new + (int64_t)seq * p.kv_new_stride + (int64_t)kvh * D + d0, kn);
+      Vec8<T>::load((const T *)p.v_new + (int64_t)seq * p.kv_new_stride + (int64_t)kvh * D + d0, vn);
+      rope_slice<T, D>(kn, cosp, sinp, gl);
+      update(kn, vn, kv_len - 1, grp == 0);
+      const int64_t slot = p.slot_mapping[seq];
+      if (grp == 0 && blockIdx.z == 0 && slot >= 0) {
+        const int64_t page = slot / p.page_size;
+        const int off = (int)(slot % p.page_size);
+        const int64_t base = page * p.kv_block_stride + (int64_t)kvh * p.kv_head_stride;
+        T *kcw = (T *)p.kc, *vcw = (T *)p.vc;
+        if constexpr (LAYOUT == 1) {
+          Vec8<T>::store(kcw + base + (int64_t)off * D + d0, kn);
+          Vec8<T>::store(vcw + base + (int64_t)off * D + d0, vn);
+        } else {
+          Vec8<T>::store(kcw + base + ((int64_t)gl * p.page_size + off) * 8, kn);
 #pragma unroll
-      for (int g = 0; g < G; g++) {
-        float a = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) a = fmaf(qf[g][i], kf[u][i], a);
-        s[g] = a;
-      }
-      // reduce across the LPT lanes of the group (LPT is a power of two <= 32)
-#pragma unroll
-      for (int mask = LPT / 2; mask > 0; mask >>= 1)
-#pragma unroll
-        for (int g = 0; g < G; g++) s[g] += __shfl_xor_sync(0xffffffffu, s[g], mask);
-      const bool in_window = t >= win_lo && ok[u];
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-        float x = s[g];
-        if (p.softcap > 0.f) x = p.softcap * tanhf(x / p.softcap);
-        x += slope[g] * (float)(t - kv_len + 1);
-        if (!in_window) x = -INFINITY;
-        const float mn = fmaxf(m[g], x);
-        if (mn > -INFINITY) {
-          const float corr = __expf(m[g] - mn);
-          const float pv = __expf(x - mn);
-          l[g] = l[g] * corr + pv;
-#pragma unroll
-          for (int i = 0; i < 8; i++) o[g][i] = fmaf(pv, vf[u][i], o[g][i] * corr);
-          m[g] = mn;
+          for (int i = 0; i < 8; i++) vcw[base + (int64_t)(d0 + i) * p.page_size + off] = (T)vn[i];
         }
       }
     }
@@ -217,7 +298,8 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   static_assert(LPT <= 16 || NGRP == NSTATE, "one token group per warp when LPT == 32");
   __shared__ float sm_m[NSTATE][G], sm_l[NSTATE][G];
   __shared__ float sm_o[NSTATE][G][D];
-  // pairwise pre-merge inside a warp when two groups share one (LPT == 16)
+  __shared__ int sm_last;
+  // pairwise pre-merge inside a warp when several groups share one (LPT < 32)
   if constexpr (LPT <= 16) {
 #pragma unroll
     for (int mask = LPT; mask < 32; mask <<= 1) {
@@ -278,6 +360,45 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
       ((T *)p.out)[((int64_t)seq * p.num_heads + h0 + g) * D + d] = (T)val;
     }
   }
+
+  if constexpr (FUSED) {
+    if (partial) {
+      // last tile of this (sequence, kv head, sub-group) merges the partials in place of a
+      // second launch.  counters are zero on entry and left zero.
+      const int t0 = p.o_indptr[seq], t1 = p.o_indptr[seq + 1];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        int *ctr = p.counters + ((int64_t)seq * p.num_kv_heads + kvh) * gridDim.z + blockIdx.z;
+        const int old = atomicAdd(ctr, 1);
+        sm_last = (old == (t1 - t0) - 1);
+        if (sm_last) *ctr = 0;
+      }
+      __syncthreads();
+      if (sm_last) {
+        __threadfence();
+        for (int idx = tid; idx < G * D; idx += PA_THREADS) {
+          const int g = idx / D, d = idx % D;
+          if (g >= gsize) continue;
+          const int h = h0 + g;
+          float M = -INFINITY;
+          for (int t = t0; t < t1; t++) M = fmaxf(M, __ldcg(p.tmp_lse + (int64_t)t * p.num_heads + h));
+          float W = 0.f, acc = 0.f;
+          if (M > -INFINITY) {
+            for (int t = t0; t < t1; t++) {
+              const float w = __expf(__ldcg(p.tmp_lse + (int64_t)t * p.num_heads + h) - M);
+              const unsigned short raw = __ldcg((const unsigned short *)p.tmp_o + ((int64_t)t * p.num_heads + h) * D + d);
+              T tv;
+              memcpy(&tv, &raw, 2);
+              W += w;
+              acc += w * (float)tv;
+            }
+          }
+          ((T *)p.out)[((int64_t)seq * p.num_heads + h) * D + d] = (T)((W > 0.f) ? acc / W : 0.f);
+        }
+      }
+    }
+  }
 }
 
 // merge split-KV partials: out[s,h,:] = sum_p w_p o_p / sum_p w_p, w_p = exp(lse_p - max lse)
@@ -312,7 +433,18 @@ __global__ void merge_partials_kernel(const T *__restrict__ tmp_o, const float *
   }
 }
 
-template <typename T, int D, int LAYOUT>
+template <typename K>
+static cudaError_t launch_pa(K kern, dim3 grid, const PagedParams &p, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(PA_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = p.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <typename T, int D, int LAYOUT, bool FUSED>
 static cudaError_t launch_decode_g(PagedParams p, int tiles, cudaStream_t st) {
   const int group = p.num_heads / p.num_kv_heads;
   constexpr int GMAX = (D <= 128) ? 8 : 4;  // static smem budget: 8 states x G x D floats
@@ -320,24 +452,21 @@ static cudaError_t launch_decode_g(PagedParams p, int tiles, cudaStream_t st) {
   const int per = (group + nsub - 1) / nsub;
   p.heads_per_cta = per;
   dim3 grid(tiles, p.num_kv_heads, nsub);
-  if (per <= 1) paged_decode_kernel<T, D, 1, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
-  else if (per <= 2) paged_decode_kernel<T, D, 2, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
-  else if (per <= 4) paged_decode_kernel<T, D, 4, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
-  else {
-    if constexpr (D <= 128) paged_decode_kernel<T, D, 8, LAYOUT><<<grid, PA_THREADS, 0, st>>>(p);
-    else return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  if (per <= 1) return launch_pa(paged_decode_kernel<T, D, 1, LAYOUT, FUSED>, grid, p, st);
+  if (per <= 2) return launch_pa(paged_decode_kernel<T, D, 2, LAYOUT, FUSED>, grid, p, st);
+  if (per <= 4) return launch_pa(paged_decode_kernel<T, D, 4, LAYOUT, FUSED>, grid, p, st);
+  if constexpr (D <= 128) return launch_pa(paged_decode_kernel<T, D, 8, LAYOUT, FUSED>, grid, p, st);
+  return cudaErrorInvalidValue;
 }
 
-template <typename T, int LAYOUT>
+template <typename T, int LAYOUT, bool FUSED = false>
 static cudaError_t launch_decode(const PagedParams &p, int head_size, int tiles, cudaStream_t st) {
   if (tiles <= 0) return cudaSuccess;
   if (p.num_heads % p.num_kv_heads) return cudaErrorInvalidValue;
   switch (head_size) {
-  case 64: return launch_decode_g<T, 64, LAYOUT>(p, tiles, st);
-  case 128: return launch_decode_g<T, 128, LAYOUT>(p, tiles, st);
-  case 256: return launch_decode_g<T, 256, LAYOUT>(p, tiles, st);
+  case 64: return launch_decode_g<T, 64, LAYOUT, FUSED>(p, tiles, st);
+  case 128: return launch_decode_g<T, 128, LAYOUT, FUSED>(p, tiles, st);
+  case 256: return launch_decode_g<T, 256, LAYOUT, FUSED>(p, tiles, st);
   default: return cudaErrorInvalidValue;
   }
 }
@@ -480,3 +609,44 @@ static void paged_v2(void *out, float *exp_sums, float *max_logits, void *tmp_ou
   }
 MRS_PAGED(f16, __half)
 MRS_PAGED(bf16, __nv_bfloat16)
+
+// ---------------------------------------------------------------- B200-native fused decode attention
+// RoPE(q, k_new) + KV-cache write + paged decode attention + split-KV merge in ONE launch over
+// the HND cache.  q [B, H*D], k_new/v_new [B, KVH*D] are the raw QKV GEMV outputs; cos/sin
+// [max_pos, D/2]; positions [B] i32; slot_mapping [B] i64; counters: zeroed int32
+// [B * KVH * ceil(group/8)] scratch (left zero).  Same arithmetic as the separate
+// rotary_embedding_positions -> reshape_and_cache_flashinfer -> flashinfer_decode chain.
+extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, void *key_cache, void *value_cache,
+                                          const void *rope_cos, const void *rope_sin, const int32_t *positions,
+                                          const int64_t *slot_mapping, const int32_t *kv_indptr,
+                                          const int32_t *kv_indices, const int32_t *kv_last_page_len,
+                                          const int32_t *request_indices, const int32_t *kv_tile_indices,
+                                          const int32_t *o_indptr, const int32_t *kv_chunk_size_ptr,
+                                          const uint8_t *block_valid_mask, void *o, void *tmp_v, float *tmp_s,
+                                          int32_t *counters, int32_t batch_size, int32_t padded_batch_size,
+                                          int32_t num_qo_heads, int32_t num_kv_heads, int32_t head_size,
+                                          int32_t page_size, float sm_scale, uint32_t dtype, int32_t pdl,
+                                          void *stream) {
+  if (dtype != 0 && dtype != 1) return (int32_t)cudaErrorInvalidValue;
+  PagedParams p = {};
+  p.q = q; p.kc = key_cache; p.vc = value_cache; p.out = o;
+  const bool split = tmp_v != nullptr && padded_batch_size > batch_size;
+  p.tmp_o = split ? tmp_v : nullptr; p.tmp_lse = split ? tmp_s : nullptr;
+  if (split) {
+    p.request_indices = request_indices; p.kv_tile_indices = kv_tile_indices;
+    p.block_valid_mask = block_valid_mask; p.kv_chunk_size_ptr = kv_chunk_size_ptr;
+  }
+  p.kv_indptr = kv_indptr; p.kv_indices = kv_indices; p.kv_last_page_len = kv_last_page_len;
+  p.kv_block_stride = (int64_t)num_kv_heads * page_size * head_size; p.kv_head_stride = (int64_t)page_size * head_size;
+  p.num_heads = num_qo_heads; p.num_kv_heads = num_kv_heads; p.page_size = page_size;
+  p.q_stride_n = (int64_t)num_qo_heads * head_size; p.q_stride_h = head_size; p.sm_scale = sm_scale;
+  p.window_left = -1; p.pdl = pdl;
+  p.k_new = k_new; p.v_new = v_new; p.kv_new_stride = (int64_t)num_kv_heads * head_size;
+  p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.positions = positions; p.slot_mapping = slot_mapping;
+  p.o_indptr = o_indptr; p.counters = counters;
+  const int tiles = split ? padded_batch_size : batch_size;
+  const cudaError_t e = (dtype == 0) ? launch_decode<__half, 1, true>(p, head_size, tiles, (cudaStream_t)stream)
+                                     : launch_decode<__nv_bfloat16, 1, true>(p, head_size, tiles, (cudaStream_t)stream);
+  if (e != cudaSuccess) fprintf(stderr, "mrs_b200: mrs_paged_decode_fused failed: %s\n", cudaGetErrorString(e));
+  return (int32_t)e;
+}

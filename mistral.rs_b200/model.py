@@ -115,11 +115,12 @@ class _Step(ctypes.Structure):
                 ("pdl", ctypes.c_int32), ("layers", ctypes.POINTER(_Layer)), ("tok_embd", _QW), ("lm_head", _QW),
                 ("final_norm", ctypes.c_void_p), ("rope_cos", ctypes.c_void_p), ("rope_sin", ctypes.c_void_p),
                 ("batch", ctypes.c_int32), ("padded_tiles", ctypes.c_int32), ("max_blocks_per_seq", ctypes.c_int32),
-                ("skip_mask", ctypes.c_int32)] + \
+                ("skip_mask", ctypes.c_int32), ("fused_attention", ctypes.c_int32), ("reserved0", ctypes.c_int32)] + \
                [(n, ctypes.c_void_p) for n in ("token_ids", "positions", "slot_mapping", "kv_indptr", "kv_indices",
                                                "kv_last_page_len", "request_indices", "kv_tile_indices", "o_indptr",
                                                "kv_chunk_size", "block_valid_mask", "x", "x2", "q", "k", "v",
-                                               "attn_out", "act", "logits", "tmp_v", "tmp_s", "out_token")] + \
+                                               "attn_out", "act", "logits", "tmp_v", "tmp_s", "out_token",
+                                               "attn_counters", "argmax_scratch")] + \
                [("all_reduce", _AR_FN), ("all_reduce_user", ctypes.c_void_p)]
 
 
@@ -212,7 +213,8 @@ class LlamaRunner:
     """Owns KV cache + scratch + per-step metadata for a batch of sequences and drives
     mrs_llama_decode_step / mrs_decode_advance (eagerly or as a captured CUDA graph)."""
 
-    def __init__(self, weights: LlamaWeights, batch=1, max_ctx=512, pdl=False, sm_count=148, comm=None):
+    def __init__(self, weights: LlamaWeights, batch=1, max_ctx=512, pdl=False, sm_count=148, comm=None,
+                 fused_attention=True):
         cfg, dev, dt = weights.cfg, weights.device, weights.dtype
         self.w, self.cfg, self.dev, self.dt, self.B = weights, cfg, dev, dt, batch
         tp = weights.tp_size
@@ -240,7 +242,9 @@ class LlamaRunner:
                         attn_out=a(batch, self.n_heads * cfg.head_dim), act=a(batch, cfg.inter // tp),
                         logits=a(batch, cfg.vocab), tmp_v=a(self.padded_tiles, self.n_heads, cfg.head_dim),
                         tmp_s=torch.zeros(self.padded_tiles, self.n_heads, dtype=torch.float32, device=dev),
-                        out_token=self.meta["token_ids"])  # argmax feeds the next step directly
+                        out_token=self.meta["token_ids"],  # argmax feeds the next step directly
+                        attn_counters=torch.zeros(batch * self.n_kv * 2, dtype=torch.int32, device=dev),
+                        argmax_scratch=torch.zeros(16 * batch + 16, dtype=torch.uint8, device=dev))
         self.k_cache = [a(nb, self.n_kv, bs, cfg.head_dim) for _ in range(cfg.n_layers)]
         self.v_cache = [a(nb, self.n_kv, bs, cfg.head_dim) for _ in range(cfg.n_layers)]
         self._layers = (_Layer * cfg.n_layers)()
@@ -264,6 +268,7 @@ class LlamaRunner:
         s.lm_head = _QW(t.data_ptr(), GGML[ty], rows, cols)
         s.final_norm, s.rope_cos, s.rope_sin = weights.output_norm.data_ptr(), weights.rope_cos.data_ptr(), weights.rope_sin.data_ptr()
         s.batch, s.padded_tiles, s.max_blocks_per_seq = batch, self.padded_tiles, self.max_blocks
+        s.fused_attention = int(fused_attention)
         for n, t in self.meta.items():
             setattr(s, n, t.data_ptr())
         for n, t in self.buf.items():
