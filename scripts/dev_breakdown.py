@@ -1,0 +1,33 @@
+"""Dev: per-token time breakdown of the decode graph (full / GEMV-only / attention-only)."""
+import sys, os, json
+import numpy as np, torch
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R)
+import __graft_entry__ as g
+g.load_package()
+from mistralrs_b200 import model as M
+dev = torch.device("cuda:0")
+layers = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+cfg = M.LlamaConfig.llama3_8b(); cfg.n_layers = layers
+w = M.LlamaWeights(cfg, dev)
+def timed(run, mask, reps=30):
+    run.step_struct.skip_mask = mask
+    run.reset(); run.context_lens.fill_(256)
+    run.step(); torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        run.step()
+    for _ in range(3): gr.replay()
+    torch.cuda.synchronize()
+    run.context_lens.fill_(256)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): gr.replay()
+    e1.record(); torch.cuda.synchronize()
+    run.step_struct.skip_mask = 0
+    return e0.elapsed_time(e1) / reps * 1e3
+for pdl in (0, 1):
+    for fused in (1, 0):
+        run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=bool(pdl), fused_attention=bool(fused))
+        full, gemv, attn = timed(run, 0), timed(run, 1), timed(run, 2)
+        print(f"layers={layers} pdl={pdl} fused_attn={fused}: full {full:8.1f} us  gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)

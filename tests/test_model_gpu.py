@@ -33,13 +33,18 @@ def test_decode_logits_and_tokens(cuda, quant):
         err = np.abs(got - want).max() / scale
         worst = max(worst, err)
         nxt = run.meta["token_ids"].cpu().numpy().tolist()
-        assert nxt == np.argmax(want, axis=1).tolist() or err < 1e-3, (pos, nxt)
-        assert err <= 5.1 * 2.0 ** -8, (pos, err)  # a handful of bf16 ulps of the logit scale
+        # bf16 logits: spacing is up to 2^-7 of the value.  Sampled ids must agree unless the
+        # oracle's own top-2 gap is within a few ulps (a genuine tie at bf16 resolution).
+        for b in range(len(toks)):
+            top2 = np.sort(want[b])[-2:]
+            if top2[1] - top2[0] > 4 * 2.0 ** -7 * scale:
+                assert nxt[b] == int(np.argmax(want[b])), (pos, b, nxt)
+        assert err <= 4.1 * 2.0 ** -7, (pos, err)
         toks = np.argmax(want, axis=1).tolist()
         run.set_tokens(toks)  # teacher-force the oracle's tokens so both stay on one trajectory
     # Measured: differences are isolated 1-3 ulp bf16 rounding flips on the largest logits
     # (the f16 single-layer case below is bit-exact), i.e. the arithmetic is the oracle's.
-    assert worst <= 5.1 * 2.0 ** -8, worst
+    assert worst <= 4.1 * 2.0 ** -7, worst
 
 
 def test_single_layer_f16_is_exact(cuda):
