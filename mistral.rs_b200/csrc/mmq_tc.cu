@@ -1,0 +1,397 @@
+// mmq_tc.cu — prefill GEMM over ggml quant blocks on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Replaces the reference's batch>8 path `fast_mmq::plain` (REF mistralrs-quant/src/gguf/
+// fast_mmq.rs:762-826 -> launch_mmq_quantize_q8_1_* + launch_mmq_gguf_<q>, int8 `mma.sync`
+// m16n8k32 with Q8_1 activations; kernels/mmq_gguf/mmq_gguf.cuh) and the opt-in Marlin repack
+// path (gguf/packed_affine.rs:604): Y[M,N] = X[M,K] . W[N,K]^T with W in raw ggml blocks.
+//
+// Design (per CTA, one 256-token x 256-row output tile, 320 threads, 1 CTA/SM):
+//   warp 0      TMA producer: activation tiles X[128 x 64] (x2 token sub-tiles) through a
+//               2-D tensor map (SWIZZLE_128B) into the stage ring, mbarrier complete_tx.
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//               (M=128, N=256, K=16) from shared-memory descriptors; accumulators live in
+//               TMEM (2 x 256 f32 columns = all 512 columns); tcgen05.commit frees the stage.
+//   warps 2..9  dequantisers: each thread owns one weight row of the tile, reads its ggml
+//               blocks straight from global/L2 (each weight byte is touched once per 256-token
+//               tile), expands 64 weights per K-step to f16 and writes them K-major into the
+//               128-byte-swizzled B stage; fence.proxy.async + mbarrier hand-off to the MMA
+//               warp.  After the K loop the same warps are the epilogue: tcgen05.ld -> bf16/f16
+//               -> global.
+// Numerics: weights are dequantised exactly and rounded once to f16 (11-bit mantissa),
+// activations are used as they are (bf16/f16) — no activation quantisation — f32 accumulation
+// in TMEM.  This is closer to the exact product than the reference's int8-activation MMQ.
+#include "dequant.cuh"
+
+#include <cuda.h>
+#include <stdio.h>
+
+namespace mrs {
+
+constexpr int TC_BM = 128;        // UMMA M (tokens per sub-tile)
+constexpr int TC_MT = 2;          // token sub-tiles per CTA
+constexpr int TC_BN = 256;        // UMMA N (weight rows per CTA)
+constexpr int TC_BK = 64;         // K per stage (128 bytes of 16-bit -> one swizzle atom row)
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 320;
+constexpr int A_STAGE_BYTES = TC_MT * TC_BM * TC_BK * 2;   // 32 KB
+constexpr int B_STAGE_BYTES = TC_BN * TC_BK * 2;           // 32 KB
+constexpr int TC_SMEM = 1024 + TC_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+
+// ---- tcgen05 / TMA wrappers ---------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (f16/bf16 inputs, f32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor (REF layout: cute/atom/mma_traits_sm100.hpp
+// make_umma_desc<Major::K>): start>>4 | LBO=1 | SBO=1024B>>4 | version 1 | layout 2
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem_ptr) {
+  const uint64_t addr = (uint64_t)(smem_u32(smem_ptr) >> 4) & 0x3FFF;
+  return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// 32 lanes x 32 columns of f32 accumulators -> 32 registers per thread (lane == TMEM lane)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- exact block decoders: 64 consecutive weights of one row -> f16 ------------------------
+// (formulas identical to oracle/mrs_oracle.c unpack_block; REF layouts mmvq_gguf.cu:134-225)
+__device__ __forceinline__ float h2f_at(const uint8_t *p) {
+  return __half2float(__ushort_as_half(*(const unsigned short *)p));
+}
+__device__ __forceinline__ void k4_scale_min(int j, const uint8_t *q, int &sc, int &m) {
+  if (j < 4) { sc = q[j] & 63; m = q[j + 4] & 63; }
+  else { sc = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4); m = (q[j + 4] >> 4) | ((q[j] >> 6) << 4); }
+}
+
+// out: 64 floats for elements [k0, k0+64) of the row starting at `row` (k0 multiple of 64)
+template <int TYPE>
+__device__ __forceinline__ void dequant64(const uint8_t *row, int k0, float *out) {
+  if constexpr (TYPE == MRS_Q8_0) {
+    const uint8_t *b = row + (size_t)(k0 / 32) * 34;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const float d = h2f_at(b + 34 * h);
+      const uint16_t *q16 = (const uint16_t *)(b + 34 * h + 2);
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const uint16_t v = q16[i];
+        out[32 * h + 2 * i] = d * (float)(int8_t)(v & 0xFF);
+        out[32 * h + 2 * i + 1] = d * (float)(int8_t)(v >> 8);
+      }
+    }
+  } else if constexpr (TYPE == MRS_Q4_K) {
+    const uint8_t *b = row + (size_t)(k0 / 256) * 144;
+    const int j = (k0 % 256) / 64;
+    const float d = h2f_at(b), dmin = h2f_at(b + 2);
+    int sc0, m0, sc1, m1;
+    k4_scale_min(2 * j, b + 4, sc0, m0);
+    k4_scale_min(2 * j + 1, b + 4, sc1, m1);
+    const float d0 = d * (float)sc0, d1 = d * (float)sc1, o0 = dmin * (float)m0, o1 = dmin * (float)m1;
+    const uint4 *qs = (const uint4 *)(b + 16 + 32 * j);
+    const uint4 qa = qs[0], qb = qs[1];
+    const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t byte = (w[i] >> (8 * k)) & 0xFF;
+        out[4 * i + k] = d0 * (float)(byte & 0xF) - o0;
+        out[32 + 4 * i + k] = d1 * (float)(byte >> 4) - o1;
+      }
+  } else if constexpr (TYPE == MRS_Q6_K) {
+    const uint8_t *b = row + (size_t)(k0 / 256) * 210;
+    const int n = (k0 % 256) / 128, hi = ((k0 % 128) / 64);  // hi: elements 64..127 of the half use the high nibbles
+    const uint16_t *ql = (const uint16_t *)(b + 64 * n);
+    const uint16_t *qh = (const uint16_t *)(b + 128 + 32 * n);
+    const int8_t *sc = (const int8_t *)(b + 192 + 8 * n + 4 * hi);
+    const float d = h2f_at(b + 208);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {  // l = 2i, 2i+1
+      const uint32_t la = ql[i], lb = ql[16 + i], h = qh[i];
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int l = 2 * i + k;
+        const uint32_t qa8 = (la >> (8 * k)) & 0xFF, qb8 = (lb >> (8 * k)) & 0xFF, h8 = (h >> (8 * k)) & 0xFF;
+        const int q1 = (int)((hi ? (qa8 >> 4) : (qa8 & 0xF)) | (((h8 >> (4 * hi)) & 3) << 4)) - 32;
+        const int q2 = (int)((hi ? (qb8 >> 4) : (qb8 & 0xF)) | (((h8 >> (4 * hi + 2)) & 3) << 4)) - 32;
+        out[l] = d * (float)sc[l / 16] * (float)q1;
+        out[32 + l] = d * (float)sc[2 + l / 16] * (float)q2;
+      }
+    }
+  } else {
+    // other ggml types: correct but unoptimised per-element path
+    const int be = (TYPE >= MRS_Q2_K) ? 256 : 32;
+    constexpr int bb = (TYPE == MRS_Q4_0) ? 18 : (TYPE == MRS_Q4_1) ? 20 : (TYPE == MRS_Q5_0) ? 22 : (TYPE == MRS_Q5_1) ? 24
+                     : (TYPE == MRS_Q2_K) ? 84 : (TYPE == MRS_Q3_K) ? 110 : (TYPE == MRS_Q5_K) ? 176 : 0;
+    for (int i = 0; i < 64; i++) {
+      const int e = k0 + i;
+      out[i] = dequant_elem(TYPE, row + (size_t)(e / be) * bb, e % be);
+    }
+  }
+}
+
+struct TcParams {
+  const uint8_t *w;
+  void *y;
+  int M, N, K, row_bytes, out_dtype;
+  int b_fmt;  // operand format of the dequantised weights: 0 f16, 1 bf16
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+mmq_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned carve-up (SWIZZLE_128B atoms)
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *a_st = smem;                                   // [STAGES][2][128 rows][128 B]
+  uint8_t *b_st = smem + TC_STAGES * A_STAGE_BYTES;       // [STAGES][256 rows][128 B]
+  uint64_t *bars = (uint64_t *)(smem + TC_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t *a_full = bars, *b_full = bars + TC_STAGES, *empty = bars + 2 * TC_STAGES, *acc_full = bars + 3 * TC_STAGES;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 3 * TC_STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * (TC_MT * TC_BM), n0 = blockIdx.x * TC_BN;
+  const int nk = p.K / TC_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&a_full[s], 1); mbar_init(&b_full[s], 8); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (activations) =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int kb = 0; kb < nk; kb++) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&a_full[stage], A_STAGE_BYTES);
+#pragma unroll
+        for (int t = 0; t < TC_MT; t++)
+          tma_load_2d(a_st + (size_t)stage * A_STAGE_BYTES + (size_t)t * (TC_BM * 128), &tmap_x, kb * TC_BK, m0 + t * TC_BM, &a_full[stage]);
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: c=f32 (1<<4), a=f16/bf16 (bit 7), b=f16 (0), K-major both,
+    // N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t a_fmt = (p.out_dtype == MRS_BF16) ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (a_fmt << 7) | ((uint32_t)p.b_fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int stage = 0, phase = 0;
+    for (int kb = 0; kb < nk; kb++) {
+      mbar_wait(&a_full[stage], phase);
+      mbar_wait(&b_full[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint8_t *bs = b_st + (size_t)stage * B_STAGE_BYTES;
+#pragma unroll
+        for (int t = 0; t < TC_MT; t++) {
+          const uint8_t *as = a_st + (size_t)stage * A_STAGE_BYTES + (size_t)t * (TC_BM * 128);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; k++) {
+            // advancing 16 elements (32 bytes) along K inside the swizzle atom = +2 in the
+            // 16-byte-granular start address
+            const uint64_t ad = umma_desc_sw128(as) + (uint64_t)(2 * k);
+            const uint64_t bd = umma_desc_sw128(bs) + (uint64_t)(2 * k);
+            umma_f16(tmem_base + (uint32_t)(t * TC_BN), ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[stage]);             // frees the smem stage when these MMAs retire
+        if (kb == nk - 1) umma_commit(acc_full);  // accumulators complete
+      }
+      __syncwarp();
+      if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================== dequantisers (8 warps, thread == weight row) =====================
+    const int r = tid - 64;                 // 0..255 row within the tile
+    const int row = n0 + r;
+    const bool live = row < p.N;
+    const uint8_t *wrow = p.w + (size_t)(live ? row : 0) * p.row_bytes;
+    int stage = 0, phase = 0;
+    for (int kb = 0; kb < nk; kb++) {
+      float v[64];
+      if (live) dequant64<TYPE>(wrow, kb * TC_BK, v);
+      else {
+#pragma unroll
+        for (int i = 0; i < 64; i++) v[i] = 0.f;
+      }
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t *dst = b_st + (size_t)stage * B_STAGE_BYTES + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {          // 16-byte chunk c of the row lands at chunk c ^ (r % 8)
+        uint4 pk;
+        if (p.b_fmt == 0) {
+          __half2 *h = (__half2 *)&pk;
+#pragma unroll
+          for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+        } else {
+          __nv_bfloat162 *h = (__nv_bfloat162 *)&pk;
+#pragma unroll
+          for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+        }
+        *(uint4 *)(dst + ((c ^ (r & 7)) << 4)) = pk;
+      }
+      fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_full[stage]);
+      if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+    }
+
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // two warps per quarter: columns [0,128) / [128,256)
+#pragma unroll 1
+    for (int t = 0; t < TC_MT; t++) {
+      const int tok = m0 + t * TC_BM + q * 32 + lane;
+#pragma unroll 1
+      for (int cb = 0; cb < 4; cb++) {
+        const int col0 = half * 128 + cb * 32;
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * TC_BN + col0), acc);
+        if (tok < p.M) {
+          if (p.out_dtype == MRS_BF16) {
+            __nv_bfloat16 *yo = (__nv_bfloat16 *)p.y + (size_t)tok * p.N + n0 + col0;
+            if (n0 + col0 + 32 <= p.N && (p.N % 8) == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                uint4 pk;
+                __nv_bfloat162 *h = (__nv_bfloat162 *)&pk;
+#pragma unroll
+                for (int k = 0; k < 4; k++) h[k] = __floats2bfloat162_rn(__uint_as_float(acc[8 * i + 2 * k]), __uint_as_float(acc[8 * i + 2 * k + 1]));
+                *(uint4 *)(yo + 8 * i) = pk;
+              }
+            } else {
+              for (int i = 0; i < 32; i++) if (n0 + col0 + i < p.N) yo[i] = __float2bfloat16_rn(__uint_as_float(acc[i]));
+            }
+          } else {
+            __half *yo = (__half *)p.y + (size_t)tok * p.N + n0 + col0;
+            for (int i = 0; i < 32; i++) if (n0 + col0 + i < p.N) yo[i] = __float2half_rn(__uint_as_float(acc[i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host -----------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+template <int TYPE>
+static cudaError_t launch_tc(const TcParams &p, const CUtensorMap &tmap, cudaStream_t st) {
+  auto kern = mmq_tc_kernel<TYPE>;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); set = true; }
+  dim3 grid((p.N + TC_BN - 1) / TC_BN, (p.M + TC_MT * TC_BM - 1) / (TC_MT * TC_BM));
+  kern<<<grid, TC_THREADS, TC_SMEM, st>>>(tmap, p);
+  return cudaGetLastError();
+}
+
+}  // namespace mrs
+
+using namespace mrs;
+
+static int tc_row_bytes(int type, int K) {
+  switch (type) {
+  case MRS_Q4_0: return K / 32 * 18; case MRS_Q4_1: return K / 32 * 20; case MRS_Q5_0: return K / 32 * 22;
+  case MRS_Q5_1: return K / 32 * 24; case MRS_Q8_0: return K / 32 * 34; case MRS_Q2_K: return K / 256 * 84;
+  case MRS_Q3_K: return K / 256 * 110; case MRS_Q4_K: return K / 256 * 144; case MRS_Q5_K: return K / 256 * 176;
+  case MRS_Q6_K: return K / 256 * 210; default: return 0;
+  }
+}
+
+// Y[M, N] (dtype) = X[M, K] (dtype, row-major contiguous) . W[N, K]^T (ggml blocks).
+// dtype 0 = f16, 1 = bf16.  K must be a multiple of 64 (and of the type's block size).
+static int g_tc_b_fmt = 0;  // f16 weights by default (3 more mantissa bits than bf16)
+extern "C" void mrs_mmq_set_weight_format(int32_t fmt) { g_tc_b_fmt = fmt ? 1 : 0; }
+
+extern "C" int32_t mrs_mmq_gguf(int32_t ggml_type, const void *w, const void *x, void *y, int32_t M, int32_t N,
+                                int32_t K, int32_t dtype, void *stream) {
+  if (M <= 0 || N <= 0) return 0;
+  const int rb = tc_row_bytes(ggml_type, K);
+  if (rb == 0 || K % 64 != 0 || (dtype != 0 && dtype != 1)) return (int32_t)cudaErrorInvalidValue;
+  if (ggml_type >= MRS_Q2_K && K % 256 != 0) return (int32_t)cudaErrorInvalidValue;
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) return (int32_t)cudaErrorNotSupported;
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(&tmap, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                         const_cast<void *>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { fprintf(stderr, "mrs_b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r); return (int32_t)cudaErrorInvalidValue; }
+  if (((uintptr_t)w & 15) || ((uintptr_t)x & 15) || ((uintptr_t)y & 15)) return (int32_t)cudaErrorMisalignedAddress;
+  TcParams p = {(const uint8_t *)w, y, M, N, K, rb, dtype, g_tc_b_fmt};
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ggml_type) {
+  case MRS_Q4_0: return (int32_t)launch_tc<MRS_Q4_0>(p, tmap, st);
+  case MRS_Q4_1: return (int32_t)launch_tc<MRS_Q4_1>(p, tmap, st);
+  case MRS_Q5_0: return (int32_t)launch_tc<MRS_Q5_0>(p, tmap, st);
+  case MRS_Q5_1: return (int32_t)launch_tc<MRS_Q5_1>(p, tmap, st);
+  case MRS_Q8_0: return (int32_t)launch_tc<MRS_Q8_0>(p, tmap, st);
+  case MRS_Q2_K: return (int32_t)launch_tc<MRS_Q2_K>(p, tmap, st);
+  case MRS_Q3_K: return (int32_t)launch_tc<MRS_Q3_K>(p, tmap, st);
+  case MRS_Q4_K: return (int32_t)launch_tc<MRS_Q4_K>(p, tmap, st);
+  case MRS_Q5_K: return (int32_t)launch_tc<MRS_Q5_K>(p, tmap, st);
+  case MRS_Q6_K: return (int32_t)launch_tc<MRS_Q6_K>(p, tmap, st);
+  default: return (int32_t)cudaErrorInvalidValue;
+  }
+}

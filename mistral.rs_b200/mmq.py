@@ -1,0 +1,38 @@
+"""Prefill (batch > 8) quantized GEMM — mirror of `fast_mmq::plain`
+(REF mistralrs-quant/src/gguf/fast_mmq.rs:762-826) on the tcgen05 dequant-GEMM kernel
+(`mrs_mmq_gguf`, csrc/mmq_tc.cu).  Unlike the reference there is no activation quantisation
+pass: activations stay bf16/f16 and weights are dequantised on the fly into shared memory."""
+import ctypes
+
+import torch
+
+from . import GGML, lib
+
+_DT_CODE = {torch.float16: 0, torch.bfloat16: 1}
+
+
+def forward(w, xs: torch.Tensor) -> torch.Tensor:
+    """w: quant.QTensor [N, K]; xs [..., K] bf16/f16 -> [..., N]."""
+    if xs.dtype not in _DT_CODE:
+        raise ValueError(f"fast_mmq: input dtype must be BF16 or F16, got {xs.dtype}")
+    nrows, ncols = w.shape
+    if xs.shape[-1] != ncols:
+        raise ValueError(f"fast_mmq: shape mismatch: weight [{nrows}, {ncols}] vs input tail {xs.shape[-1]}")
+    if xs.device != w.device:
+        raise ValueError("fast_mmq: input and weight are on different devices")
+    if ncols % 64:
+        raise ValueError("fast_mmq: K must be a multiple of 64")
+    xs = xs.contiguous()
+    M = xs.numel() // ncols
+    out = torch.empty(*xs.shape[:-1], nrows, dtype=xs.dtype, device=xs.device)
+    rc = lib().mrs_mmq_gguf(ctypes.c_int(GGML[w.dtype]), ctypes.c_void_p(w.data.data_ptr()), ctypes.c_void_p(xs.data_ptr()),
+                            ctypes.c_void_p(out.data_ptr()), ctypes.c_int(M), ctypes.c_int(nrows), ctypes.c_int(ncols),
+                            ctypes.c_int(_DT_CODE[xs.dtype]), ctypes.c_void_p(torch.cuda.current_stream(xs.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"mrs_mmq_gguf failed with cudaError {rc}")
+    return out
+
+
+def set_weight_format(fmt: str):
+    """'f16' (default) or 'bf16' operand format for the dequantised weights."""
+    lib().mrs_mmq_set_weight_format(ctypes.c_int(0 if fmt == "f16" else 1))
