@@ -358,8 +358,8 @@ static int tc_row_bytes(int type, int K) {
 
 // Y[M, N] (dtype) = X[M, K] (dtype, row-major contiguous) . W[N, K]^T (ggml blocks).
 // dtype 0 = f16, 1 = bf16.  K must be a multiple of 64 (and of the type's block size).
-static int g_tc_b_fmt = 0;  // f16 weights by default (3 more mantissa bits than bf16)
-extern "C" void mrs_mmq_set_weight_format(int32_t fmt) { g_tc_b_fmt = fmt ? 1 : 0; }
+static int g_tc_b_fmt = -1;  // -1: same 16-bit format as the activations; 0 force f16; 1 force bf16
+extern "C" void mrs_mmq_set_weight_format(int32_t fmt) { g_tc_b_fmt = fmt; }
 
 extern "C" int32_t mrs_mmq_gguf(int32_t ggml_type, const void *w, const void *x, void *y, int32_t M, int32_t N,
                                 int32_t K, int32_t dtype, void *stream) {
@@ -379,7 +379,7 @@ extern "C" int32_t mrs_mmq_gguf(int32_t ggml_type, const void *w, const void *x,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { fprintf(stderr, "mrs_b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r); return (int32_t)cudaErrorInvalidValue; }
   if (((uintptr_t)w & 15) || ((uintptr_t)x & 15) || ((uintptr_t)y & 15)) return (int32_t)cudaErrorMisalignedAddress;
-  TcParams p = {(const uint8_t *)w, y, M, N, K, rb, dtype, g_tc_b_fmt};
+  TcParams p = {(const uint8_t *)w, y, M, N, K, rb, dtype, g_tc_b_fmt < 0 ? dtype : g_tc_b_fmt};
   cudaStream_t st = (cudaStream_t)stream;
   switch (ggml_type) {
   case MRS_Q4_0: return (int32_t)launch_tc<MRS_Q4_0>(p, tmap, st);

@@ -34,5 +34,5 @@ def forward(w, xs: torch.Tensor) -> torch.Tensor:
 
 
 def set_weight_format(fmt: str):
-    """'f16' (default) or 'bf16' operand format for the dequantised weights."""
-    lib().mrs_mmq_set_weight_format(ctypes.c_int(0 if fmt == "f16" else 1))
+    """'same' (default: the activations' 16-bit format), 'f16' or 'bf16' for the dequantised weights."""
+    lib().mrs_mmq_set_weight_format(ctypes.c_int({"same": -1, "f16": 0, "bf16": 1}[fmt]))
