@@ -16,7 +16,7 @@ def bench(fn, reps=10):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-for fmt in ("f16", "bf16"):
+for fmt in ("same",):
     mmq.set_weight_format(fmt)
     for dtype in ("q8_0", "q4_k", "q6_k"):
         for (M, N, K) in [(4096, 4096, 4096), (4096, 14336, 4096), (4096, 4096, 14336)]:

@@ -1,0 +1,79 @@
+"""Tensor-parallel host logic on CPU (gloo, world_size 2): the column / row sharding rules of
+the reference (distributed/layers.rs:1167-1294 column = output rows; :695-975 row = K columns on
+quant-block boundaries, outputs sum-all-reduced) applied to ggml blocks, checked with the CPU
+oracle: gathered column shards and all-reduced row shards must reproduce the unsharded product."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.load_package()
+    import oracle
+    from mistralrs_b200 import model as M
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = M.LlamaConfig.tiny_test(quant="q4_k_m", n_layers=2, hidden=512, inter=1024)
+    full = M.LlamaWeights(cfg, torch.device("cpu"), keep_host=True)
+    shard = M.LlamaWeights(cfg, torch.device("cpu"), tp_rank=rank, tp_size=world, keep_host=True)
+    rng = np.random.default_rng(5)
+    ok = True
+    for layer in range(cfg.n_layers):
+        # column parallel (ffn_gate): rows [rank*N/w, (rank+1)*N/w) -> all-gather == full
+        ty = M.tensor_type(cfg, "ffn_gate", layer)
+        x = rng.standard_normal((1, cfg.hidden)).astype(np.float32)
+        xq, st = oracle.quantize_q8_1(x)
+        y_full = oracle.mmvq_q8_1(ty, full.host[(layer, "ffn_gate")], xq, cfg.hidden, cfg.inter, st, 1)
+        y_part = oracle.mmvq_q8_1(ty, shard.host[(layer, "ffn_gate")], xq, cfg.hidden, cfg.inter // world, st, 1)
+        parts = [torch.zeros(1, cfg.inter // world, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(y_part))
+        ok &= bool(np.array_equal(torch.cat(parts, dim=1).numpy(), y_full))
+        # row parallel (ffn_down): K slice on block boundaries, partial sums all-reduced
+        ty = M.tensor_type(cfg, "ffn_down", layer)
+        a = rng.standard_normal((1, cfg.inter)).astype(np.float32)
+        aq, st = oracle.quantize_q8_1(a)
+        y_full = oracle.mmvq_q8_1(ty, full.host[(layer, "ffn_down")], aq, cfg.inter, cfg.hidden, st, 1)
+        kl = cfg.inter // world
+        a_loc = np.ascontiguousarray(a[:, rank * kl:(rank + 1) * kl])
+        aq_loc, st_loc = oracle.quantize_q8_1(a_loc)
+        y_part = torch.from_numpy(oracle.mmvq_q8_1(ty, shard.host[(layer, "ffn_down")], aq_loc, kl, cfg.hidden, st_loc, 1))
+        dist.all_reduce(y_part)
+        ok &= bool(np.allclose(y_part.numpy(), y_full, rtol=1e-12, atol=1e-9))
+    # replicated tensors are identical on every rank
+    ok &= bool(np.array_equal(full.host[(0, "output")], shard.host[(0, "output")]))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_column_and_row_parallel_sharding_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
+
+
+def test_kv_head_and_block_alignment_rules():
+    sys.path.insert(0, ROOT)
+    from mistralrs_b200 import model as M
+    cfg = M.LlamaConfig.llama3_8b()
+    for w in (2, 4, 8):   # K shards stay multiples of the 256 super-block
+        assert (cfg.inter // w) % 256 == 0 and (cfg.n_heads * cfg.head_dim // w) % 256 == 0
+        assert cfg.n_kv_heads % w == 0
+    c70 = M.LlamaConfig.llama3_70b()
+    assert (c70.inter // 8) % 256 == 0 and c70.n_kv_heads // 8 == 1

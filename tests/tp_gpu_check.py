@@ -1,0 +1,54 @@
+"""Run under torchrun (N ranks, NCCL): tensor-parallel decode of a tiny model must match the
+single-GPU decode of the same synthetic weights (the all-reduce sums bf16 partials, so a few
+bf16 ulps of difference are expected — same as the reference's RowParallelLayer)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g  # noqa: E402
+
+g.load_package()
+from mistralrs_b200 import model as M  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    cfg = M.LlamaConfig.tiny_test(quant="q4_k_m", n_layers=4, hidden=1024, inter=2048, n_heads=16, n_kv_heads=8)
+    full = M.LlamaWeights(cfg, dev)
+    shard = M.LlamaWeights(cfg, dev, tp_rank=rank, tp_size=world)
+    bufs = {}
+
+    def comm(buf, count, dtype, stream, user):
+        dist.all_reduce(bufs[buf])
+
+    ref = M.LlamaRunner(full, batch=2, max_ctx=64)
+    tp = M.LlamaRunner(shard, batch=2, max_ctx=64, comm=comm)
+    for n in ("x", "x2"):
+        bufs[tp.buf[n].data_ptr()] = tp.buf[n]
+    tp.capture()   # exercises NCCL inside CUDA-graph capture
+    ref.set_tokens([11, 400]); tp.set_tokens([11, 400])
+    worst = 0.0
+    for step in range(8):
+        ref.step(); tp.graph.replay()
+        torch.cuda.synchronize()
+        a, b = ref.logits().float(), tp.logits().float()
+        worst = max(worst, ((a - b).abs().max() / a.abs().max()).item())
+        tp.set_tokens(ref.meta["token_ids"].cpu().tolist())
+    ok = worst <= 4 * 2.0 ** -7
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"TP{world} vs TP1 worst rel logit diff {worst:.3e} -> {'OK' if t.item() == 1.0 else 'FAIL'}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
