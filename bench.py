@@ -330,7 +330,11 @@ def main():
             out["cpu_baseline"] = cpu
         print(json.dumps(out))
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL teardown with captured collectives still alive can hang: synchronise and leave
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -46,8 +46,11 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"TP{world} vs TP1 worst rel logit diff {worst:.3e} -> {'OK' if t.item() == 1.0 else 'FAIL'}", flush=True)
-    dist.destroy_process_group()
-    sys.exit(0 if t.item() == 1.0 else 1)
+    rc = 0 if t.item() == 1.0 else 1
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(rc)   # skip NCCL teardown (hangs while captured collectives are alive)
 
 
 if __name__ == "__main__":
