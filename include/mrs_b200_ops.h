@@ -1,0 +1,39 @@
+/* mrs_b200_ops.h — C ABI of the small fused ops between the GEMMs (libmrs_b200.so). */
+#ifndef MRS_B200_OPS_H
+#define MRS_B200_OPS_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct CUstream_st *mrs_ops_stream_t;
+
+/* REF mistralrs-quant/src/rotary/ffi.rs:4-43, kernels/rotary/rotary.cu:110-196.
+ * `rot_dim` is the number of rotated PAIRS (cos/sin row length), as in the reference. */
+void rotary_embedding(void *query, void *key, void *cos_cache, void *sin_cache, int32_t is_neox, int32_t head_size,
+                      int64_t num_tokens, int32_t rot_dim, int32_t num_heads, int32_t num_kv_heads,
+                      int64_t query_stride, int64_t key_stride, uint32_t dtype, int64_t stream);
+void rotary_embedding_positions(void *query, void *key, void *cos_cache, void *sin_cache, void *positions,
+                                int32_t is_neox, int32_t head_size, int64_t num_tokens, int32_t rot_dim,
+                                int32_t seq_len, int32_t num_heads, int32_t num_kv_heads, int64_t query_stride,
+                                int64_t key_stride, uint32_t dtype, int64_t stream);
+
+/* REF mistralrs-quant/src/utils/ffi.rs:274-330, kernels/ops/ops.cu:848-1060 */
+#define MRS_GLU_DECL(t)                                                                                        \
+  void fused_glu_##t(const void *a, const void *b, void *output, uint32_t rows, uint32_t cols,                 \
+                     uint32_t a_row_stride, uint32_t b_row_stride, int activation, mrs_ops_stream_t stream);   \
+  void fused_split_glu_##t(const void *input, void *output, uint32_t rows, uint32_t split_size, int activation, \
+                           mrs_ops_stream_t stream);
+MRS_GLU_DECL(f16) MRS_GLU_DECL(bf16) MRS_GLU_DECL(f32)
+
+/* REF mistralrs-core/src/cuda/ffi.rs (add_rms_norm_*), sort.cu:403-461,701-727; mrs_rms_norm_* is
+ * the plain RMSNorm the reference gets from candle_nn::ops::rms_norm (core/src/layers.rs:403-413). */
+#define MRS_RMS_DECL(t)                                                                                         \
+  void add_rms_norm_##t(const void *x, const void *residual, const void *weight, void *residual_dst,            \
+                        void *norm_dst, const int nrows, const int ncols, const float eps, int64_t stream);     \
+  void mrs_rms_norm_##t(const void *x, const void *weight, void *dst, const int nrows, const int ncols,         \
+                        const float eps, int64_t stream);
+MRS_RMS_DECL(f16) MRS_RMS_DECL(bf16) MRS_RMS_DECL(f32)
+#ifdef __cplusplus
+}
+#endif
+#endif

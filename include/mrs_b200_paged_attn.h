@@ -1,0 +1,86 @@
+/* mrs_b200_paged_attn.h — C ABI of the paged-KV attention path (libmrs_b200.so).
+ * Same symbols and signatures as mistralrs-paged-attn/src/cuda/ffi.rs:96-509 for the in-scope
+ * ops; dtype codes 0 = f16, 1 = bf16, 2 = f32, 3 = fp8_e4m3 (cache only).  Cache layouts:
+ *   vLLM  K [NB,KVH,D/x,BS,x], V [NB,KVH,D,BS]      (paged_attention_v1/v2, reshape_and_cache)
+ *   HND   K,V [NB,KVH,BS,D]                          (flashinfer_decode, *_flashinfer)
+ * Errors: cache/vLLM kernels report on stderr and exit(err) like the reference
+ * (pagedattention.cuh:46-56); flashinfer_decode returns the cudaError. */
+#ifndef MRS_B200_PAGED_ATTN_H
+#define MRS_B200_PAGED_ATTN_H
+#include <stdbool.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct CUstream_st *mrs_stream_t;
+
+/* REF ffi.rs:96-116 / reshape_and_cache_kernel.cu:89-140 */
+void reshape_and_cache(void *key, void *value, void *key_cache, void *value_cache, int64_t *slot_mapping,
+                       int32_t num_tokens, int32_t num_heads, int32_t head_size, int32_t block_size, int32_t x,
+                       int32_t key_stride, int32_t value_stride, mrs_stream_t stream, uint32_t dtype,
+                       uint32_t cache_dtype, float *k_scale, float *v_scale);
+/* REF ffi.rs:159-176 / flashinfer_decode.cu:250-312 */
+void reshape_and_cache_flashinfer(void *key, void *value, void *key_cache, void *value_cache, int64_t *slot_mapping,
+                                  int32_t num_tokens, int32_t num_heads, int32_t head_size, int32_t block_size,
+                                  int32_t key_stride, int32_t value_stride, float k_scale, float v_scale,
+                                  uint32_t dtype, uint32_t cache_dtype, mrs_stream_t stream);
+/* REF ffi.rs:178-209 / flashinfer_decode.cu:314-363 */
+int32_t flashinfer_decode(void *q, void *key_cache, void *value_cache, const int32_t *kv_indptr,
+                          const int32_t *kv_indices, const int32_t *kv_last_page_len, const int32_t *request_indices,
+                          const int32_t *kv_tile_indices, const int32_t *o_indptr, const int32_t *kv_chunk_size_ptr,
+                          const bool *block_valid_mask, void *o, void *tmp_v, void *tmp_s, int32_t batch_size,
+                          int32_t padded_batch_size, int32_t num_qo_heads, int32_t num_kv_heads, int32_t head_size,
+                          int32_t page_size, int32_t q_stride_n, int32_t q_stride_h, float sm_scale,
+                          int32_t window_left, float logits_soft_cap, float k_scale, float v_scale, uint32_t dtype,
+                          uint32_t cache_dtype, mrs_stream_t stream);
+/* REF ffi.rs:211-268 */
+void gather_kv_cache_flashinfer(void *key_cache, void *value_cache, void *k_out, void *v_out,
+                                const int32_t *block_table, const int32_t *cu_seq_lens, int32_t num_tokens,
+                                int32_t num_seqs, int32_t block_size, int32_t block_table_stride, int32_t num_kv_heads,
+                                int32_t head_size, uint32_t out_dtype, uint32_t cache_dtype, float k_scale,
+                                float v_scale, mrs_stream_t stream);
+void gather_kv_cache(void *key_cache, void *value_cache, void *k_out, void *v_out, const float *k_scale,
+                     const float *v_scale, const int32_t *block_table, const int32_t *cu_seq_lens, int32_t num_tokens,
+                     int32_t num_seqs, int32_t block_size, int32_t block_table_stride, int32_t num_kv_heads,
+                     int32_t head_size, int32_t x, mrs_stream_t stream, uint32_t out_dtype, uint32_t cache_dtype);
+
+/* REF ffi.rs:269-438 / pagedattention.cuh:687-876 */
+#define MRS_PAGED_DECL(t)                                                                                          \
+  void paged_attention_v1_##t(void *out, void *query, void *key_cache, void *value_cache, void *alibi_slopes,      \
+                              int32_t num_kv_heads, float scale, float softcapping, uint32_t *block_tables,        \
+                              uint32_t *context_lens, int32_t block_size, int32_t max_context_len, int32_t num_seqs, \
+                              int32_t num_heads, int32_t head_size, int32_t max_num_blocks_per_seq, int32_t q_stride, \
+                              int32_t kv_block_stride, int32_t kv_head_stride, mrs_stream_t stream,                \
+                              uint32_t cache_dtype, float *k_scale, float *v_scale, const float *sinks);           \
+  void paged_attention_v2_##t(void *out, float *exp_sums, float *max_logits, void *tmp_out, void *query,           \
+                              void *key_cache, void *value_cache, void *alibi_slopes, int32_t num_kv_heads,        \
+                              float scale, float softcapping, uint32_t *block_tables, uint32_t *context_lens,      \
+                              int32_t block_size, int32_t max_context_len, int32_t num_seqs, int32_t num_heads,    \
+                              int32_t head_size, int32_t max_num_blocks_per_seq, int32_t q_stride,                 \
+                              int32_t kv_block_stride, int32_t kv_head_stride, mrs_stream_t stream,                \
+                              uint32_t cache_dtype, float *k_scale, float *v_scale, const float *sinks);
+MRS_PAGED_DECL(f16) MRS_PAGED_DECL(bf16)
+
+/* REF ffi.rs:440-482 / copy_blocks_kernel.cu */
+#define MRS_COPY_DECL(t)                                                                                     \
+  void copy_blocks_##t(int64_t *key_cache_ptrs, int64_t *value_cache_ptrs, const int64_t *block_mapping,     \
+                       int32_t num_layers, int32_t num_pairs, int32_t numel_per_block_key,                   \
+                       int32_t numel_per_block_value, int64_t stream);
+MRS_COPY_DECL(f32) MRS_COPY_DECL(f16) MRS_COPY_DECL(bf16) MRS_COPY_DECL(u8)
+
+/* ---- B200-native addition: RoPE + KV write + decode attention + split-KV merge in one launch
+ * over the HND cache (replaces rotary_embedding_positions + reshape_and_cache_flashinfer +
+ * flashinfer_decode + its merge kernel); see csrc/paged_attn.cu. */
+int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, void *key_cache, void *value_cache,
+                               const void *rope_cos, const void *rope_sin, const int32_t *positions,
+                               const int64_t *slot_mapping, const int32_t *kv_indptr, const int32_t *kv_indices,
+                               const int32_t *kv_last_page_len, const int32_t *request_indices,
+                               const int32_t *kv_tile_indices, const int32_t *o_indptr,
+                               const int32_t *kv_chunk_size_ptr, const uint8_t *block_valid_mask, void *o, void *tmp_v,
+                               float *tmp_s, int32_t *counters, int32_t batch_size, int32_t padded_batch_size,
+                               int32_t num_qo_heads, int32_t num_kv_heads, int32_t head_size, int32_t page_size,
+                               float sm_scale, uint32_t dtype, int32_t pdl, void *stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

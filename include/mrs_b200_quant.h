@@ -1,0 +1,67 @@
+/* mrs_b200_quant.h — C ABI of the quantized-linear hot path (libmrs_b200.so).
+ *
+ * Every `launch_mmvq_gguf_*` symbol below has exactly the name, argument order and meaning of
+ * the reference launcher it replaces, so mistralrs-quant's `extern "C"` block
+ * (mistralrs-quant/src/gguf/ffi.rs, consumed by src/gguf/fast_mmvq.rs:116-157) links against
+ * this library unchanged.  Contract: raw device pointers already offset by the
+ * tensor's start_offset; the caller owns all memory incl. the Q8_1 scratch; every call is
+ * asynchronous on `stream`, allocation-free and CUDA-graph capturable; launchers return void and
+ * do not check cudaGetLastError (like the reference); batch b_size outside 1..8 is a no-op.
+ */
+#ifndef MRS_B200_QUANT_H
+#define MRS_B200_QUANT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Q8_1 activation quantiser — REF kernels/mmvq_gguf/mmvq_gguf.cu:1606-1641.
+ * x [num_rows, kx] -> vy block_q8_1[num_rows][kx_padded/32] (36 B blocks, zero padded). */
+void launch_mmvq_gguf_quantize_q8_1_bf16(const void *x, void *vy, int kx, int kx_padded, int num_rows, void *stream);
+void launch_mmvq_gguf_quantize_q8_1_f16(const void *x, void *vy, int kx, int kx_padded, int num_rows, void *stream);
+void launch_mmvq_gguf_quantize_q8_1_f32(const void *x, void *vy, int kx, int kx_padded, int num_rows, void *stream);
+
+/* Decode GEMV, batch 1..8 — REF mmvq_gguf.cu:1322-1604 (launchers), fast_mmvq.rs:116-157.
+ *  plain:      dst[b, row] = sum_k deq(vx[row, k]) * q8_1(vy)[b, k]
+ *  fused_glu:  dst = dst_t(act(dst_t(gate.x))) * dst_t(up.x), activation = GluActivationType 0..4
+ *  fused_qkv:  three projections sharing vy; outputs are dense [b, nrows_*]
+ * vx*: ggml blocks [nrows, ncols_x/qk]; vy: block_q8_1 [b][stride_col_y]; dst [b][stride_col_dst]. */
+#define MRS_MMVQ_DECL(q, t)                                                                                    \
+  void launch_mmvq_gguf_##q##_##t##_plain(const void *vx, const void *vy, void *dst, int ncols_x, int nrows_x, \
+                                          int stride_col_y, int stride_col_dst, int b_size, void *stream);     \
+  void launch_mmvq_gguf_##q##_##t##_fused_glu(const void *vx_gate, const void *vx_up, const void *vy,          \
+                                              void *dst, int ncols_x, int nrows_x, int stride_col_y,           \
+                                              int stride_col_dst, int b_size, int activation, void *stream);   \
+  void launch_mmvq_gguf_##q##_##t##_fused_qkv(const void *vx_q, const void *vx_k, const void *vx_v,            \
+                                              const void *vy, void *q_dst, void *k_dst, void *v_dst,           \
+                                              int ncols_x, int nrows_q, int nrows_k, int nrows_v,              \
+                                              int stride_col_y, int b_size, void *stream);
+#define MRS_MMVQ_DECL_T(q) MRS_MMVQ_DECL(q, bf16) MRS_MMVQ_DECL(q, f16) MRS_MMVQ_DECL(q, f32)
+MRS_MMVQ_DECL_T(q4_0) MRS_MMVQ_DECL_T(q4_1) MRS_MMVQ_DECL_T(q5_0) MRS_MMVQ_DECL_T(q5_1) MRS_MMVQ_DECL_T(q8_0)
+MRS_MMVQ_DECL_T(q2_k) MRS_MMVQ_DECL_T(q3_k) MRS_MMVQ_DECL_T(q4_k) MRS_MMVQ_DECL_T(q5_k) MRS_MMVQ_DECL_T(q6_k)
+
+/* ---- B200-native additions (not in the reference; see INTEGRATION.md for the Rust-side use) ---- */
+
+/* Programmatic dependent launch for the reference-shaped launchers (default off). */
+void mrs_set_pdl(int enabled);
+
+/* One launch for [RMSNorm ->] Q8_1 -> GEMV [-> GLU | + residual]: replaces rms_norm +
+ * launch_mmvq_gguf_quantize_q8_1_* + launch_mmvq_gguf_*  (+ the residual add).
+ * mode 0 plain (w0), 1 fused GLU (w0 = gate, w1 = up), 2 fused QKV (w0,w1[,w2]; n2 may be 0).
+ * x [b_size, K] of dtype dt (0 f16 / 1 bf16 / 2 f32), 16-byte aligned; norm_w / residual may be NULL.
+ * ggml_type: GgmlDType code (2 q4_0 .. 14 q6_k).  Returns a cudaError_t. */
+int mrs_mmvq_fused(int ggml_type, int mode, int dt, const void *w0, const void *w1, const void *w2, const void *x,
+                   const void *norm_w, float eps, const void *residual, void *dst0, void *dst1, void *dst2, int K,
+                   int n0, int n1, int n2, int b_size, int activation, int pdl, void *stream);
+
+/* Prefill GEMM (batch > 8) on tcgen05/TMEM: Y[M,N] = X[M,K] . W[N,K]^T, W in ggml blocks,
+ * X/Y dtype 0 f16 / 1 bf16, K % 64 == 0.  Replaces launch_mmq_quantize_q8_1_* +
+ * launch_mmq_gguf_<q> (REF fast_mmq.rs:102-185): no activation quantisation pass. */
+int32_t mrs_mmq_gguf(int32_t ggml_type, const void *w, const void *x, void *y, int32_t M, int32_t N, int32_t K,
+                     int32_t dtype, void *stream);
+void mrs_mmq_set_weight_format(int32_t fmt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
