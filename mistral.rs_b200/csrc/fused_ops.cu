@@ -29,6 +29,11 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float
 template <typename T> __device__ __forceinline__ T mul_t(T a, T b) { return from_f<T>(to_f(a) * to_f(b)); }
 template <typename T> __device__ __forceinline__ T add_t(T a, T b) { return from_f<T>(to_f(a) + to_f(b)); }
 template <typename T> __device__ __forceinline__ T sub_t(T a, T b) { return from_f<T>(to_f(a) - to_f(b)); }
+// a*b + c with ONE rounding in T (native fma.rn.{f16,bf16,f32})
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ __half fma_t(__half a, __half b, __half c) { return __hfma(a, b, c); }
+__device__ __forceinline__ __nv_bfloat16 fma_t(__nv_bfloat16 a, __nv_bfloat16 b, __nv_bfloat16 c) { return __hfma(a, b, c); }
+template <typename T> __device__ __forceinline__ T neg_t(T a) { return from_f<T>(-to_f(a)); }
 
 // ------------------------------------------------------------------ RoPE
 template <typename T, bool NEOX>
@@ -37,8 +42,10 @@ __device__ __forceinline__ void rope_pair(T *arr, const T *cosp, const T *sinp, 
   const int yi = NEOX ? rot_half + off : 2 * off + 1;
   const T c = cosp[off], s = sinp[off];
   const T x = arr[xi], y = arr[yi];
-  arr[xi] = sub_t(mul_t(x, c), mul_t(y, s));
-  arr[yi] = add_t(mul_t(y, c), mul_t(x, s));
+  // as the reference kernel is compiled (checked against its outputs, tests/golden/ref_golden.npz):
+  // the second product is rounded, the first is fused into the add -> fma(x, cos, -T(y*sin))
+  arr[xi] = fma_t(x, c, neg_t(mul_t(y, s)));
+  arr[yi] = fma_t(y, c, mul_t(x, s));
 }
 
 template <typename T, bool NEOX>

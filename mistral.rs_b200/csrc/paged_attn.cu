@@ -114,9 +114,10 @@ __device__ __forceinline__ void rope_slice(float *x, const T *cosp, const T *sin
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const float other = __shfl_xor_sync(0xffffffffu, x[i], LPT / 2);
-    const float a = rnd<T>(x[i] * c[i]);       // x*cos (lower) / y*cos (upper)
+    // out_x = fma(x, cos, -T(y*sin)); out_y = fma(y, cos, T(x*sin)) with one rounding in T, as the
+    // reference kernel is compiled (tests/golden/ref_golden.npz)
     const float b = rnd<T>(other * sn[i]);     // y*sin (lower) / x*sin (upper)
-    x[i] = upper ? rnd<T>(a + b) : rnd<T>(a - b);
+    x[i] = (float)__hfma((T)x[i], (T)c[i], (T)(upper ? b : -b));
   }
 }
 

@@ -646,14 +646,32 @@ void mrs_add_rms_norm(const float *x, const float *res, const float *w, float *s
 }
 
 /* ------------------------------------------------------------------ RoPE
- * REF: rotary.cu:10-34: arr[x] = x*cos - y*sin; arr[y] = y*cos + x*sin evaluated with the
- * scalar type's operators, i.e. every product and the sum/difference is rounded to dtype. */
+ * REF: rotary.cu:10-34: arr[x] = x*cos - y*sin; arr[y] = y*cos + x*sin with the scalar type's
+ * operators.  As compiled for the GPU (verified against the reference kernel's outputs,
+ * tests/golden/ref_golden.npz) the second product is rounded to dtype and the first is fused:
+ *   out_x = fma(x, cos, -round(y*sin)),  out_y = fma(y, cos, round(x*sin))   (one rounding each). */
+static float fma_round(float a, float b, float c, int dtype) {
+  if (dtype == MRS_F32) return fmaf(a, b, c);
+  /* 16-bit inputs: a*b and the sum with c are exact in double.  Round once to dtype by going
+   * through float with round-to-odd (24 bits >= dtype bits + 2, so no double rounding). */
+  const double e = (double)a * (double)b + (double)c;
+  float f = (float)e;
+  if ((double)f != e) {
+    float t = (fabs((double)f) > fabs(e)) ? nextafterf(f, 0.0f) : f; /* truncate toward zero */
+    uint32_t bits;
+    memcpy(&bits, &t, 4);
+    bits |= 1u;                                                      /* sticky: make it odd */
+    memcpy(&t, &bits, 4);
+    f = t;
+  }
+  return mrs_round_dtype(f, dtype);
+}
+
 static void rope_pair(float *arr, int xi, int yi, float c, float s, int dtype) {
-  float x = arr[xi], y = arr[yi];
-  float xc = mrs_round_dtype(x * c, dtype), ys = mrs_round_dtype(y * s, dtype);
-  float yc = mrs_round_dtype(y * c, dtype), xs = mrs_round_dtype(x * s, dtype);
-  arr[xi] = mrs_round_dtype(xc - ys, dtype);
-  arr[yi] = mrs_round_dtype(yc + xs, dtype);
+  const float x = arr[xi], y = arr[yi];
+  const float ys = mrs_round_dtype(y * s, dtype), xs = mrs_round_dtype(x * s, dtype);
+  arr[xi] = fma_round(x, c, -ys, dtype);
+  arr[yi] = fma_round(y, c, xs, dtype);
 }
 
 void mrs_rotary(float *q, float *k, const float *cosb, const float *sinb, const uint32_t *positions,
