@@ -100,7 +100,7 @@ def paged_attention(q, k_scale, v_scale, key_cache, value_cache, block_tables, c
     use_v1 = (max_parts == 1 or S * H > 512) and PARTITION_SIZE % bs == 0  # paged_attention.rs:302-307
     common = (_p(key_cache), _p(value_cache), _p(alibi_slopes), ctypes.c_int(kvh), ctypes.c_float(softmax_scale),
               ctypes.c_float(softcapping), _p(block_tables), _p(context_lens), ctypes.c_int(bs),
-              ctypes.c_int(max_context_len), ctypes.c_int(S), ctypes.c_int(H), ctypes.c_int(D),
+              ctypes.c_int(eff), ctypes.c_int(S), ctypes.c_int(H), ctypes.c_int(D),  # effective_max_context_len (paged_attention.rs:299-301)
               ctypes.c_int(max_blocks), ctypes.c_int(q.stride(0)), ctypes.c_int(key_cache.stride(0)),
               ctypes.c_int(key_cache.stride(1)), _stream(q.device), ctypes.c_uint32(_cache_dtype_code(key_cache)),
               _p(k_scale), _p(v_scale), _p(sinks))
