@@ -85,7 +85,9 @@ __device__ __forceinline__ float glu_activation(float x, int act) {
   case 1: {  // GELU tanh approximation
     const float x3 = x * x * x;
     const float inner = 0.7978845608f * (x + 0.044715f * x3);
-    return 0.5f * x * (1.0f + tanhf(inner));
+    float th;  // the reference's tanhf under --use_fast_math is tanh.approx.f32
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(inner));
+    return 0.5f * x * (1.0f + th);
   }
   case 2: return fmaxf(x, 0.0f);
   case 3: return x * normcdff(x);
