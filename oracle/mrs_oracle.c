@@ -6,9 +6,12 @@
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared -pthread (oracle/Makefile).  -ffp-contract=off
  * matters: the quantiser's f32 butterfly sums must not be fused.
  */
+#define _GNU_SOURCE
 #include "mrs_oracle.h"
 
 #include <math.h>
+#include <sched.h>
+#include <unistd.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -544,8 +547,7 @@ typedef struct {
   const uint8_t *w; const void *yq; const float *yd; float *out;
 } cpu_job_t;
 
-static void *cpu_worker(void *arg) {
-  cpu_job_t *j = (cpu_job_t *)arg;
+static void cpu_job_run(cpu_job_t *j) {
   int be = mrs_block_elems(j->type), bb = mrs_block_bytes(j->type), nb = j->ncols / be;
   for (int r = j->r0; r < j->r1; r++) {
     const uint8_t *wr = j->w + (size_t)r * nb * bb;
@@ -565,7 +567,50 @@ static void *cpu_worker(void *arg) {
       j->out[(size_t)b * j->nrows + r] = v;
     }
   }
+}
+
+/* persistent pool (the reference's CPU path runs on rayon's persistent pool; spawning threads
+ * per GEMV would dominate a 1-row-per-thread decode step) */
+#define MRS_MAX_THREADS 256
+static struct {
+  pthread_t th[MRS_MAX_THREADS];
+  cpu_job_t jobs[MRS_MAX_THREADS];
+  pthread_mutex_t mu;
+  pthread_cond_t cv_start, cv_done;
+  int nthreads, generation, pending, ids[MRS_MAX_THREADS];
+} g_pool = {.mu = PTHREAD_MUTEX_INITIALIZER, .cv_start = PTHREAD_COND_INITIALIZER, .cv_done = PTHREAD_COND_INITIALIZER};
+
+static void *pool_worker(void *arg) {
+  const int id = *(int *)arg;
+  int seen = 0;
+  { /* the embedding process (numpy/OpenBLAS) may have pinned the creating thread to one core;
+     * workers must be free to run anywhere */
+    cpu_set_t all;
+    CPU_ZERO(&all);
+    const long n = sysconf(_SC_NPROCESSORS_CONF);
+    for (long c = 0; c < n && c < CPU_SETSIZE; c++) CPU_SET((int)c, &all);
+    pthread_setaffinity_np(pthread_self(), sizeof all, &all);
+  }
+  for (;;) {
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.generation == seen) pthread_cond_wait(&g_pool.cv_start, &g_pool.mu);
+    seen = g_pool.generation;
+    cpu_job_t job = g_pool.jobs[id];
+    pthread_mutex_unlock(&g_pool.mu);
+    if (job.r1 > job.r0) cpu_job_run(&job);
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.pending == 0) pthread_cond_signal(&g_pool.cv_done);
+    pthread_mutex_unlock(&g_pool.mu);
+  }
   return NULL;
+}
+
+static void pool_ensure(int n) {
+  while (g_pool.nthreads < n) {
+    g_pool.ids[g_pool.nthreads] = g_pool.nthreads;
+    pthread_create(&g_pool.th[g_pool.nthreads], NULL, pool_worker, &g_pool.ids[g_pool.nthreads]);
+    g_pool.nthreads++;
+  }
 }
 
 int mrs_qmatmul_cpu(int type, const void *w, const float *x, float *out, int ncols, int nrows,
@@ -584,15 +629,29 @@ int mrs_qmatmul_cpu(int type, const void *w, const float *x, float *out, int nco
   }
   if (threads < 1) threads = 1;
   if (threads > nrows) threads = nrows;
-  if (threads > 256) threads = 256;
-  pthread_t th[256]; cpu_job_t jobs[256];
-  for (int t = 0; t < threads; t++) {
-    jobs[t] = (cpu_job_t){type, ncols, (int)((int64_t)nrows * t / threads), (int)((int64_t)nrows * (t + 1) / threads),
-                          nrows, batch, (const uint8_t *)w, yq, yd, out};
-    if (t > 0) pthread_create(&th[t], NULL, cpu_worker, &jobs[t]);
+  if (threads > MRS_MAX_THREADS) threads = MRS_MAX_THREADS;
+  if (threads == 1) {
+    cpu_job_t job = {type, ncols, 0, nrows, nrows, batch, (const uint8_t *)w, yq, yd, out};
+    cpu_job_run(&job);
+  } else {
+    pthread_mutex_lock(&g_pool.mu);
+    pool_ensure(threads - 1);
+    const int nw = g_pool.nthreads;  /* all pool threads wake; extra ones get empty jobs */
+    for (int t = 0; t < nw; t++) {
+      cpu_job_t job = {type, ncols, 0, 0, nrows, batch, (const uint8_t *)w, yq, yd, out};
+      if (t < threads - 1) { job.r0 = (int)((int64_t)nrows * (t + 1) / threads); job.r1 = (int)((int64_t)nrows * (t + 2) / threads); }
+      g_pool.jobs[t] = job;
+    }
+    g_pool.pending = nw;
+    g_pool.generation++;
+    pthread_cond_broadcast(&g_pool.cv_start);
+    pthread_mutex_unlock(&g_pool.mu);
+    cpu_job_t mine = {type, ncols, 0, (int)((int64_t)nrows / threads), nrows, batch, (const uint8_t *)w, yq, yd, out};
+    cpu_job_run(&mine);
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.pending > 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+    pthread_mutex_unlock(&g_pool.mu);
   }
-  cpu_worker(&jobs[0]);
-  for (int t = 1; t < threads; t++) pthread_join(th[t], NULL);
   free(yq); free(yd);
   return 0;
 }
