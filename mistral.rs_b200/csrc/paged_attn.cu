@@ -238,6 +238,62 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
     if (owns_new) t_end = kv_len - 1;  // the cache loop stops before the new token
   }
 
+  if constexpr (LAYOUT == 1) {
+    // ---- HND: stage the chunk's pages through shared memory with the TMA engine.  A page is a
+    // contiguous [page_size, D] slab per KV head, so one cp.async.bulk per (page, K|V) moves it;
+    // all copies of a 128-token sub-chunk are in flight at once (one HBM latency per sub-chunk
+    // instead of one per 4 tokens), double buffered.
+    extern __shared__ __align__(128) uint8_t pa_stage[];
+    constexpr int SUB = (D <= 128) ? 128 : 64;          // tokens per sub-chunk
+    constexpr int SUB_BYTES = SUB * D * (int)sizeof(T);  // per K or V buffer
+    __shared__ __align__(8) uint64_t st_full[2];
+    T *st_k[2] = {(T *)pa_stage, (T *)(pa_stage + 2 * SUB_BYTES)};
+    T *st_v[2] = {(T *)(pa_stage + SUB_BYTES), (T *)(pa_stage + 3 * SUB_BYTES)};
+    if (tid == 0) { mbar_init(&st_full[0], 1); mbar_init(&st_full[1], 1); fence_mbar_init(); }
+    __syncthreads();
+    const int nsub = (t_end > t_begin) ? (t_end - t_begin + SUB - 1) / SUB : 0;
+    auto issue = [&](int si) {  // thread 0 only
+      const int s0 = t_begin + si * SUB, s1 = min(t_end, s0 + SUB);
+      const int b = si & 1;
+      mbar_arrive_expect_tx(&st_full[b], (uint32_t)(2 * (s1 - s0) * D * (int)sizeof(T)));
+      for (int t = s0; t < s1;) {
+        const int off = t % p.page_size;
+        const int n = min(p.page_size - off, s1 - t);   // tokens of this page inside the sub-chunk
+        const int64_t base = (int64_t)pages[t / p.page_size] * p.kv_block_stride + (int64_t)kvh * p.kv_head_stride + (int64_t)off * D;
+        const uint32_t bytes = (uint32_t)(n * D * (int)sizeof(T));
+        bulk_g2s(st_k[b] + (size_t)(t - s0) * D, kc + base, bytes, &st_full[b]);
+        bulk_g2s(st_v[b] + (size_t)(t - s0) * D, vc + base, bytes, &st_full[b]);
+        t += n;
+      }
+    };
+    if (tid == 0 && nsub > 0) issue(0);
+    for (int si = 0; si < nsub; si++) {
+      const int b = si & 1;
+      if (tid == 0 && si + 1 < nsub) issue(si + 1);   // buffer (si+1)&1 was released by the barrier below
+      mbar_wait(&st_full[b], (uint32_t)((si >> 1) & 1));
+      const int s0 = t_begin + si * SUB, s1 = min(t_end, s0 + SUB);
+      // trip count is uniform across the CTA (the shuffles need every lane of the warp)
+      for (int tb0 = s0; tb0 < s1; tb0 += NGRP * PA_UNROLL) {
+        const int tb = tb0 + grp;
+        float kf[PA_UNROLL][8], vf[PA_UNROLL][8];
+        bool ok[PA_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PA_UNROLL; u++) {
+          const int t = tb + u * NGRP;
+          ok[u] = t < s1;
+#pragma unroll
+          for (int i = 0; i < 8; i++) { kf[u][i] = 0.f; vf[u][i] = 0.f; }
+          if (ok[u]) {
+            Vec8<T>::load(st_k[b] + (size_t)(t - s0) * D + d0, kf[u]);
+            Vec8<T>::load(st_v[b] + (size_t)(t - s0) * D + d0, vf[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PA_UNROLL; u++) update(kf[u], vf[u], tb + u * NGRP, ok[u]);
+      }
+      __syncthreads();  // everyone is done with buffer b before it is refilled
+    }
+  } else {
   // trip count is uniform across the CTA (the shuffles need every lane of the warp)
   for (int tb0 = t_begin; tb0 < t_end; tb0 += NGRP * PA_UNROLL) {
     const int tb = tb0 + grp;
@@ -253,18 +309,14 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
         const int64_t page = pages[t / p.page_size];
         const int off = t % p.page_size;
         const int64_t base = page * p.kv_block_stride + (int64_t)kvh * p.kv_head_stride;
-        if constexpr (LAYOUT == 1) {
-          Vec8<T>::load(kc + base + (int64_t)off * D + d0, kf[u]);
-          Vec8<T>::load(vc + base + (int64_t)off * D + d0, vf[u]);
-        } else {
-          Vec8<T>::load(kc + base + ((int64_t)gl * p.page_size + off) * 8, kf[u]);
+        Vec8<T>::load(kc + base + ((int64_t)gl * p.page_size + off) * 8, kf[u]);
 #pragma unroll
-          for (int i = 0; i < 8; i++) vf[u][i] = Vec8<T>::one(vc + base + (int64_t)(d0 + i) * p.page_size + off);
-        }
+        for (int i = 0; i < 8; i++) vf[u][i] = Vec8<T>::one(vc + base + (int64_t)(d0 + i) * p.page_size + off);
       }
     }
 #pragma unroll
     for (int u = 0; u < PA_UNROLL; u++) update(kf[u], vf[u], tb + u * NGRP, ok[u]);
+  }
   }
 
   if constexpr (FUSED) {
@@ -435,9 +487,10 @@ __global__ void merge_partials_kernel(const T *__restrict__ tmp_o, const float *
 }
 
 template <typename K>
-static cudaError_t launch_pa(K kern, dim3 grid, const PagedParams &p, cudaStream_t st) {
+static cudaError_t launch_pa(K kern, dim3 grid, const PagedParams &p, cudaStream_t st, size_t dyn_smem) {
+  if (dyn_smem > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(PA_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.gridDim = grid; cfg.blockDim = dim3(PA_THREADS); cfg.dynamicSmemBytes = dyn_smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -453,10 +506,12 @@ static cudaError_t launch_decode_g(PagedParams p, int tiles, cudaStream_t st) {
   const int per = (group + nsub - 1) / nsub;
   p.heads_per_cta = per;
   dim3 grid(tiles, p.num_kv_heads, nsub);
-  if (per <= 1) return launch_pa(paged_decode_kernel<T, D, 1, LAYOUT, FUSED>, grid, p, st);
-  if (per <= 2) return launch_pa(paged_decode_kernel<T, D, 2, LAYOUT, FUSED>, grid, p, st);
-  if (per <= 4) return launch_pa(paged_decode_kernel<T, D, 4, LAYOUT, FUSED>, grid, p, st);
-  if constexpr (D <= 128) return launch_pa(paged_decode_kernel<T, D, 8, LAYOUT, FUSED>, grid, p, st);
+  // HND: two double-buffered (K, V) sub-chunk stages of 128 (D<=128) / 64 tokens
+  const size_t dyn = (LAYOUT == 1) ? (size_t)4 * ((D <= 128) ? 128 : 64) * D * sizeof(T) : 0;
+  if (per <= 1) return launch_pa(paged_decode_kernel<T, D, 1, LAYOUT, FUSED>, grid, p, st, dyn);
+  if (per <= 2) return launch_pa(paged_decode_kernel<T, D, 2, LAYOUT, FUSED>, grid, p, st, dyn);
+  if (per <= 4) return launch_pa(paged_decode_kernel<T, D, 4, LAYOUT, FUSED>, grid, p, st, dyn);
+  if constexpr (D <= 128) return launch_pa(paged_decode_kernel<T, D, 8, LAYOUT, FUSED>, grid, p, st, dyn);
   return cudaErrorInvalidValue;
 }
 
