@@ -121,6 +121,24 @@ __device__ __forceinline__ void rope_slice(float *x, const T *cosp, const T *sin
   }
 }
 
+#define MRS_LOAD_Q \
+  if (p.pdl) pdl_wait(); \
+    if constexpr (FUSED) { \
+      const int64_t pos = p.positions[seq]; \
+      cosp = (const T *)p.rope_cos + pos * (D / 2); \
+      sinp = (const T *)p.rope_sin + pos * (D / 2); \
+    } \
+   \
+    for (int g = 0; g < G; g++) { \
+      if (g < gsize) { \
+        Vec8<T>::load((const T *)p.q + (int64_t)seq * p.q_stride_n + (int64_t)(h0 + g) * p.q_stride_h + d0, qf[g]); \
+      } else { \
+        for (int i = 0; i < 8; i++) qf[g][i] = 0.f; \
+      } \
+      if constexpr (FUSED) rope_slice<T, D>(qf[g], cosp, sinp, gl); \
+      for (int i = 0; i < 8; i++) qf[g][i] *= p.sm_scale; \
+    } \
+
 // LAYOUT 0: vLLM (K [NB,KVH,D/8,BS,8], V [NB,KVH,D,BS]); 1: HND ([NB,KVH,BS,D])
 // FUSED: q/k/v of the new token arrive un-rotated; the kernel applies RoPE, writes the new K/V
 // row into the cache (the tile that owns the last position) and merges split-KV partials itself
@@ -134,7 +152,6 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   const int grp = tid / LPT, gl = tid % LPT;  // group, lane within group
   const int d0 = gl * 8;
 
-  if (p.pdl) pdl_wait();
   if (p.block_valid_mask != nullptr && p.block_valid_mask[tile] == 0) return;
   int seq, chunk_idx;
   if (p.tiles_are_partitions) { seq = tile / p.num_partitions; chunk_idx = tile % p.num_partitions; }
@@ -162,27 +179,10 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   const int h0 = kvh * group + blockIdx.z * p.heads_per_cta;      // first query head of this CTA
   const int gsize = min(p.heads_per_cta, group - (int)blockIdx.z * p.heads_per_cta);  // heads here (<= G)
 
-  const T *cosp = nullptr, *sinp = nullptr;
-  if constexpr (FUSED) {
-    const int64_t pos = p.positions[seq];
-    cosp = (const T *)p.rope_cos + pos * (D / 2);
-    sinp = (const T *)p.rope_sin + pos * (D / 2);
-  }
-
-  // q slice of this lane for all heads of the group, (rotated,) pre-scaled
+  // q slice of this lane for all heads of the group; filled by MRS_LOAD_Q after the page copies
+  // are in flight and after griddepcontrol.wait (q/k_new/v_new come from the upstream kernel)
   float qf[G][8];
-#pragma unroll
-  for (int g = 0; g < G; g++) {
-    if (g < gsize) {
-      Vec8<T>::load((const T *)p.q + (int64_t)seq * p.q_stride_n + (int64_t)(h0 + g) * p.q_stride_h + d0, qf[g]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; i++) qf[g][i] = 0.f;
-    }
-    if constexpr (FUSED) rope_slice<T, D>(qf[g], cosp, sinp, gl);
-#pragma unroll
-    for (int i = 0; i < 8; i++) qf[g][i] *= p.sm_scale;
-  }
+  const T *cosp = nullptr, *sinp = nullptr;
   float slope[G];
 #pragma unroll
   for (int g = 0; g < G; g++) slope[g] = (p.alibi_slopes != nullptr && g < gsize) ? p.alibi_slopes[h0 + g] : 0.f;
@@ -252,6 +252,14 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
     if (tid == 0) { mbar_init(&st_full[0], 1); mbar_init(&st_full[1], 1); fence_mbar_init(); }
     __syncthreads();
     const int nsub = (t_end > t_begin) ? (t_end - t_begin + SUB - 1) / SUB : 0;
+    // page ids of the chunk -> shared memory in one parallel round (a serial walk by the
+    // issuing thread would pay one L2 latency per page)
+    __shared__ int st_pages[2048 / 8 + 2];
+    const int pg0 = t_begin / p.page_size;
+    const int npg = (t_end > t_begin) ? (t_end - 1) / p.page_size - pg0 + 1 : 0;
+    for (int i = tid; i < npg && i < (int)(sizeof(st_pages) / sizeof(int)); i += PA_THREADS) st_pages[i] = pages[pg0 + i];
+    __syncthreads();
+    const bool pages_in_smem = npg <= (int)(sizeof(st_pages) / sizeof(int));
     auto issue = [&](int si) {  // thread 0 only
       const int s0 = t_begin + si * SUB, s1 = min(t_end, s0 + SUB);
       const int b = si & 1;
@@ -259,7 +267,9 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
       for (int t = s0; t < s1;) {
         const int off = t % p.page_size;
         const int n = min(p.page_size - off, s1 - t);   // tokens of this page inside the sub-chunk
-        const int64_t base = (int64_t)pages[t / p.page_size] * p.kv_block_stride + (int64_t)kvh * p.kv_head_stride + (int64_t)off * D;
+        const int pgi = t / p.page_size;
+        const int64_t pg = pages_in_smem ? st_pages[pgi - pg0] : pages[pgi];
+        const int64_t base = pg * p.kv_block_stride + (int64_t)kvh * p.kv_head_stride + (int64_t)off * D;
         const uint32_t bytes = (uint32_t)(n * D * (int)sizeof(T));
         bulk_g2s(st_k[b] + (size_t)(t - s0) * D, kc + base, bytes, &st_full[b]);
         bulk_g2s(st_v[b] + (size_t)(t - s0) * D, vc + base, bytes, &st_full[b]);
@@ -267,6 +277,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
       }
     };
     if (tid == 0 && nsub > 0) issue(0);
+    MRS_LOAD_Q
     for (int si = 0; si < nsub; si++) {
       const int b = si & 1;
       if (tid == 0 && si + 1 < nsub) issue(si + 1);   // buffer (si+1)&1 was released by the barrier below
@@ -294,6 +305,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
       __syncthreads();  // everyone is done with buffer b before it is refilled
     }
   } else {
+  MRS_LOAD_Q
   // trip count is uniform across the CTA (the shuffles need every lane of the warp)
   for (int tb0 = t_begin; tb0 < t_end; tb0 += NGRP * PA_UNROLL) {
     const int tb = tb0 + grp;
