@@ -61,6 +61,14 @@ int32_t mrs_mmq_gguf(int32_t ggml_type, const void *w, const void *x, void *y, i
                      int32_t dtype, void *stream);
 void mrs_mmq_set_weight_format(int32_t fmt);
 
+/* GPTQ / AWQ int4 linear from the raw checkpoint tensors (no Marlin repack) on the same
+ * tcgen05 kernel: Y[M,N] f16 = X[M,K] f16 . W; GPTQ qweight [K/8,N] (w = (q-8)*s, optional
+ * act-order g_idx [K]), AWQ qweight [K,N/8] + qzeros [K/g,N/8] (w = (q-z)*s); scales f16 [K/g,N].
+ * Stands in for marlin_{gptq,awq}_4bit_f16 + {gptq,awq}_marlin_repack (REF gptq/marlin_ffi.rs:6-81). */
+int32_t mrs_gptq_gemm(const void *x, const int32_t *qweight, const void *scales, const int32_t *qzeros,
+                      const int32_t *g_idx, void *y, int32_t M, int32_t K, int32_t N, int32_t group_size,
+                      int32_t is_awq, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -162,12 +162,51 @@ __device__ __forceinline__ void dequant64(const uint8_t *row, int k0, float *out
   }
 }
 
+struct TcParams;
+template <int TYPE> struct IsInt4Ckpt { static constexpr bool value = (TYPE == 100 || TYPE == 101); };
+
 struct TcParams {
   const uint8_t *w;
   void *y;
   int M, N, K, row_bytes, out_dtype;
   int b_fmt;  // operand format of the dequantised weights: 0 f16, 1 bf16
+  // GPTQ / AWQ int4 checkpoints (TYPE_GPTQ4 / TYPE_AWQ4): raw HF tensors, no Marlin repack
+  const int32_t *qweight;   // GPTQ [K/8, N] (nibbles along K); AWQ [K, N/8] (nibbles along N, order 0,2,4,6,1,3,5,7)
+  const __half *scales;     // [K/group, N]
+  const int32_t *qzeros;    // AWQ [K/group, N/8]; GPTQ: ignored (symmetric, w = (q-8)*s — REF marlin kU4B8)
+  const int32_t *g_idx;     // GPTQ act-order group of each k, or nullptr (k / group)
+  int group;
 };
+constexpr int TYPE_GPTQ4 = 100, TYPE_AWQ4 = 101;
+
+// 64 weights k0..k0+63 of output channel n from a GPTQ / AWQ int4 checkpoint, as the Marlin
+// path of the reference computes them: w = f16((q - 8) * s) (GPTQ, REF marlin_matmul_f16.cu /
+// marlin_kernel.cuh dequant kU4B8) or f16((q - z) * s) (AWQ, kU4 + zero points).
+template <int TYPE>
+__device__ __forceinline__ void dequant64_ckpt(const TcParams &p, int n, int k0, float *out) {
+  if constexpr (TYPE == TYPE_GPTQ4) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t w = (uint32_t)p.qweight[(size_t)(k0 / 8 + i) * p.N + n];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = k0 + 8 * i + j;
+        const int g = p.g_idx ? p.g_idx[k] : k / p.group;
+        const float sc = __half2float(p.scales[(size_t)g * p.N + n]);
+        out[8 * i + j] = (float)((int)((w >> (4 * j)) & 0xF) - 8) * sc;
+      }
+    }
+  } else {
+    const int sh = 4 * ((n & 7) == 0 ? 0 : (n & 7) == 1 ? 4 : (n & 7) == 2 ? 1 : (n & 7) == 3 ? 5 : (n & 7) == 4 ? 2 : (n & 7) == 5 ? 6 : (n & 7) == 6 ? 3 : 7);
+#pragma unroll 8
+    for (int i = 0; i < 64; i++) {
+      const int k = k0 + i, g = k / p.group;
+      const int q = (int)(((uint32_t)p.qweight[(size_t)k * (p.N / 8) + n / 8] >> sh) & 0xF);
+      const int z = (int)(((uint32_t)p.qzeros[(size_t)g * (p.N / 8) + n / 8] >> sh) & 0xF);
+      out[i] = (float)(q - z) * __half2float(p.scales[(size_t)g * p.N + n]);
+    }
+  }
+}
 
 template <int TYPE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -249,7 +288,10 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcParams p) {
     int stage = 0, phase = 0;
     for (int kb = 0; kb < nk; kb++) {
       float v[64];
-      if (live) dequant64<TYPE>(wrow, kb * TC_BK, v);
+      if (live) {
+        if constexpr (IsInt4Ckpt<TYPE>::value) dequant64_ckpt<TYPE>(p, row, kb * TC_BK, v);
+        else dequant64<TYPE>(wrow, kb * TC_BK, v);
+      }
       else {
 #pragma unroll
         for (int i = 0; i < 64; i++) v[i] = 0.f;
@@ -394,4 +436,31 @@ extern "C" int32_t mrs_mmq_gguf(int32_t ggml_type, const void *w, const void *x,
   case MRS_Q6_K: return (int32_t)launch_tc<MRS_Q6_K>(p, tmap, st);
   default: return (int32_t)cudaErrorInvalidValue;
   }
+}
+
+// GPTQ / AWQ int4 linear on the tcgen05 path, straight from the checkpoint tensors (no Marlin
+// repack): Y[M,N] f16 = X[M,K] f16 . W, W[k,n] = (q-8)*s (GPTQ, symmetric) or (q-z)*s (AWQ).
+// Mirrors GptqLayer::forward_raw -> marlin_matmul (REF mistralrs-quant/src/gptq/gptq_cuda.rs:357-398,
+// marlin_backend.rs); activations are f16 (`quantized_act_type`), bits == 4 only.
+extern "C" int32_t mrs_gptq_gemm(const void *x, const int32_t *qweight, const void *scales, const int32_t *qzeros,
+                                 const int32_t *g_idx, void *y, int32_t M, int32_t K, int32_t N, int32_t group_size,
+                                 int32_t is_awq, void *stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (K % 64 != 0 || N % 8 != 0 || group_size <= 0 || K % group_size != 0) return (int32_t)cudaErrorInvalidValue;
+  if (is_awq && qzeros == nullptr) return (int32_t)cudaErrorInvalidValue;
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) return (int32_t)cudaErrorNotSupported;
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(x), dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return (int32_t)cudaErrorInvalidValue;
+  TcParams p = {};
+  p.y = y; p.M = M; p.N = N; p.K = K; p.out_dtype = MRS_F16; p.b_fmt = 0;
+  p.qweight = qweight; p.scales = (const __half *)scales; p.qzeros = qzeros; p.g_idx = g_idx; p.group = group_size;
+  return (int32_t)(is_awq ? launch_tc<TYPE_AWQ4>(p, tmap, (cudaStream_t)stream) : launch_tc<TYPE_GPTQ4>(p, tmap, (cudaStream_t)stream));
 }
