@@ -32,7 +32,8 @@ constexpr int TC_MT = 2;          // token sub-tiles per CTA
 constexpr int TC_BN = 256;        // UMMA N (weight rows per CTA)
 constexpr int TC_BK = 64;         // K per stage (128 bytes of 16-bit -> one swizzle atom row)
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 320;
+constexpr int TC_DQ_WARPS = 16;                       // dequantiser warps: two threads per weight row
+constexpr int TC_THREADS = 64 + TC_DQ_WARPS * 32;
 constexpr int A_STAGE_BYTES = TC_MT * TC_BM * TC_BK * 2;   // 32 KB
 constexpr int B_STAGE_BYTES = TC_BN * TC_BK * 2;           // 32 KB
 constexpr int TC_SMEM = 1024 + TC_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
@@ -162,6 +163,106 @@ __device__ __forceinline__ void dequant64(const uint8_t *row, int k0, float *out
   }
 }
 
+
+// ---- register-staged decoding of 32 consecutive weights (two threads share a row's K-step) ----
+// load_raw32 only issues loads (so the next K-step's bytes are in flight while the current one
+// is expanded); expand32 turns them into 32 floats.
+__device__ __forceinline__ void ld_unaligned_words9(const uint8_t *a, uint32_t *w, uint32_t &phase) {
+  const uintptr_t u = (uintptr_t)a;
+  const uint32_t *a0 = (const uint32_t *)(u & ~(uintptr_t)3);
+  phase = (uint32_t)(u & 3) * 8;
+#pragma unroll
+  for (int i = 0; i < 9; i++) w[i] = a0[i];
+}
+// byte stream starting at the unaligned address: word i of the stream
+__device__ __forceinline__ uint32_t stream_word(const uint32_t *w, int i, uint32_t phase) {
+  return __funnelshift_r(w[i], (i + 1 < 9) ? w[i + 1] : 0u, phase);
+}
+
+template <int TYPE> struct Raw32 { uint32_t w[1]; };
+template <> struct Raw32<MRS_Q4_K> { uint4 hdr, q0, q1; };
+template <> struct Raw32<MRS_Q8_0> { uint32_t w[9]; uint32_t phase; };
+template <> struct Raw32<MRS_Q6_K> { uint32_t ql[9], qh[9]; uint32_t pl, ph; uint32_t sc; uint32_t d; };
+
+template <int TYPE>
+__device__ __forceinline__ void load_raw32(const uint8_t *row, int k, Raw32<TYPE> &r) {
+  if constexpr (TYPE == MRS_Q4_K) {
+    const uint8_t *b = row + (size_t)(k / 256) * 144;
+    const int j = ((k % 256) / 32) >> 1;
+    r.hdr = *(const uint4 *)b;
+    r.q0 = *(const uint4 *)(b + 16 + 32 * j);
+    r.q1 = *(const uint4 *)(b + 32 + 32 * j);
+  } else if constexpr (TYPE == MRS_Q8_0) {
+    ld_unaligned_words9(row + (size_t)(k / 32) * 34, r.w, r.phase);
+  } else if constexpr (TYPE == MRS_Q6_K) {
+    const uint8_t *b = row + (size_t)(k / 256) * 210;
+    const int n = (k % 256) / 128, kk = (k % 128) / 32;
+    ld_unaligned_words9(b + 64 * n + 32 * (kk & 1), r.ql, r.pl);
+    ld_unaligned_words9(b + 128 + 32 * n, r.qh, r.ph);
+    r.sc = *(const uint16_t *)(b + 192 + 8 * n + 2 * kk);
+    r.d = *(const uint16_t *)(b + 208);
+  }
+}
+
+template <int TYPE>
+__device__ __forceinline__ void expand32(const Raw32<TYPE> &r, const uint8_t *row, int k, float *out) {
+  if constexpr (TYPE == MRS_Q4_K) {
+    const int sub = (k % 256) / 32, hi = sub & 1;
+    const float d = __half2float(__ushort_as_half((unsigned short)(r.hdr.x & 0xFFFF)));
+    const float dmin = __half2float(__ushort_as_half((unsigned short)(r.hdr.x >> 16)));
+    // 6-bit scale / min of sub-block `sub` from the 12 scale bytes held in hdr.y/z/w (registers only)
+    auto qb = [&](int i) -> int {
+      const uint32_t wsel = (i < 4) ? r.hdr.y : ((i < 8) ? r.hdr.z : r.hdr.w);
+      return (int)((wsel >> (8 * (i & 3))) & 0xFF);
+    };
+    int sc, m;
+    if (sub < 4) { sc = qb(sub) & 63; m = qb(sub + 4) & 63; }
+    else { sc = (qb(sub + 4) & 0xF) | ((qb(sub - 4) >> 6) << 4); m = (qb(sub + 4) >> 4) | ((qb(sub) >> 6) << 4); }
+    const float ds = d * (float)sc, om = dmin * (float)m;
+    const uint32_t w[8] = {r.q0.x, r.q0.y, r.q0.z, r.q0.w, r.q1.x, r.q1.y, r.q1.z, r.q1.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t v = hi ? (w[i] >> 4) : w[i];
+#pragma unroll
+      for (int b = 0; b < 4; b++) out[4 * i + b] = ds * (float)((v >> (8 * b)) & 0xF) - om;
+    }
+  } else if constexpr (TYPE == MRS_Q8_0) {
+    const uint32_t s0 = stream_word(r.w, 0, r.phase);
+    const float d = __half2float(__ushort_as_half((unsigned short)(s0 & 0xFFFF)));
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      // qs word i = stream bytes 2+4i .. 5+4i = high half of stream word i, low half of word i+1
+      const uint32_t lo = stream_word(r.w, i, r.phase), hi2 = stream_word(r.w, i + 1, r.phase);
+      const uint32_t q = __funnelshift_r(lo, hi2, 16);
+#pragma unroll
+      for (int b = 0; b < 4; b++) out[4 * i + b] = d * (float)(int8_t)((q >> (8 * b)) & 0xFF);
+    }
+  } else if constexpr (TYPE == MRS_Q6_K) {
+    const int kk = (k % 128) / 32, hs = kk >> 1;   // hs: 1 -> high nibbles, qh bits shift by 4
+    const float d = __half2float(__ushort_as_half((unsigned short)r.d));
+    const float d0 = d * (float)(int8_t)(r.sc & 0xFF), d1 = d * (float)(int8_t)(r.sc >> 8);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t l = stream_word(r.ql, i, r.pl), h = stream_word(r.qh, i, r.ph);
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const uint32_t lb = (l >> (8 * b)) & 0xFF, hb = (h >> (8 * b)) & 0xFF;
+        const int q = (int)((hs ? (lb >> 4) : (lb & 0xF)) | (((hb >> (2 * kk)) & 3) << 4)) - 32;
+        out[4 * i + b] = ((4 * i + b) < 16 ? d0 : d1) * (float)q;
+      }
+    }
+  } else {
+    // other ggml types: exact per-element decode (correct, not tuned)
+    const int be = (TYPE >= MRS_Q2_K) ? 256 : 32;
+    constexpr int bb = (TYPE == MRS_Q4_0) ? 18 : (TYPE == MRS_Q4_1) ? 20 : (TYPE == MRS_Q5_0) ? 22 : (TYPE == MRS_Q5_1) ? 24
+                     : (TYPE == MRS_Q2_K) ? 84 : (TYPE == MRS_Q3_K) ? 110 : (TYPE == MRS_Q5_K) ? 176 : 1;
+    for (int i = 0; i < 32; i++) {
+      const int e = k + i;
+      out[i] = dequant_elem(TYPE, row + (size_t)(e / be) * bb, e % be);
+    }
+  }
+}
+
 struct TcParams;
 template <int TYPE> struct IsInt4Ckpt { static constexpr bool value = (TYPE == 100 || TYPE == 101); };
 
@@ -209,6 +310,31 @@ __device__ __forceinline__ void dequant64_ckpt(const TcParams &p, int n, int k0,
 }
 
 template <int TYPE>
+__device__ __forceinline__ void dequant32_ckpt(const TcParams &p, int n, int k0, float *out) {
+  if constexpr (TYPE == TYPE_GPTQ4) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t w = (uint32_t)p.qweight[(size_t)(k0 / 8 + i) * p.N + n];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = k0 + 8 * i + j;
+        const int g = p.g_idx ? p.g_idx[k] : k / p.group;
+        out[8 * i + j] = (float)((int)((w >> (4 * j)) & 0xF) - 8) * __half2float(p.scales[(size_t)g * p.N + n]);
+      }
+    }
+  } else {
+    const int sh = 4 * ((n & 7) == 0 ? 0 : (n & 7) == 1 ? 4 : (n & 7) == 2 ? 1 : (n & 7) == 3 ? 5 : (n & 7) == 4 ? 2 : (n & 7) == 5 ? 6 : (n & 7) == 6 ? 3 : 7);
+#pragma unroll 8
+    for (int i = 0; i < 32; i++) {
+      const int k = k0 + i, g = k / p.group;
+      const int q = (int)(((uint32_t)p.qweight[(size_t)k * (p.N / 8) + n / 8] >> sh) & 0xF);
+      const int z = (int)(((uint32_t)p.qzeros[(size_t)g * (p.N / 8) + n / 8] >> sh) & 0xF);
+      out[i] = (float)(q - z) * __half2float(p.scales[(size_t)g * p.N + n]);
+    }
+  }
+}
+
+template <int TYPE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mmq_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -225,7 +351,7 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcParams p) {
   const int nk = p.K / TC_BK;
 
   if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&a_full[s], 1); mbar_init(&b_full[s], 8); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&a_full[s], 1); mbar_init(&b_full[s], TC_DQ_WARPS); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -280,35 +406,44 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcParams p) {
       if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
-    // ===================== dequantisers (8 warps, thread == weight row) =====================
-    const int r = tid - 64;                 // 0..255 row within the tile
+    // ===================== dequantisers (16 warps, two threads per weight row) =====================
+    const int dt_ = tid - 64;               // 0..511
+    const int r = dt_ >> 1, hf = dt_ & 1;   // row within the tile, which 32-weight half of the K-step
     const int row = n0 + r;
     const bool live = row < p.N;
     const uint8_t *wrow = p.w + (size_t)(live ? row : 0) * p.row_bytes;
     int stage = 0, phase = 0;
+    Raw32<TYPE> raw;
+    if constexpr (!IsInt4Ckpt<TYPE>::value) { if (live) load_raw32<TYPE>(wrow, 32 * hf, raw); }
     for (int kb = 0; kb < nk; kb++) {
-      float v[64];
+      const int k = kb * TC_BK + 32 * hf;
+      float v[32];
       if (live) {
-        if constexpr (IsInt4Ckpt<TYPE>::value) dequant64_ckpt<TYPE>(p, row, kb * TC_BK, v);
-        else dequant64<TYPE>(wrow, kb * TC_BK, v);
-      }
-      else {
+        if constexpr (IsInt4Ckpt<TYPE>::value) {
+          dequant32_ckpt<TYPE>(p, row, k, v);
+        } else {
+          const Raw32<TYPE> cur = raw;
+          if (kb + 1 < nk) load_raw32<TYPE>(wrow, k + TC_BK, raw);   // next K-step in flight
+          expand32<TYPE>(cur, wrow, k, v);
+        }
+      } else {
 #pragma unroll
-        for (int i = 0; i < 64; i++) v[i] = 0.f;
+        for (int i = 0; i < 32; i++) v[i] = 0.f;
       }
       mbar_wait(&empty[stage], phase ^ 1);
       uint8_t *dst = b_st + (size_t)stage * B_STAGE_BYTES + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
 #pragma unroll
-      for (int c = 0; c < 8; c++) {          // 16-byte chunk c of the row lands at chunk c ^ (r % 8)
+      for (int cc = 0; cc < 4; cc++) {       // 16-byte chunk c of the row lands at chunk c ^ (r % 8)
+        const int c = 4 * hf + cc;
         uint4 pk;
         if (p.b_fmt == 0) {
           __half2 *h = (__half2 *)&pk;
 #pragma unroll
-          for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+          for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[8 * cc + 2 * i], v[8 * cc + 2 * i + 1]);
         } else {
           __nv_bfloat162 *h = (__nv_bfloat162 *)&pk;
 #pragma unroll
-          for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+          for (int i = 0; i < 4; i++) h[i] = __floats2bfloat162_rn(v[8 * cc + 2 * i], v[8 * cc + 2 * i + 1]);
         }
         *(uint4 *)(dst + ((c ^ (r & 7)) << 4)) = pk;
       }
@@ -322,13 +457,13 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcParams p) {
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;        // two warps per quarter: columns [0,128) / [128,256)
+    const int cg = (warp - 2) >> 2;          // four warps per quarter: 64 columns each
 #pragma unroll 1
     for (int t = 0; t < TC_MT; t++) {
       const int tok = m0 + t * TC_BM + q * 32 + lane;
 #pragma unroll 1
-      for (int cb = 0; cb < 4; cb++) {
-        const int col0 = half * 128 + cb * 32;
+      for (int cb = 0; cb < 2; cb++) {
+        const int col0 = cg * 64 + cb * 32;
         uint32_t acc[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * TC_BN + col0), acc);
         if (tok < p.M) {
