@@ -304,6 +304,34 @@ def main():
                           2 + (2 if runner.padded_tiles > 1 else 1) for l in range(cfg.n_layers)]
     launches_per_token = 2 + sum(per_layer_launches) + 2  # advance+embed, layers, lm_head+argmax
 
+    # ---- prefill (BASELINE configs[2] shape, same Q4_K_M weights): the seven linear GEMMs of
+    # every layer for a 4096-token prompt on the tcgen05 dequant-GEMM (prefill attention is a
+    # SURVEY §8(f) "next" row and is not included) ------------------------------------------------
+    prefill = None
+    if world == 1:
+        from mistralrs_b200 import mmq, quant
+        PT = 4096
+        xs = {c: torch.randn(PT, c, device=dev).to(weights.dtype) for c in (cfg.hidden, cfg.inter, cfg.n_heads * cfg.head_dim)}
+        mats = []
+        for L in weights.layers:
+            for name in ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down"):
+                t, ty, rows, cols = L[name]
+                mats.append(quant.QTensor(t, ty, (rows, cols)))
+
+        def prefill_pass():
+            for w_ in mats:
+                mmq.forward(w_, xs[w_.shape[1]])
+        prefill_pass(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); prefill_pass(); e1.record(); torch.cuda.synchronize()
+        pf_s = e0.elapsed_time(e1) / 1e3
+        pf_flop = 2.0 * PT * sum(m.shape[0] * m.shape[1] for m in mats)
+        tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+        prefill = {"prompt_tokens": PT, "linears_tok_s": PT / pf_s, "linears_ms": pf_s * 1e3, "tflops": pf_flop / pf_s / 1e12,
+                   "tensor_peak_tflops": tpeak, "tensor_frac": pf_flop / pf_s / 1e12 / tpeak,
+                   "note": "linear layers only (7 GEMMs x layers, tcgen05 dequant-GEMM); prefill attention not included"}
+        del xs
+
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -328,6 +356,8 @@ def main():
         }
         if cpu:
             out["cpu_baseline"] = cpu
+        if prefill:
+            out["prefill"] = prefill
         print(json.dumps(out))
     if world > 1:
         # NCCL teardown with captured collectives still alive can hang: synchronise and leave

@@ -164,7 +164,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 
   if (warp == NCW) {
     // =========================== producer warp: lane == slot ===========================
-    // Weights are immutable, so streaming may start before the upstream kernel finished.
+    // Weights are immutable, so streaming may start before the upstream kernel finished.  Let the
+    // downstream kernel launch as early as possible too: it only prefetches ITS weights until its
+    // own griddepcontrol.wait, which orders it after this whole grid.
+    if (p.pdl) pdl_launch_dependents();
     int stage = 0, phase = 0;
     const int slot = lane;
     for (int base = vr0; base < vr1; base += P) {
@@ -193,7 +196,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
         if (++stage == nst) { stage = 0; phase ^= 1; }
       }
     }
-    if (p.pdl) pdl_launch_dependents();
     return;
   }
 

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   const int grp = tid / LPT, gl = tid % LPT;  // group, lane within group
   const int d0 = gl * 8;
 
+  if (p.pdl && tid == 0) pdl_launch_dependents();  // downstream GEMV may start prefetching its weights
   if (p.block_valid_mask != nullptr && p.block_valid_mask[tile] == 0) return;
   int seq, chunk_idx;
   if (p.tiles_are_partitions) { seq = tile / p.num_partitions; chunk_idx = tile % p.num_partitions; }
