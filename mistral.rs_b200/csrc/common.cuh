@@ -71,6 +71,18 @@ __device__ __forceinline__ void load_act8(const void *p, int64_t i, int dtype, f
     out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
   }
 }
+// 8 activations of a 16-bit dtype already held as one 16-byte register quad
+__device__ __forceinline__ void unpack_act8(const uint4 &v, int dtype, float *out) {
+  if (dtype == MRS_BF16) {
+    const __nv_bfloat162 *h = (const __nv_bfloat162 *)&v;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const float2 t = __bfloat1622float2(h[k]); out[2 * k] = t.x; out[2 * k + 1] = t.y; }
+  } else {
+    const __half2 *h = (const __half2 *)&v;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const float2 t = __half22float2(h[k]); out[2 * k] = t.x; out[2 * k + 1] = t.y; }
+  }
+}
 // round an f32 through the activation dtype (what materialising a tensor would do)
 __device__ __forceinline__ float round_act(float v, int dtype) {
   if (dtype == MRS_BF16) return __bfloat162float(__float2bfloat16_rn(v));

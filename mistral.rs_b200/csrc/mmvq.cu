@@ -33,6 +33,17 @@ constexpr int SLOTS = 2 * NCW;            // row-segments per stage (2 per consu
 constexpr int MAX_STAGES = 12;
 
 enum { MODE_PLAIN = 0, MODE_GLU = 1, MODE_QKV = 2 };
+
+#ifdef MRS_TIMELINE
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define MRS_STAMP(i) do { if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 16 + (i)] = gtimer(); } while (0)
+#else
+#define MRS_STAMP(i) do { } while (0)
+#endif
 enum { X_Q8_1 = 0, X_RAW = 1 };
 
 struct MmvqParams {
@@ -46,7 +57,10 @@ struct MmvqParams {
   int xkind, xdtype;
   int K, stride_col_y, stride_col_dst, ncols;
   int mode, activation, dst_dtype;
-  int nstages, vrows, pdl;
+  int nstages, vrows, pdl, flags;
+#ifdef MRS_TIMELINE
+  unsigned long long *dbg;  // dev build: [gridDim.x][16] globaltimer stamps of this launch
+#endif
 };
 
 template <int T> struct Geo {
@@ -152,10 +166,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
   uint8_t *ring = smem + off_ring;
 
   if (tid == 0) {
+    MRS_STAMP(0);
     for (int i = 0; i < nst; i++) { mbar_init(&full[i], 32); mbar_init(&empty[i], NCW); }
     fence_mbar_init();
   }
   __syncthreads();
+  if (tid == 0) MRS_STAMP(1);
 
   // contiguous virtual-row range of this CTA
   const int vr0 = (int)((long long)p.vrows * blockIdx.x / gridDim.x);
@@ -193,17 +209,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
         } else {
           mbar_arrive(&full[stage]);
         }
+        if (lane == 0 && base == vr0 && s == 0) MRS_STAMP(2);
         if (++stage == nst) { stage = 0; phase ^= 1; }
       }
     }
+    if (lane == 0) MRS_STAMP(10);
     return;
   }
 
   // ============================= consumer warps =============================
-  if (p.pdl) pdl_wait();  // activations come from the upstream kernel
-
   const int ctid = tid;  // 0 .. NCW*32-1
   constexpr int NCT = NCW * 32;
+  // The RMSNorm weight is immutable: pull it towards the SM before the PDL wait.
+  if (p.xkind == X_RAW && p.norm_w != nullptr) {
+    const int nbytes = p.K * ((p.xdtype == MRS_F32) ? 4 : 2);
+    for (int off = ctid * 128; off < nbytes; off += NCT * 128)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"((const char *)p.norm_w + off));
+  }
+  if (p.pdl) pdl_wait();  // activations come from the upstream kernel
+  if (tid == 0) MRS_STAMP(3);
   if (p.xkind == X_Q8_1) {
     // gather pre-quantised Q8_1 blocks straight into consumption order
     const block_q8_1 *y = (const block_q8_1 *)p.x;
@@ -239,9 +263,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
     const int nq8 = p.K / 32;
     float *red = (float *)(smem + 192);  // 8 floats of scratch inside the header page
     float2 *dsall = (float2 *)(smem + off_ds);
+    const int nchunks = p.K >> 3;                  // 8-element chunks; 4 neighbouring lanes = one Q8_1 block
+    const int nchunks_w = (nchunks + 31) & ~31;    // whole warps iterate together (shuffles below)
     for (int col = 0; col < NCOLS; col++) {
+      const bool live = col < p.ncols;
       float inv_rms = 1.0f;
-      if (p.norm_w != nullptr && col < p.ncols) {
+      if (p.norm_w != nullptr && live) {
         // pass 0: sum of squares, 8 elements (16 B for 16-bit dtypes) per thread per trip
         float ss = 0.f;
         for (int i = ctid * 8; i < p.K; i += NCT * 8) {
@@ -259,36 +286,61 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
         for (int i = 0; i < NCW; i++) tot += red[i];
         inv_rms = rsqrtf(tot / (float)p.K + p.eps);
       }
+      if (tid == 0) MRS_STAMP(4);
       int4 *n0 = xq0 + (size_t)col * npos, *n1 = xq1 + (size_t)col * npos;
       float2 *dsbuf = dsall + (size_t)col * nq8;
-      // pass 1: one thread per 32-element Q8_1 block, vector loads
-      for (int b = ctid; b < nq8; b += NCT) {
-        float v[32];
-        __align__(16) int8_t q[32];
-        if (col < p.ncols) {
-#pragma unroll
-          for (int k = 0; k < 4; k++) load_act8(p.x, (int64_t)col * p.K + b * 32 + 8 * k, p.xdtype, v + 8 * k);
+      // pass 1: one 8-element chunk per thread per trip (x re-read hits L1); the Q8_1 block of 4
+      // lanes is quantize_block_q8_1's arithmetic with its butterfly sum (i+16, i+8, then 4/2/1
+      // inside the lane) done by shuffles.  A compact loop: the prologue is issue-bound.
+#pragma unroll 1
+      for (int ch = ctid; ch < nchunks_w; ch += NCT) {
+        const bool ok = ch < nchunks;
+        float v[8];
+        if (ok && live) {
+          load_act8(p.x, (int64_t)col * p.K + ch * 8, p.xdtype, v);
           if (p.norm_w != nullptr) {
+            float wv[8];
+            load_act8(p.norm_w, ch * 8, p.xdtype, wv);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              float wv[8];
-              load_act8(p.norm_w, b * 32 + 8 * k, p.xdtype, wv);
-#pragma unroll
-              for (int i = 0; i < 8; i++) v[8 * k + i] = round_act(v[8 * k + i] * inv_rms * wv[i], p.xdtype);
-            }
+            for (int i = 0; i < 8; i++) v[i] = round_act(v[i] * inv_rms * wv[i], p.xdtype);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; i++) v[i] = 0.f;
+          for (int i = 0; i < 8; i++) v[i] = 0.f;
         }
-        float d, s;
-        quantize_block_q8_1(v, q, d, s);
-        dsbuf[b] = make_float2(d, s);
-        n0[b] = *(const int4 *)q;
-        n1[b] = *(const int4 *)(q + 16);
+        float am = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) am = fmaxf(am, fabsf(v[i]));
+        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) t[i] = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) t[i] = t[i] + __shfl_xor_sync(0xffffffffu, t[i], 1);
+#pragma unroll
+        for (int m = 4; m > 0; m >>= 1) {
+#pragma unroll
+          for (int i = 0; i < m; i++) t[i] = t[i] + t[i + m];
+        }
+        const float d = __fdividef(am, 127.0f);
+        uint32_t wq[2] = {0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int qi = (am == 0.0f) ? 0 : (int)(int8_t)roundf(__fdividef(v[i], d));
+          wq[i >> 2] |= (uint32_t)(qi & 0xff) << (8 * (i & 3));
+        }
+        if (ok) {
+          const int b = ch >> 2, part = ch & 3;
+          int2 *dstp = (int2 *)((part < 2 ? n0 : n1) + b) + (part & 1);
+          *dstp = make_int2((int)wq[0], (int)wq[1]);
+          if (part == 0)
+            dsbuf[b] = make_float2(__half2float(__float2half_rn(d)), __half2float(__float2half_rn(t[0])));
+        }
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NCT));
+    if (tid == 0) MRS_STAMP(5);
     // pass 2: natural order -> consumption order through registers
     {
       constexpr int MAXU = 4;  // positions per thread per column: K <= MAXU * 256 * 32
@@ -301,6 +353,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 #pragma unroll
         for (int k = 0; k < MAXU; k++) {
           const int pos = ctid + k * NCT;
+          if (k * NCT >= npos) break;  // CTA-uniform
           int blk = 0, c = 0;
           if (pos < npos) pos_to_unit<T>(pos, blk, c);
           if (pos < npos && blk < nblocks) {
@@ -322,6 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 #pragma unroll
         for (int k = 0; k < MAXU; k++) {
           const int pos = ctid + k * NCT;
+          if (k * NCT >= npos) break;  // CTA-uniform
           if (pos < npos) {
             const size_t idx = (size_t)col * npos + pos;
             xq0[idx] = make_int4(q[k][0], q[k][1], q[k][2], q[k][3]);
@@ -335,6 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
   }
   asm volatile("bar.sync 1, %0;" ::"n"(NCT));
 
+  if (tid == 0) MRS_STAMP(6);
   // ----------------------------- main streaming loop -----------------------------
   int stage = 0, phase = 0;
   const int lblk = lane % G::NBL;   // block within the segment owned by this lane
@@ -361,6 +416,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 
     for (int s = 0; s < nseg; s++) {
       mbar_wait(&full[stage], phase);
+      if (tid == 0 && base == vr0 && s == 0) MRS_STAMP(7);
       const uint8_t *st = ring + (uint32_t)stage * G::STAGE_BYTES + (uint32_t)(2 * warp) * G::SLOT_BYTES;
       // phase of this segment's start: (row phase + s * SEG_BYTES) mod 16
       const uint32_t sp = (uint32_t)(s * G::SEG_BYTES) & 15u;
@@ -406,6 +462,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
       if (++stage == nst) { stage = 0; phase ^= 1; }
     }
 
+    if (tid == 0 && base + P >= vr1) MRS_STAMP(8);
     // ----------------------------- reduce + epilogue -----------------------------
 #pragma unroll
     for (int r = 0; r < 2; r++)
@@ -448,11 +505,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
       }
     }
   }
+  if (tid == 0) {
+    MRS_STAMP(9);
+#ifdef MRS_TIMELINE
+    if (p.dbg != nullptr) { p.dbg[(size_t)blockIdx.x * 16 + 15] = gridDim.x; p.dbg[(size_t)blockIdx.x * 16 + 14] = (unsigned long long)p.vrows << 32 | (unsigned)p.K; }
+#endif
+  }
 }
 
 // ---------------------------------------------------------------- host side
+#ifdef MRS_TIMELINE
+static unsigned long long *g_dbg = nullptr;
+static int g_dbg_launch = 0, g_dbg_max = 0;
+// dev build only: stamps of launch i land at buf[i * 320 * 16 ...]; returns launches recorded so far
+extern "C" int mrs_mmvq_timeline(unsigned long long *buf, int max_launches) {
+  const int n = g_dbg_launch;
+  g_dbg = buf; g_dbg_max = max_launches; g_dbg_launch = 0;
+  return n;
+}
+#endif
 static int g_num_sms = 0;
 static int g_max_smem = 0;
+static int g_flags = 0;
+static int g_ctas_per_sm = 2;  // CTAs of ONE launch per SM; 1 leaves half an SM for the next launch (PDL overlap)
 
 static void query_device() {
   if (g_num_sms) return;
@@ -478,11 +553,23 @@ static cudaError_t launch_one(MmvqParams p, cudaStream_t stream) {
   int nst = MAX_STAGES;
   while (nst > 2 && xbytes + scratch + (size_t)nst * G::STAGE_BYTES > budget) nst--;
   size_t smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
+  int ctas_per_sm = g_ctas_per_sm;
+  if (smem > budget) {
+    // two CTAs do not fit (long K x wide blocks): one CTA per SM with a deeper ring, and a grid of
+    // one wave — a second wave of late CTAs would double the kernel's latency
+    ctas_per_sm = 1;
+    while (nst < 4 && xbytes + scratch + (size_t)(nst + 1) * G::STAGE_BYTES <= (size_t)g_max_smem - 1024) nst++;
+    smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
+  }
   if (smem > (size_t)g_max_smem) return cudaErrorInvalidConfiguration;
   p.nstages = nst;
+  p.flags = g_flags;
+#ifdef MRS_TIMELINE
+  p.dbg = (g_dbg != nullptr && g_dbg_launch < g_dbg_max) ? g_dbg + (size_t)(g_dbg_launch++) * 320 * 16 : nullptr;
+#endif
   const int P = (p.mode == MODE_GLU) ? NCW : SLOTS;
   int grid = (p.vrows + P - 1) / P;
-  const int max_grid = 2 * g_num_sms;
+  const int max_grid = ctas_per_sm * g_num_sms;
   if (grid > max_grid) grid = max_grid;
   if (grid < 1) grid = 1;
   auto kern = mmvq_stream_kernel<T, NCOLS, FAST>;
@@ -565,6 +652,8 @@ using namespace mrs;
 static int g_mrs_pdl = 0;  // PDL on reference-shaped launchers is opt-in (mrs_set_pdl)
 
 extern "C" void mrs_set_pdl(int enabled) { g_mrs_pdl = enabled; }
+extern "C" void mrs_set_mmvq_flags(int f) { g_flags = f; }
+extern "C" void mrs_set_mmvq_ctas_per_sm(int n) { g_ctas_per_sm = n < 1 ? 1 : (n > 2 ? 2 : n); }
 
 static inline void report(cudaError_t e, const char *what) {
   if (e != cudaSuccess) fprintf(stderr, "mrs_b200: %s failed: %s\n", what, cudaGetErrorString(e));

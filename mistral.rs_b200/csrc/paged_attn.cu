@@ -448,9 +448,11 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
           if (g >= gsize) continue;
           const int h = h0 + g;
           float M = -INFINITY;
+#pragma unroll 4
           for (int t = t0; t < t1; t++) M = fmaxf(M, __ldcg(p.tmp_lse + (int64_t)t * p.num_heads + h));
           float W = 0.f, acc = 0.f;
           if (M > -INFINITY) {
+#pragma unroll 4
             for (int t = t0; t < t1; t++) {
               const float w = __expf(__ldcg(p.tmp_lse + (int64_t)t * p.num_heads + h) - M);
               const unsigned short raw = __ldcg((const unsigned short *)p.tmp_o + ((int64_t)t * p.num_heads + h) * D + d);

@@ -209,12 +209,23 @@ class LlamaWeights:
         return (t, dt, rows, cols)
 
 
+def runner_split_pages(block_size, batch, n_kv_heads, max_ctx, sm_count=148, min_tokens=64):
+    """Split-KV chunk (in pages) for the whole-token decode path: enough tiles that
+    batch x kv_heads x tiles covers the SMs (one attention CTA per SM), chunks of at least
+    `min_tokens`.  The reference's host policy (metadata.rs:61-86, kv_index.decode_split_pages) never
+    goes below 256-token chunks, which leaves 16 CTAs for a batch-1 8-KV-head decode; the kernels
+    accept any plan, this one only changes how finely the same sum is split."""
+    tiles = max(1, sm_count // max(1, batch * n_kv_heads))
+    tokens = max(min_tokens, -(-max_ctx // tiles))
+    return max(1, -(-tokens // block_size))
+
+
 class LlamaRunner:
     """Owns KV cache + scratch + per-step metadata for a batch of sequences and drives
     mrs_llama_decode_step / mrs_decode_advance (eagerly or as a captured CUDA graph)."""
 
     def __init__(self, weights: LlamaWeights, batch=1, max_ctx=512, pdl=False, sm_count=148, comm=None,
-                 fused_attention=True):
+                 fused_attention=True, split_policy="sm_fill", split_min_tokens=64):
         cfg, dev, dt = weights.cfg, weights.device, weights.dtype
         self.w, self.cfg, self.dev, self.dt, self.B = weights, cfg, dev, dt, batch
         tp = weights.tp_size
@@ -226,7 +237,9 @@ class LlamaRunner:
         self.tables = [self.pool.get_new_blocks(self.max_blocks) for _ in range(batch)]
         self.block_tables = torch.tensor(self.tables, dtype=torch.int32, device=dev)
         self.context_lens = torch.zeros(batch, dtype=torch.int32, device=dev)
-        self.split_pages = kv_index.decode_split_pages(bs, batch, self.n_kv, max_ctx, sm_count=sm_count)
+        self.split_pages = (kv_index.decode_split_pages(bs, batch, self.n_kv, max_ctx, sm_count=sm_count)
+                            if split_policy == "reference" else
+                            runner_split_pages(bs, batch, self.n_kv, max_ctx, sm_count, split_min_tokens))
         self.padded_tiles = batch * -(-self.max_blocks // self.split_pages)
         if self.padded_tiles <= batch:        # a single chunk per request: unsplit plan
             self.split_pages, self.padded_tiles = 0, batch

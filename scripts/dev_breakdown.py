@@ -4,7 +4,9 @@ import numpy as np, torch
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
 import __graft_entry__ as g
-g.load_package()
+pkg = g.load_package()
+if os.environ.get("MRS_DEV_LIB"):
+    pkg.LIB_PATH = os.environ["MRS_DEV_LIB"]   # dev A/B against another build
 from mistralrs_b200 import model as M
 dev = torch.device("cuda:0")
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 32
@@ -26,8 +28,7 @@ def timed(run, mask, reps=30):
     e1.record(); torch.cuda.synchronize()
     run.step_struct.skip_mask = 0
     return e0.elapsed_time(e1) / reps * 1e3
-for pdl in (0, 1):
-    for fused in (1, 0):
-        run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=bool(pdl), fused_attention=bool(fused))
-        full, gemv, attn = timed(run, 0), timed(run, 1), timed(run, 2)
-        print(f"layers={layers} pdl={pdl} fused_attn={fused}: full {full:8.1f} us  gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)
+for pol, mt in (("reference", 0), ("sm_fill", 64), ("sm_fill", 32), ("sm_fill", 16)):
+    run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=True, fused_attention=True, split_policy=pol, split_min_tokens=mt)
+    full, gemv, attn = timed(run, 0), timed(run, 1), timed(run, 2)
+    print(f"layers={layers} split={pol}/{mt} pages={run.split_pages} tiles={run.padded_tiles}: full {full:8.1f} us  gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)
