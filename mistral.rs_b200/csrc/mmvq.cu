@@ -34,6 +34,10 @@ constexpr int MAX_STAGES = 12;
 
 enum { MODE_PLAIN = 0, MODE_GLU = 1, MODE_QKV = 2 };
 
+__device__ __forceinline__ uint4 sel_u4(bool first, const uint4 &a, const uint4 &b) {
+  return make_uint4(first ? a.x : b.x, first ? a.y : b.y, first ? a.z : b.z, first ? a.w : b.w);
+}
+
 #ifdef MRS_TIMELINE
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -220,11 +224,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
   // ============================= consumer warps =============================
   const int ctid = tid;  // 0 .. NCW*32-1
   constexpr int NCT = NCW * 32;
-  // The RMSNorm weight is immutable: pull it towards the SM before the PDL wait.
+  // The RMSNorm weight is immutable: fetch it before the PDL wait — the first two chunks of every
+  // thread (all of K <= 4096) into registers, anything longer only towards the cache.
+  const bool reg16 = p.xkind == X_RAW && p.xdtype != MRS_F32;
+  uint4 nwr0 = make_uint4(0u, 0u, 0u, 0u), nwr1 = nwr0;
   if (p.xkind == X_RAW && p.norm_w != nullptr) {
-    const int nbytes = p.K * ((p.xdtype == MRS_F32) ? 4 : 2);
-    for (int off = ctid * 128; off < nbytes; off += NCT * 128)
-      asm volatile("prefetch.global.L1 [%0];" ::"l"((const char *)p.norm_w + off));
+    if (reg16) {
+      if (ctid < (p.K >> 3)) nwr0 = __ldg((const uint4 *)p.norm_w + ctid);
+      if (ctid + NCT < (p.K >> 3)) nwr1 = __ldg((const uint4 *)p.norm_w + ctid + NCT);
+    }
+    if (!reg16 || (p.K >> 3) > 2 * NCT) {
+      const int nbytes = p.K * ((p.xdtype == MRS_F32) ? 4 : 2);
+      for (int off = ctid * 128; off < nbytes; off += NCT * 128)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"((const char *)p.norm_w + off));
+    }
   }
   if (p.pdl) pdl_wait();  // activations come from the upstream kernel
   if (tid == 0) MRS_STAMP(3);
@@ -268,10 +281,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
     for (int col = 0; col < NCOLS; col++) {
       const bool live = col < p.ncols;
       float inv_rms = 1.0f;
+      // the first two chunks of each thread stay in registers between the passes (16-bit dtypes)
+      uint4 xr0 = make_uint4(0u, 0u, 0u, 0u), xr1 = xr0;
+      if (reg16 && live) {
+        const uint4 *xc = (const uint4 *)((const uint16_t *)p.x + (int64_t)col * p.K);
+        if (ctid < nchunks) xr0 = xc[ctid];
+        if (ctid + NCT < nchunks) xr1 = xc[ctid + NCT];
+      }
       if (p.norm_w != nullptr && live) {
-        // pass 0: sum of squares, 8 elements (16 B for 16-bit dtypes) per thread per trip
+        // pass 0: sum of squares, 8 elements (16 B for 16-bit dtypes) per thread per trip, in
+        // chunk order ctid, ctid+NCT, ... (zero chunks add exactly nothing)
         float ss = 0.f;
-        for (int i = ctid * 8; i < p.K; i += NCT * 8) {
+        int i0 = ctid * 8;
+        if (reg16) {
+          float v[8];
+          unpack_act8(xr0, p.xdtype, v);
+#pragma unroll
+          for (int e = 0; e < 8; e++) ss = fmaf(v[e], v[e], ss);
+          unpack_act8(xr1, p.xdtype, v);
+#pragma unroll
+          for (int e = 0; e < 8; e++) ss = fmaf(v[e], v[e], ss);
+          i0 += 2 * NCT * 8;
+        }
+        for (int i = i0; i < p.K; i += NCT * 8) {
           float v[8];
           load_act8(p.x, (int64_t)col * p.K + i, p.xdtype, v);
 #pragma unroll
@@ -292,15 +324,19 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
       // pass 1: one 8-element chunk per thread per trip (x re-read hits L1); the Q8_1 block of 4
       // lanes is quantize_block_q8_1's arithmetic with its butterfly sum (i+16, i+8, then 4/2/1
       // inside the lane) done by shuffles.  A compact loop: the prologue is issue-bound.
+      int it = 0;
 #pragma unroll 1
-      for (int ch = ctid; ch < nchunks_w; ch += NCT) {
+      for (int ch = ctid; ch < nchunks_w; ch += NCT, it++) {
         const bool ok = ch < nchunks;
+        const bool inreg = reg16 && it < 2;
         float v[8];
         if (ok && live) {
-          load_act8(p.x, (int64_t)col * p.K + ch * 8, p.xdtype, v);
+          if (inreg) unpack_act8(sel_u4(it == 0, xr0, xr1), p.xdtype, v);
+          else load_act8(p.x, (int64_t)col * p.K + ch * 8, p.xdtype, v);
           if (p.norm_w != nullptr) {
             float wv[8];
-            load_act8(p.norm_w, ch * 8, p.xdtype, wv);
+            if (inreg) unpack_act8(sel_u4(it == 0, nwr0, nwr1), p.xdtype, wv);
+            else load_act8(p.norm_w, ch * 8, p.xdtype, wv);
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = round_act(v[i] * inv_rms * wv[i], p.xdtype);
           }
@@ -428,7 +464,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
         const int c = (Q::UPB == 1) ? 0 : ui * G::CPS + lsub;
         const uint32_t boff = (Q::UPB == 1) ? (uint32_t)(ui * 32 * Q::BYTES) : 0u;
         const bool ulive = (Q::UPB == 1) ? (s * G::SEG_BLOCKS + ui * 32 + lblk) < nblocks : live;
-        if (ulive) {
+        if (ulive && (valid[0] || valid[1])) {  // a warp whose two slots are both padding skips the math
           typename Q::W w0, w1;
           Q::template load<FAST>(wp0 + boff, c, w0);
           Q::template load<FAST>(wp1 + boff, c, w1);
