@@ -26,9 +26,10 @@
 
 namespace mrs {
 
-constexpr int NCW = 8;                    // consumer warps
-constexpr int NTHREADS = (NCW + 1) * 32;  // + producer warp
-constexpr int SLOTS = 2 * NCW;            // row-segments per stage (2 per consumer warp)
+// Two CTA shapes: NCW = 8 consumer warps (two CTAs per SM) or 16 (one CTA per SM: the activation
+// prologue, identical in every CTA, is then computed once per SM instead of twice).  + 1 producer
+// warp; a stage holds 2 row-segments per consumer warp.
+constexpr int SSW = 8;  // warps that take part in the RMSNorm sum of squares (fixes its summation order)
 
 constexpr int MAX_STAGES = 12;
 
@@ -67,8 +68,9 @@ struct MmvqParams {
 #endif
 };
 
-template <int T> struct Geo {
+template <int T, int NCW> struct Geo {
   using Q = QT<T>;
+  static constexpr int SLOTS = 2 * NCW;
   static constexpr int UPL = Q::UPL;                         // units per lane per K segment
   static constexpr int SEG_UNITS = 32 * UPL;                 // 32-weight units per K segment
   static constexpr int SEG_BLOCKS = SEG_UNITS / Q::UPB;      // weight blocks per segment (NB)
@@ -84,7 +86,7 @@ template <int T> struct Geo {
 
 // position p in the consumption-ordered activation array <-> (weight block, chunk)
 template <int T> __device__ __forceinline__ void pos_to_unit(int pos, int &blk, int &c) {
-  using G = Geo<T>;
+  using G = Geo<T, 8>;  // segment geometry does not depend on the CTA shape
   if constexpr (QT<T>::UPB == 1) {
     blk = pos; c = 0;
   } else {
@@ -141,10 +143,11 @@ __device__ __forceinline__ void quantize_block_q8_1(const float *v, int8_t *q, f
   s_out = __half2float(__float2half_rn(s[0]));
 }
 
-template <int T, int NCOLS, bool FAST>
-__global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqParams p) {
+template <int T, int NCOLS, bool FAST, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, NCW == 8 ? 2 : 1) mmvq_stream_kernel(const MmvqParams p) {
   using Q = QT<T>;
-  using G = Geo<T>;
+  using G = Geo<T, NCW>;
+  constexpr int SLOTS = 2 * NCW;
   extern __shared__ __align__(128) uint8_t smem[];
 
   const int tid = threadIdx.x;
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
   // ============================= consumer warps =============================
   const int ctid = tid;  // 0 .. NCW*32-1
   constexpr int NCT = NCW * 32;
+  constexpr int SST = SSW * 32;  // threads in the sum-of-squares pass (canonical order for both CTA shapes)
   // The RMSNorm weight is immutable: fetch it before the PDL wait — the first two chunks of every
   // thread (all of K <= 4096) into registers, anything longer only towards the cache.
   const bool reg16 = p.xkind == X_RAW && p.xdtype != MRS_F32;
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
   if (p.xkind == X_RAW && p.norm_w != nullptr) {
     if (reg16) {
       if (ctid < (p.K >> 3)) nwr0 = __ldg((const uint4 *)p.norm_w + ctid);
-      if (ctid + NCT < (p.K >> 3)) nwr1 = __ldg((const uint4 *)p.norm_w + ctid + NCT);
+      if (NCW == SSW && ctid + NCT < (p.K >> 3)) nwr1 = __ldg((const uint4 *)p.norm_w + ctid + NCT);
     }
     if (!reg16 || (p.K >> 3) > 2 * NCT) {
       const int nbytes = p.K * ((p.xdtype == MRS_F32) ? 4 : 2);
@@ -286,14 +290,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
       if (reg16 && live) {
         const uint4 *xc = (const uint4 *)((const uint16_t *)p.x + (int64_t)col * p.K);
         if (ctid < nchunks) xr0 = xc[ctid];
-        if (ctid + NCT < nchunks) xr1 = xc[ctid + NCT];
+        if (ctid < SST && ctid + SST < nchunks) xr1 = xc[ctid + SST];
       }
       if (p.norm_w != nullptr && live) {
-        // pass 0: sum of squares, 8 elements (16 B for 16-bit dtypes) per thread per trip, in
-        // chunk order ctid, ctid+NCT, ... (zero chunks add exactly nothing)
+        // pass 0: sum of squares by the first SST threads, 8 elements (16 B for 16-bit dtypes)
+        // per thread per trip, in chunk order ctid, ctid+SST, ... (zero chunks add exactly nothing)
         float ss = 0.f;
         int i0 = ctid * 8;
-        if (reg16) {
+        if (ctid >= SST) {
+          i0 = p.K;
+        } else if (reg16) {
           float v[8];
           unpack_act8(xr0, p.xdtype, v);
 #pragma unroll
@@ -301,9 +307,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
           unpack_act8(xr1, p.xdtype, v);
 #pragma unroll
           for (int e = 0; e < 8; e++) ss = fmaf(v[e], v[e], ss);
-          i0 += 2 * NCT * 8;
+          i0 += 2 * SST * 8;
         }
-        for (int i = i0; i < p.K; i += NCT * 8) {
+        for (int i = i0; i < p.K; i += SST * 8) {
           float v[8];
           load_act8(p.x, (int64_t)col * p.K + i, p.xdtype, v);
 #pragma unroll
@@ -311,11 +317,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
         }
         ss = warp_sum(ss);
         asm volatile("bar.sync 1, %0;" ::"n"(NCT));
-        if (lane == 0) red[warp] = ss;
+        if (lane == 0 && warp < SSW) red[warp] = ss;
         asm volatile("bar.sync 1, %0;" ::"n"(NCT));
         float tot = 0.f;
 #pragma unroll
-        for (int i = 0; i < NCW; i++) tot += red[i];
+        for (int i = 0; i < SSW; i++) tot += red[i];
         inv_rms = rsqrtf(tot / (float)p.K + p.eps);
       }
       if (tid == 0) MRS_STAMP(4);
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) mmvq_stream_kernel(const MmvqPara
 #pragma unroll 1
       for (int ch = ctid; ch < nchunks_w; ch += NCT, it++) {
         const bool ok = ch < nchunks;
-        const bool inreg = reg16 && it < 2;
+        const bool inreg = reg16 && (it == 0 || (it == 1 && NCW == SSW));
         float v[8];
         if (ok && live) {
           if (inreg) unpack_act8(sel_u4(it == 0, xr0, xr1), p.xdtype, v);
@@ -575,27 +581,41 @@ static void query_device() {
   if (g_max_smem <= 0) g_max_smem = 227 * 1024;
 }
 
-template <int T, int NCOLS, bool FAST>
-static cudaError_t launch_one(MmvqParams p, cudaStream_t stream) {
-  using G = Geo<T>;
+template <int T, int NCOLS, bool FAST, int NCW>
+static cudaError_t launch_one(MmvqParams p, cudaStream_t stream, bool probe_only) {
+  using G = Geo<T, NCW>;
+  constexpr int SLOTS = 2 * NCW;
   query_device();
   const int nblocks = p.K / QT<T>::QK;
   const int nseg = (nblocks + G::SEG_BLOCKS - 1) / G::SEG_BLOCKS;
   const int npos = nseg * G::SEG_UNITS;
   const size_t xbytes = 256 + (size_t)NCOLS * npos * G::XU_BYTES + 128;
   const size_t scratch = (p.xkind == X_RAW) ? (size_t)NCOLS * (p.K / 32) * 8 : 0;
-  // two CTAs per SM by design: keep each under half of the SM's shared memory
-  const size_t budget = (size_t)g_max_smem / 2 - 1024;
-  int nst = MAX_STAGES;
-  while (nst > 2 && xbytes + scratch + (size_t)nst * G::STAGE_BYTES > budget) nst--;
-  size_t smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
-  int ctas_per_sm = g_ctas_per_sm;
-  if (smem > budget) {
-    // two CTAs do not fit (long K x wide blocks): one CTA per SM with a deeper ring, and a grid of
-    // one wave — a second wave of late CTAs would double the kernel's latency
+  const size_t full = (size_t)g_max_smem - 1024;
+  int nst, ctas_per_sm;
+  size_t smem;
+  if (NCW == 16) {
+    // one fat CTA per SM: needs at least a double-buffered ring
     ctas_per_sm = 1;
-    while (nst < 4 && xbytes + scratch + (size_t)(nst + 1) * G::STAGE_BYTES <= (size_t)g_max_smem - 1024) nst++;
+    nst = MAX_STAGES;
+    while (nst > 2 && xbytes + scratch + (size_t)nst * G::STAGE_BYTES > full) nst--;
     smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
+    if (smem > full) return cudaErrorInvalidConfiguration;
+    if (probe_only) return cudaSuccess;
+  } else {
+    // two CTAs per SM by design: keep each under half of the SM's shared memory
+    const size_t budget = (size_t)g_max_smem / 2 - 1024;
+    nst = MAX_STAGES;
+    while (nst > 2 && xbytes + scratch + (size_t)nst * G::STAGE_BYTES > budget) nst--;
+    smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
+    ctas_per_sm = g_ctas_per_sm;
+    if (smem > budget) {
+      // two CTAs do not fit (long K x wide blocks): one CTA per SM with a deeper ring, and a grid
+      // of one wave — a second wave of late CTAs would double the kernel's latency
+      ctas_per_sm = 1;
+      while (nst < 4 && xbytes + scratch + (size_t)(nst + 1) * G::STAGE_BYTES <= full) nst++;
+      smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
+    }
   }
   if (smem > (size_t)g_max_smem) return cudaErrorInvalidConfiguration;
   p.nstages = nst;
@@ -608,7 +628,7 @@ static cudaError_t launch_one(MmvqParams p, cudaStream_t stream) {
   const int max_grid = ctas_per_sm * g_num_sms;
   if (grid > max_grid) grid = max_grid;
   if (grid < 1) grid = 1;
-  auto kern = mmvq_stream_kernel<T, NCOLS, FAST>;
+  auto kern = mmvq_stream_kernel<T, NCOLS, FAST, NCW>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
@@ -616,7 +636,7 @@ static cudaError_t launch_one(MmvqParams p, cudaStream_t stream) {
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(NTHREADS);
+  cfg.blockDim = dim3((NCW + 1) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -636,8 +656,15 @@ static cudaError_t launch_type(MmvqParams p, cudaStream_t stream) {
   for (int m = 0; m < 3; m++)
     if (p.w[m] != nullptr && ((uintptr_t)p.w[m] % Q::WALIGN) != 0) fast = false;
   const int b = p.ncols;
-#define MRS_DISPATCH(NC)                                                        \
-  return fast ? launch_one<T, NC, true>(p, stream) : launch_one<T, NC, false>(p, stream)
+  // CTA shape: 16 consumer warps / one CTA per SM whenever a double-buffered ring fits (the
+  // prologue is then computed once per SM); flags bit1 forces the 8-warp shape (dev A/B)
+#define MRS_DISPATCH(NC)                                                                         \
+  do {                                                                                           \
+    bool wide = !(g_flags & 2) &&                                                                \
+                (fast ? launch_one<T, NC, true, 16>(p, stream, true) : launch_one<T, NC, false, 16>(p, stream, true)) == cudaSuccess; \
+    if (wide) return fast ? launch_one<T, NC, true, 16>(p, stream, false) : launch_one<T, NC, false, 16>(p, stream, false); \
+    return fast ? launch_one<T, NC, true, 8>(p, stream, false) : launch_one<T, NC, false, 8>(p, stream, false); \
+  } while (0)
   if (b == 1) { MRS_DISPATCH(1); }
   if (b == 2) { MRS_DISPATCH(2); }
   if (b <= 4) { MRS_DISPATCH(4); }
@@ -789,6 +816,6 @@ extern "C" int mrs_mmvq_fused(int ggml_type, int mode, int dt, const void *w0, c
   p.K = K; p.stride_col_dst = n0; p.ncols = b_size; p.mode = mode; p.activation = activation;
   p.dst_dtype = dt; p.pdl = pdl;
   p.vrows = (mode == MODE_QKV) ? n0 + n1 + n2 : n0;
-  if (K > 4 * NCW * 32 * 32) return (int)cudaErrorInvalidValue;  // fused prologue limit (MAXU)
+  if (K > 4 * 8 * 32 * 32) return (int)cudaErrorInvalidValue;  // fused prologue limit (MAXU, 8-warp shape)
   return (int)mmvq_dispatch(ggml_type, p, (cudaStream_t)stream);
 }

@@ -28,7 +28,10 @@ def timed(run, mask, reps=30):
     e1.record(); torch.cuda.synchronize()
     run.step_struct.skip_mask = 0
     return e0.elapsed_time(e1) / reps * 1e3
-for pol, mt in (("reference", 0), ("sm_fill", 64), ("sm_fill", 32), ("sm_fill", 16)):
-    run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=True, fused_attention=True, split_policy=pol, split_min_tokens=mt)
+import ctypes
+from mistralrs_b200 import lib
+for flags in (0, 2):
+    lib().mrs_set_mmvq_flags(ctypes.c_int(flags))
+    run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=True, fused_attention=True)
     full, gemv, attn = timed(run, 0), timed(run, 1), timed(run, 2)
-    print(f"layers={layers} split={pol}/{mt} pages={run.split_pages} tiles={run.padded_tiles}: full {full:8.1f} us  gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)
+    print(f"layers={layers} mmvq_flags={flags} (2 = force 8-warp CTAs): full {full:8.1f} us  gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)
