@@ -45,6 +45,11 @@ MRS_MMVQ_DECL_T(q2_k) MRS_MMVQ_DECL_T(q3_k) MRS_MMVQ_DECL_T(q4_k) MRS_MMVQ_DECL_
 /* Programmatic dependent launch for the reference-shaped launchers (default off). */
 void mrs_set_pdl(int enabled);
 
+/* Tuning/diagnostic switches of the decode GEMV.  bit 1 (value 2): always use the 8-consumer-warp
+ * CTA shape (two CTAs per SM) instead of picking the 16-warp, one-CTA-per-SM shape when its
+ * double-buffered ring fits.  Both shapes produce bit-identical results (tests/test_mmvq_gpu.py). */
+void mrs_set_mmvq_flags(int flags);
+
 /* One launch for [RMSNorm ->] Q8_1 -> GEMV [-> GLU | + residual]: replaces rms_norm +
  * launch_mmvq_gguf_quantize_q8_1_* + launch_mmvq_gguf_*  (+ the residual add).
  * mode 0 plain (w0), 1 fused GLU (w0 = gate, w1 = up), 2 fused QKV (w0,w1[,w2]; n2 may be 0).

@@ -119,6 +119,33 @@ def test_fused_prologue_matches_two_step(cuda):
         assert diff <= 2.0 ** -6 * want.float().abs().max().item(), (dtype, diff)
 
 
+@pytest.mark.parametrize("dtype", ["q4_k", "q6_k", "q8_0", "q4_0", "q2_k"])
+def test_cta_shapes_agree(cuda, dtype):
+    # the 16-warp (one CTA per SM) and 8-warp (two per SM) kernels must agree bit for bit, with
+    # pre-quantised activations, with the fused RMSNorm prologue, fused GLU and batch > 1
+    import ctypes
+    from mistralrs_b200 import lib
+    K, N = 4096, 200
+    w = quant.QTensor(to_dev(make_weight(dtype, N, K, 40).reshape(-1), cuda), dtype, (N, K))
+    w2 = quant.QTensor(to_dev(make_weight(dtype, N, K, 41).reshape(-1), cuda), dtype, (N, K))
+    nw = to_dev(1.0 + 0.1 * make_acts(1, K, 42, "bf16")[0], cuda, "bf16")
+    outs = []
+    try:
+        for flags in (0, 2):
+            lib().mrs_set_mmvq_flags(ctypes.c_int(flags))
+            o = []
+            for batch in (1, 3):
+                x = to_dev(make_acts(batch, K, 43 + batch, "bf16"), cuda, "bf16")
+                o.append(quant.plain(w, x))
+                o.append(quant.fused_glu(w, w2, x, quant.GluActivationType(0)))
+                o.append(quant.mmvq_fused(w, x, norm_w=nw, eps=1e-5))
+            outs.append(o)
+    finally:
+        lib().mrs_set_mmvq_flags(ctypes.c_int(0))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def test_argument_errors(cuda):
     w = quant.QTensor(torch.zeros(144 * 4, dtype=torch.uint8, device=cuda), "q4_k", (4, 256))
     with pytest.raises(ValueError, match="batch size 9"):
