@@ -300,9 +300,12 @@ def main():
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     achieved = weight_bytes / gemv_s / 1e9
-    per_layer_launches = [(5 if M.tensor_type(cfg, "attn_v", l) == M.tensor_type(cfg, "attn_q", l) else 6) +
-                          2 + (2 if runner.padded_tiles > 1 else 1) for l in range(cfg.n_layers)]
-    launches_per_token = 2 + sum(per_layer_launches) + 2  # advance+embed, layers, lm_head+argmax
+    # our kernels per token: per layer qkv (1, or 2 where attn_v has its own ggml type) + fused
+    # rope/cache/attention/merge (1) + o_proj + gate_up + down (+2 residual adds under TP), plus
+    # advance + embedding + lm_head + argmax
+    per_layer_launches = [(1 if M.tensor_type(cfg, "attn_v", l) == M.tensor_type(cfg, "attn_q", l) else 2) + 1 + 3 +
+                          (2 if world > 1 else 0) for l in range(cfg.n_layers)]
+    launches_per_token = 2 + sum(per_layer_launches) + 2
 
     # ---- prefill (BASELINE configs[2] shape, same Q4_K_M weights): the seven linear GEMMs of
     # every layer for a 4096-token prompt on the tcgen05 dequant-GEMM (prefill attention is a
@@ -345,7 +348,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": "Llama-3-8B GGUF Q4_K_M decode batch=1, 128-token prompt -> +256 tokens, paged KV block_size=16 (HND)",
                        "parallelism": f"tp{world}", "l2": "inputs larger than L2 (4.6 GB of weights streamed per token)",
-                       "layers": cfg.n_layers, "pdl": bool(args.pdl)},
+                       "layers": cfg.n_layers, "pdl": bool(args.pdl),
+                       "kv_split": f"{runner.split_pages * cfg.block_size}-token chunks, {runner.padded_tiles} tiles (SM-filling plan)"},
             "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": 4 * ntok, "d2h_bytes_per_step": 4 * ntok},
             "gpu_launches": launches_per_token * ntok,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

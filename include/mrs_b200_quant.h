@@ -45,10 +45,11 @@ MRS_MMVQ_DECL_T(q2_k) MRS_MMVQ_DECL_T(q3_k) MRS_MMVQ_DECL_T(q4_k) MRS_MMVQ_DECL_
 /* Programmatic dependent launch for the reference-shaped launchers (default off). */
 void mrs_set_pdl(int enabled);
 
-/* Tuning/diagnostic switches of the decode GEMV.  bit 1 (value 2): always use the 8-consumer-warp
- * CTA shape (two CTAs per SM) instead of picking the 16-warp, one-CTA-per-SM shape when its
- * double-buffered ring fits.  Both shapes produce bit-identical results (tests/test_mmvq_gpu.py). */
+/* Tuning/diagnostic switches of the decode GEMV.  bit 2 (value 4): allow the 16-consumer-warp,
+ * one-CTA-per-SM kernel shape (only in builds with -DMRS_MMVQ_WIDE, see mrs_mmvq_has_wide) for launches
+ * that stream at most (flags >> 8) MiB of weights.  Both shapes produce bit-identical results. */
 void mrs_set_mmvq_flags(int flags);
+int mrs_mmvq_has_wide(void);
 
 /* One launch for [RMSNorm ->] Q8_1 -> GEMV [-> GLU | + residual]: replaces rms_norm +
  * launch_mmvq_gguf_quantize_q8_1_* + launch_mmvq_gguf_*  (+ the residual add).

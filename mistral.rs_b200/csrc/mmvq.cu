@@ -569,6 +569,7 @@ extern "C" int mrs_mmvq_timeline(unsigned long long *buf, int max_launches) {
 static int g_num_sms = 0;
 static int g_max_smem = 0;
 static int g_flags = 0;
+static long long g_wide_max_bytes = 24ll << 20;
 static int g_ctas_per_sm = 2;  // CTAs of ONE launch per SM; 1 leaves half an SM for the next launch (PDL overlap)
 
 static void query_device() {
@@ -656,15 +657,26 @@ static cudaError_t launch_type(MmvqParams p, cudaStream_t stream) {
   for (int m = 0; m < 3; m++)
     if (p.w[m] != nullptr && ((uintptr_t)p.w[m] % Q::WALIGN) != 0) fast = false;
   const int b = p.ncols;
-  // CTA shape: 16 consumer warps / one CTA per SM whenever a double-buffered ring fits (the
-  // prologue is then computed once per SM); flags bit1 forces the 8-warp shape (dev A/B)
+  size_t wbytes = 0;  // weight bytes this launch streams
+  for (int m = 0; m < 3; m++)
+    if (p.w[m] != nullptr) wbytes += (size_t)p.nrows[m] * row_bytes;
+  // CTA shape.  Default: 8 consumer warps, two CTAs per SM — with the short K segments (UPL) the
+  // two rings hand stages over at CTA granularity and pipeline best.  The 16-warp / one-CTA-per-SM
+  // shape (activation prologue once per SM) is compiled with -DMRS_MMVQ_WIDE and chosen for launches
+  // streaming at most g_wide_max_bytes when flags bit 2 is set; it measured slower end to end.
+#ifdef MRS_MMVQ_WIDE
 #define MRS_DISPATCH(NC)                                                                         \
   do {                                                                                           \
-    bool wide = !(g_flags & 2) &&                                                                \
+    bool wide = (g_flags & 4) && wbytes <= (size_t)g_wide_max_bytes &&                           \
                 (fast ? launch_one<T, NC, true, 16>(p, stream, true) : launch_one<T, NC, false, 16>(p, stream, true)) == cudaSuccess; \
     if (wide) return fast ? launch_one<T, NC, true, 16>(p, stream, false) : launch_one<T, NC, false, 16>(p, stream, false); \
     return fast ? launch_one<T, NC, true, 8>(p, stream, false) : launch_one<T, NC, false, 8>(p, stream, false); \
   } while (0)
+#else
+#define MRS_DISPATCH(NC)                                                                         \
+  return fast ? launch_one<T, NC, true, 8>(p, stream, false) : launch_one<T, NC, false, 8>(p, stream, false)
+  (void)wbytes;
+#endif
   if (b == 1) { MRS_DISPATCH(1); }
   if (b == 2) { MRS_DISPATCH(2); }
   if (b <= 4) { MRS_DISPATCH(4); }
@@ -715,7 +727,14 @@ using namespace mrs;
 static int g_mrs_pdl = 0;  // PDL on reference-shaped launchers is opt-in (mrs_set_pdl)
 
 extern "C" void mrs_set_pdl(int enabled) { g_mrs_pdl = enabled; }
-extern "C" void mrs_set_mmvq_flags(int f) { g_flags = f; }
+extern "C" void mrs_set_mmvq_flags(int f) { g_flags = f & 0xff; if (f >> 8) g_wide_max_bytes = (long long)(f >> 8) << 20; }
+extern "C" int mrs_mmvq_has_wide(void) {
+#ifdef MRS_MMVQ_WIDE
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" void mrs_set_mmvq_ctas_per_sm(int n) { g_ctas_per_sm = n < 1 ? 1 : (n > 2 ? 2 : n); }
 
 static inline void report(cudaError_t e, const char *what) {

@@ -44,7 +44,7 @@ template <int TYPE> struct QT;
 // ------------------------------------------------------------------ Q4_K (144 B / 256)
 // layout: half2 dm | scales[12] | qs[128]   REF mmvq_gguf.cu:171-177; dot :386-407,:586-618
 template <> struct QT<MRS_Q4_K> {
-  static constexpr int BYTES = 144, QK = 256, UPB = 8, AUX = 4, WALIGN = 16, UPL = 4;
+  static constexpr int BYTES = 144, QK = 256, UPB = 8, AUX = 4, WALIGN = 16, UPL = 2;
   // unit c: chunk c of qs; j = c>>1 (64-wide group), h = c&1 (16-byte half)
   __device__ static __forceinline__ int x_elem(int c, int w) {
     const int j = c >> 1, h = c & 1;
@@ -136,7 +136,7 @@ template <> struct QT<MRS_Q5_K> {
 // unit c = 4n + t: ql chunk c; low nibbles -> elements 128n + 32(t>>1) + 16(t&1) + i,
 // high nibbles -> +64; qh[32n + 16(t&1) + i] bits 2(t>>1) (+4 for the high group).
 template <> struct QT<MRS_Q6_K> {
-  static constexpr int BYTES = 210, QK = 256, UPB = 8, AUX = 2, WALIGN = 2, UPL = 4;
+  static constexpr int BYTES = 210, QK = 256, UPB = 8, AUX = 2, WALIGN = 2, UPL = 2;
   __device__ static __forceinline__ int x_elem(int c, int w) {
     const int n = c >> 2, t = c & 3;
     const int lo = 128 * n + 32 * (t >> 1) + 16 * (t & 1);

@@ -129,3 +129,19 @@ def test_decode_tiles_vs_oracle():
     assert o_indptr.tolist() == [0, 3, 4, 5, 11]
     r2 = kv_index.make_paged_kv_decode_tensors(tables, ctx, bs, None, 4)
     assert r2[0].tolist() == [0, 1, 2, 3] and int(r2[3][0]) == 16 and r2[4].tolist() == [1, 1, 1, 1]
+
+
+def test_runner_split_policy_fills_the_sms():
+    # whole-token runner's own split-KV plan (model.runner_split_pages): chunks of >= 64 tokens, and
+    # never more tiles than one attention CTA per SM for the (batch x kv-head) grid
+    from mistralrs_b200 import model as M
+    for bs in (8, 16, 32):
+        for batch in (1, 2, 8, 64):
+            for kvh in (1, 8, 32):
+                for ctx in (64, 400, 4096, 32768):
+                    pages = M.runner_split_pages(bs, batch, kvh, ctx)
+                    assert pages >= 1 and pages * bs >= 64
+                    tiles = -(-(-(-ctx // bs)) // pages)
+                    assert tiles * batch * kvh <= max(148, batch * kvh)
+    assert M.runner_split_pages(16, 1, 8, 400) == 4          # bench shape: 64-token chunks, 7 tiles
+    assert M.runner_split_pages(16, 64, 8, 400) == 25         # large batch: one chunk per request

@@ -125,13 +125,15 @@ def test_cta_shapes_agree(cuda, dtype):
     # pre-quantised activations, with the fused RMSNorm prologue, fused GLU and batch > 1
     import ctypes
     from mistralrs_b200 import lib
+    if not lib().mrs_mmvq_has_wide():
+        pytest.skip("library built without -DMRS_MMVQ_WIDE")
     K, N = 4096, 200
     w = quant.QTensor(to_dev(make_weight(dtype, N, K, 40).reshape(-1), cuda), dtype, (N, K))
     w2 = quant.QTensor(to_dev(make_weight(dtype, N, K, 41).reshape(-1), cuda), dtype, (N, K))
     nw = to_dev(1.0 + 0.1 * make_acts(1, K, 42, "bf16")[0], cuda, "bf16")
     outs = []
     try:
-        for flags in (0, 2):
+        for flags in (0, 4 | (4096 << 8)):
             lib().mrs_set_mmvq_flags(ctypes.c_int(flags))
             o = []
             for batch in (1, 3):
