@@ -60,6 +60,16 @@ int mrs_mmvq_fused(int ggml_type, int mode, int dt, const void *w0, const void *
                    const void *norm_w, float eps, const void *residual, void *dst0, void *dst1, void *dst2, int K,
                    int n0, int n1, int n2, int b_size, int activation, int pdl, void *stream);
 
+/* QKV projection where attn_v carries its own ggml type (llama.cpp's k-quant "M" recipes, e.g.
+ * Q4_K_M: attn_q/attn_k Q4_K, attn_v Q6_K on half the layers): q||k rows and v rows read the same
+ * [RMSNorm'd] activations.  One grid for the supported pairs (Q4_K+Q6_K, Q5_K+Q6_K, Q4_K+Q5_K) at
+ * batch 1, otherwise the two launches it stands for; results identical to
+ * mrs_mmvq_fused(mode 2, w2 = NULL) followed by mrs_mmvq_fused(mode 0) on wv.  Replaces the
+ * reference's fused_qkv fallback to three plain launches (REF fast_mmvq.rs fused_qkv dtype check). */
+int mrs_mmvq_fused_qkv_mixed(int type_qk, int type_v, int dt, const void *wq, const void *wk, const void *wv,
+                             const void *x, const void *norm_w, float eps, void *q, void *k, void *v, int K, int nq,
+                             int nk, int nv, int b_size, int pdl, void *stream);
+
 /* Prefill GEMM (batch > 8) on tcgen05/TMEM: Y[M,N] = X[M,K] . W[N,K]^T, W in ggml blocks,
  * X/Y dtype 0 f16 / 1 bf16, K % 64 == 0.  Replaces launch_mmq_quantize_q8_1_* +
  * launch_mmq_gguf_<q> (REF fast_mmq.rs:102-185): no activation quantisation pass. */

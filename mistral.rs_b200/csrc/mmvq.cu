@@ -143,8 +143,10 @@ __device__ __forceinline__ void quantize_block_q8_1(const float *v, int8_t *q, f
   s_out = __half2float(__float2half_rn(s[0]));
 }
 
+// The whole CTA program; `cta` of `ncta` CTAs share the virtual rows of `p` (the wrappers below pass
+// blockIdx/gridDim, or the position inside one half of a two-type launch).
 template <int T, int NCOLS, bool FAST, int NCW>
-__global__ void __launch_bounds__((NCW + 1) * 32, NCW == 8 ? 2 : 1) mmvq_stream_kernel(const MmvqParams p) {
+__device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, const int ncta) {
   using Q = QT<T>;
   using G = Geo<T, NCW>;
   constexpr int SLOTS = 2 * NCW;
@@ -181,8 +183,8 @@ __global__ void __launch_bounds__((NCW + 1) * 32, NCW == 8 ? 2 : 1) mmvq_stream_
   if (tid == 0) MRS_STAMP(1);
 
   // contiguous virtual-row range of this CTA
-  const int vr0 = (int)((long long)p.vrows * blockIdx.x / gridDim.x);
-  const int vr1 = (int)((long long)p.vrows * (blockIdx.x + 1) / gridDim.x);
+  const int vr0 = (int)((long long)p.vrows * cta / ncta);
+  const int vr1 = (int)((long long)p.vrows * (cta + 1) / ncta);
   const int P = (p.mode == MODE_GLU) ? NCW : SLOTS;  // virtual rows per pass
 
   if (warp == NCW) {
@@ -555,6 +557,20 @@ __global__ void __launch_bounds__((NCW + 1) * 32, NCW == 8 ? 2 : 1) mmvq_stream_
   }
 }
 
+template <int T, int NCOLS, bool FAST, int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32, NCW == 8 ? 2 : 1) mmvq_stream_kernel(const MmvqParams p) {
+  mmvq_body<T, NCOLS, FAST, NCW>(p, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Two launches that read the same activations but hold different ggml types (Q4_K_M keeps attn_v in
+// Q6_K on half the layers) as ONE grid: CTAs [0, g1) run the first program, the rest the second.
+// Batch 1, aligned rows, 8-warp shape only.
+template <int T1, int T2>
+__global__ void __launch_bounds__(9 * 32, 2) mmvq_dual_kernel(const MmvqParams pa, const MmvqParams pb, const int g1) {
+  if ((int)blockIdx.x < g1) mmvq_body<T1, 1, true, 8>(pa, (int)blockIdx.x, g1);
+  else mmvq_body<T2, 1, true, 8>(pb, (int)blockIdx.x - g1, (int)gridDim.x - g1);
+}
+
 // ---------------------------------------------------------------- host side
 #ifdef MRS_TIMELINE
 static unsigned long long *g_dbg = nullptr;
@@ -646,6 +662,80 @@ static cudaError_t launch_one(MmvqParams p, cudaStream_t stream, bool probe_only
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+// shared-memory plan of the 8-warp shape (same rules as launch_one): false when two CTAs per SM do not fit
+template <int T>
+static bool plan8(const MmvqParams &p, int ncols, int &nst, size_t &smem) {
+  using G = Geo<T, 8>;
+  query_device();
+  const int nblocks = p.K / QT<T>::QK;
+  const int nseg = (nblocks + G::SEG_BLOCKS - 1) / G::SEG_BLOCKS;
+  const int npos = nseg * G::SEG_UNITS;
+  const size_t xbytes = 256 + (size_t)ncols * npos * G::XU_BYTES + 128;
+  const size_t scratch = (p.xkind == X_RAW) ? (size_t)ncols * (p.K / 32) * 8 : 0;
+  const size_t budget = (size_t)g_max_smem / 2 - 1024;
+  nst = MAX_STAGES;
+  while (nst > 2 && xbytes + scratch + (size_t)nst * G::STAGE_BYTES > budget) nst--;
+  smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
+  return smem <= budget;
+}
+
+template <int T> static bool rows_aligned(const MmvqParams &p) {
+  using Q = QT<T>;
+  const int row_bytes = (p.K / Q::QK) * Q::BYTES;
+  bool fast = (row_bytes % Q::WALIGN) == 0;
+  for (int m = 0; m < 3; m++)
+    if (p.w[m] != nullptr && ((uintptr_t)p.w[m] % Q::WALIGN) != 0) fast = false;
+  return fast;
+}
+
+template <int T1, int T2>
+static cudaError_t launch_dual(MmvqParams pa, MmvqParams pb, cudaStream_t stream) {
+  int nsa, nsb;
+  size_t sma, smb;
+  if (pa.ncols != 1 || pb.ncols != 1 || !rows_aligned<T1>(pa) || !rows_aligned<T2>(pb) || !plan8<T1>(pa, 1, nsa, sma) ||
+      !plan8<T2>(pb, 1, nsb, smb))
+    return cudaErrorNotSupported;
+  pa.nstages = nsa; pb.nstages = nsb; pa.flags = pb.flags = g_flags;
+#ifdef MRS_TIMELINE
+  pa.dbg = (g_dbg != nullptr && g_dbg_launch < g_dbg_max) ? g_dbg + (size_t)(g_dbg_launch++) * 320 * 16 : nullptr;
+  pb.dbg = pa.dbg;
+#endif
+  // one wave: 2 CTAs per SM in total, the second (smaller) program gets what it asks for first
+  const int slots = 2 * g_num_sms;
+  const int Pa = (pa.mode == MODE_GLU) ? 8 : 16, Pb = (pb.mode == MODE_GLU) ? 8 : 16;
+  int ga = (pa.vrows + Pa - 1) / Pa, gb = (pb.vrows + Pb - 1) / Pb;
+  if (ga < 1 || gb < 1) return cudaErrorNotSupported;
+  if (ga + gb > slots) {
+    if (gb > slots / 2) gb = slots / 2;
+    if (ga > slots - gb) ga = slots - gb;
+  }
+  auto kern = mmvq_dual_kernel<T1, T2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ga + gb);
+  cfg.blockDim = dim3(9 * 32);
+  cfg.dynamicSmemBytes = sma > smb ? sma : smb;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pa.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, pa, pb, ga);
+}
+
+// supported type pairs of the two-type launch (the k-quant "M" recipes: attn_v one step up)
+static cudaError_t mmvq_dispatch_dual(int t1, const MmvqParams &pa, int t2, const MmvqParams &pb, cudaStream_t stream) {
+  if (t1 == MRS_Q4_K && t2 == MRS_Q6_K) return launch_dual<MRS_Q4_K, MRS_Q6_K>(pa, pb, stream);
+  if (t1 == MRS_Q5_K && t2 == MRS_Q6_K) return launch_dual<MRS_Q5_K, MRS_Q6_K>(pa, pb, stream);
+  if (t1 == MRS_Q4_K && t2 == MRS_Q5_K) return launch_dual<MRS_Q4_K, MRS_Q5_K>(pa, pb, stream);
+  return cudaErrorNotSupported;
 }
 
 template <int T>
@@ -820,6 +910,9 @@ MRS_MMVQ_TYPE(q4_k, MRS_Q4_K)
 MRS_MMVQ_TYPE(q5_k, MRS_Q5_K)
 MRS_MMVQ_TYPE(q6_k, MRS_Q6_K)
 
+// forward declaration (defined below in this file)
+static cudaError_t mmvq_dispatch_dual_entry(int t1, const MmvqParams &pa, int t2, const MmvqParams &pb, cudaStream_t stream);
+
 // ---- B200-native fused entry points (same arithmetic, fewer launches) ------------------------
 // y = W . q8_1( [rmsnorm_w *] x ) [+ residual]; mode 0 plain, 1 fused GLU, 2 fused QKV.
 // x is raw activations [b_size, K] of dtype `dt`; norm_w may be NULL; residual may be NULL.
@@ -837,4 +930,33 @@ extern "C" int mrs_mmvq_fused(int ggml_type, int mode, int dt, const void *w0, c
   p.vrows = (mode == MODE_QKV) ? n0 + n1 + n2 : n0;
   if (K > 4 * 8 * 32 * 32) return (int)cudaErrorInvalidValue;  // fused prologue limit (MAXU, 8-warp shape)
   return (int)mmvq_dispatch(ggml_type, p, (cudaStream_t)stream);
+}
+
+static cudaError_t mmvq_dispatch_dual_entry(int t1, const MmvqParams &pa, int t2, const MmvqParams &pb, cudaStream_t stream) {
+  return mrs::mmvq_dispatch_dual(t1, pa, t2, pb, stream);
+}
+
+// QKV of one token block where attn_v has its own ggml type (k-quant "M" files): q∥k rows of type
+// type_qk and the v rows of type type_v read the same [RMSNorm'd] activations; one grid when the
+// pair is supported (batch 1, aligned rows), otherwise the two launches it replaces.  Arithmetic
+// identical to mrs_mmvq_fused(mode 2, w2 = NULL) + mrs_mmvq_fused(mode 0) on wv.
+extern "C" int mrs_mmvq_fused_qkv_mixed(int type_qk, int type_v, int dt, const void *wq, const void *wk, const void *wv,
+                                        const void *x, const void *norm_w, float eps, void *q, void *k, void *v,
+                                        int K, int nq, int nk, int nv, int b_size, int pdl, void *stream) {
+  if (K > 4 * 8 * 32 * 32) return (int)cudaErrorInvalidValue;
+  MmvqParams pa = {}, pb = {};
+  pa.w[0] = (const uint8_t *)wq; pa.w[1] = (const uint8_t *)wk; pa.dst[0] = q; pa.dst[1] = k;
+  pa.nrows[0] = nq; pa.nrows[1] = nk; pa.nrows[2] = 0;
+  pa.x = x; pa.xkind = X_RAW; pa.xdtype = dt; pa.norm_w = norm_w; pa.eps = eps;
+  pa.K = K; pa.stride_col_dst = nq; pa.ncols = b_size; pa.mode = MODE_QKV; pa.dst_dtype = dt; pa.pdl = pdl;
+  pa.vrows = nq + nk;
+  pb.w[0] = (const uint8_t *)wv; pb.dst[0] = v; pb.nrows[0] = nv;
+  pb.x = x; pb.xkind = X_RAW; pb.xdtype = dt; pb.norm_w = norm_w; pb.eps = eps;
+  pb.K = K; pb.stride_col_dst = nv; pb.ncols = b_size; pb.mode = MODE_PLAIN; pb.dst_dtype = dt; pb.pdl = pdl;
+  pb.vrows = nv;
+  cudaError_t e = (b_size == 1) ? mmvq_dispatch_dual_entry(type_qk, pa, type_v, pb, (cudaStream_t)stream) : cudaErrorNotSupported;
+  if (e != cudaErrorNotSupported) return (int)e;
+  e = mmvq_dispatch(type_qk, pa, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  return (int)mmvq_dispatch(type_v, pb, (cudaStream_t)stream);
 }

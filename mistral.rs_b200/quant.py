@@ -206,6 +206,26 @@ def mmvq_fused(w0: QTensor, xs: torch.Tensor, *, mode=0, w1=None, w2=None, norm_
     return outs[0] if mode != 2 else tuple(outs)
 
 
+def fused_qkv_mixed(wq: QTensor, wk: QTensor, wv: QTensor, xs: torch.Tensor, *, norm_w=None, eps=1e-5, pdl=False):
+    """`mrs_mmvq_fused_qkv_mixed`: QKV where attn_v has its own ggml type (Q4_K_M: Q4_K q/k, Q6_K v) —
+    one grid for the supported pairs at batch 1, else the two launches it stands for."""
+    _, _, k, b_size = _check_common("mrs_mmvq_fused_qkv_mixed", wq, xs)
+    if wk.dtype != wq.dtype or wk.shape[1] != k or wv.shape[1] != k:
+        raise ValueError("mrs_mmvq_fused_qkv_mixed: q/k must share a dtype and all three the input width")
+    xs = xs.contiguous()
+    outs = [torch.empty(*xs.shape[:-1], w.shape[0], dtype=xs.dtype, device=xs.device) for w in (wq, wk, wv)]
+    null = ctypes.c_void_p(0)
+    rc = lib().mrs_mmvq_fused_qkv_mixed(
+        ctypes.c_int(_ggml_code(wq.dtype)), ctypes.c_int(_ggml_code(wv.dtype)), ctypes.c_int(_DT_CODE[xs.dtype]),
+        _ptr(wq.data), _ptr(wk.data), _ptr(wv.data), _ptr(xs), _ptr(norm_w) if norm_w is not None else null,
+        ctypes.c_float(eps), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), ctypes.c_int(k),
+        ctypes.c_int(wq.shape[0]), ctypes.c_int(wk.shape[0]), ctypes.c_int(wv.shape[0]), ctypes.c_int(b_size),
+        ctypes.c_int(1 if pdl else 0), _stream_ptr(xs.device))
+    if rc != 0:
+        raise RuntimeError(f"mrs_mmvq_fused_qkv_mixed failed with cudaError {rc}")
+    return tuple(outs)
+
+
 def _ggml_code(name):
     from . import GGML
     return GGML[name]

@@ -28,10 +28,7 @@ def timed(run, mask, reps=30):
     e1.record(); torch.cuda.synchronize()
     run.step_struct.skip_mask = 0
     return e0.elapsed_time(e1) / reps * 1e3
-import ctypes
-from mistralrs_b200 import lib
-for flags in (2, 4 | (24 << 8), 4 | (12 << 8), 4 | (80 << 8)):
-    lib().mrs_set_mmvq_flags(ctypes.c_int(flags))
-    run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=True, fused_attention=True)
+for mt in (64, 96, 128):
+    run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=True, fused_attention=True, split_min_tokens=mt)
     full, gemv, attn = timed(run, 0), timed(run, 1), timed(run, 2)
-    print(f"layers={layers} mmvq_flags={flags} (2 = 8-warp only; 4|MB<<8 = wide up to MB): full {full:8.1f} us  gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)
+    print(f"layers={layers} split_min_tokens={mt} tiles={run.padded_tiles}: full {full:8.1f} us  gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)

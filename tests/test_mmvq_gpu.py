@@ -148,6 +148,23 @@ def test_cta_shapes_agree(cuda, dtype):
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("pair", [("q4_k", "q6_k"), ("q5_k", "q6_k"), ("q4_k", "q5_k"), ("q4_0", "q8_0")])
+@pytest.mark.parametrize("batch", [1, 3])
+def test_fused_qkv_mixed_matches_separate_launches(cuda, pair, batch):
+    # two-type QKV grid (attn_v in its own ggml type) == mode-2 q||k launch + plain v launch, bit for
+    # bit; unsupported pairs / batch > 1 take the two-launch fallback inside the same entry point
+    tq, tv = pair
+    K, nq, nk, nv = 2048, 320, 64, 64
+    wq, wk = (quant.QTensor(to_dev(make_weight(tq, n, K, 50 + i).reshape(-1), cuda), tq, (n, K)) for i, n in enumerate((nq, nk)))
+    wv = quant.QTensor(to_dev(make_weight(tv, nv, K, 52).reshape(-1), cuda), tv, (nv, K))
+    x = to_dev(make_acts(batch, K, 53, "bf16"), cuda, "bf16")
+    nw = to_dev(1.0 + 0.1 * make_acts(1, K, 54, "bf16")[0], cuda, "bf16")
+    q, k, v = quant.fused_qkv_mixed(wq, wk, wv, x, norm_w=nw, eps=1e-5)
+    q2, k2 = quant.mmvq_fused(wq, x, mode=2, w1=wk, norm_w=nw, eps=1e-5)[:2]
+    v2 = quant.mmvq_fused(wv, x, norm_w=nw, eps=1e-5)
+    assert torch.equal(q, q2) and torch.equal(k, k2) and torch.equal(v, v2)
+
+
 def test_argument_errors(cuda):
     w = quant.QTensor(torch.zeros(144 * 4, dtype=torch.uint8, device=cuda), "q4_k", (4, 256))
     with pytest.raises(ValueError, match="batch size 9"):
