@@ -18,7 +18,13 @@ def test_fused_glu(cuda, dt, act):
     got = ops.fused_glu(to_dev(a, cuda, dt), to_dev(b, cuda, dt), act).float().cpu().numpy()
     want = oracle.fused_glu(a, b, act, dt)
     eps = {"bf16": 2.0 ** -6, "f16": 2.0 ** -9, "f32": 2e-5}[dt]  # fast exp/div may flip the activation by 1 ulp; product rounds again
-    assert (np.abs(got - want) <= eps * np.abs(want) + 1e-6).all()
+    tol = eps * np.abs(want) + 1e-6
+    if act == 1:
+        # tanh-form GELU: the reference builds with --use_fast_math, so tanhf is tanh.approx.f32
+        # (abs error ~2^-11, tests/golden/ref_golden.npz pins the kernel against the reference's
+        # own output); it reaches the result through 0.5*a*(1+tanh)*b where 1+tanh cancels
+        tol = tol + 2.0 ** -10 * np.abs(a * b)
+    assert (np.abs(got - want) <= tol).all()
     x = np.concatenate([a, b], axis=1)
     got2 = ops.fused_split_glu(to_dev(x, cuda, dt), act).float().cpu().numpy()
     assert np.array_equal(got2, got)
