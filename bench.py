@@ -300,6 +300,14 @@ def main():
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     achieved = weight_bytes / gemv_s / 1e9
+    # DRAM traffic per GEMV launch from the committed ncu --set full capture (dram__bytes_read+write
+    # over algorithmic bytes of the same launches), applied to this run's average launch
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))
+        traffic = tr["dram_bytes_over_algorithmic"] * weight_bytes / n_gemv
+    except Exception:
+        pass
     # our kernels per token: per layer qkv (1, or 2 where attn_v has its own ggml type) + fused
     # rope/cache/attention/merge (1) + o_proj + gate_up + down (+2 residual adds under TP), plus
     # advance + embedding + lm_head + argmax
@@ -353,7 +361,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": 4 * ntok, "d2h_bytes_per_step": 4 * ntok},
             "gpu_launches": launches_per_token * ntok,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "mmvq_stream_kernel (all quantized GEMVs of one token)",
+                         "traffic": traffic, "algorithmic_bytes_per_launch": weight_bytes / n_gemv, "peak_source": peak_src, "kernel": "mmvq_stream_kernel (all quantized GEMVs of one token)",
                          "launches": n_gemv, "avg_launch_us": gemv_s / n_gemv * 1e6, "bytes_per_token": weight_bytes},
             "step_hbm_frac": total_bytes * value / 1e9 / peak,
             "clocks": clocks,
