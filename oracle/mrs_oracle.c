@@ -572,6 +572,11 @@ static void cpu_job_run(cpu_job_t *j) {
 /* persistent pool (the reference's CPU path runs on rayon's persistent pool; spawning threads
  * per GEMV would dominate a 1-row-per-thread decode step) */
 #define MRS_MAX_THREADS 256
+#if defined(__x86_64__) && defined(__GNUC__)
+#define MRS_CPU_RELAX() __builtin_ia32_pause()
+#else
+#define MRS_CPU_RELAX() do { } while (0)
+#endif
 static struct {
   pthread_t th[MRS_MAX_THREADS];
   cpu_job_t jobs[MRS_MAX_THREADS];
@@ -583,15 +588,36 @@ static struct {
 static void *pool_worker(void *arg) {
   const int id = *(int *)arg;
   int seen = 0;
-  { /* the embedding process (numpy/OpenBLAS) may have pinned the creating thread to one core;
-     * workers must be free to run anywhere */
-    cpu_set_t all;
+  { /* Workers are pinned one per allowed CPU.  First widen the mask (the embedding process —
+     * numpy/OpenBLAS — may have pinned the creating thread to one core; every id the mask can hold,
+     * the kernel intersects with the cpuset we are allowed), read back what we really got, then take
+     * the (id+1)-th CPU of it.  Unpinned sleepers were woken "affine" to the dispatching thread's CPU
+     * and ran one after another on it (measured: 8 workers, one core, zero speed-up). */
+    cpu_set_t all, got;
     CPU_ZERO(&all);
-    const long n = sysconf(_SC_NPROCESSORS_CONF);
-    for (long c = 0; c < n && c < CPU_SETSIZE; c++) CPU_SET((int)c, &all);
+    for (int c = 0; c < CPU_SETSIZE; c++) CPU_SET(c, &all);
     pthread_setaffinity_np(pthread_self(), sizeof all, &all);
+    if (pthread_getaffinity_np(pthread_self(), sizeof got, &got) == 0) {
+      const int n = CPU_COUNT(&got);
+      if (n > 1) {
+        int want = (id + 1) % n, k = 0;
+        for (int c = 0; c < CPU_SETSIZE; c++) {
+          if (!CPU_ISSET(c, &got)) continue;
+          if (k++ == want) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(c, &one);
+            pthread_setaffinity_np(pthread_self(), sizeof one, &one);
+            break;
+          }
+        }
+      }
+    }
   }
   for (;;) {
+    /* spin briefly before sleeping: a decode step is a chain of sub-millisecond GEMVs */
+    for (int spin = 0; spin < 20000 && __atomic_load_n(&g_pool.generation, __ATOMIC_ACQUIRE) == seen; spin++)
+      MRS_CPU_RELAX();
     pthread_mutex_lock(&g_pool.mu);
     while (g_pool.generation == seen) pthread_cond_wait(&g_pool.cv_start, &g_pool.mu);
     seen = g_pool.generation;
@@ -634,6 +660,14 @@ int mrs_qmatmul_cpu(int type, const void *w, const float *x, float *out, int nco
     cpu_job_t job = {type, ncols, 0, nrows, nrows, batch, (const uint8_t *)w, yq, yd, out};
     cpu_job_run(&job);
   } else {
+    /* the calling thread takes the first allowed CPU for the duration of the call (workers sit on
+     * the others and spin between jobs; an unpinned caller gets scheduled behind one of them) */
+    cpu_set_t saved, one;
+    int restore = 0;
+    if (sched_getaffinity(0, sizeof saved, &saved) == 0 && CPU_COUNT(&saved) > 1) {
+      for (int c = 0; c < CPU_SETSIZE; c++)
+        if (CPU_ISSET(c, &saved)) { CPU_ZERO(&one); CPU_SET(c, &one); restore = sched_setaffinity(0, sizeof one, &one) == 0; break; }
+    }
     pthread_mutex_lock(&g_pool.mu);
     pool_ensure(threads - 1);
     const int nw = g_pool.nthreads;  /* all pool threads wake; extra ones get empty jobs */
@@ -648,9 +682,12 @@ int mrs_qmatmul_cpu(int type, const void *w, const float *x, float *out, int nco
     pthread_mutex_unlock(&g_pool.mu);
     cpu_job_t mine = {type, ncols, 0, (int)((int64_t)nrows / threads), nrows, batch, (const uint8_t *)w, yq, yd, out};
     cpu_job_run(&mine);
+    for (int spin = 0; spin < 200000 && __atomic_load_n(&g_pool.pending, __ATOMIC_ACQUIRE) > 0; spin++)
+      MRS_CPU_RELAX();
     pthread_mutex_lock(&g_pool.mu);
     while (g_pool.pending > 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
     pthread_mutex_unlock(&g_pool.mu);
+    if (restore) sched_setaffinity(0, sizeof saved, &saved);
   }
   free(yq); free(yd);
   return 0;
