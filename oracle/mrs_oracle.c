@@ -489,17 +489,19 @@ MRS_CLONES static float dot_q6k_q8k(const blk_q6_k *w, const blk_q8_k *y, int nb
     for (int n = 0; n < 2; n++) {
       const uint8_t *ql = w[i].ql + 64 * n, *qh = w[i].qh + 32 * n;
       const int8_t *a = y[i].qs + 128 * n, *sc = w[i].scales + 8 * n;
-      int32_t s[8] = {0};
-      for (int l = 0; l < 32; l++) {
-        int is = l / 16;
-        int q1 = ((ql[l] & 0xF) | (((qh[l] >> 0) & 3) << 4)) - 32;
-        int q2 = ((ql[l + 32] & 0xF) | (((qh[l] >> 2) & 3) << 4)) - 32;
-        int q3 = ((ql[l] >> 4) | (((qh[l] >> 4) & 3) << 4)) - 32;
-        int q4 = ((ql[l + 32] >> 4) | (((qh[l] >> 6) & 3) << 4)) - 32;
-        s[is + 0] += q1 * a[l]; s[is + 2] += q2 * a[l + 32];
-        s[is + 4] += q3 * a[l + 64]; s[is + 6] += q4 * a[l + 96];
+      /* 16-element runs with scalar accumulators (same integers as the l/16-indexed form of
+       * REF k_quants vec_dot_q6_K, written so the compiler can vectorise it) */
+      for (int is = 0; is < 2; is++) {
+        int32_t s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+        for (int l = 16 * is; l < 16 * is + 16; l++) {
+          const int q1 = ((ql[l] & 0xF) | (((qh[l] >> 0) & 3) << 4)) - 32;
+          const int q2 = ((ql[l + 32] & 0xF) | (((qh[l] >> 2) & 3) << 4)) - 32;
+          const int q3 = ((ql[l] >> 4) | (((qh[l] >> 4) & 3) << 4)) - 32;
+          const int q4 = ((ql[l + 32] >> 4) | (((qh[l] >> 6) & 3) << 4)) - 32;
+          s1 += q1 * a[l]; s2 += q2 * a[l + 32]; s3 += q3 * a[l + 64]; s4 += q4 * a[l + 96];
+        }
+        sumi += s1 * sc[is] + s2 * sc[is + 2] + s3 * sc[is + 4] + s4 * sc[is + 6];
       }
-      for (int g = 0; g < 8; g++) sumi += s[g] * sc[g];
     }
     sumf += mrs_f16_to_f32(w[i].d) * y[i].d * (float)sumi;
   }
