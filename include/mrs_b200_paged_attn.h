@@ -68,6 +68,19 @@ MRS_PAGED_DECL(f16) MRS_PAGED_DECL(bf16)
                        int32_t numel_per_block_value, int64_t stream);
 MRS_COPY_DECL(f32) MRS_COPY_DECL(f16) MRS_COPY_DECL(bf16) MRS_COPY_DECL(u8)
 
+/* REF ffi.rs:484-509 / update_kvscales.cu: *k_scales = max(*k_scales, absmax(k) / 240), same for v
+ * (FP8 KV-cache scale tracking; one f32 scalar each, updated atomically). */
+void update_kv_scales_f32(void *k, void *v, const long num_elements, float *k_scales, float *v_scales, int64_t stream);
+void update_kv_scales_f16(void *k, void *v, const long num_elements, float *k_scales, float *v_scales, int64_t stream);
+void update_kv_scales_bf16(void *k, void *v, const long num_elements, float *k_scales, float *v_scales, int64_t stream);
+
+/* REF backend/cache.rs:194-300 (`swap_blocks`, Rust-side memcpy loop in the reference): copy cache
+ * blocks src[src_block] -> dst[dst_block] for every pair; src/dst may each be device or (pinned) host
+ * memory of the same block geometry.  pairs: HOST array [n_pairs][2].  Asynchronous on `stream`;
+ * returns a cudaError_t. */
+int32_t mrs_swap_blocks(const void *src, void *dst, int64_t block_bytes, const int64_t *pairs, int64_t n_pairs,
+                        void *stream);
+
 /* ---- B200-native addition: RoPE + KV write + decode attention + split-KV merge in one launch
  * over the HND cache (replaces rotary_embedding_positions + reshape_and_cache_flashinfer +
  * flashinfer_decode + its merge kernel); see csrc/paged_attn.cu. */

@@ -276,3 +276,101 @@ MRS_COPY_BLOCKS(f32, uint32_t)
 MRS_COPY_BLOCKS(f16, uint16_t)
 MRS_COPY_BLOCKS(bf16, uint16_t)
 MRS_COPY_BLOCKS(u8, uint8_t)
+
+// ---------------------------------------------------------------- update_kv_scales (FP8 scale tracking)
+// k_scale = max(k_scale, absmax(k) / 240), same for v — REF update_kvscales.cu:45-124 (one scalar per
+// cache; 240 leaves headroom below e4m3's 448).  Here: 16-byte loads where the pointers allow, shuffle
+// + shared-memory reduction, and one integer atomicMax per CTA (non-negative floats order like their
+// bit patterns) instead of the reference's CAS loop.  NaNs are ignored, as in the reference's `>` scan;
+// the reference is built with --use_fast_math, hence the approximate division.
+template <typename T> __device__ __forceinline__ float kv_abs(T x);
+template <> __device__ __forceinline__ float kv_abs<float>(float x) { return fabsf(x); }
+template <> __device__ __forceinline__ float kv_abs<__half>(__half x) { return fabsf(__half2float(x)); }
+template <> __device__ __forceinline__ float kv_abs<__nv_bfloat16>(__nv_bfloat16 x) { return fabsf(__bfloat162float(x)); }
+
+template <typename T>
+__device__ __forceinline__ float absmax_stream(const T *__restrict__ p, int64_t n, int64_t tid, int64_t nthreads) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  float m = 0.f;
+  int64_t head = 0;  // elements before the first 16-byte boundary
+  const uintptr_t mis = (uintptr_t)p & 15;
+  if (mis) head = (int64_t)((16 - mis) / sizeof(T));
+  if (head > n) head = n;
+  for (int64_t i = tid; i < head; i += nthreads) m = fmaxf(m, kv_abs<T>(p[i]));
+  const int64_t nvec = (n - head) / VEC;
+  const uint4 *pv = (const uint4 *)(p + head);
+  for (int64_t i = tid; i < nvec; i += nthreads) {
+    const uint4 raw = pv[i];
+    const T *e = (const T *)&raw;
+#pragma unroll
+    for (int k = 0; k < VEC; k++) m = fmaxf(m, kv_abs<T>(e[k]));
+  }
+  for (int64_t i = head + nvec * VEC + tid; i < n; i += nthreads) m = fmaxf(m, kv_abs<T>(p[i]));
+  return m;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) update_kv_scales_kernel(const T *__restrict__ k, const T *__restrict__ v, int64_t n,
+                                                                 float *__restrict__ k_scale, float *__restrict__ v_scale) {
+  __shared__ float red[2][8];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+  float mk = absmax_stream<T>(k, n, tid, nthreads);
+  float mv = absmax_stream<T>(v, n, tid, nthreads);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    mk = fmaxf(mk, __shfl_xor_sync(0xffffffffu, mk, s));
+    mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, s));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = mk; red[1][warp] = mv; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; w++) { mk = fmaxf(mk, red[0][w]); mv = fmaxf(mv, red[1][w]); }
+    const float ck = __fdividef(mk, 240.0f), cv = __fdividef(mv, 240.0f);
+    if (ck > 0.0f) atomicMax((int *)k_scale, __float_as_int(ck));
+    if (cv > 0.0f) atomicMax((int *)v_scale, __float_as_int(cv));
+  }
+}
+
+template <typename T>
+static void launch_update_kv_scales(void *k, void *v, long n, float *k_scales, float *v_scales, int64_t stream) {
+  if (n <= 0) return;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long blocks = (n + 256 * 16 - 1) / (256 * 16);  // >= 16 elements per thread before adding CTAs
+  if (blocks < 1) blocks = 1;
+  if (blocks > 8L * sms) blocks = 8L * sms;
+  update_kv_scales_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T *)k, (const T *)v, (int64_t)n,
+                                                                              k_scales, v_scales);
+}
+
+extern "C" void update_kv_scales_f32(void *k, void *v, const long num_elements, float *k_scales, float *v_scales, int64_t stream) {
+  launch_update_kv_scales<float>(k, v, num_elements, k_scales, v_scales, stream);
+}
+extern "C" void update_kv_scales_f16(void *k, void *v, const long num_elements, float *k_scales, float *v_scales, int64_t stream) {
+  launch_update_kv_scales<__half>(k, v, num_elements, k_scales, v_scales, stream);
+}
+extern "C" void update_kv_scales_bf16(void *k, void *v, const long num_elements, float *k_scales, float *v_scales, int64_t stream) {
+  launch_update_kv_scales<__nv_bfloat16>(k, v, num_elements, k_scales, v_scales, stream);
+}
+
+// ---------------------------------------------------------------- swap_blocks
+// REF backend/cache.rs:194-300 (`swap_blocks`): for every (src_block -> dst_block) copy one cache
+// block between two caches on the same device, or between a host cache and a device cache (swap
+// out / swap in).  The reference loops over memcpy_dtod / htod / dtoh in Rust; this is the same loop
+// behind one C call, asynchronous on `stream` (host memory must be pinned for true overlap).
+// pairs: host array [n_pairs][2] of (src_block, dst_block).  Returns a cudaError_t.
+extern "C" int32_t mrs_swap_blocks(const void *src, void *dst, int64_t block_bytes, const int64_t *pairs,
+                                   int64_t n_pairs, void *stream) {
+  if (block_bytes <= 0 || n_pairs < 0 || (n_pairs > 0 && pairs == nullptr)) return (int32_t)cudaErrorInvalidValue;
+  for (int64_t i = 0; i < n_pairs; i++) {
+    const int64_t s = pairs[2 * i], d = pairs[2 * i + 1];
+    if (s < 0 || d < 0) return (int32_t)cudaErrorInvalidValue;
+    const cudaError_t e = cudaMemcpyAsync((uint8_t *)dst + d * block_bytes, (const uint8_t *)src + s * block_bytes,
+                                          (size_t)block_bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int32_t)e;
+  }
+  return 0;
+}

@@ -208,3 +208,44 @@ def copy_blocks(key_caches, value_caches, block_mapping):
                                          ctypes.c_int(key_caches[0][0].numel()), ctypes.c_int(value_caches[0][0].numel()),
                                          ctypes.c_int64(torch.cuda.current_stream(dev).cuda_stream))
     return kptr, vptr, bm  # keep alive until the stream has consumed them
+
+
+def swap_blocks(src: torch.Tensor, dst: torch.Tensor, block_mapping):
+    """`swap_blocks` (backend/cache.rs:194): copy cache blocks src[s] -> dst[d] for every (s, d) in
+    `block_mapping` (dict or list of pairs).  Either side may be a CUDA tensor or a (pinned) host
+    tensor — swap-out / swap-in; both on CUDA must be the same device, as in the reference."""
+    pairs = list(block_mapping.items()) if isinstance(block_mapping, dict) else list(block_mapping)
+    if not pairs:
+        return
+    if src.dtype != dst.dtype or src.shape[1:] != dst.shape[1:]:
+        raise ValueError("swap_blocks: src and dst must share dtype and block geometry")
+    if src.is_cuda and dst.is_cuda and src.device != dst.device:
+        raise ValueError(f"Tensors must be on the same device to copy, got {src.device} (src) and {dst.device} (dst).")
+    if not (src.is_cuda or dst.is_cuda):
+        raise ValueError("swap_blocks: at least one side must be a CUDA tensor")
+    if not (src.is_contiguous() and dst.is_contiguous()):
+        raise ValueError("swap_blocks: caches must be contiguous")
+    dev = src.device if src.is_cuda else dst.device
+    block_bytes = src[0].numel() * src.element_size()
+    flat = (ctypes.c_int64 * (2 * len(pairs)))(*[int(x) for p in pairs for x in p])
+    if max(p[0] for p in pairs) >= src.shape[0] or max(p[1] for p in pairs) >= dst.shape[0] or min(min(p) for p in pairs) < 0:
+        raise IndexError("swap_blocks: block number out of range")
+    rc = lib().mrs_swap_blocks(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), ctypes.c_int64(block_bytes),
+                               flat, ctypes.c_int64(len(pairs)), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"mrs_swap_blocks failed with cudaError {rc}")
+
+
+def kv_scale_update(key: torch.Tensor, value: torch.Tensor, k_scales: torch.Tensor, v_scales: torch.Tensor):
+    """`kv_scale_update` (backend/scale_update.rs:114): k_scales[0] = max(k_scales[0], absmax(key)/240),
+    same for value; one f32 scalar each, updated in place on the device."""
+    if key.dtype != value.dtype or key.numel() != value.numel():
+        raise ValueError("kv_scale_update: key and value must share dtype and element count")
+    if k_scales.dtype != torch.float32 or v_scales.dtype != torch.float32:
+        raise ValueError("kv_scale_update: scales must be f32")
+    tag = {torch.float32: "f32", torch.float16: "f16", torch.bfloat16: "bf16"}.get(key.dtype)
+    if tag is None:
+        raise ValueError("Invalid dtype for kv scale update!")
+    key, value = key.contiguous(), value.contiguous()
+    getattr(lib(), f"update_kv_scales_{tag}")(_p(key), _p(value), ctypes.c_long(key.numel()), _p(k_scales), _p(v_scales),
+                                              ctypes.c_int64(torch.cuda.current_stream(key.device).cuda_stream))

@@ -126,3 +126,47 @@ def test_cache_write_gather_round_trip(cuda):
     keep = paged_attn.copy_blocks([kc], [vc], [(3, 9), (7, 8)])
     assert torch.equal(kc[9], kc[3]) and torch.equal(vc[8], vc[7])
     del keep
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16", "f32"])
+def test_kv_scale_update(cuda, dt):
+    # update_kv_scales_*: scale = max(old, absmax/240); exact up to the reference's fast-math division
+    rng = np.random.default_rng(21)
+    for n in (1, 7, 4096 + 3, 300_001):            # ragged tails, unaligned heads (offset slice below)
+        k = oracle.round_dtype((rng.standard_normal(n + 1) * 3).astype(np.float32), dt)
+        v = oracle.round_dtype((rng.standard_normal(n + 1) * 0.02).astype(np.float32), dt)
+        tk, tv = to_dev(k, cuda, dt)[1:], to_dev(v, cuda, dt)[1:]      # element-offset views: not 16-byte aligned
+        ks = torch.tensor([0.001], dtype=torch.float32, device=cuda)   # below the candidate: replaced
+        vs = torch.tensor([5.0], dtype=torch.float32, device=cuda)     # above the candidate: kept
+        paged_attn.kv_scale_update(tk, tv, ks, vs)
+        want_k = max(np.float32(0.001), np.float32(np.abs(k[1:]).max()) / np.float32(240.0))
+        assert abs(ks.item() - want_k) <= 2.0 ** -22 * want_k
+        assert vs.item() == 5.0
+    z = torch.zeros(64, dtype=TORCH_DT[dt], device=cuda)
+    ks = torch.zeros(1, dtype=torch.float32, device=cuda)
+    paged_attn.kv_scale_update(z, z, ks, ks)                            # all-zero input leaves the scale alone
+    assert ks.item() == 0.0
+
+
+def test_swap_blocks(cuda):
+    # device<->device and device<->pinned host block copies by (src, dst) mapping; untouched blocks stay
+    NB, KVH, BS, D = 12, 2, 16, 64
+    src = torch.randn(NB, KVH, BS, D, device=cuda).to(torch.bfloat16)
+    dst = torch.zeros_like(src)
+    mapping = {3: 0, 7: 11, 1: 5}
+    paged_attn.swap_blocks(src, dst, mapping)
+    torch.cuda.synchronize()
+    for s, d in mapping.items():
+        assert torch.equal(dst[d], src[s])
+    untouched = [i for i in range(NB) if i not in mapping.values()]
+    assert not dst[untouched].any()
+    host = torch.zeros(NB, KVH, BS, D, dtype=torch.bfloat16).pin_memory()
+    paged_attn.swap_blocks(src, host, [(2, 9), (4, 4)])                  # swap out
+    torch.cuda.synchronize()
+    assert torch.equal(host[9], src[2].cpu()) and torch.equal(host[4], src[4].cpu())
+    back = torch.zeros_like(src)
+    paged_attn.swap_blocks(host, back, [(9, 1)])                         # swap in
+    torch.cuda.synchronize()
+    assert torch.equal(back[1], src[2])
+    with pytest.raises(IndexError):
+        paged_attn.swap_blocks(src, dst, [(NB, 0)])
