@@ -33,6 +33,14 @@ MRS_GLU_DECL(f16) MRS_GLU_DECL(bf16) MRS_GLU_DECL(f32)
   void mrs_rms_norm_##t(const void *x, const void *weight, void *dst, const int nrows, const int ncols,         \
                         const float eps, int64_t stream);
 MRS_RMS_DECL(f16) MRS_RMS_DECL(bf16) MRS_RMS_DECL(f32)
+
+/* REF mistralrs-core/src/cuda/ffi.rs:183-227, sort.cu:619-672: per-head RMSNorm of a strided
+ * [batch, heads, seq, head_dim] view (element strides) into a contiguous tensor of that shape. */
+#define MRS_RMS4D_DECL(t)                                                                                       \
+  void rms_norm_strided_4d_##t(const void *x, const void *weight, void *dst, int64_t stride_b, int64_t stride_h, \
+                               int64_t stride_s, int64_t stride_d, int32_t batch, int32_t heads, int32_t seq_len, \
+                               int32_t head_dim, float eps, int64_t stream);
+MRS_RMS4D_DECL(f16) MRS_RMS4D_DECL(bf16) MRS_RMS4D_DECL(f32)
 #ifdef __cplusplus
 }
 #endif

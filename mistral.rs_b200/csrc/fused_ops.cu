@@ -145,6 +145,43 @@ static void launch_rms(const void *x, const void *res, const void *w, void *sum_
   rms_norm_kernel<T><<<rows, block, 0, st>>>((const T *)x, (const T *)res, (const T *)w, (T *)sum_out, (T *)out, cols, eps);
 }
 
+// Per-head RMSNorm of a strided [B, H, S, D] view into a contiguous [B, H, S, D] tensor (QK-norm of
+// Qwen3 / Gemma-3 style models) — REF sort.cu:619-672 (one CTA per row there).  Here one warp per
+// row, eight rows per CTA: D is a head size (64..256), so a shuffle reduction is enough and a
+// decode step (a few hundred rows) still fills the SMs.  Same rounding points: f32 sum of squares,
+// T(x * inv_rms * w).
+template <typename T>
+__global__ void __launch_bounds__(256) rms_norm_strided_4d_kernel(const T *__restrict__ x, const T *__restrict__ w,
+                                                                  T *__restrict__ dst, int64_t stride_b, int64_t stride_h,
+                                                                  int64_t stride_s, int64_t stride_d, int heads,
+                                                                  int seq_len, int head_dim, int64_t rows, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;  // whole warps leave together
+  const int lane = threadIdx.x & 31;
+  const int seq = (int)(row % seq_len);
+  const int64_t t = row / seq_len;
+  const int head = (int)(t % heads);
+  const int64_t b = t / heads;
+  const T *src = x + b * stride_b + head * stride_h + seq * stride_s;
+  float ss = 0.f;
+  for (int c = lane; c < head_dim; c += 32) {
+    const float v = to_f(src[c * stride_d]);
+    ss += v * v;
+  }
+  const float inv = rsqrtf(warp_sum(ss) / (float)head_dim + eps);
+  T *out = dst + row * head_dim;
+  for (int c = lane; c < head_dim; c += 32) out[c] = from_f<T>(to_f(src[c * stride_d]) * inv * to_f(w[c]));
+}
+
+template <typename T>
+static void launch_rms_strided_4d(const void *x, const void *w, void *dst, int64_t sb, int64_t sh, int64_t ss, int64_t sd,
+                                  int batch, int heads, int seq_len, int head_dim, float eps, cudaStream_t st) {
+  if (batch <= 0 || heads <= 0 || seq_len <= 0 || head_dim <= 0) return;
+  const int64_t rows = (int64_t)batch * heads * seq_len;
+  rms_norm_strided_4d_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const T *)x, (const T *)w, (T *)dst, sb, sh, ss,
+                                                                           sd, heads, seq_len, head_dim, rows, eps);
+}
+
 }  // namespace mrs
 
 using namespace mrs;
@@ -199,3 +236,15 @@ MRS_GLU(f32, float)
 MRS_RMS(f16, __half)
 MRS_RMS(bf16, __nv_bfloat16)
 MRS_RMS(f32, float)
+
+#define MRS_RMS4D(tag, T)                                                                                     \
+  extern "C" void rms_norm_strided_4d_##tag(const void *x, const void *weight, void *dst, int64_t stride_b,   \
+                                            int64_t stride_h, int64_t stride_s, int64_t stride_d, int32_t batch, \
+                                            int32_t heads, int32_t seq_len, int32_t head_dim, float eps,      \
+                                            int64_t stream) {                                                 \
+    launch_rms_strided_4d<T>(x, weight, dst, stride_b, stride_h, stride_s, stride_d, batch, heads, seq_len,   \
+                             head_dim, eps, (cudaStream_t)stream);                                            \
+  }
+MRS_RMS4D(f16, __half)
+MRS_RMS4D(bf16, __nv_bfloat16)
+MRS_RMS4D(f32, float)

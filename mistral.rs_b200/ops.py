@@ -78,6 +78,21 @@ def rms_norm(x, weight, eps):
     return out
 
 
+def rms_norm_strided_4d(x, weight, eps):
+    """Per-head RMSNorm of a (possibly strided) [B, H, S, D] view -> contiguous [B, H, S, D]
+    (`rms_norm_strided_4d_*`, core/src/cuda/ffi.rs:183; the QK-norm fast path of layers.rs)."""
+    if x.dim() != 4 or weight.shape[-1] != x.shape[-1]:
+        raise ValueError("rms_norm_strided_4d expects [batch, heads, seq, head_dim] and a [head_dim] weight")
+    b, h, s, d = x.shape
+    out = torch.empty(b, h, s, d, dtype=x.dtype, device=x.device)
+    sb, sh, ss, sd = x.stride()
+    getattr(lib(), f"rms_norm_strided_4d_{_TAG[x.dtype]}")(
+        _p(x), _p(weight.contiguous()), _p(out), ctypes.c_int64(sb), ctypes.c_int64(sh), ctypes.c_int64(ss),
+        ctypes.c_int64(sd), ctypes.c_int(b), ctypes.c_int(h), ctypes.c_int(s), ctypes.c_int(d), ctypes.c_float(eps),
+        ctypes.c_int64(_stream(x.device)))
+    return out
+
+
 def add_rms_norm(x, residual, weight, eps):
     """(sum, normed) = (x + residual, rmsnorm(x + residual)) — layers.rs:328 forward_add_rms_norm."""
     x, residual = x.contiguous(), residual.contiguous()

@@ -170,3 +170,22 @@ def test_swap_blocks(cuda):
     assert torch.equal(back[1], src[2])
     with pytest.raises(IndexError):
         paged_attn.swap_blocks(src, dst, [(NB, 0)])
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16", "f32"])
+@pytest.mark.parametrize("D", [64, 128, 80])
+def test_rms_norm_strided_4d(cuda, dt, D):
+    # per-head RMSNorm read through a transposed ([B,S,H,D] -> [B,H,S,D]) and a sliced (q of a fused
+    # qkv row) view; the output is contiguous [B,H,S,D]
+    B, H, S = 2, 3, 5
+    w = oracle.round_dtype(1.0 + 0.1 * make_acts(1, D, 6, "f32")[0], dt)
+    ulp = {"bf16": 2.0 ** -7, "f16": 2.0 ** -10, "f32": 1e-6}[dt]
+    base = make_acts(B * S, H * D * 3, 7, dt).reshape(B, S, 3 * H * D)
+    t = to_dev(base, cuda, dt)
+    view = t[:, :, H * D:2 * H * D].reshape(B, S, H, D).transpose(1, 2)       # strides (S*3HD, D, 3HD, 1)
+    assert not view.is_contiguous()
+    got = ops.rms_norm_strided_4d(view, to_dev(w, cuda, dt), 1e-6).float().cpu().numpy()
+    rows = base[:, :, H * D:2 * H * D].reshape(B, S, H, D).transpose(0, 2, 1, 3).reshape(-1, D)
+    want = oracle.rms_norm(rows, w, 1e-6, dt).reshape(B, H, S, D)
+    assert got.shape == want.shape
+    assert (np.abs(got - want) <= ulp * np.abs(want) * 1.01 + 1e-7).all()
