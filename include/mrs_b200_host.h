@@ -1,0 +1,66 @@
+/* mrs_b200_host.h — C ABI of libmrs_b200_host.so: the host-side (no CUDA) pieces either side of the
+ * hot path.  Plain pointers and sizes only.
+ *
+ *  - KV index producers: block pool, slot mapping, paged-KV CSR and split-KV tile plans — integers
+ *    that must match the reference bit for bit.
+ *      REF mistralrs-core/src/paged_attention/block_pool.rs:290-442 (BlockPool),
+ *          mistralrs-core/src/pipeline/inputs_processor.rs:896-923 (slots),
+ *          mistralrs-core/src/flashinfer/metadata.rs:61-216 (split size, CSR, tiles)
+ *  - GGUF archives: header / metadata / tensor catalogue / split shards over mmap; tensor payloads
+ *    are handed out as pointers into the mapping for a straight host->device copy.
+ *      REF mistralrs-quant/src/gguf/archive.rs:351-611 (GgufArchive)
+ */
+#ifndef MRS_B200_HOST_H
+#define MRS_B200_HOST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- block pool (block 0 is the null block; FIFO free list) ---- */
+void *mrs_block_pool_new(int64_t num_gpu_blocks);
+void mrs_block_pool_free(void *pool);
+int64_t mrs_block_pool_null_block_id(void *pool);
+int64_t mrs_block_pool_num_free_blocks(void *pool);
+int64_t mrs_block_pool_ref_cnt(void *pool, int64_t block_id);
+int mrs_block_pool_get_new_blocks(void *pool, int64_t num, int64_t *out); /* 1 ok, 0 not enough free blocks */
+void mrs_block_pool_free_blocks(void *pool, const int64_t *ids, int64_t n);
+void mrs_block_pool_touch(void *pool, const int64_t *ids, int64_t n);
+
+/* ---- slots / CSR / tile plans ---- */
+int mrs_slot_mapping(const int64_t *table, int64_t table_len, int64_t block_size, int64_t start, int64_t end,
+                     int64_t *out);
+int mrs_make_paged_kv(const int64_t *tables, int64_t batch, int64_t max_blocks, const int64_t *context_lens,
+                      int64_t block_size, int64_t padded_indices_len, int32_t *indptr, int32_t *indices,
+                      int32_t *last_page_len);
+int64_t mrs_decode_split_pages(int64_t block_size, int64_t batch, int64_t kv_heads, int64_t sm_count, int64_t max_ctx);
+int64_t mrs_make_decode_tiles(const int64_t *table_lens, const int64_t *context_lens, int64_t batch, int64_t block_size,
+                              int64_t split_pages, int64_t padded_tiles_len, int32_t *request_indices,
+                              int32_t *kv_tile_indices, int32_t *o_indptr, int32_t *kv_chunk_size, uint8_t *mask);
+
+/* ---- GGUF archives ---- */
+/* paths: all shards of one model, any order (split.no decides).  NULL + message in err on failure. */
+void *mrs_gguf_open(const char *const *paths, int32_t n_paths, char *err, int64_t err_cap);
+void mrs_gguf_close(void *archive);
+int64_t mrs_gguf_alignment(void *archive);
+int64_t mrs_gguf_n_tensors(void *archive);
+int64_t mrs_gguf_n_metadata(void *archive);
+int64_t mrs_gguf_find_tensor(void *archive, const char *name); /* index or -1 */
+/* dims: up to 8 entries, ggml order (dims[0] innermost); offset is absolute inside shard `shard`;
+ * nbytes = -1 when the ggml type's block size is unknown.  Returns the name length, -1 on a bad index. */
+int32_t mrs_gguf_tensor_info(void *archive, int64_t i, char *name, int64_t name_cap, int32_t *ggml_type, int32_t *n_dims,
+                             int64_t *dims, int32_t *shard, int64_t *offset, int64_t *nbytes);
+const void *mrs_gguf_tensor_data(void *archive, int64_t i); /* pointer into the mapping, valid until close */
+/* metadata: value types as in the GGUF spec (0 u8 .. 8 string, 9 array, 10 u64, 11 i64, 12 f64) */
+int32_t mrs_gguf_meta_key(void *archive, int64_t i, char *key, int64_t cap, int32_t *vtype, int32_t *arr_type,
+                          int64_t *arr_len);
+int32_t mrs_gguf_meta_int(void *archive, const char *key, int64_t *out);   /* 1 found, 0 absent / not an integer */
+int32_t mrs_gguf_meta_float(void *archive, const char *key, double *out);
+int64_t mrs_gguf_meta_str(void *archive, const char *key, char *buf, int64_t cap); /* length, -1 absent */
+int64_t mrs_gguf_meta_arr_str(void *archive, const char *key, int64_t idx, char *buf, int64_t cap);
+int64_t mrs_gguf_meta_arr_num(void *archive, const char *key, int64_t start, int64_t cap, double *out, int64_t *out_int);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

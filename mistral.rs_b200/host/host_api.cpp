@@ -1,4 +1,5 @@
 // host_api.cpp — C API over the C++ host layer (kv_index.hpp) for the Python test/bench harness.
+#include "gguf_reader.hpp"
 #include "kv_index.hpp"
 
 #include <cstring>
@@ -74,6 +75,101 @@ int64_t mrs_make_decode_tiles(const int64_t *table_lens, const int64_t *context_
     *kv_chunk_size = r.kv_chunk_size;
     return (int64_t)r.o_indptr.back();
   } catch (...) { return -1; }
+}
+
+
+// ---------------------------------------------------------------- GGUF archives (gguf_reader.hpp)
+static int copy_out(const std::string &v, char *buf, int64_t cap) {
+  if (buf != nullptr && cap > 0) {
+    const size_t n = v.size() < (size_t)cap - 1 ? v.size() : (size_t)cap - 1;
+    memcpy(buf, v.data(), n);
+    buf[n] = 0;
+  }
+  return (int)v.size();
+}
+
+// paths: n_paths shard files (any order; split.no decides).  NULL + message in err on failure.
+void *mrs_gguf_open(const char *const *paths, int32_t n_paths, char *err, int64_t err_cap) {
+  try {
+    std::vector<std::string> v;
+    for (int i = 0; i < n_paths; i++) v.emplace_back(paths[i]);
+    return new GgufArchive(v);
+  } catch (const std::exception &e) {
+    copy_out(e.what(), err, err_cap);
+    return nullptr;
+  }
+}
+void mrs_gguf_close(void *h) { delete (GgufArchive *)h; }
+int64_t mrs_gguf_alignment(void *h) { return (int64_t)((GgufArchive *)h)->alignment(); }
+int64_t mrs_gguf_n_tensors(void *h) { return (int64_t)((GgufArchive *)h)->tensors().size(); }
+int64_t mrs_gguf_n_metadata(void *h) { return (int64_t)((GgufArchive *)h)->metadata_keys().size(); }
+int64_t mrs_gguf_find_tensor(void *h, const char *name) { return ((GgufArchive *)h)->find_tensor(name); }
+
+// dims: up to 8 entries in ggml order (dims[0] innermost).  Returns the name length, -1 on a bad index.
+int32_t mrs_gguf_tensor_info(void *h, int64_t i, char *name, int64_t name_cap, int32_t *ggml_type, int32_t *n_dims,
+                             int64_t *dims, int32_t *shard, int64_t *offset, int64_t *nbytes) {
+  const auto &ts = ((GgufArchive *)h)->tensors();
+  if (i < 0 || (size_t)i >= ts.size()) return -1;
+  const GgufTensor &t = ts[(size_t)i];
+  *ggml_type = (int32_t)t.ggml_type;
+  *n_dims = (int32_t)t.dims.size();
+  for (size_t d = 0; d < t.dims.size() && d < 8; d++) dims[d] = t.dims[d];
+  *shard = t.shard;
+  *offset = (int64_t)t.offset;
+  *nbytes = t.nbytes;
+  return copy_out(t.name, name, name_cap);
+}
+const void *mrs_gguf_tensor_data(void *h, int64_t i) {
+  const auto &ts = ((GgufArchive *)h)->tensors();
+  if (i < 0 || (size_t)i >= ts.size()) return nullptr;
+  return ((GgufArchive *)h)->tensor_data((size_t)i);
+}
+
+// metadata: key by index; value type / array element type / array length
+int32_t mrs_gguf_meta_key(void *h, int64_t i, char *key, int64_t cap, int32_t *vtype, int32_t *arr_type, int64_t *arr_len) {
+  const auto &keys = ((GgufArchive *)h)->metadata_keys();
+  if (i < 0 || (size_t)i >= keys.size()) return -1;
+  const GgufValue *v = ((GgufArchive *)h)->metadata(keys[(size_t)i]);
+  *vtype = (int32_t)v->type;
+  *arr_type = (int32_t)v->arr_type;
+  *arr_len = v->type == GV_ARR ? (int64_t)v->arr_len() : 0;
+  return copy_out(keys[(size_t)i], key, cap);
+}
+// 1 = found and of a compatible kind, 0 otherwise
+int32_t mrs_gguf_meta_int(void *h, const char *key, int64_t *out) {
+  const GgufValue *v = ((GgufArchive *)h)->metadata(key);
+  if (v == nullptr || !v->is_int()) return 0;
+  *out = v->as_int();
+  return 1;
+}
+int32_t mrs_gguf_meta_float(void *h, const char *key, double *out) {
+  const GgufValue *v = ((GgufArchive *)h)->metadata(key);
+  if (v == nullptr) return 0;
+  if (v->type == GV_F32 || v->type == GV_F64) { *out = v->f; return 1; }
+  if (v->is_int()) { *out = (double)v->as_int(); return 1; }
+  return 0;
+}
+// returns the string length (copying at most cap-1 bytes), -1 when absent / not a string
+int64_t mrs_gguf_meta_str(void *h, const char *key, char *buf, int64_t cap) {
+  const GgufValue *v = ((GgufArchive *)h)->metadata(key);
+  if (v == nullptr || v->type != GV_STR) return -1;
+  return copy_out(v->s, buf, cap);
+}
+int64_t mrs_gguf_meta_arr_str(void *h, const char *key, int64_t idx, char *buf, int64_t cap) {
+  const GgufValue *v = ((GgufArchive *)h)->metadata(key);
+  if (v == nullptr || v->type != GV_ARR || v->arr_type != GV_STR || idx < 0 || (size_t)idx >= v->arr_str.size()) return -1;
+  return copy_out(v->arr_str[(size_t)idx], buf, cap);
+}
+// numeric arrays: copies up to `cap` elements starting at `start` as f64 (and exact ints when out_int != NULL)
+int64_t mrs_gguf_meta_arr_num(void *h, const char *key, int64_t start, int64_t cap, double *out, int64_t *out_int) {
+  const GgufValue *v = ((GgufArchive *)h)->metadata(key);
+  if (v == nullptr || v->type != GV_ARR || v->arr_type == GV_STR || start < 0) return -1;
+  int64_t n = 0;
+  for (size_t k = (size_t)start; k < v->arr_num.size() && n < cap; k++, n++) {
+    if (out != nullptr) out[n] = v->arr_num[k];
+    if (out_int != nullptr) out_int[n] = v->arr_int[k];
+  }
+  return n;
 }
 
 }  // extern "C"

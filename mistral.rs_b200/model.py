@@ -37,6 +37,8 @@ class LlamaConfig:
     quant: str = "q4_k_m"      # "q4_k_m" | any ggml type name for a uniform model
     block_size: int = 16
     name: str = "llama-3-8b"
+    rope_neox: bool = True     # rotate-half pairing; GGUF llama files use the interleaved pairing (False)
+    rope_freq_factors: object = None   # optional per-frequency divisors (GGUF `rope_freqs.weight`, Llama-3.1 scaling)
 
     @staticmethod
     def llama3_8b(**kw):
@@ -144,6 +146,8 @@ def rope_tables(cfg: LlamaConfig):
                          (np.float32(sc["high_freq_factor"]) - np.float32(sc["low_freq_factor"]))
                 out.append((1 - smooth) * f / np.float32(sc["factor"]) + smooth * f)
         inv = np.array(out, dtype=np.float32)
+    if cfg.rope_freq_factors is not None:   # llama.cpp stores Llama-3.1's scaling as theta / factor per frequency
+        inv = (inv / np.asarray(cfg.rope_freq_factors, dtype=np.float32)).astype(np.float32)
     freqs = np.arange(cfg.max_pos, dtype=np.float32)[:, None] * inv[None, :]
     assert freqs.shape[1] == half
     return np.cos(freqs).astype(np.float32), np.sin(freqs).astype(np.float32)
@@ -176,6 +180,106 @@ class LlamaWeights:
         cos, sin = rope_tables(cfg)
         self.rope_cos = torch.from_numpy(cos).to(device).to(dtype)
         self.rope_sin = torch.from_numpy(sin).to(device).to(dtype)
+
+    # ---- real weights -------------------------------------------------------------------------
+    GGUF_NAMES = {"attn_q": "col", "attn_k": "col", "attn_v": "col", "attn_output": "row", "ffn_gate": "col",
+                  "ffn_up": "col", "ffn_down": "row"}
+
+    @staticmethod
+    def config_from_gguf(ar) -> "LlamaConfig":
+        """Hyper-parameters from GGUF metadata (`llama.*` keys, as the reference's
+        `quantized_llama.rs::PropsGGUF` reads them)."""
+        md = ar.metadata()
+        arch = md.get("general.architecture", "llama")
+
+        def g(key, default=None):
+            v = md.get(f"{arch}.{key}", default)
+            if v is None:
+                raise KeyError(f"GGUF metadata key `{arch}.{key}` is missing")
+            return v
+        hidden, n_heads = int(g("embedding_length")), int(g("attention.head_count"))
+        head_dim = int(md.get(f"{arch}.attention.key_length", md.get(f"{arch}.rope.dimension_count", hidden // n_heads)))
+        emb = ar.tensor_info("token_embd.weight")
+        factors = None
+        if ar.contains_tensor("rope_freqs.weight"):
+            factors = ar.load_dense("rope_freqs.weight", "cpu").float().numpy()
+        return LlamaConfig(hidden=hidden, inter=int(g("feed_forward_length")), n_layers=int(g("block_count")),
+                           n_heads=n_heads, n_kv_heads=int(g("attention.head_count_kv", n_heads)), head_dim=head_dim,
+                           vocab=int(md.get(f"{arch}.vocab_size", emb.shape[0])),
+                           rms_eps=float(g("attention.layer_norm_rms_epsilon", 1e-5)),
+                           rope_theta=float(g("rope.freq_base", 10000.0)), rope_scaling=None,
+                           max_pos=int(g("context_length", 4096)), quant="gguf",
+                           name=str(md.get("general.name", arch)), rope_neox=False, rope_freq_factors=factors)
+
+    @classmethod
+    def from_gguf(cls, ar, device, dtype=torch.bfloat16, tp_rank=0, tp_size=1, keep_host=False, max_pos=None):
+        """Device-resident weights of a llama-architecture GGUF archive (`gguf_file.GgufArchive`):
+        ggml blocks uploaded as stored (column/row TP shards cut on block boundaries, as for the
+        synthetic model), norm vectors converted to the activation dtype, `output.weight` falling
+        back to the tied `token_embd.weight`.  Tensor names: llama.cpp's (`blk.N.attn_q.weight` …)."""
+        self = cls.__new__(cls)
+        cfg = cls.config_from_gguf(ar)
+        if max_pos is not None:
+            cfg.max_pos = int(max_pos)
+        self.cfg, self.device, self.dtype = cfg, device, dtype
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+        self.host = {} if keep_host else None
+        self.layers, self.nbytes = [], 0
+        if cfg.n_heads % tp_size or cfg.n_kv_heads % tp_size:
+            raise ValueError("tensor-parallel size must divide the head counts")
+        for l in range(cfg.n_layers):
+            L = {}
+            for name, kind in cls.GGUF_NAMES.items():
+                L[name] = self._gguf_qtensor(ar, f"blk.{l}.{name}.weight", (l, name), kind)
+            for name in ("attn_norm", "ffn_norm"):
+                L[name] = self._gguf_norm(ar, f"blk.{l}.{name}.weight", (l, name))
+            self.layers.append(L)
+        self.tok_embd = self._gguf_qtensor(ar, "token_embd.weight", (0, "token_embd"), "rep")
+        out_name = "output.weight" if ar.contains_tensor("output.weight") else "token_embd.weight"
+        self.output = self._gguf_qtensor(ar, out_name, (0, "output"), "rep")
+        self.output_norm = self._gguf_norm(ar, "output_norm.weight", (0, "output_norm"))
+        cos, sin = rope_tables(cfg)
+        self.rope_cos = torch.from_numpy(cos).to(device).to(dtype)
+        self.rope_sin = torch.from_numpy(sin).to(device).to(dtype)
+        return self
+
+    def _gguf_norm(self, ar, name, key):
+        t = ar.load_dense(name, self.device, self.dtype).reshape(-1).contiguous()
+        if self.host is not None:
+            self.host[key] = t.float().cpu().numpy()
+        return t
+
+    def _gguf_qtensor(self, ar, name, key, kind):
+        info = ar.tensor_info(name)
+        if info.dtype not in BLOCK_BYTES:
+            raise NotImplementedError(f"GGUF tensor `{name}` is {info.dtype}: the decode kernels take ggml block types "
+                                      f"({', '.join(sorted(BLOCK_BYTES))})")
+        if len(info.shape) != 2:
+            raise ValueError(f"GGUF tensor `{name}` must be a matrix, got shape {info.shape}")
+        rows, cols = info.shape
+        be, bb = BLOCK_ELEMS[info.dtype], BLOCK_BYTES[info.dtype]
+        full = ar.tensor_data(name).reshape(rows, cols // be, bb)
+        full, rows, cols = self._shard(full, rows, cols, be, kind)
+        flat = np.ascontiguousarray(full).reshape(-1)
+        t = torch.from_numpy(np.array(flat)).to(self.device)
+        self.nbytes += t.numel()
+        if self.host is not None:
+            self.host[key] = np.array(flat)
+        return (t, info.dtype, rows, cols)
+
+    def _shard(self, full, rows, cols, be, kind):
+        """kind: 'col' (rows sharded), 'row' (K sharded on block boundaries), 'rep' (replicated)."""
+        r, w = self.tp_rank, self.tp_size
+        if kind == "col" and w > 1:
+            if rows % w:
+                raise ValueError("column-parallel rows do not divide by the tensor-parallel size")
+            return full[r * rows // w:(r + 1) * rows // w], rows // w, cols
+        if kind == "row" and w > 1:
+            nb = cols // be
+            if nb % w:
+                raise ValueError("row-parallel K does not split on block boundaries")
+            return full[:, r * nb // w:(r + 1) * nb // w], rows, cols // w
+        return full, rows, cols
 
     def _norm(self, layer, name):
         rng = np.random.Generator(np.random.PCG64(tensor_seed(layer, name)))
@@ -227,6 +331,10 @@ class LlamaRunner:
     def __init__(self, weights: LlamaWeights, batch=1, max_ctx=512, pdl=False, sm_count=148, comm=None,
                  fused_attention=True, split_policy="sm_fill", split_min_tokens=64):
         cfg, dev, dt = weights.cfg, weights.device, weights.dtype
+        if not cfg.rope_neox:
+            # the fused attention kernel rotates q/k with the rotate-half pairing only; interleaved
+            # (GGUF llama) models go through rotary_embedding_positions + reshape_and_cache + decode
+            fused_attention = False
         self.w, self.cfg, self.dev, self.dt, self.B = weights, cfg, dev, dt, batch
         tp = weights.tp_size
         self.n_heads, self.n_kv = cfg.n_heads // tp, cfg.n_kv_heads // tp
@@ -273,7 +381,7 @@ class LlamaRunner:
         s = _Step()
         s.hidden, s.n_layers, s.n_heads, s.n_kv_heads, s.head_dim, s.vocab = H, cfg.n_layers, self.n_heads, self.n_kv, cfg.head_dim, cfg.vocab
         s.block_size, s.act_dtype = bs, {torch.float16: 0, torch.bfloat16: 1}[dt]
-        s.rms_eps, s.sm_scale, s.rope_neox, s.pdl = cfg.rms_eps, 1.0 / float(np.sqrt(cfg.head_dim)), 1, int(pdl)
+        s.rms_eps, s.sm_scale, s.rope_neox, s.pdl = cfg.rms_eps, 1.0 / float(np.sqrt(cfg.head_dim)), int(cfg.rope_neox), int(pdl)
         s.layers = ctypes.cast(self._layers, ctypes.POINTER(_Layer))
         t, ty, rows, cols = weights.tok_embd
         s.tok_embd = _QW(t.data_ptr(), GGML[ty], rows, cols)

@@ -57,7 +57,7 @@ class OracleLlama:
             q = self._gemv(l, "attn_q", h, H * D, c.hidden)
             k = self._gemv(l, "attn_k", h, KVH * D, c.hidden)
             v = self._gemv(l, "attn_v", h, KVH * D, c.hidden)
-            q, k = oracle.rotary(q, k, self.cos, self.sin, np.full(B, pos, dtype=np.uint32), True, D, D // 2, H, KVH, dt)
+            q, k = oracle.rotary(q, k, self.cos, self.sin, np.full(B, pos, dtype=np.uint32), bool(getattr(c, "rope_neox", True)), D, D // 2, H, KVH, dt)
             self.k[l].append(k.copy()); self.v[l].append(v.copy())
             kk = np.stack(self.k[l], axis=1).reshape(B, -1, KVH, D).astype(np.float64)   # [B, T, KVH, D]
             vv = np.stack(self.v[l], axis=1).reshape(B, -1, KVH, D).astype(np.float64)

@@ -11,9 +11,13 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
+def _declared_symbols(host=False):
+    """symbols declared by include/*.h; mrs_b200_host.h belongs to libmrs_b200_host.so, the rest to
+    the CUDA library"""
     names = set()
     for h in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        if h.endswith("_host.h") != host:
+            continue
         src = subprocess.run(["gcc", "-E", "-P", h], capture_output=True, text=True, check=True).stdout
         src = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
         for m in re.finditer(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(([^;{}]*)\)\s*;", src):
@@ -30,6 +34,16 @@ def test_every_declared_symbol_is_exported():
     missing = [n for n in sorted(decl) if not hasattr(lib, n)]
     assert not missing, missing
     assert sum(n.startswith("launch_mmvq_gguf_") for n in decl) == 93
+
+
+def test_host_library_exports_its_header():
+    from mistralrs_b200.kv_index import HOST_LIB_PATH
+    assert os.path.exists(HOST_LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(HOST_LIB_PATH)
+    decl = _declared_symbols(host=True)
+    assert len(decl) >= 26, len(decl)
+    missing = [n for n in sorted(decl) if not hasattr(lib, n)]
+    assert not missing, missing
 
 
 def test_reference_symbol_names_match_ffi_rs():
