@@ -60,6 +60,20 @@ int64_t mrs_gguf_meta_str(void *archive, const char *key, char *buf, int64_t cap
 int64_t mrs_gguf_meta_arr_str(void *archive, const char *key, int64_t idx, char *buf, int64_t cap);
 int64_t mrs_gguf_meta_arr_num(void *archive, const char *key, int64_t start, int64_t cap, double *out, int64_t *out_int);
 
+/* ---- safetensors containers (UQFF shards, residual.safetensors) ----
+ * REF docs/src/content/docs/reference/uqff-format.md, mistralrs-quant/src/uqff/reader.rs: a UQFF shard
+ * is a safetensors file whose entries follow naming conventions (see mistral.rs_b200/uqff_file.py). */
+void *mrs_st_open(const char *path, char *err, int64_t err_cap); /* NULL + message on failure */
+void mrs_st_close(void *file);
+int64_t mrs_st_n_tensors(void *file);
+int64_t mrs_st_find(void *file, const char *name); /* index or -1 */
+/* dtype: safetensors dtype string into a >= 16-byte buffer; dims: up to 8 entries, row-major */
+int32_t mrs_st_tensor_info(void *file, int64_t i, char *name, int64_t name_cap, char *dtype, int32_t *n_dims,
+                           int64_t *dims, int64_t *offset, int64_t *nbytes);
+const void *mrs_st_tensor_data(void *file, int64_t i);
+int64_t mrs_st_n_metadata(void *file);
+int64_t mrs_st_metadata(void *file, int64_t i, char *key, int64_t key_cap, char *val, int64_t val_cap);
+
 #ifdef __cplusplus
 }
 #endif

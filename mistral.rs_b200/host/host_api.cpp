@@ -1,6 +1,7 @@
 // host_api.cpp — C API over the C++ host layer (kv_index.hpp) for the Python test/bench harness.
 #include "gguf_reader.hpp"
 #include "kv_index.hpp"
+#include "safetensors_reader.hpp"
 
 #include <cstring>
 
@@ -170,6 +171,46 @@ int64_t mrs_gguf_meta_arr_num(void *h, const char *key, int64_t start, int64_t c
     if (out_int != nullptr) out_int[n] = v->arr_int[k];
   }
   return n;
+}
+
+
+// ---------------------------------------------------------------- safetensors containers (UQFF shards)
+void *mrs_st_open(const char *path, char *err, int64_t err_cap) {
+  try {
+    return new SafetensorsFile(path);
+  } catch (const std::exception &e) {
+    copy_out(e.what(), err, err_cap);
+    return nullptr;
+  }
+}
+void mrs_st_close(void *h) { delete (SafetensorsFile *)h; }
+int64_t mrs_st_n_tensors(void *h) { return (int64_t)((SafetensorsFile *)h)->tensors().size(); }
+int64_t mrs_st_find(void *h, const char *name) { return ((SafetensorsFile *)h)->find(name); }
+// dtype: safetensors dtype string ("U8", "U32", "BF16", ...) into a >= 16-byte buffer; dims: up to 8
+int32_t mrs_st_tensor_info(void *h, int64_t i, char *name, int64_t name_cap, char *dtype, int32_t *n_dims, int64_t *dims,
+                           int64_t *offset, int64_t *nbytes) {
+  const auto &ts = ((SafetensorsFile *)h)->tensors();
+  if (i < 0 || (size_t)i >= ts.size()) return -1;
+  const StTensor &t = ts[(size_t)i];
+  copy_out(t.dtype, dtype, 16);
+  *n_dims = (int32_t)t.shape.size();
+  for (size_t d = 0; d < t.shape.size() && d < 8; d++) dims[d] = t.shape[d];
+  *offset = (int64_t)t.begin;
+  *nbytes = (int64_t)(t.end - t.begin);
+  return copy_out(t.name, name, name_cap);
+}
+const void *mrs_st_tensor_data(void *h, int64_t i) {
+  const auto &ts = ((SafetensorsFile *)h)->tensors();
+  if (i < 0 || (size_t)i >= ts.size()) return nullptr;
+  return ((SafetensorsFile *)h)->data((size_t)i);
+}
+int64_t mrs_st_n_metadata(void *h) { return (int64_t)((SafetensorsFile *)h)->metadata().size(); }
+// returns the value length (key/value copied with truncation), -1 on a bad index
+int64_t mrs_st_metadata(void *h, int64_t i, char *key, int64_t key_cap, char *val, int64_t val_cap) {
+  const auto &m = ((SafetensorsFile *)h)->metadata();
+  if (i < 0 || (size_t)i >= m.size()) return -1;
+  copy_out(m[(size_t)i].first, key, key_cap);
+  return copy_out(m[(size_t)i].second, val, val_cap);
 }
 
 }  // extern "C"

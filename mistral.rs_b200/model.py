@@ -243,6 +243,85 @@ class LlamaWeights:
         self.rope_sin = torch.from_numpy(sin).to(device).to(dtype)
         return self
 
+    UQFF_NAMES = {"attn_q": "self_attn.q_proj", "attn_k": "self_attn.k_proj", "attn_v": "self_attn.v_proj",
+                  "attn_output": "self_attn.o_proj", "ffn_gate": "mlp.gate_proj", "ffn_up": "mlp.up_proj",
+                  "ffn_down": "mlp.down_proj"}
+
+    @staticmethod
+    def config_from_hf(cj: dict) -> "LlamaConfig":
+        """Hyper-parameters from a Hugging Face `config.json` (llama family), the source the
+        reference's non-GGUF loaders read (`models/llama.rs::Config`)."""
+        heads = int(cj["num_attention_heads"])
+        sc = cj.get("rope_scaling")
+        if sc is not None:
+            kind = sc.get("rope_type", sc.get("type"))
+            if kind != "llama3":
+                raise NotImplementedError(f"rope_scaling type {kind!r} is not supported (llama3 only)")
+            sc = {k: sc[k] for k in ("factor", "low_freq_factor", "high_freq_factor", "original_max_position_embeddings")}
+        return LlamaConfig(hidden=int(cj["hidden_size"]), inter=int(cj["intermediate_size"]),
+                           n_layers=int(cj["num_hidden_layers"]), n_heads=heads,
+                           n_kv_heads=int(cj.get("num_key_value_heads", heads)),
+                           head_dim=int(cj.get("head_dim") or int(cj["hidden_size"]) // heads), vocab=int(cj["vocab_size"]),
+                           rms_eps=float(cj.get("rms_norm_eps", 1e-5)), rope_theta=float(cj.get("rope_theta", 10000.0)),
+                           rope_scaling=sc, max_pos=int(cj.get("max_position_embeddings", 4096)), quant="uqff",
+                           name=str(cj.get("_name_or_path") or cj.get("model_type", "llama")), rope_neox=True)
+
+    @classmethod
+    def from_uqff(cls, ar, device, dtype=torch.bfloat16, tp_rank=0, tp_size=1, keep_host=False, max_pos=None):
+        """Device-resident weights of a UQFF artifact (`uqff_file.UqffArchive`): GGML-family layer
+        entries uploaded as stored, norms from `residual.safetensors`, hyper-parameters from
+        `config.json`; Hugging Face tensor paths (`model.layers.N.self_attn.q_proj` …) and the
+        rotate-half RoPE pairing, so the fused attention path applies."""
+        if ar.config is None:
+            raise ValueError("UQFF artifact has no config.json next to its shards")
+        self = cls.__new__(cls)
+        cfg = cls.config_from_hf(ar.config)
+        if max_pos is not None:
+            cfg.max_pos = int(max_pos)
+        self.cfg, self.device, self.dtype = cfg, device, dtype
+        self.tp_rank, self.tp_size = tp_rank, tp_size
+        self.host = {} if keep_host else None
+        self.layers, self.nbytes = [], 0
+        if cfg.n_heads % tp_size or cfg.n_kv_heads % tp_size:
+            raise ValueError("tensor-parallel size must divide the head counts")
+        for l in range(cfg.n_layers):
+            L = {}
+            for name, kind in cls.GGUF_NAMES.items():
+                L[name] = self._uqff_qtensor(ar, f"model.layers.{l}.{cls.UQFF_NAMES[name]}", (l, name), kind)
+            L["attn_norm"] = self._uqff_norm(ar, f"model.layers.{l}.input_layernorm.weight", (l, "attn_norm"))
+            L["ffn_norm"] = self._uqff_norm(ar, f"model.layers.{l}.post_attention_layernorm.weight", (l, "ffn_norm"))
+            self.layers.append(L)
+        if not ar.contains("model.embed_tokens.weight.format"):
+            raise NotImplementedError("this UQFF artifact keeps dense token embeddings in residual.safetensors (UQFF <= 1.1); "
+                                      "the embedding gather kernel takes ggml block types")
+        self.tok_embd = self._uqff_qtensor(ar, "model.embed_tokens", (0, "token_embd"), "rep")
+        tied = bool(ar.config.get("tie_word_embeddings", False)) or not ar.contains("lm_head.weight.format")
+        self.output = self._uqff_qtensor(ar, "model.embed_tokens" if tied else "lm_head", (0, "output"), "rep")
+        self.output_norm = self._uqff_norm(ar, "model.norm.weight", (0, "output_norm"))
+        cos, sin = rope_tables(cfg)
+        self.rope_cos = torch.from_numpy(cos).to(device).to(dtype)
+        self.rope_sin = torch.from_numpy(sin).to(device).to(dtype)
+        return self
+
+    def _uqff_norm(self, ar, name, key):
+        t = ar.load_tensor(name, self.device, self.dtype).reshape(-1).contiguous()
+        if self.host is not None:
+            self.host[key] = t.float().cpu().numpy()
+        return t
+
+    def _uqff_qtensor(self, ar, key_path, key, kind):
+        q = ar.load_qtensor(key_path, "cpu")
+        rows, cols = q.shape
+        be, bb = BLOCK_ELEMS[q.dtype], BLOCK_BYTES[q.dtype]
+        full = q.data.numpy().reshape(rows, cols // be, bb)
+        full, rows, cols = self._shard(full, rows, cols, be, kind)
+        flat = np.ascontiguousarray(full).reshape(-1)
+        t = torch.from_numpy(np.array(flat)).to(self.device)
+        self.nbytes += t.numel()
+        if self.host is not None:
+            self.host[key] = np.array(flat)
+        return (t, q.dtype, rows, cols)
+
     def _gguf_norm(self, ar, name, key):
         t = ar.load_dense(name, self.device, self.dtype).reshape(-1).contiguous()
         if self.host is not None:

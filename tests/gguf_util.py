@@ -83,3 +83,72 @@ def write_llama_gguf(path, cfg, tensors=None, names=None, split=None, alignment=
     w.write_tensors_to_file()
     w.close()
     return tensors
+
+
+# ---- UQFF artifacts (safetensors shards following REF docs/.../reference/uqff-format.md) -------------
+UQFF_KEYS = {"attn_q": "self_attn.q_proj", "attn_k": "self_attn.k_proj", "attn_v": "self_attn.v_proj",
+             "attn_output": "self_attn.o_proj", "ffn_gate": "mlp.gate_proj", "ffn_up": "mlp.up_proj",
+             "ffn_down": "mlp.down_proj"}
+GGML_CODE = {"q4_0": 2, "q4_1": 3, "q5_0": 6, "q5_1": 7, "q8_0": 8, "q2_k": 10, "q3_k": 11, "q4_k": 12, "q5_k": 13,
+             "q6_k": 14}
+
+
+def uqff_layer_entries(key, dtype, rows, cols, blocks):
+    """the four entries of a GGML-family layer"""
+    return {f"{key}.weight": np.ascontiguousarray(blocks).reshape(-1).astype(np.uint8),
+            f"{key}.weight.format": np.array(0, dtype=np.uint8),
+            f"{key}.weight.dtype": np.array(GGML_CODE[dtype], dtype=np.uint32),
+            f"{key}.weight.shape": np.array([rows, cols], dtype=np.uint32)}
+
+
+def uqff_version_entries(version=(1, 2, 0)):
+    return {f"uqff.version.{n}": np.array(v, dtype=np.uint32) for n, v in zip(("major", "minor", "patch"), version)}
+
+
+def write_llama_uqff(dirpath, cfg, n_shards=2, version=(1, 2, 0), tie=False):
+    """Write the synthetic llama model of model.py as a UQFF artifact directory: `q-<n>.uqff` shards,
+    residual.safetensors (norms, bf16) and config.json.  Returns name -> blocks / f32 norm arrays."""
+    import json
+    import os
+
+    import torch
+    from safetensors.numpy import save_file
+    from safetensors.torch import save_file as save_torch
+    t = llama_tensors(cfg)
+    layers, resid, src = {}, {}, {}
+
+    def q(key, gname):
+        _, dt, rows, cols, blocks = t[gname]
+        layers[key] = uqff_layer_entries(key, dt, rows, cols, blocks)
+        src[key] = (dt, rows, cols, blocks)
+
+    def norm(name, gname):
+        resid[name] = torch.from_numpy(t[gname][1]).to(torch.bfloat16)
+        src[name] = t[gname][1]
+    q("model.embed_tokens", "token_embd.weight")
+    for l in range(cfg.n_layers):
+        for g, h in UQFF_KEYS.items():
+            q(f"model.layers.{l}.{h}", f"blk.{l}.{g}.weight")
+        norm(f"model.layers.{l}.input_layernorm.weight", f"blk.{l}.attn_norm.weight")
+        norm(f"model.layers.{l}.post_attention_layernorm.weight", f"blk.{l}.ffn_norm.weight")
+    norm("model.norm.weight", "output_norm.weight")
+    if not tie:
+        q("lm_head", "output.weight")
+    os.makedirs(dirpath, exist_ok=True)
+    keys = list(layers)
+    per = -(-len(keys) // n_shards)
+    paths = []
+    for s in range(n_shards):
+        entries = dict(uqff_version_entries(version))
+        for k in keys[s * per:(s + 1) * per]:
+            entries.update(layers[k])
+        p = os.path.join(dirpath, f"q-{s}.uqff")
+        save_file(entries, p, metadata={"uqff.producer": "mrs-b200 tests", "uqff.producer.mistralrs.version": "test"})
+        paths.append(p)
+    save_torch(resid, os.path.join(dirpath, "residual.safetensors"))
+    json.dump({"model_type": "llama", "hidden_size": cfg.hidden, "intermediate_size": cfg.inter,
+               "num_hidden_layers": cfg.n_layers, "num_attention_heads": cfg.n_heads,
+               "num_key_value_heads": cfg.n_kv_heads, "head_dim": cfg.head_dim, "vocab_size": cfg.vocab,
+               "rms_norm_eps": cfg.rms_eps, "rope_theta": cfg.rope_theta, "max_position_embeddings": cfg.max_pos,
+               "tie_word_embeddings": tie}, open(os.path.join(dirpath, "config.json"), "w"))
+    return paths, src

@@ -39,3 +39,33 @@ def test_gguf_llama_decode_matches_oracle(cuda, tmp_path):
         assert err <= 4.1 * 2.0 ** -7, (pos, err)     # bf16 logits: isolated 1-3 ulp flips, as in test_model_gpu
         toks = np.argmax(want, axis=1).tolist()
         run.set_tokens(toks)
+
+
+def test_uqff_llama_decode_matches_oracle(cuda, tmp_path):
+    # UQFF artifact (safetensors shards + residual + config.json) -> from_uqff -> fused decode path
+    from gguf_util import write_llama_uqff
+    from mistralrs_b200 import uqff_file
+    cfg0 = M.LlamaConfig.tiny_test(quant="q4_k_m", n_layers=3)
+    d = str(tmp_path / "art")
+    write_llama_uqff(d, cfg0, n_shards=2)
+    with uqff_file.UqffArchive(d) as ar:
+        w = M.LlamaWeights.from_uqff(ar, cuda, keep_host=True)
+    cfg = w.cfg
+    assert cfg.rope_neox is True
+    types = {(l, n): w.layers[l][n][1] for l in range(cfg.n_layers) for n in M.LlamaWeights.GGUF_NAMES}
+    types[(0, "token_embd")], types[(0, "output")] = w.tok_embd[1], w.output[1]
+    run = M.LlamaRunner(w, batch=2, max_ctx=64)
+    cos, sin = M.rope_tables(cfg)
+    ref = OracleLlama(cfg, w.host, lambda c, name, layer: types[(layer if name not in ("token_embd", "output") else 0, name)],
+                      cos, sin, "bf16")
+    toks = [5, 731]
+    run.set_tokens(toks)
+    for pos in range(4):
+        run.step()
+        torch.cuda.synchronize()
+        got = run.logits().float().cpu().numpy()
+        want = ref.step(toks, pos)
+        err = np.abs(got - want).max() / np.abs(want).max()
+        assert err <= 4.1 * 2.0 ** -7, (pos, err)
+        toks = np.argmax(want, axis=1).tolist()
+        run.set_tokens(toks)
