@@ -1,18 +1,24 @@
-"""Dev: per-token time breakdown of the decode graph (full / GEMV-only / attention-only)."""
-import sys, os, json
-import numpy as np, torch
+"""Dev: per-token time breakdown of the decode graph (full / GEMV-only / attention-only), optionally
+sweeping the split-KV chunk size.  usage: dev_breakdown.py [layers] [min_tokens ...]
+MRS_DEV_LIB=path runs against another build of libmrs_b200.so (A/B)."""
+import sys, os
+import torch
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
 import __graft_entry__ as g
 pkg = g.load_package()
 if os.environ.get("MRS_DEV_LIB"):
-    pkg.LIB_PATH = os.environ["MRS_DEV_LIB"]   # dev A/B against another build
+    pkg.LIB_PATH = os.environ["MRS_DEV_LIB"]
 from mistralrs_b200 import model as M
 dev = torch.device("cuda:0")
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+sweep = [int(a) for a in sys.argv[2:]] or [64]
 cfg = M.LlamaConfig.llama3_8b(); cfg.n_layers = layers
 w = M.LlamaWeights(cfg, dev)
+
+
 def timed(run, mask, reps=30):
+    """mask: 0 full step, 1 GEMVs only (attention skipped), 2 attention only"""
     run.step_struct.skip_mask = mask
     run.reset(); run.context_lens.fill_(256)
     run.step(); torch.cuda.synchronize()
@@ -28,7 +34,11 @@ def timed(run, mask, reps=30):
     e1.record(); torch.cuda.synchronize()
     run.step_struct.skip_mask = 0
     return e0.elapsed_time(e1) / reps * 1e3
-for mt in (64, 96, 128):
-    run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=True, fused_attention=True, split_min_tokens=mt)
-    full, gemv, attn = timed(run, 0), timed(run, 1), timed(run, 2)
-    print(f"layers={layers} split_min_tokens={mt} tiles={run.padded_tiles}: full {full:8.1f} us  gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)
+
+
+for pdl in (1, 0):
+    for mt in sweep:
+        run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=bool(pdl), fused_attention=True, split_min_tokens=mt)
+        full, gemv, attn = timed(run, 0), timed(run, 1), timed(run, 2)
+        print(f"layers={layers} pdl={pdl} split_min_tokens={mt} tiles={run.padded_tiles}: full {full:8.1f} us  "
+              f"gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)
