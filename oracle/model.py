@@ -21,8 +21,14 @@ import oracle
 
 
 class OracleLlama:
-    def __init__(self, cfg, host_weights, tensor_type, rope_cos, rope_sin, dt="bf16", cpu_path=False, threads=1):
+    def __init__(self, cfg, host_weights, tensor_type, rope_cos, rope_sin, dt="bf16", cpu_path=False, threads=1,
+                 exact_gemm=False):
+        """exact_gemm: the linears are the exact product of the dequantised weights with the (dtype-
+        rounded) activations — the known-answer form the prefill dequant-GEMM is tested against —
+        instead of the decode path's Q8_1 integer dots.  Stepping token by token then restates a
+        prefill forward (causal attention == attention over the cache so far)."""
         self.cfg, self.hw, self.tt, self.dt = cfg, host_weights, tensor_type, dt
+        self.exact_gemm = exact_gemm
         self.cos, self.sin = oracle.round_dtype(rope_cos, dt), oracle.round_dtype(rope_sin, dt)
         self.cpu_path, self.threads = cpu_path, threads
         self.k = [[] for _ in range(cfg.n_layers)]  # per layer list of [kvh*D] rows (dense cache)
@@ -31,7 +37,9 @@ class OracleLlama:
     def _gemv(self, layer, name, x, rows, cols):
         ty = self.tt(self.cfg, name, layer)
         w = self.hw[(layer, name)]
-        if self.cpu_path:
+        if self.exact_gemm:
+            y = oracle.matmul_exact(ty, w, x, cols, rows)
+        elif self.cpu_path:
             y = oracle.qmatmul_cpu(ty, w, x, cols, rows, self.threads)
         else:
             xq, stride = oracle.quantize_q8_1(x)
