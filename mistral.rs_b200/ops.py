@@ -69,6 +69,24 @@ def apply_rotary_qk(q, k, cos, sin, positions=None, is_neox=True):
                                          ctypes.c_uint32(_DT_CODE[q.dtype]), ctypes.c_int64(_stream(q.device)))
 
 
+def embedding_gather(w, ids: torch.Tensor, dtype=torch.bfloat16):
+    """Rows `ids` of a ggml-block embedding table, dequantised to `dtype` — the
+    `GgufMatMul::embedding_forward_raw` gather (REF gguf/mod.rs:790-845: dequantize().index_select()).
+    w: quant.QTensor [vocab, cols]; ids: i32 tensor of any shape -> [..., cols]."""
+    from . import GGML
+    if ids.dtype != torch.int32:
+        raise ValueError("embedding_gather expects i32 ids")
+    flat = ids.reshape(-1).contiguous()
+    out = torch.empty(flat.numel(), w.shape[1], dtype=dtype, device=w.data.device)
+    rc = lib().mrs_embedding_gather(ctypes.c_int32(GGML[w.dtype]), _p(w.data), ctypes.c_int32(w.shape[1]), _p(flat),
+                                    ctypes.c_int32(flat.numel()), _p(out),
+                                    ctypes.c_int32({torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}[dtype]),
+                                    ctypes.c_void_p(_stream(w.data.device)))
+    if rc != 0:
+        raise RuntimeError(f"mrs_embedding_gather failed with cudaError {rc}")
+    return out.reshape(*ids.shape, w.shape[1])
+
+
 def rms_norm(x, weight, eps):
     x = x.contiguous()
     cols = x.shape[-1]

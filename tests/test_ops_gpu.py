@@ -189,3 +189,22 @@ def test_rms_norm_strided_4d(cuda, dt, D):
     want = oracle.rms_norm(rows, w, 1e-6, dt).reshape(B, H, S, D)
     assert got.shape == want.shape
     assert (np.abs(got - want) <= ulp * np.abs(want) * 1.01 + 1e-7).all()
+
+
+@pytest.mark.parametrize("dtype", ["q6_k", "q8_0", "q4_k", "q5_k", "q3_k", "q2_k", "q4_0", "q4_1", "q5_0", "q5_1"])
+def test_embedding_gather_matches_dequantized_rows(cuda, dtype):
+    # the reference's `assert_embedding_matches_dequantized_gather` (gguf/mod.rs:813-845: ids [2,3],
+    # gather == dequantize().index_select(), <= 1e-6) for every block type, f32 and bf16 outputs
+    from mistralrs_b200 import quant
+    from util import make_weight
+    vocab, cols = 40, 512
+    wb = make_weight(dtype, vocab, cols, 77)
+    w = quant.QTensor(to_dev(wb.reshape(-1), cuda), dtype, (vocab, cols))
+    ids = torch.tensor([[3, 0, 39], [3, 17, 8]], dtype=torch.int32, device=cuda)
+    full = oracle.dequantize(dtype, wb).reshape(vocab, cols)
+    want = full[ids.cpu().numpy().reshape(-1)].reshape(2, 3, cols)
+    got = ops.embedding_gather(w, ids, torch.float32).cpu().numpy()
+    assert got.shape == (2, 3, cols)
+    assert np.abs(got - want).max() <= 1e-6 * max(1.0, np.abs(want).max())
+    got16 = ops.embedding_gather(w, ids, torch.bfloat16).float().cpu().numpy()
+    assert (np.abs(got16 - oracle.round_dtype(want, "bf16")) <= 2.0 ** -8 * np.abs(want) + 1e-9).all()
