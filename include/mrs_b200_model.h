@@ -61,12 +61,15 @@ int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream);
 /* On-device restatement of the scheduler-side index producers for a running decode batch
  * (REF inputs_processor.rs:896-923, flashinfer/metadata.rs:88-216): context_lens[b] += 1,
  * positions, slot_mapping, the paged-KV CSR and the split-KV tile plan for the new lengths,
- * all from the dense block table — so a whole generation replays as one CUDA graph. */
+ * all from the dense block table — so a whole generation replays as one CUDA graph.
+ * batch <= 256.  A sequence at min(max_blocks_per_seq*block_size, max_pos) (max_pos <= 0: no RoPE
+ * bound) stops growing: slot -1 (no KV write) and bit 0 of *error_flag (nullable) is set. */
 int32_t mrs_decode_advance(const int32_t *block_tables, int32_t max_blocks_per_seq, int32_t *context_lens,
                            int32_t batch, int32_t block_size, int32_t split_pages, int32_t padded_tiles,
                            int32_t *positions, int64_t *slot_mapping, int32_t *kv_indptr, int32_t *kv_indices,
                            int32_t *kv_last_page_len, int32_t *request_indices, int32_t *kv_tile_indices,
-                           int32_t *o_indptr, int32_t *kv_chunk_size, uint8_t *block_valid_mask, void *stream);
+                           int32_t *o_indptr, int32_t *kv_chunk_size, uint8_t *block_valid_mask,
+                           int32_t max_pos, int32_t *error_flag, void *stream);
 
 /* rows of a quantised table -> activation dtype (embedding gather). ids on device. */
 int32_t mrs_embedding_gather(int32_t ggml_type, const void *table, int32_t cols, const int32_t *ids, int32_t n,

@@ -83,7 +83,9 @@ int32_t mrs_swap_blocks(const void *src, void *dst, int64_t block_bytes, const i
 
 /* ---- B200-native addition: RoPE + KV write + decode attention + split-KV merge in one launch
  * over the HND cache (replaces rotary_embedding_positions + reshape_and_cache_flashinfer +
- * flashinfer_decode + its merge kernel); see csrc/paged_attn.cu. */
+ * flashinfer_decode + its merge kernel); see csrc/paged_attn.cu.  `pdl`: bit 0 = the launch uses
+ * programmatic stream serialisation, bit 1 = interleaved (GPT-J / GGUF llama) RoPE pairing instead
+ * of rotate-half. */
 int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, void *key_cache, void *value_cache,
                                const void *rope_cos, const void *rope_sin, const int32_t *positions,
                                const int64_t *slot_mapping, const int32_t *kv_indptr, const int32_t *kv_indices,

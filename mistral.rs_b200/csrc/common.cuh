@@ -182,7 +182,3 @@ __device__ __forceinline__ uint32_t lds_u16(const uint8_t *p) {  // 2-byte align
 __device__ __forceinline__ float half_bits_to_float(uint32_t h16) {
   return __half2float(__ushort_as_half((unsigned short)h16));
 }
-
-#define MRS_CUDA_CHECK_LAUNCH()                                                              \
-  do {                                                                                       \
-  } while (0)

@@ -114,43 +114,58 @@ __global__ void add_residual_kernel(void *__restrict__ dst, const void *__restri
   if (i < n) store_act(dst, i, load_act(dst, i, dt) + load_act(res, i, dt), dt);
 }
 
-// one CTA, thread 0 walks the (tiny) batch: integers only, must match the host producers
+// one CTA: integers only, must match the host producers.  Thread b owns sequence b (lengths, slot,
+// chunk count), thread 0 turns the per-sequence counts into the two prefix sums, then all threads
+// fill the tile list and the page indices.  A sequence that has used up its block table or the RoPE
+// table (pos >= min(max_blocks*bs, max_pos)) is frozen: its context does not grow, its KV write is
+// skipped (slot -1, the reference's _PAD_SLOT_ID) and *error_flag gets bit 0 — generation past the
+// allocated context must never turn into an out-of-bounds cache write.
+constexpr int ADV_MAX_BATCH = 256;
 __global__ void decode_advance_kernel(const int32_t *__restrict__ block_tables, int max_blocks,
                                       int32_t *__restrict__ context_lens, int batch, int bs, int split_pages,
-                                      int padded_tiles, int32_t *positions, int64_t *slot_mapping, int32_t *kv_indptr,
-                                      int32_t *kv_indices, int32_t *kv_last_page_len, int32_t *request_indices,
-                                      int32_t *kv_tile_indices, int32_t *o_indptr, int32_t *kv_chunk_size,
-                                      uint8_t *block_valid_mask) {
-  __shared__ int s_indptr[65], s_oind[65];
+                                      int padded_tiles, int max_pos, int32_t *positions, int64_t *slot_mapping,
+                                      int32_t *kv_indptr, int32_t *kv_indices, int32_t *kv_last_page_len,
+                                      int32_t *request_indices, int32_t *kv_tile_indices, int32_t *o_indptr,
+                                      int32_t *kv_chunk_size, uint8_t *block_valid_mask, int32_t *error_flag) {
+  __shared__ int s_nb[ADV_MAX_BATCH], s_chunks[ADV_MAX_BATCH], s_indptr[ADV_MAX_BATCH + 1], s_oind[ADV_MAX_BATCH + 1];
+  const int cap = min(max_blocks * bs, max_pos > 0 ? max_pos : max_blocks * bs);
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    int pos = context_lens[b];             // position of the token being processed now
+    const bool full = pos >= cap;
+    if (full) { pos = cap - 1; if (error_flag != nullptr) atomicOr(error_flag, 1); }
+    const int ctx = pos + 1;               // context length including it
+    context_lens[b] = ctx;
+    positions[b] = pos;
+    slot_mapping[b] = full ? (int64_t)-1 : (int64_t)block_tables[(int64_t)b * max_blocks + pos / bs] * bs + pos % bs;
+    const int nb = (ctx + bs - 1) / bs;
+    s_nb[b] = nb;
+    kv_last_page_len[b] = ctx - (nb - 1) * bs;
+    s_chunks[b] = (split_pages > 0) ? ((nb < 1 ? 1 : nb) + split_pages - 1) / split_pages : 1;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     int nnz = 0, tiles = 0;
     s_indptr[0] = 0; s_oind[0] = 0;
     for (int b = 0; b < batch; b++) {
-      const int pos = context_lens[b];       // position of the token being processed now
-      const int ctx = pos + 1;               // context length including it
-      context_lens[b] = ctx;
-      positions[b] = pos;
-      slot_mapping[b] = (int64_t)block_tables[(int64_t)b * max_blocks + pos / bs] * bs + pos % bs;
-      const int nb = (ctx + bs - 1) / bs;
-      nnz += nb;
-      s_indptr[b + 1] = nnz;
-      kv_last_page_len[b] = ctx - (nb - 1) * bs;
-      const int chunks = (split_pages > 0) ? ((nb < 1 ? 1 : nb) + split_pages - 1) / split_pages : 1;
-      for (int t = 0; t < chunks && tiles < padded_tiles; t++, tiles++) { request_indices[tiles] = b; kv_tile_indices[tiles] = t; }
-      s_oind[b + 1] = tiles;
-    }
-    for (int b = 0; b <= batch; b++) { kv_indptr[b] = s_indptr[b]; o_indptr[b] = s_oind[b]; }
-    for (int t = 0; t < padded_tiles; t++) {
-      block_valid_mask[t] = t < tiles ? 1 : 0;
-      if (t >= tiles) { request_indices[t] = 0; kv_tile_indices[t] = 0; }
+      nnz += s_nb[b];
+      tiles = min(tiles + s_chunks[b], padded_tiles);
+      s_indptr[b + 1] = nnz; s_oind[b + 1] = tiles;
     }
     kv_chunk_size[0] = (split_pages > 0 ? split_pages : 1) * bs;
   }
   __syncthreads();
-  // page indices: parallel over (b, i)
+  const int tiles = s_oind[batch];
+  for (int b = threadIdx.x; b <= batch; b += blockDim.x) { kv_indptr[b] = s_indptr[b]; o_indptr[b] = s_oind[b]; }
   for (int b = 0; b < batch; b++) {
+    const int t0 = s_oind[b], nt = s_oind[b + 1] - t0;
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) { request_indices[t0 + t] = b; kv_tile_indices[t0 + t] = t; }
+    // page indices: parallel over (b, i)
     const int p0 = s_indptr[b], nb = s_indptr[b + 1] - p0;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) kv_indices[p0 + i] = block_tables[(int64_t)b * max_blocks + i];
+  }
+  for (int t = threadIdx.x; t < padded_tiles; t += blockDim.x) {
+    block_valid_mask[t] = t < tiles ? 1 : 0;
+    if (t >= tiles) { request_indices[t] = 0; kv_tile_indices[t] = 0; }
   }
 }
 
@@ -188,13 +203,13 @@ extern "C" int32_t mrs_decode_advance(const int32_t *block_tables, int32_t max_b
                                       int32_t *positions, int64_t *slot_mapping, int32_t *kv_indptr,
                                       int32_t *kv_indices, int32_t *kv_last_page_len, int32_t *request_indices,
                                       int32_t *kv_tile_indices, int32_t *o_indptr, int32_t *kv_chunk_size,
-                                      uint8_t *block_valid_mask, void *stream) {
-  if (batch < 1 || batch > 64) return (int32_t)cudaErrorInvalidValue;
-  decode_advance_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(block_tables, max_blocks_per_seq, context_lens, batch,
-                                                             block_size, split_pages, padded_tiles, positions,
+                                      uint8_t *block_valid_mask, int32_t max_pos, int32_t *error_flag, void *stream) {
+  if (batch < 1 || batch > ADV_MAX_BATCH || max_blocks_per_seq < 1 || block_size < 1) return (int32_t)cudaErrorInvalidValue;
+  decode_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(block_tables, max_blocks_per_seq, context_lens, batch,
+                                                             block_size, split_pages, padded_tiles, max_pos, positions,
                                                              slot_mapping, kv_indptr, kv_indices, kv_last_page_len,
                                                              request_indices, kv_tile_indices, o_indptr, kv_chunk_size,
-                                                             block_valid_mask);
+                                                             block_valid_mask, error_flag);
   return (int32_t)cudaGetLastError();
 }
 
@@ -219,8 +234,17 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
   for (int l = 0; l < s->n_layers; l++) {
     const mrs_llama_layer &L = s->layers[l];
     // --- attention block: x = x + o_proj(attn(rope(qkv(norm(x)))))
+    // the fused launches decode every matrix of a group with ONE ggml type: per-tensor type
+    // overrides (GGUF --tensor-type, per-layer UQFF topologies) take separate launches
     if (!do_gemv) {
-    } else if (L.wq.ggml_type == L.wk.ggml_type && L.wk.ggml_type == L.wv.ggml_type) {
+    } else if (L.wq.ggml_type != L.wk.ggml_type) {
+      MRS_TRY(mrs_mmvq_fused(L.wq.ggml_type, 0, dt, L.wq.data, nullptr, nullptr, hidden, L.attn_norm, s->rms_eps,
+                             nullptr, s->q, nullptr, nullptr, H, nq, 0, 0, B, 0, pdl, stream));
+      MRS_TRY(mrs_mmvq_fused(L.wk.ggml_type, 0, dt, L.wk.data, nullptr, nullptr, hidden, L.attn_norm, s->rms_eps,
+                             nullptr, s->k, nullptr, nullptr, H, nkv, 0, 0, B, 0, pdl, stream));
+      MRS_TRY(mrs_mmvq_fused(L.wv.ggml_type, 0, dt, L.wv.data, nullptr, nullptr, hidden, L.attn_norm, s->rms_eps,
+                             nullptr, s->v, nullptr, nullptr, H, nkv, 0, 0, B, 0, pdl, stream));
+    } else if (L.wk.ggml_type == L.wv.ggml_type) {
       MRS_TRY(mrs_mmvq_fused(L.wq.ggml_type, 2, dt, L.wq.data, L.wk.data, L.wv.data, hidden, L.attn_norm, s->rms_eps,
                              nullptr, s->q, s->k, s->v, H, nq, nkv, nkv, B, 0, pdl, stream));
     } else {
@@ -239,7 +263,7 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
                                      s->block_valid_mask, s->attn_out, s->padded_tiles > B ? s->tmp_v : nullptr,
                                      s->padded_tiles > B ? s->tmp_s : nullptr, s->attn_counters, B, s->padded_tiles,
                                      s->n_heads, s->n_kv_heads, s->head_dim, s->block_size, s->sm_scale, (uint32_t)dt,
-                                     pdl, stream));
+                                     pdl | (s->rope_neox ? 0 : 2), stream));
     } else if (do_attn) {
     rotary_embedding_positions(s->q, s->k, (void *)s->rope_cos, (void *)s->rope_sin, s->positions, s->rope_neox,
                                s->head_dim, B, s->head_dim / 2, 0, s->n_heads, s->n_kv_heads, nq, nkv, (uint32_t)dt,
@@ -264,6 +288,7 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
       add_residual_kernel<<<(unsigned)(((int64_t)B * H + 255) / 256), 256, 0, st>>>(hidden2, hidden, (int64_t)B * H, dt);
     }
     // --- MLP block: x = x + down(silu(gate(norm(x))) * up(norm(x)))
+    if (L.w_gate.ggml_type != L.w_up.ggml_type || L.w_gate.rows != L.w_up.rows) return (int32_t)cudaErrorInvalidValue;
     MRS_TRY(mrs_mmvq_fused(L.w_gate.ggml_type, 1, dt, L.w_gate.data, L.w_up.data, nullptr, hidden2, L.ffn_norm,
                            s->rms_eps, nullptr, s->act, nullptr, nullptr, H, L.w_gate.rows, L.w_gate.rows, 0, B, 0,
                            pdl, stream));

@@ -172,7 +172,10 @@ __device__ __forceinline__ void ld_unaligned_words9(const uint8_t *a, uint32_t *
   const uint32_t *a0 = (const uint32_t *)(u & ~(uintptr_t)3);
   phase = (uint32_t)(u & 3) * 8;
 #pragma unroll
-  for (int i = 0; i < 9; i++) w[i] = a0[i];
+  for (int i = 0; i < 8; i++) w[i] = a0[i];
+  // a 34-byte Q8_0 block that starts on a word boundary ends in the middle of word 8: fetch only
+  // its two valid bytes, so the LAST block of a tensor is never read past
+  w[8] = (phase != 0) ? a0[8] : (uint32_t)*(const uint16_t *)(a0 + 8);
 }
 // byte stream starting at the unaligned address: word i of the stream
 __device__ __forceinline__ uint32_t stream_word(const uint32_t *w, int i, uint32_t phase) {
@@ -513,8 +516,7 @@ static PFN_encodeTiled get_encode() {
 template <int TYPE>
 static cudaError_t launch_tc(const TcParams &p, const CUtensorMap &tmap, cudaStream_t st) {
   auto kern = mmq_tc_kernel<TYPE>;
-  static bool set = false;
-  if (!set) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM); set = true; }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);  // per device: set on every launch
   dim3 grid((p.N + TC_BN - 1) / TC_BN, (p.M + TC_MT * TC_BM - 1) / (TC_MT * TC_BM));
   kern<<<grid, TC_THREADS, TC_SMEM, st>>>(tmap, p);
   return cudaGetLastError();

@@ -26,9 +26,9 @@
 
 namespace mrs {
 
-// Two CTA shapes: NCW = 8 consumer warps (two CTAs per SM) or 16 (one CTA per SM: the activation
-// prologue, identical in every CTA, is then computed once per SM instead of twice).  + 1 producer
-// warp; a stage holds 2 row-segments per consumer warp.
+// CTA shape: NCW = 8 consumer warps + 1 producer warp, two CTAs per SM; a stage holds 2
+// row-segments per consumer warp.  (A 16-warp one-CTA-per-SM shape measured slower end to end in
+// round 1 — profiles/r01_experiments.md — and was removed.)
 constexpr int SSW = 8;  // warps that take part in the RMSNorm sum of squares (fixes its summation order)
 
 constexpr int MAX_STAGES = 12;
@@ -68,10 +68,10 @@ struct MmvqParams {
 #endif
 };
 
-template <int T, int NCW> struct Geo {
+template <int T, int NCW, int UPLX = QT<T>::UPL> struct Geo {
   using Q = QT<T>;
   static constexpr int SLOTS = 2 * NCW;
-  static constexpr int UPL = Q::UPL;                         // units per lane per K segment
+  static constexpr int UPL = UPLX;                           // units per lane per K segment (per-launch: long streams take 2x)
   static constexpr int SEG_UNITS = 32 * UPL;                 // 32-weight units per K segment
   static constexpr int SEG_BLOCKS = SEG_UNITS / Q::UPB;      // weight blocks per segment (NB)
   static constexpr int SEG_BYTES = SEG_BLOCKS * Q::BYTES;    // bytes per row-segment (~2-3.5 KB)
@@ -85,8 +85,17 @@ template <int T, int NCW> struct Geo {
 };
 
 // position p in the consumption-ordered activation array <-> (weight block, chunk)
-template <int T> __device__ __forceinline__ void pos_to_unit(int pos, int &blk, int &c) {
-  using G = Geo<T, 8>;  // segment geometry does not depend on the CTA shape
+template <int T, int UPL> __device__ __forceinline__ int unit_to_pos(int blk, int c) {
+  using G = Geo<T, 8, UPL>;
+  if constexpr (QT<T>::UPB == 1) {
+    return blk;
+  } else {
+    const int s = blk / G::SEG_BLOCKS, bl = blk - s * G::SEG_BLOCKS;
+    return s * G::SEG_UNITS + (c / G::CPS) * 32 + bl + G::NBL * (c % G::CPS);
+  }
+}
+template <int T, int UPL> __device__ __forceinline__ void pos_to_unit(int pos, int &blk, int &c) {
+  using G = Geo<T, 8, UPL>;  // segment geometry does not depend on the CTA shape
   if constexpr (QT<T>::UPB == 1) {
     blk = pos; c = 0;
   } else {
@@ -145,10 +154,10 @@ __device__ __forceinline__ void quantize_block_q8_1(const float *v, int8_t *q, f
 
 // The whole CTA program; `cta` of `ncta` CTAs share the virtual rows of `p` (the wrappers below pass
 // blockIdx/gridDim, or the position inside one half of a two-type launch).
-template <int T, int NCOLS, bool FAST, int NCW>
+template <int T, int NCOLS, bool FAST, int NCW, int UPL = QT<T>::UPL>
 __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, const int ncta) {
   using Q = QT<T>;
-  using G = Geo<T, NCW>;
+  using G = Geo<T, NCW, UPL>;
   constexpr int SLOTS = 2 * NCW;
   extern __shared__ __align__(128) uint8_t smem[];
 
@@ -168,7 +177,6 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
   const uint32_t off_xq1 = off_xq0 + (uint32_t)NCOLS * npos * 16;
   const uint32_t off_xa = off_xq1 + (uint32_t)NCOLS * npos * 16;
   const uint32_t off_ring = (off_xa + (uint32_t)NCOLS * npos * Q::AUX * 4 + 127u) & ~127u;
-  const uint32_t off_ds = off_ring + (uint32_t)nst * G::STAGE_BYTES;
   int4 *xq0 = (int4 *)(smem + off_xq0);   // [NCOLS][npos]
   int4 *xq1 = (int4 *)(smem + off_xq1);   // [NCOLS][npos]
   float *xa = (float *)(smem + off_xa);   // [NCOLS][npos][AUX]
@@ -253,7 +261,7 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
     for (int idx = ctid; idx < NCOLS * npos; idx += NCT) {
       const int col = idx / npos, pos = idx - col * npos;
       int blk, c;
-      pos_to_unit<T>(pos, blk, c);
+      pos_to_unit<T, UPL>(pos, blk, c);
       int q[8];
       float a[Q::AUX];
       if (col < p.ncols && blk < nblocks) {
@@ -277,11 +285,11 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
     }
   } else {
     // fused prologue: (optional RMSNorm) -> round to activation dtype -> Q8_1 -> consumption
-    // order.  Pass 1 stages natural-order q8 data in the x region itself (q8 block b: first
-    // 16 B in xq0[col][b], last 16 B in xq1[col][b]) and (d,s) in a strip behind the ring.
-    const int nq8 = p.K / 32;
+    // order, in ONE pass: every thread owns 8-element chunks (one 16-byte load), four
+    // neighbouring lanes form a Q8_1 block, and each thread stores its 8 quantised bytes and the
+    // unit's aux terms straight at their consumption-order position (QT::chunk_dest/chunk_aux) —
+    // no natural-order staging, no permute pass.
     float *red = (float *)(smem + 192);  // 8 floats of scratch inside the header page
-    float2 *dsall = (float2 *)(smem + off_ds);
     const int nchunks = p.K >> 3;                  // 8-element chunks; 4 neighbouring lanes = one Q8_1 block
     const int nchunks_w = (nchunks + 31) & ~31;    // whole warps iterate together (shuffles below)
     for (int col = 0; col < NCOLS; col++) {
@@ -327,11 +335,8 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
         inv_rms = rsqrtf(tot / (float)p.K + p.eps);
       }
       if (tid == 0) MRS_STAMP(4);
-      int4 *n0 = xq0 + (size_t)col * npos, *n1 = xq1 + (size_t)col * npos;
-      float2 *dsbuf = dsall + (size_t)col * nq8;
-      // pass 1: one 8-element chunk per thread per trip (x re-read hits L1); the Q8_1 block of 4
-      // lanes is quantize_block_q8_1's arithmetic with its butterfly sum (i+16, i+8, then 4/2/1
-      // inside the lane) done by shuffles.  A compact loop: the prologue is issue-bound.
+      int4 *c0 = xq0 + (size_t)col * npos, *c1 = xq1 + (size_t)col * npos;
+      float *ca = xa + (size_t)col * npos * Q::AUX;
       int it = 0;
 #pragma unroll 1
       for (int ch = ctid; ch < nchunks_w; ch += NCT, it++) {
@@ -357,15 +362,20 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
         for (int i = 0; i < 8; i++) am = fmaxf(am, fabsf(v[i]));
         am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
         am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
-        float t[8];
+        float bsum = 0.f;
+        if constexpr (Q::NEEDS_SUM) {
+          // the reference's butterfly sum of the 32 block elements (i+16, i+8, then 4/2/1)
+          float t[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) t[i] = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 2);
+          for (int i = 0; i < 8; i++) t[i] = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 2);
 #pragma unroll
-        for (int i = 0; i < 8; i++) t[i] = t[i] + __shfl_xor_sync(0xffffffffu, t[i], 1);
+          for (int i = 0; i < 8; i++) t[i] = t[i] + __shfl_xor_sync(0xffffffffu, t[i], 1);
 #pragma unroll
-        for (int m = 4; m > 0; m >>= 1) {
+          for (int m = 4; m > 0; m >>= 1) {
 #pragma unroll
-          for (int i = 0; i < m; i++) t[i] = t[i] + t[i + m];
+            for (int i = 0; i < m; i++) t[i] = t[i] + t[i + m];
+          }
+          bsum = __half2float(__float2half_rn(t[0]));
         }
         const float d = __fdividef(am, 127.0f);
         uint32_t wq[2] = {0u, 0u};
@@ -374,59 +384,16 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
           const int qi = (am == 0.0f) ? 0 : (int)(int8_t)roundf(__fdividef(v[i], d));
           wq[i >> 2] |= (uint32_t)(qi & 0xff) << (8 * (i & 3));
         }
+        const int isum8 = __dp4a((int)wq[0], 0x01010101, __dp4a((int)wq[1], 0x01010101, 0));
+        const int isum16 = isum8 + __shfl_xor_sync(0xffffffffu, isum8, 1);
         if (ok) {
-          const int b = ch >> 2, part = ch & 3;
-          int2 *dstp = (int2 *)((part < 2 ? n0 : n1) + b) + (part & 1);
-          *dstp = make_int2((int)wq[0], (int)wq[1]);
-          if (part == 0)
-            dsbuf[b] = make_float2(__half2float(__float2half_rn(d)), __half2float(__float2half_rn(t[0])));
-        }
-      }
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(NCT));
-    if (tid == 0) MRS_STAMP(5);
-    // pass 2: natural order -> consumption order through registers
-    {
-      constexpr int MAXU = 4;  // positions per thread per column: K <= MAXU * 256 * 32
-      for (int col = 0; col < NCOLS; col++) {
-        int q[MAXU][8];
-        float a[MAXU][Q::AUX];
-        const int8_t *n0 = (const int8_t *)(xq0 + (size_t)col * npos);
-        const int8_t *n1 = (const int8_t *)(xq1 + (size_t)col * npos);
-        const float2 *dsbuf = dsall + (size_t)col * nq8;
-#pragma unroll
-        for (int k = 0; k < MAXU; k++) {
-          const int pos = ctid + k * NCT;
-          if (k * NCT >= npos) break;  // CTA-uniform
-          int blk = 0, c = 0;
-          if (pos < npos) pos_to_unit<T>(pos, blk, c);
-          if (pos < npos && blk < nblocks) {
-#pragma unroll
-            for (int w = 0; w < 8; w++) {
-              const int e = Q::x_elem(c, w) + blk * Q::QK;  // element index along K
-              const int b32 = e >> 5, o = e & 31;
-              q[k][w] = (o < 16) ? *(const int *)(n0 + b32 * 16 + o) : *(const int *)(n1 + b32 * 16 + (o - 16));
-            }
-            Q::aux(q[k], c, YSmem{dsbuf + (size_t)blk * (Q::QK / 32)}, a[k]);
-          } else {
-#pragma unroll
-            for (int w = 0; w < 8; w++) q[k][w] = 0;
-#pragma unroll
-            for (int i = 0; i < Q::AUX; i++) a[k][i] = 0.f;
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(NCT));
-#pragma unroll
-        for (int k = 0; k < MAXU; k++) {
-          const int pos = ctid + k * NCT;
-          if (k * NCT >= npos) break;  // CTA-uniform
-          if (pos < npos) {
-            const size_t idx = (size_t)col * npos + pos;
-            xq0[idx] = make_int4(q[k][0], q[k][1], q[k][2], q[k][3]);
-            xq1[idx] = make_int4(q[k][4], q[k][5], q[k][6], q[k][7]);
-#pragma unroll
-            for (int i = 0; i < Q::AUX; i++) xa[idx * Q::AUX + i] = a[k][i];
-          }
+          const int e0 = ch * 8;
+          const int blk = e0 / Q::QK, e = e0 - blk * Q::QK;
+          int c, hi, w8;
+          Q::chunk_dest(e, c, hi, w8);
+          const int pos = unit_to_pos<T, UPL>(blk, c);
+          *((int2 *)((hi ? c1 : c0) + pos) + w8) = make_int2((int)wq[0], (int)wq[1]);
+          Q::chunk_aux(e, __half2float(__float2half_rn(d)), bsum, isum8, isum16, ca + (size_t)pos * Q::AUX);
         }
       }
     }
@@ -557,14 +524,14 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
   }
 }
 
-template <int T, int NCOLS, bool FAST, int NCW>
-__global__ void __launch_bounds__((NCW + 1) * 32, NCW == 8 ? 2 : 1) mmvq_stream_kernel(const MmvqParams p) {
-  mmvq_body<T, NCOLS, FAST, NCW>(p, (int)blockIdx.x, (int)gridDim.x);
+template <int T, int NCOLS, bool FAST, int NCW, int UPL>
+__global__ void __launch_bounds__((NCW + 1) * 32, NCOLS == 1 ? 3 : 2) mmvq_stream_kernel(const MmvqParams p) {
+  mmvq_body<T, NCOLS, FAST, NCW, UPL>(p, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // Two launches that read the same activations but hold different ggml types (Q4_K_M keeps attn_v in
 // Q6_K on half the layers) as ONE grid: CTAs [0, g1) run the first program, the rest the second.
-// Batch 1, aligned rows, 8-warp shape only.
+// Batch 1, aligned rows.
 template <int T1, int T2>
 __global__ void __launch_bounds__(9 * 32, 2) mmvq_dual_kernel(const MmvqParams pa, const MmvqParams pb, const int g1) {
   if ((int)blockIdx.x < g1) mmvq_body<T1, 1, true, 8>(pa, (int)blockIdx.x, g1);
@@ -582,59 +549,68 @@ extern "C" int mrs_mmvq_timeline(unsigned long long *buf, int max_launches) {
   return n;
 }
 #endif
-static int g_num_sms = 0;
-static int g_max_smem = 0;
+// per-device properties (a process may drive several GPUs: device-mapped layers, threaded TP)
+constexpr int MAX_DEVICES = 64;
+struct DevInfo { int num_sms, max_smem; };
+static DevInfo g_dev[MAX_DEVICES] = {};
 static int g_flags = 0;
-static long long g_wide_max_bytes = 24ll << 20;
+static long long g_long_min_bytes = 128ll << 20;  // streams at least this long take 2x K segments
 static int g_ctas_per_sm = 2;  // CTAs of ONE launch per SM; 1 leaves half an SM for the next launch (PDL overlap)
 
-static void query_device() {
-  if (g_num_sms) return;
+static const DevInfo &query_device() {
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&g_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (g_num_sms <= 0) g_num_sms = 148;
-  if (g_max_smem <= 0) g_max_smem = 227 * 1024;
+  if (dev < 0 || dev >= MAX_DEVICES) dev = 0;
+  DevInfo &d = g_dev[dev];
+  if (d.num_sms == 0) {
+    int sms = 0, smem = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    d.max_smem = smem > 0 ? smem : 227 * 1024;
+    d.num_sms = sms > 0 ? sms : 148;
+  }
+  return d;
 }
 
-template <int T, int NCOLS, bool FAST, int NCW>
-static cudaError_t launch_one(MmvqParams p, cudaStream_t stream, bool probe_only) {
-  using G = Geo<T, NCW>;
-  constexpr int SLOTS = 2 * NCW;
-  query_device();
+// shared-memory plan of a launch: ring depth and bytes; two CTAs per SM by design, one CTA per SM
+// with a deeper ring (and a one-wave grid) when two do not fit (long K x wide blocks)
+template <int T, int UPL>
+static bool plan8(const MmvqParams &p, int ncols, const DevInfo &d, int &nst, size_t &smem, int &ctas_per_sm) {
+  using G = Geo<T, 8, UPL>;
   const int nblocks = p.K / QT<T>::QK;
   const int nseg = (nblocks + G::SEG_BLOCKS - 1) / G::SEG_BLOCKS;
   const int npos = nseg * G::SEG_UNITS;
-  const size_t xbytes = 256 + (size_t)NCOLS * npos * G::XU_BYTES + 128;
-  const size_t scratch = (p.xkind == X_RAW) ? (size_t)NCOLS * (p.K / 32) * 8 : 0;
-  const size_t full = (size_t)g_max_smem - 1024;
+  const size_t xbytes = 256 + (size_t)ncols * npos * G::XU_BYTES + 128;
+  // batch 1 may run three CTAs per SM (72-register kernels): 24 consumer warps hide the shared-memory
+  // and dp4a latencies better than 16
+  ctas_per_sm = (ncols == 1) ? g_ctas_per_sm : (g_ctas_per_sm > 2 ? 2 : g_ctas_per_sm);
+  size_t budget = (size_t)d.max_smem / (ctas_per_sm < 2 ? 2 : ctas_per_sm) - 1024;
+  const size_t full = (size_t)d.max_smem - 1024;
+  nst = MAX_STAGES;
+  while (nst > 2 && xbytes + (size_t)nst * G::STAGE_BYTES > budget) nst--;
+  smem = xbytes + (size_t)nst * G::STAGE_BYTES;
+  if (smem > budget && ctas_per_sm == 3) {   // does not fit three times: two CTAs per SM
+    ctas_per_sm = 2;
+    budget = (size_t)d.max_smem / 2 - 1024;
+    nst = MAX_STAGES;
+    while (nst > 2 && xbytes + (size_t)nst * G::STAGE_BYTES > budget) nst--;
+    smem = xbytes + (size_t)nst * G::STAGE_BYTES;
+  }
+  if (smem > budget) {
+    ctas_per_sm = 1;
+    while (nst < 4 && xbytes + (size_t)(nst + 1) * G::STAGE_BYTES <= full) nst++;
+    smem = xbytes + (size_t)nst * G::STAGE_BYTES;
+  }
+  return smem <= (size_t)d.max_smem;
+}
+
+template <int T, int NCOLS, bool FAST, int UPL>
+static cudaError_t launch_one(MmvqParams p, cudaStream_t stream) {
+  constexpr int NCW = 8, SLOTS = 2 * NCW;
+  const DevInfo &d = query_device();
   int nst, ctas_per_sm;
   size_t smem;
-  if (NCW == 16) {
-    // one fat CTA per SM: needs at least a double-buffered ring
-    ctas_per_sm = 1;
-    nst = MAX_STAGES;
-    while (nst > 2 && xbytes + scratch + (size_t)nst * G::STAGE_BYTES > full) nst--;
-    smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
-    if (smem > full) return cudaErrorInvalidConfiguration;
-    if (probe_only) return cudaSuccess;
-  } else {
-    // two CTAs per SM by design: keep each under half of the SM's shared memory
-    const size_t budget = (size_t)g_max_smem / 2 - 1024;
-    nst = MAX_STAGES;
-    while (nst > 2 && xbytes + scratch + (size_t)nst * G::STAGE_BYTES > budget) nst--;
-    smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
-    ctas_per_sm = g_ctas_per_sm;
-    if (smem > budget) {
-      // two CTAs do not fit (long K x wide blocks): one CTA per SM with a deeper ring, and a grid
-      // of one wave — a second wave of late CTAs would double the kernel's latency
-      ctas_per_sm = 1;
-      while (nst < 4 && xbytes + scratch + (size_t)(nst + 1) * G::STAGE_BYTES <= full) nst++;
-      smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
-    }
-  }
-  if (smem > (size_t)g_max_smem) return cudaErrorInvalidConfiguration;
+  if (!plan8<T, UPL>(p, NCOLS, d, nst, smem, ctas_per_sm)) return cudaErrorInvalidConfiguration;
   p.nstages = nst;
   p.flags = g_flags;
 #ifdef MRS_TIMELINE
@@ -642,15 +618,13 @@ static cudaError_t launch_one(MmvqParams p, cudaStream_t stream, bool probe_only
 #endif
   const int P = (p.mode == MODE_GLU) ? NCW : SLOTS;
   int grid = (p.vrows + P - 1) / P;
-  const int max_grid = ctas_per_sm * g_num_sms;
+  const int max_grid = ctas_per_sm * d.num_sms;
   if (grid > max_grid) grid = max_grid;
   if (grid < 1) grid = 1;
-  auto kern = mmvq_stream_kernel<T, NCOLS, FAST, NCW>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
-    attr_set = true;
-  }
+  auto kern = mmvq_stream_kernel<T, NCOLS, FAST, NCW, UPL>;
+  // the attribute is per device (context): set it on every launch — it is cheap, and a process-wide
+  // "already set" flag would leave the second GPU of a multi-device process at the 48 KB default
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3((NCW + 1) * 32);
@@ -664,23 +638,6 @@ static cudaError_t launch_one(MmvqParams p, cudaStream_t stream, bool probe_only
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-// shared-memory plan of the 8-warp shape (same rules as launch_one): false when two CTAs per SM do not fit
-template <int T>
-static bool plan8(const MmvqParams &p, int ncols, int &nst, size_t &smem) {
-  using G = Geo<T, 8>;
-  query_device();
-  const int nblocks = p.K / QT<T>::QK;
-  const int nseg = (nblocks + G::SEG_BLOCKS - 1) / G::SEG_BLOCKS;
-  const int npos = nseg * G::SEG_UNITS;
-  const size_t xbytes = 256 + (size_t)ncols * npos * G::XU_BYTES + 128;
-  const size_t scratch = (p.xkind == X_RAW) ? (size_t)ncols * (p.K / 32) * 8 : 0;
-  const size_t budget = (size_t)g_max_smem / 2 - 1024;
-  nst = MAX_STAGES;
-  while (nst > 2 && xbytes + scratch + (size_t)nst * G::STAGE_BYTES > budget) nst--;
-  smem = xbytes + scratch + (size_t)nst * G::STAGE_BYTES;
-  return smem <= budget;
-}
-
 template <int T> static bool rows_aligned(const MmvqParams &p) {
   using Q = QT<T>;
   const int row_bytes = (p.K / Q::QK) * Q::BYTES;
@@ -692,18 +649,25 @@ template <int T> static bool rows_aligned(const MmvqParams &p) {
 
 template <int T1, int T2>
 static cudaError_t launch_dual(MmvqParams pa, MmvqParams pb, cudaStream_t stream) {
-  int nsa, nsb;
+  const DevInfo &d = query_device();
+  int nsa, nsb, ca, cb;
   size_t sma, smb;
-  if (pa.ncols != 1 || pb.ncols != 1 || !rows_aligned<T1>(pa) || !rows_aligned<T2>(pb) || !plan8<T1>(pa, 1, nsa, sma) ||
-      !plan8<T2>(pb, 1, nsb, smb))
+  if (pa.ncols != 1 || pb.ncols != 1 || !rows_aligned<T1>(pa) || !rows_aligned<T2>(pb) ||
+      !plan8<T1, QT<T1>::UPL>(pa, 1, d, nsa, sma, ca) || !plan8<T2, QT<T2>::UPL>(pb, 1, d, nsb, smb, cb) || ca < 2 || cb < 2)
     return cudaErrorNotSupported;
+  if (ca != 2 || cb != 2) {   // the dual grid is planned for two CTAs per SM
+    const int keep = g_ctas_per_sm; g_ctas_per_sm = 2;
+    const bool ok = plan8<T1, QT<T1>::UPL>(pa, 1, d, nsa, sma, ca) && plan8<T2, QT<T2>::UPL>(pb, 1, d, nsb, smb, cb) && ca == 2 && cb == 2;
+    g_ctas_per_sm = keep;
+    if (!ok) return cudaErrorNotSupported;
+  }
   pa.nstages = nsa; pb.nstages = nsb; pa.flags = pb.flags = g_flags;
 #ifdef MRS_TIMELINE
   pa.dbg = (g_dbg != nullptr && g_dbg_launch < g_dbg_max) ? g_dbg + (size_t)(g_dbg_launch++) * 320 * 16 : nullptr;
   pb.dbg = pa.dbg;
 #endif
   // one wave: 2 CTAs per SM in total, the second (smaller) program gets what it asks for first
-  const int slots = 2 * g_num_sms;
+  const int slots = 2 * d.num_sms;
   const int Pa = (pa.mode == MODE_GLU) ? 8 : 16, Pb = (pb.mode == MODE_GLU) ? 8 : 16;
   int ga = (pa.vrows + Pa - 1) / Pa, gb = (pb.vrows + Pb - 1) / Pb;
   if (ga < 1 || gb < 1) return cudaErrorNotSupported;
@@ -712,11 +676,7 @@ static cudaError_t launch_dual(MmvqParams pa, MmvqParams pb, cudaStream_t stream
     if (ga > slots - gb) ga = slots - gb;
   }
   auto kern = mmvq_dual_kernel<T1, T2>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
-    attr_set = true;
-  }
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ga + gb);
   cfg.blockDim = dim3(9 * 32);
@@ -738,35 +698,29 @@ static cudaError_t mmvq_dispatch_dual(int t1, const MmvqParams &pa, int t2, cons
   return cudaErrorNotSupported;
 }
 
+// long streams (lm_head-sized) take K segments twice as long: 2.3 KB copies run the TMA engine at
+// 91 % of the HBM peak where 1.15 KB ones reach 76 %; layer-sized matrices keep the short segments,
+// whose pipeline bubbles are smaller.  Only the k-quants the "M" recipes put on `output`.
+template <int T> struct HasLong { static constexpr bool value = (T == MRS_Q4_K || T == MRS_Q6_K); };
+
 template <int T>
 static cudaError_t launch_type(MmvqParams p, cudaStream_t stream) {
   using Q = QT<T>;
   // FAST: every block start is aligned to the type's natural alignment
+  const bool fast = rows_aligned<T>(p);
   const int row_bytes = (p.K / Q::QK) * Q::BYTES;
-  bool fast = (row_bytes % Q::WALIGN) == 0;
-  for (int m = 0; m < 3; m++)
-    if (p.w[m] != nullptr && ((uintptr_t)p.w[m] % Q::WALIGN) != 0) fast = false;
-  const int b = p.ncols;
   size_t wbytes = 0;  // weight bytes this launch streams
   for (int m = 0; m < 3; m++)
     if (p.w[m] != nullptr) wbytes += (size_t)p.nrows[m] * row_bytes;
-  // CTA shape.  Default: 8 consumer warps, two CTAs per SM — with the short K segments (UPL) the
-  // two rings hand stages over at CTA granularity and pipeline best.  The 16-warp / one-CTA-per-SM
-  // shape (activation prologue once per SM) is compiled with -DMRS_MMVQ_WIDE and chosen for launches
-  // streaming at most g_wide_max_bytes when flags bit 2 is set; it measured slower end to end.
-#ifdef MRS_MMVQ_WIDE
-#define MRS_DISPATCH(NC)                                                                         \
-  do {                                                                                           \
-    bool wide = (g_flags & 4) && wbytes <= (size_t)g_wide_max_bytes &&                           \
-                (fast ? launch_one<T, NC, true, 16>(p, stream, true) : launch_one<T, NC, false, 16>(p, stream, true)) == cudaSuccess; \
-    if (wide) return fast ? launch_one<T, NC, true, 16>(p, stream, false) : launch_one<T, NC, false, 16>(p, stream, false); \
-    return fast ? launch_one<T, NC, true, 8>(p, stream, false) : launch_one<T, NC, false, 8>(p, stream, false); \
+  const int b = p.ncols;
+#define MRS_DISPATCH(NC)                                                                          \
+  do {                                                                                            \
+    if constexpr (HasLong<T>::value) {                                                            \
+      if (fast && NC == 1 && !(g_flags & 8) && wbytes >= (size_t)g_long_min_bytes)                \
+        return launch_one<T, NC, true, 2 * Q::UPL>(p, stream);                                    \
+    }                                                                                             \
+    return fast ? launch_one<T, NC, true, Q::UPL>(p, stream) : launch_one<T, NC, false, Q::UPL>(p, stream); \
   } while (0)
-#else
-#define MRS_DISPATCH(NC)                                                                         \
-  return fast ? launch_one<T, NC, true, 8>(p, stream, false) : launch_one<T, NC, false, 8>(p, stream, false)
-  (void)wbytes;
-#endif
   if (b == 1) { MRS_DISPATCH(1); }
   if (b == 2) { MRS_DISPATCH(2); }
   if (b <= 4) { MRS_DISPATCH(4); }
@@ -817,15 +771,10 @@ using namespace mrs;
 static int g_mrs_pdl = 0;  // PDL on reference-shaped launchers is opt-in (mrs_set_pdl)
 
 extern "C" void mrs_set_pdl(int enabled) { g_mrs_pdl = enabled; }
-extern "C" void mrs_set_mmvq_flags(int f) { g_flags = f & 0xff; if (f >> 8) g_wide_max_bytes = (long long)(f >> 8) << 20; }
-extern "C" int mrs_mmvq_has_wide(void) {
-#ifdef MRS_MMVQ_WIDE
-  return 1;
-#else
-  return 0;
-#endif
-}
-extern "C" void mrs_set_mmvq_ctas_per_sm(int n) { g_ctas_per_sm = n < 1 ? 1 : (n > 2 ? 2 : n); }
+// flags: bit 3 = never use the long-segment variant; bits 8.. = long-segment threshold in MiB
+extern "C" void mrs_set_mmvq_flags(int f) { g_flags = f & 0xff; if (f >> 8) g_long_min_bytes = (long long)(f >> 8) << 20; }
+extern "C" int mrs_mmvq_has_wide(void) { return 0; }
+extern "C" void mrs_set_mmvq_ctas_per_sm(int n) { g_ctas_per_sm = n < 1 ? 1 : (n > 3 ? 3 : n); }
 
 static inline void report(cudaError_t e, const char *what) {
   if (e != cudaSuccess) fprintf(stderr, "mrs_b200: %s failed: %s\n", what, cudaGetErrorString(e));
@@ -928,7 +877,6 @@ extern "C" int mrs_mmvq_fused(int ggml_type, int mode, int dt, const void *w0, c
   p.K = K; p.stride_col_dst = n0; p.ncols = b_size; p.mode = mode; p.activation = activation;
   p.dst_dtype = dt; p.pdl = pdl;
   p.vrows = (mode == MODE_QKV) ? n0 + n1 + n2 : n0;
-  if (K > 4 * 8 * 32 * 32) return (int)cudaErrorInvalidValue;  // fused prologue limit (MAXU, 8-warp shape)
   return (int)mmvq_dispatch(ggml_type, p, (cudaStream_t)stream);
 }
 
@@ -943,7 +891,6 @@ static cudaError_t mmvq_dispatch_dual_entry(int t1, const MmvqParams &pa, int t2
 extern "C" int mrs_mmvq_fused_qkv_mixed(int type_qk, int type_v, int dt, const void *wq, const void *wk, const void *wv,
                                         const void *x, const void *norm_w, float eps, void *q, void *k, void *v,
                                         int K, int nq, int nk, int nv, int b_size, int pdl, void *stream) {
-  if (K > 4 * 8 * 32 * 32) return (int)cudaErrorInvalidValue;
   MmvqParams pa = {}, pb = {};
   pa.w[0] = (const uint8_t *)wq; pa.w[1] = (const uint8_t *)wk; pa.dst[0] = q; pa.dst[1] = k;
   pa.nrows[0] = nq; pa.nrows[1] = nk; pa.nrows[2] = 0;

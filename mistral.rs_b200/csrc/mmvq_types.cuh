@@ -46,6 +46,17 @@ template <int TYPE> struct QT;
 template <> struct QT<MRS_Q4_K> {
   static constexpr int BYTES = 144, QK = 256, UPB = 8, AUX = 4, WALIGN = 16, UPL = 2;
   // unit c: chunk c of qs; j = c>>1 (64-wide group), h = c&1 (16-byte half)
+  static constexpr bool NEEDS_SUM = false;
+  // fused prologue: where the 8 activations at element e (multiple of 8) of a weight block go —
+  // unit c, image half hi (0: xq0, 1: xq1), 8-byte half w8 — and what they add to the unit's aux
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) {
+    const int r = e & 63;
+    c = 2 * (e >> 6) + ((r >> 4) & 1); hi = r >> 5; w8 = (r >> 3) & 1;
+  }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float, int, int isum16, float *a) {
+    const int r = e & 63, hi = r >> 5;
+    if (((r >> 3) & 1) == 0) { a[hi] = hi ? d * 0.0625f : d; a[2 + hi] = d * (float)isum16; }
+  }
   __device__ static __forceinline__ int x_elem(int c, int w) {
     const int j = c >> 1, h = c & 1;
     return 64 * j + 16 * h + (w < 4 ? 4 * w : 32 + 4 * (w - 4));
@@ -100,6 +111,12 @@ template <> struct QT<MRS_Q4_K> {
 // layout: half2 dm | scales[12] | qh[32] | qs[128]  REF :179-186; dot :409-432,:620-660
 template <> struct QT<MRS_Q5_K> {
   static constexpr int BYTES = 176, QK = 256, UPB = 8, AUX = 4, WALIGN = 16, UPL = 4;
+  static constexpr bool NEEDS_SUM = false;
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) { QT<MRS_Q4_K>::chunk_dest(e, c, hi, w8); }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float, int, int isum16, float *a) {
+    const int r = e & 63, hi = r >> 5;
+    if (((r >> 3) & 1) == 0) { a[hi] = d; a[2 + hi] = d * (float)isum16; }
+  }
   __device__ static __forceinline__ int x_elem(int c, int w) { return QT<MRS_Q4_K>::x_elem(c, w); }
   template <typename Y> __device__ static __forceinline__ void aux(const int *q, int c, Y y, float *a) {
     QT<MRS_Q4_K>::aux(q, c, y, a);
@@ -137,6 +154,15 @@ template <> struct QT<MRS_Q5_K> {
 // high nibbles -> +64; qh[32n + 16(t&1) + i] bits 2(t>>1) (+4 for the high group).
 template <> struct QT<MRS_Q6_K> {
   static constexpr int BYTES = 210, QK = 256, UPB = 8, AUX = 2, WALIGN = 2, UPL = 2;
+  static constexpr bool NEEDS_SUM = false;
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) {
+    const int r = e & 127, r2 = r & 63;
+    c = 4 * (e >> 7) + 2 * (r2 >> 5) + ((r2 >> 4) & 1); hi = r >> 6; w8 = (r2 >> 3) & 1;
+  }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float, int, int, float *a) {
+    const int r = e & 127;
+    if (((r >> 3) & 1) == 0) a[r >> 6] = d;
+  }
   __device__ static __forceinline__ int x_elem(int c, int w) {
     const int n = c >> 2, t = c & 3;
     const int lo = 128 * n + 32 * (t >> 1) + 16 * (t & 1);
@@ -177,6 +203,15 @@ template <> struct QT<MRS_Q6_K> {
 // unit c = 4n + g: qs[32n + 8g .. +8); byte l holds elements 128n + 32j + 8g + l, j=0..3
 template <> struct QT<MRS_Q2_K> {
   static constexpr int BYTES = 84, QK = 256, UPB = 8, AUX = 8, WALIGN = 4, UPL = 8;
+  static constexpr bool NEEDS_SUM = false;
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) {
+    const int r = e & 127, jj = r >> 5;
+    c = 4 * (e >> 7) + ((r & 31) >> 3); hi = jj >> 1; w8 = jj & 1;
+  }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float, int isum8, int, float *a) {
+    const int jj = (e & 127) >> 5;
+    a[jj] = d; a[4 + jj] = d * (float)isum8;
+  }
   __device__ static __forceinline__ int x_elem(int c, int w) {
     const int n = c >> 2, g = c & 3;
     return 128 * n + 32 * (w >> 1) + 8 * g + 4 * (w & 1);
@@ -220,6 +255,9 @@ template <> struct QT<MRS_Q2_K> {
 // layout: hmask[32] | qs[64] | scales[12] | half d   REF :162-169; dot :368-384,:554-584
 template <> struct QT<MRS_Q3_K> {
   static constexpr int BYTES = 110, QK = 256, UPB = 8, AUX = 4, WALIGN = 2, UPL = 8;
+  static constexpr bool NEEDS_SUM = false;
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) { QT<MRS_Q2_K>::chunk_dest(e, c, hi, w8); }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float, int, int, float *a) { a[(e & 127) >> 5] = d; }
   __device__ static __forceinline__ int x_elem(int c, int w) { return QT<MRS_Q2_K>::x_elem(c, w); }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int c, Y y, float *a) {
     const int n = c >> 2;
@@ -266,6 +304,11 @@ template <int AUXN> struct X32 {
 // Q8_0 (34 B): half d | int8 qs[32]   REF :136-141; dot :336-346
 template <> struct QT<MRS_Q8_0> {
   static constexpr int BYTES = 34, QK = 32, UPB = 1, AUX = 1, WALIGN = 2, UPL = 2;
+  static constexpr bool NEEDS_SUM = false;
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) { c = 0; hi = e >> 4; w8 = (e >> 3) & 1; }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float sm, int, int, float *a) {
+    if (e == 0) { a[0] = d; }
+  }
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); }
   struct W { uint32_t q[8]; float d; };
@@ -284,6 +327,11 @@ template <> struct QT<MRS_Q8_0> {
 // Q4_0 (18 B): half d | qs[16]   REF :197-202; dot :244-258
 template <> struct QT<MRS_Q4_0> {
   static constexpr int BYTES = 18, QK = 32, UPB = 1, AUX = 2, WALIGN = 2, UPL = 4;
+  static constexpr bool NEEDS_SUM = true;
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) { c = 0; hi = e >> 4; w8 = (e >> 3) & 1; }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float sm, int, int, float *a) {
+    if (e == 0) { a[0] = d; a[1] = sm; }
+  }
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); a[1] = y.s(0); }
   struct W { uint32_t q[4]; float d; };
@@ -305,6 +353,11 @@ template <> struct QT<MRS_Q4_0> {
 // Q4_1 (20 B): half2 dm | qs[16]   REF :204-209; dot :260-277
 template <> struct QT<MRS_Q4_1> {
   static constexpr int BYTES = 20, QK = 32, UPB = 1, AUX = 2, WALIGN = 4, UPL = 4;
+  static constexpr bool NEEDS_SUM = true;
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) { c = 0; hi = e >> 4; w8 = (e >> 3) & 1; }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float sm, int, int, float *a) {
+    if (e == 0) { a[0] = d; a[1] = sm; }
+  }
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); a[1] = y.s(0); }
   struct W { uint32_t q[4]; uint32_t dm; };
@@ -340,6 +393,11 @@ __device__ __forceinline__ uint32_t q5_hi_hi(uint32_t vh) {
 // Q5_0 (22 B): half d | qh[4] | qs[16]   REF :211-217; dot :279-306
 template <> struct QT<MRS_Q5_0> {
   static constexpr int BYTES = 22, QK = 32, UPB = 1, AUX = 2, WALIGN = 2, UPL = 4;
+  static constexpr bool NEEDS_SUM = true;
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) { c = 0; hi = e >> 4; w8 = (e >> 3) & 1; }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float sm, int, int, float *a) {
+    if (e == 0) { a[0] = d; a[1] = sm; }
+  }
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); a[1] = y.s(0); }
   struct W { uint32_t q[4]; uint32_t qh; float d; };
@@ -366,6 +424,11 @@ template <> struct QT<MRS_Q5_0> {
 // Q5_1 (24 B): half2 dm | qh[4] | qs[16]   REF :219-225; dot :308-334
 template <> struct QT<MRS_Q5_1> {
   static constexpr int BYTES = 24, QK = 32, UPB = 1, AUX = 2, WALIGN = 8, UPL = 4;
+  static constexpr bool NEEDS_SUM = true;
+  __device__ static __forceinline__ void chunk_dest(int e, int &c, int &hi, int &w8) { c = 0; hi = e >> 4; w8 = (e >> 3) & 1; }
+  __device__ static __forceinline__ void chunk_aux(int e, float d, float sm, int, int, float *a) {
+    if (e == 0) { a[0] = d; a[1] = sm; }
+  }
   __device__ static __forceinline__ int x_elem(int, int w) { return 4 * w; }
   template <typename Y> __device__ static __forceinline__ void aux(const int *, int, Y y, float *a) { a[0] = y.d(0); a[1] = y.s(0); }
   struct W { uint32_t q[4]; uint32_t qh; uint32_t dm; };

@@ -55,6 +55,7 @@ struct PagedParams {
   const void *k_new, *v_new;
   int64_t kv_new_stride;
   const void *rope_cos, *rope_sin;
+  int rope_interleaved;     // 0: rotate-half (NeoX) pairing, 1: interleaved pairs (GGUF llama files)
   const int32_t *positions;
   const int64_t *slot_mapping;
   const int32_t *o_indptr;
@@ -121,6 +122,26 @@ __device__ __forceinline__ void rope_slice(float *x, const T *cosp, const T *sin
   }
 }
 
+// GPT-J / GGUF-llama pairing: (x[2i], x[2i+1]) rotate together and both live in this lane's slice;
+// cos/sin index d/2.  Same per-operation rounding as rope_slice (REF rotary.cu:10-34, is_neox = 0).
+template <typename T, int D>
+__device__ __forceinline__ void rope_slice_interleaved(float *x, const T *cosp, const T *sinp, int gl) {
+  const int o0 = gl * 4;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float c = Vec8<T>::one(cosp + o0 + i), sn = Vec8<T>::one(sinp + o0 + i);
+    const float xv = x[2 * i], yv = x[2 * i + 1];
+    const float ys = rnd<T>(yv * sn), xs = rnd<T>(xv * sn);
+    x[2 * i] = (float)__hfma((T)xv, (T)c, (T)(-ys));
+    x[2 * i + 1] = (float)__hfma((T)yv, (T)c, (T)xs);
+  }
+}
+template <typename T, int D>
+__device__ __forceinline__ void rope_any(float *x, const T *cosp, const T *sinp, int gl, bool interleaved) {
+  if (interleaved) rope_slice_interleaved<T, D>(x, cosp, sinp, gl);
+  else rope_slice<T, D>(x, cosp, sinp, gl);
+}
+
 #define MRS_LOAD_Q \
   if (p.pdl) pdl_wait(); \
     if constexpr (FUSED) { \
@@ -135,7 +156,7 @@ __device__ __forceinline__ void rope_slice(float *x, const T *cosp, const T *sin
       } else { \
         for (int i = 0; i < 8; i++) qf[g][i] = 0.f; \
       } \
-      if constexpr (FUSED) rope_slice<T, D>(qf[g], cosp, sinp, gl); \
+      if constexpr (FUSED) rope_any<T, D>(qf[g], cosp, sinp, gl, p.rope_interleaved != 0); \
       for (int i = 0; i < 8; i++) qf[g][i] *= p.sm_scale; \
     } \
 
@@ -339,7 +360,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
       float kn[8], vn[8];
       Vec8<T>::load((const T *)p.k_new + (int64_t)seq * p.kv_new_stride + (int64_t)kvh * D + d0, kn);
       Vec8<T>::load((const T *)p.v_new + (int64_t)seq * p.kv_new_stride + (int64_t)kvh * D + d0, vn);
-      rope_slice<T, D>(kn, cosp, sinp, gl);
+      rope_any<T, D>(kn, cosp, sinp, gl, p.rope_interleaved != 0);
       update(kn, vn, kv_len - 1, grp == 0);
       const int64_t slot = p.slot_mapping[seq];
       if (grp == 0 && blockIdx.z == 0 && slot >= 0) {
@@ -685,7 +706,8 @@ MRS_PAGED(bf16, __nv_bfloat16)
 // RoPE(q, k_new) + KV-cache write + paged decode attention + split-KV merge in ONE launch over
 // the HND cache.  q [B, H*D], k_new/v_new [B, KVH*D] are the raw QKV GEMV outputs; cos/sin
 // [max_pos, D/2]; positions [B] i32; slot_mapping [B] i64; counters: zeroed int32
-// [B * KVH * ceil(group/8)] scratch (left zero).  Same arithmetic as the separate
+// [B * KVH * ceil(group/8)] scratch (left zero).  `pdl`: bit 0 = launched with programmatic stream
+// serialisation, bit 1 = interleaved RoPE pairing (GGUF llama files; default rotate-half).  Same arithmetic as the separate
 // rotary_embedding_positions -> reshape_and_cache_flashinfer -> flashinfer_decode chain.
 extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, void *key_cache, void *value_cache,
                                           const void *rope_cos, const void *rope_sin, const int32_t *positions,
@@ -711,7 +733,7 @@ extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, voi
   p.kv_block_stride = (int64_t)num_kv_heads * page_size * head_size; p.kv_head_stride = (int64_t)page_size * head_size;
   p.num_heads = num_qo_heads; p.num_kv_heads = num_kv_heads; p.page_size = page_size;
   p.q_stride_n = (int64_t)num_qo_heads * head_size; p.q_stride_h = head_size; p.sm_scale = sm_scale;
-  p.window_left = -1; p.pdl = pdl;
+  p.window_left = -1; p.pdl = pdl & 1; p.rope_interleaved = (pdl >> 1) & 1;
   p.k_new = k_new; p.v_new = v_new; p.kv_new_stride = (int64_t)num_kv_heads * head_size;
   p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.positions = positions; p.slot_mapping = slot_mapping;
   p.o_indptr = o_indptr; p.counters = counters;

@@ -410,10 +410,6 @@ class LlamaRunner:
     def __init__(self, weights: LlamaWeights, batch=1, max_ctx=512, pdl=False, sm_count=148, comm=None,
                  fused_attention=True, split_policy="sm_fill", split_min_tokens=64):
         cfg, dev, dt = weights.cfg, weights.device, weights.dtype
-        if not cfg.rope_neox:
-            # the fused attention kernel rotates q/k with the rotate-half pairing only; interleaved
-            # (GGUF llama) models go through rotary_embedding_positions + reshape_and_cache + decode
-            fused_attention = False
         self.w, self.cfg, self.dev, self.dt, self.B = weights, cfg, dev, dt, batch
         tp = weights.tp_size
         self.n_heads, self.n_kv = cfg.n_heads // tp, cfg.n_kv_heads // tp
@@ -424,6 +420,9 @@ class LlamaRunner:
         self.tables = [self.pool.get_new_blocks(self.max_blocks) for _ in range(batch)]
         self.block_tables = torch.tensor(self.tables, dtype=torch.int32, device=dev)
         self.context_lens = torch.zeros(batch, dtype=torch.int32, device=dev)
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)   # bit 0: a sequence ran out of context
+        self.max_ctx = min(self.max_blocks * bs, cfg.max_pos)
+        self.steps_taken = 0              # host-side count of advances since reset() (graph replays via replay())
         self.split_pages = (kv_index.decode_split_pages(bs, batch, self.n_kv, max_ctx, sm_count=sm_count)
                             if split_policy == "reference" else
                             runner_split_pages(bs, batch, self.n_kv, max_ctx, sm_count, split_min_tokens))
@@ -492,8 +491,10 @@ class LlamaRunner:
                                       ctypes.c_int(self.padded_tiles), *[ctypes.c_void_p(m[k].data_ptr()) for k in
                                       ("positions", "slot_mapping", "kv_indptr", "kv_indices", "kv_last_page_len",
                                        "request_indices", "kv_tile_indices", "o_indptr", "kv_chunk_size",
-                                       "block_valid_mask")], self._stream())
+                                       "block_valid_mask")], ctypes.c_int(self.cfg.max_pos),
+                                      ctypes.c_void_p(self.error_flag.data_ptr()), self._stream())
         assert rc == 0, rc
+        self.steps_taken += 1
 
     def forward(self):
         rc = lib().mrs_llama_decode_step(ctypes.byref(self.step_struct), self._stream())
@@ -502,11 +503,27 @@ class LlamaRunner:
 
     def step(self):
         """advance the KV metadata for the token in `token_ids`, run the stack, argmax -> token_ids."""
+        if self.steps_taken >= self.max_ctx and not torch.cuda.is_current_stream_capturing():
+            raise RuntimeError(f"LlamaRunner: context exhausted ({self.max_ctx} tokens: block table / RoPE table)")
         self.advance()
         self.forward()
 
-    def reset(self):
-        self.context_lens.zero_()
+    def reset(self, context_len=0):
+        self.context_lens.fill_(context_len)
+        self.error_flag.zero_()
+        self.steps_taken = int(context_len)
+
+    def replay(self):
+        """one captured decode step; raises before a sequence would run past the allocated context
+        (the kernels freeze such a sequence and set error_flag, but a caller should never get there)"""
+        if self.steps_taken >= self.max_ctx:
+            raise RuntimeError(f"LlamaRunner: context exhausted ({self.max_ctx} tokens: block table / RoPE table)")
+        self.steps_taken += 1
+        self.graph.replay()
+
+    def check_overflow(self):
+        if int(self.error_flag.item()) & 1:
+            raise RuntimeError("LlamaRunner: a sequence ran past its allocated context (KV write skipped)")
 
     def capture(self):
         self.step(); self.reset()  # warm-up outside capture (module load, attributes)

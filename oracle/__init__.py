@@ -33,7 +33,7 @@ _lib = None
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("mrs_oracle.c", "mrs_oracle_model.c", "mrs_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("mrs_oracle.c", "mrs_oracle.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return LIB_PATH

@@ -10,6 +10,11 @@ pkg = g.load_package()
 if os.environ.get("MRS_DEV_LIB"):
     pkg.LIB_PATH = os.environ["MRS_DEV_LIB"]
 from mistralrs_b200 import model as M
+import ctypes
+if os.environ.get("MRS_CTAS"):
+    pkg.lib().mrs_set_mmvq_ctas_per_sm(ctypes.c_int(int(os.environ["MRS_CTAS"])))
+if os.environ.get("MRS_FLAGS"):
+    pkg.lib().mrs_set_mmvq_flags(ctypes.c_int(int(os.environ["MRS_FLAGS"], 0)))
 dev = torch.device("cuda:0")
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 sweep = [int(a) for a in sys.argv[2:]] or [64]

@@ -9,6 +9,8 @@ g.load_package()
 import oracle
 from mistralrs_b200 import quant, lib
 
+if os.environ.get("MRS_CTAS"):
+    lib().mrs_set_mmvq_ctas_per_sm(ctypes.c_int(int(os.environ["MRS_CTAS"])))
 dev = torch.device("cuda:0")
 ref = oracle.ref_lib("mmvq")
 peak = 6582.5

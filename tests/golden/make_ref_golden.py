@@ -137,6 +137,77 @@ if Lf is not None:
     torch.cuda.synchronize()
     out["fi_rc"] = np.array(rc)
     out["fi_out"] = o.float().cpu().numpy()
+# ---- MMQ (prefill GEMM with int8 activations): quantize + launch_mmq_gguf_<q> -------------------
+# call shape: REF fast_mmq.rs:388-447 (DenseMmqRun::launch), k_padded / workspace sizes :599-603,
+# ds layouts :91-100, type codes :591-596 (bf16 = 30)
+Lm = oracle.ref_lib("mmq")
+if Lm is not None:
+    Mq, Nq, Kq = 64, 256, 1024
+    xm = oracle.round_dtype(rng.standard_normal((Mq, Kq)).astype(np.float32), "bf16")
+    out["mmq_x"] = xm
+    txm = torch.from_numpy(xm).to(dev).to(torch.bfloat16)
+    kp = (Kq + 511) // 512 * 512
+    ws = torch.zeros(Mq * (kp // 128) * 144 + 128 * 144, dtype=torch.uint8, device=dev)
+    fix = torch.zeros(148 * 128 * 128, dtype=torch.float32, device=dev)
+    I64 = ctypes.c_int64
+    for t, layout in (("q4_k", "DS4"), ("q6_k", "D4"), ("q8_0", "D4")):
+        wb = oracle.random_blocks(t, Nq * Kq // oracle.BLOCK_ELEMS[t], rng)
+        w = torch.from_numpy(wb.reshape(-1)).to(dev)
+        getattr(Lm, f"launch_mmq_quantize_q8_1_{layout}")(P(txm), ctypes.c_void_p(0), P(ws), 30, I64(Kq), I64(Kq), I64(0), I64(0),
+                                                         I64(kp), I64(Mq), I64(1), I64(1), ST())
+        dst = torch.zeros(Mq, Nq, dtype=torch.bfloat16, device=dev)
+        getattr(Lm, f"launch_mmq_gguf_{t}")(P(fix), P(w), P(ws), P(dst), I64(Kq), I64(Nq), I64(Mq),
+                                           I64(Kq // oracle.BLOCK_ELEMS[t]), I64(Nq), 1000, 148, I64(232448), 32, 30, ST())
+        torch.cuda.synchronize()
+        out[f"mmq_{t}_w"] = wb
+        out[f"mmq_{t}_y"] = dst.float().cpu().numpy()
+
+# ---- Marlin GPTQ int4 (sym, group 128): gptq_marlin_repack + marlin_gptq_4bit_f16 ---------------
+# load-time transforms: REF gptq/gptq_cuda.rs:530-602 (repack with perm = argsort(g_idx), scale
+# permutation `marlin_permute_scales`), forward: gptq/marlin_backend.rs:20-140
+Lr = oracle.ref_lib("marlin")
+if Lr is not None:
+    for tag, Mg in (("m32", 32), ("m1", 1), ("m300", 300)):
+        Kg, Ng, G = 1024, 512, 128
+        xg = (rng.standard_normal((Mg, Kg)).astype(np.float32)).astype(np.float16)
+        qw = rng.integers(0, 2 ** 32, size=(Kg // 8, Ng), dtype=np.uint64).astype(np.uint32).view(np.int32)
+        sc = np.exp2(rng.uniform(-8, -6, size=(Kg // G, Ng))).astype(np.float16)
+        out[f"marlin_{tag}_x"], out[f"marlin_{tag}_qweight"], out[f"marlin_{tag}_scales"] = xg, qw, sc
+        tqw = torch.from_numpy(qw).to(dev)
+        perm = torch.arange(Kg, dtype=torch.int32, device=dev)       # g_idx[k] = k / G  ->  argsort = identity
+        rep = torch.zeros(Kg // 16, Ng * 16 // 8, dtype=torch.int32, device=dev)
+        Lr.gptq_marlin_repack(P(tqw), P(perm), P(rep), Kg, Ng, 4, ctypes.c_int64(torch.cuda.current_stream().cuda_stream))
+        scale_perm = [i + 8 * j for i in range(8) for j in range(8)]
+        sp = sc.reshape(-1, 64)[:, scale_perm].reshape(-1, Ng)       # group_size < size_k: the 64-wide permutation
+        tsp = torch.from_numpy(np.ascontiguousarray(sp)).to(dev)
+        wsg = torch.zeros(Ng // 8, dtype=torch.int32, device=dev)
+        og = torch.zeros(Mg, Ng, dtype=torch.float16, device=dev)
+        txg = torch.from_numpy(xg).to(dev)
+        Lr.marlin_gptq_4bit_f16.restype = ctypes.c_int
+        rc = Lr.marlin_gptq_4bit_f16(P(txg), P(rep), P(tsp), ctypes.c_void_p(0), P(og), Mg, Kg, Ng, P(wsg), G,
+                                     ctypes.c_int64(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        out[f"marlin_{tag}_rc"] = np.array(rc)
+        out[f"marlin_{tag}_y"] = og.float().cpu().numpy()
+        if tag == "m32":
+            out["marlin_repacked"] = rep.cpu().numpy()
+
+# ---- paged_attention_v2 (split) + ALiBi / sinks / softcap variants of v1 ------------------------
+if La is not None:
+    bt = torch.tensor(tables, dtype=torch.int32, device=dev)
+    cl = torch.tensor(ctx, dtype=torch.int32, device=dev)
+    slopes = (0.25 * 2.0 ** -np.arange(H)).astype(np.float32)
+    sinks = rng.standard_normal(H).astype(np.float32)
+    out["pa_alibi"], out["pa_sinks"] = slopes, sinks
+    tsl_, tsk_ = torch.from_numpy(slopes).to(dev), torch.from_numpy(sinks).to(dev)
+    for name, al, cap, sk in (("alibi", tsl_, 1.0, None), ("softcap", None, 30.0, None), ("sinks", None, 1.0, tsk_)):
+        o = torch.zeros(S, H, D, dtype=torch.bfloat16, device=dev)
+        La.paged_attention_v1_bf16(P(o), P(tq), P(kc), P(vc), P(al) if al is not None else ctypes.c_void_p(0), KVH,
+                                   ctypes.c_float(1.0 / np.sqrt(D)), ctypes.c_float(cap), P(bt), P(cl), BS, max(ctx), S, H, D, 5,
+                                   H * D, kc.stride(0), kc.stride(1), ST(), ctypes.c_uint32(1), ctypes.c_void_p(0), ctypes.c_void_p(0),
+                                   P(sk) if sk is not None else ctypes.c_void_p(0))
+        out[f"pa_out_v1_{name}"] = o.float().cpu().numpy()
+
 torch.cuda.synchronize()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 np.savez_compressed(os.path.join(ROOT, "gpurun_out", "ref_golden.npz"), **out)

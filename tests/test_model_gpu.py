@@ -148,3 +148,74 @@ def test_argmax_first_maximum(cuda):
         torch.cuda.synchronize()
         want = [int(torch.nonzero(x[r] == x[r].max())[0]) for r in range(rows)]
         assert out.cpu().tolist() == want
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+def test_llama3_8b_shapes_two_layers(cuda, dt):
+    """BASELINE config 2 shapes (hidden 4096, inter 14336, 32/8 heads of 128, vocab 128256; Q4_K_M
+    recipe -> layer 0 all Q4_K, layer 1 attn_v / ffn_down in Q6_K, Q6_K lm_head): two real-size
+    layers + lm_head through mrs_llama_decode_step vs the oracle.  Error stated in ulps of the
+    logit scale; f16 must meet north_star's 1e-3 relative."""
+    cfg = M.LlamaConfig.llama3_8b(n_layers=2, max_pos=64)
+    tdt = {"bf16": torch.bfloat16, "f16": torch.float16}[dt]
+    w = M.LlamaWeights(cfg, cuda, dtype=tdt, keep_host=True)
+    run = M.LlamaRunner(w, batch=1, max_ctx=32, pdl=True)
+    cos, sin = M.rope_tables(cfg)
+    ref = OracleLlama(cfg, w.host, M.tensor_type, cos, sin, dt)
+    ulp = {"bf16": 2.0 ** -8, "f16": 2.0 ** -11}[dt]
+    toks = [1000]
+    run.set_tokens(toks)
+    worst = 0.0
+    for pos in range(3):
+        run.step()
+        torch.cuda.synchronize()
+        got = run.logits().float().cpu().numpy()
+        want = ref.step(toks, pos)
+        scale = np.abs(want).max()
+        err = np.abs(got - want).max() / scale
+        worst = max(worst, err)
+        top2 = np.sort(want[0])[-2:]
+        if top2[1] - top2[0] > 8 * ulp * scale:
+            assert int(run.meta["token_ids"][0]) == int(np.argmax(want[0])), pos
+        toks = [int(np.argmax(want[0]))]
+        run.set_tokens(toks)
+    print(f"llama3-8b shapes, 2 layers, {dt}: worst |err| = {worst / ulp:.2f} ulp of the logit scale ({worst:.2e} rel)")
+    assert worst <= (1e-3 if dt == "f16" else 4.1 * 2.0 ** -7), worst
+
+
+def test_four_layer_f16_meets_1e_3(cuda):
+    # north_star tolerance (logits within 1e-3 relative) on a deeper stack: 4 layers, f16 activations
+    cfg = M.LlamaConfig.tiny_test(quant="q4_k_m", n_layers=4)
+    w = M.LlamaWeights(cfg, cuda, dtype=torch.float16, keep_host=True)
+    run = M.LlamaRunner(w, batch=2, max_ctx=64)
+    cos, sin = M.rope_tables(cfg)
+    ref = OracleLlama(cfg, w.host, M.tensor_type, cos, sin, "f16")
+    toks = [17, 900]
+    run.set_tokens(toks)
+    for pos in range(4):
+        run.step()
+        torch.cuda.synchronize()
+        got = run.logits().float().cpu().numpy()
+        want = ref.step(toks, pos)
+        assert np.abs(got - want).max() <= 1e-3 * np.abs(want).max(), (pos, np.abs(got - want).max() / np.abs(want).max())
+        toks = np.argmax(want, axis=1).tolist()
+        run.set_tokens(toks)
+
+
+def test_context_overflow_is_contained(cuda):
+    # a sequence that runs out of block table must stop growing: no out-of-bounds slot, error flag set
+    cfg = M.LlamaConfig.tiny_test(n_layers=1)
+    w = M.LlamaWeights(cfg, cuda)
+    run = M.LlamaRunner(w, batch=2, max_ctx=32)
+    run.context_lens.copy_(torch.tensor([31, 32], dtype=torch.int32))
+    run.advance()
+    torch.cuda.synchronize()
+    assert run.context_lens.cpu().tolist() == [32, 32]
+    slots = run.meta["slot_mapping"].cpu().tolist()
+    assert slots[1] == -1 and slots[0] == run.tables[0][1] * cfg.block_size + 15
+    assert int(run.error_flag.item()) == 1
+    with pytest.raises(RuntimeError):
+        run.check_overflow()
+    run.reset(32)
+    with pytest.raises(RuntimeError):
+        run.step()

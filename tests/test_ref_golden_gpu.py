@@ -96,3 +96,65 @@ def test_cache_and_attention(cuda, ref):
     o2 = paged_attn.flashinfer_decode(q, kh, vh, d(indptr), d(indices), d(last), d(req), d(tile), d(oind), d(chunk), d(mask), scale)
     want = ref["fi_out"]
     assert np.abs(o2.float().cpu().numpy() - want).max() <= 2.5 * 2.0 ** -8 * np.abs(want).max()
+
+
+def _need(ref, key):
+    if key not in ref.files:
+        pytest.skip(f"tests/golden/ref_golden.npz has no `{key}` (regenerate with tests/golden/make_ref_golden.py)")
+
+
+@pytest.mark.parametrize("t", ["q4_k", "q6_k", "q8_0"])
+def test_prefill_gemm_vs_reference_mmq(cuda, ref, t):
+    """`mrs_mmq_gguf` (bf16 activations x dequantised weights on tcgen05) against the output of the
+    reference's own MMQ kernels (`launch_mmq_quantize_q8_1_*` + `launch_mmq_gguf_<q>`, int8
+    activations).  The two differ by the reference's activation quantisation noise (its own
+    self-consistency bound is 5e-3 relative, fast_mmq.rs:1583-1703); both must sit inside that
+    envelope of each other, and ours must be the closer one to the exact product."""
+    import oracle
+    from mistralrs_b200 import mmq
+    _need(ref, f"mmq_{t}_y")
+    M, N, K = 64, 256, 1024
+    wb, x, want = ref[f"mmq_{t}_w"], ref["mmq_x"], ref[f"mmq_{t}_y"]
+    w = quant.QTensor(to_dev(wb.reshape(-1), cuda), t, (N, K))
+    got = mmq.forward(w, to_dev(x, cuda, "bf16")).float().cpu().numpy()
+    exact = oracle.matmul_exact(t, wb, x, K, N)
+    scale = np.abs(exact).max()
+    e_ref, e_ours = np.abs(want - exact).max() / scale, np.abs(got - exact).max() / scale
+    assert np.abs(got - want).max() <= 2e-2 * scale, (e_ref, e_ours)
+    assert e_ours <= 2.0 ** -7 and e_ours <= e_ref + 2.0 ** -8, (e_ref, e_ours)   # one bf16 output rounding vs int8 activations
+
+
+@pytest.mark.parametrize("tag,M", [("m32", 32), ("m1", 1), ("m300", 300)])
+def test_gptq_vs_reference_marlin(cuda, ref, tag, M):
+    """GPTQ int4 (sym, g128) through `GptqLayer` against `gptq_marlin_repack` + `marlin_gptq_4bit_f16`
+    of the reference on the same checkpoint tensors: same arithmetic class (w = f16((q-8)*s), f16
+    MMA, f32 accumulate), so agreement is limited by accumulation order and one f16 output rounding."""
+    from mistralrs_b200 import gptq
+    _need(ref, f"marlin_{tag}_y")
+    assert int(ref[f"marlin_{tag}_rc"]) == 0
+    x, qw, sc, want = ref[f"marlin_{tag}_x"], ref[f"marlin_{tag}_qweight"], ref[f"marlin_{tag}_scales"], ref[f"marlin_{tag}_y"]
+    layer = gptq.GptqLayer(torch.from_numpy(qw).to(cuda), torch.from_numpy(sc).to(cuda), group_size=128)
+    got = layer.forward_raw(torch.from_numpy(x).to(cuda)).float().cpu().numpy()
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 2.0 ** -10 * scale + 1e-6, float(np.abs(got - want).max() / scale)
+
+
+@pytest.mark.parametrize("name", ["alibi", "softcap", "sinks"])
+def test_paged_attention_v1_variants(cuda, ref, name):
+    """ALiBi slopes, logit soft-capping and attention sinks of `paged_attention_v1` against the
+    reference kernel's outputs (pagedattention.cuh:189-420)."""
+    _need(ref, f"pa_out_v1_{name}")
+    KVH, D, BS, NB, H, S = 2, 128, 16, 9, 8, 2
+    k = to_dev(ref["pa_k"], cuda, "bf16").reshape(-1, KVH, D)
+    v = to_dev(ref["pa_v"], cuda, "bf16").reshape(-1, KVH, D)
+    kc = torch.zeros(NB, KVH, D // 8, BS, 8, dtype=torch.bfloat16, device=cuda)
+    vc = torch.zeros(NB, KVH, D, BS, dtype=torch.bfloat16, device=cuda)
+    paged_attn.reshape_and_cache(k, v, None, None, kc, vc, torch.from_numpy(ref["pa_slots"]).to(cuda))
+    q = to_dev(ref["pa_q"], cuda, "bf16")
+    ctx = ref["pa_ctx"].tolist()
+    al = torch.from_numpy(ref["pa_alibi"]).to(cuda) if name == "alibi" else None
+    sk = torch.from_numpy(ref["pa_sinks"]).to(cuda) if name == "sinks" else None
+    o = paged_attn.paged_attention(q, None, None, kc, vc, to_dev(ref["pa_tables"], cuda), to_dev(ref["pa_ctx"], cuda), al,
+                                   max(ctx), 1.0 / np.sqrt(D), softcapping=30.0 if name == "softcap" else 1.0, sinks=sk)
+    want = ref[f"pa_out_v1_{name}"]
+    assert np.abs(o.float().cpu().numpy() - want).max() <= 2.5 * 2.0 ** -8 * np.abs(want).max()
