@@ -78,6 +78,33 @@ int32_t mrs_embedding_gather(int32_t ggml_type, const void *table, int32_t cols,
 int32_t mrs_argmax(const void *logits, int32_t rows, int32_t cols, int32_t act_dtype, int32_t *out, void *scratch,
                    int32_t pdl, void *stream);
 
+/* ---- GPTQ / AWQ int4 decode stack (BASELINE config 4: Mistral-7B GPTQ g128, batch 32) --------------
+ * Linears are int4 tiles produced by gptq_marlin_repack / awq_marlin_repack (mrs_b200_quant.h) with
+ * UNPERMUTED scales [K/group, N] in the activation dtype; q||k||v and gate||up are concatenated along
+ * N at load time.  cache_layout 1: HND cache + fused RoPE/KV-write/attention; 0: vLLM layout
+ * (K [NB,KVH,D/8,BS,8], V [NB,KVH,D,BS]) through rotary + reshape_and_cache + paged_attention_v1. */
+typedef struct { const void *tiles; const void *scales; const void *qzeros; int32_t k, n; } mrs_w4_weight;
+typedef struct {
+  mrs_w4_weight wqkv, wo, w_gate_up, w_down;
+  const void *attn_norm, *ffn_norm;
+  void *k_cache, *v_cache;
+} mrs_gptq_layer;
+typedef struct {
+  int32_t hidden, n_layers, n_heads, n_kv_heads, head_dim, vocab, block_size, act_dtype, group_size;
+  float rms_eps, sm_scale;
+  int32_t rope_neox, cache_layout, batch, padded_tiles, max_blocks_per_seq, skip_mask;
+  const mrs_gptq_layer *layers;            /* host array [n_layers] */
+  const void *tok_embd, *lm_head;          /* dense [vocab, hidden] in the activation dtype */
+  const void *final_norm, *rope_cos, *rope_sin;
+  int32_t *token_ids, *positions; int64_t *slot_mapping;
+  int32_t *kv_indptr, *kv_indices, *kv_last_page_len, *request_indices, *kv_tile_indices, *o_indptr, *kv_chunk_size;
+  uint8_t *block_valid_mask;
+  int32_t *block_tables, *context_lens;    /* dense table + lengths (vLLM-layout attention) */
+  void *x, *x2, *h, *qkv, *attn_out, *o, *gate_up, *act, *logits, *tmp_v; float *tmp_s;
+  int32_t *out_token, *attn_counters; void *argmax_scratch;
+} mrs_gptq_step;
+int32_t mrs_gptq_decode_step(const mrs_gptq_step *s, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,10 +45,12 @@ MRS_MMVQ_DECL_T(q2_k) MRS_MMVQ_DECL_T(q3_k) MRS_MMVQ_DECL_T(q4_k) MRS_MMVQ_DECL_
 /* Programmatic dependent launch for the reference-shaped launchers (default off). */
 void mrs_set_pdl(int enabled);
 
-/* Tuning/diagnostic switches of the decode GEMV.  bit 2 (value 4): allow the 16-consumer-warp,
- * one-CTA-per-SM kernel shape (only in builds with -DMRS_MMVQ_WIDE, see mrs_mmvq_has_wide) for launches
- * that stream at most (flags >> 8) MiB of weights.  Both shapes produce bit-identical results. */
+/* Tuning/diagnostic switches of the decode GEMV.  bit 3 (value 8): never use the long-K-segment
+ * variant; bits 8.. : smallest stream (MiB of weights per launch) that takes it (default 128).
+ * Both variants produce bit-identical results.  mrs_set_mmvq_ctas_per_sm: resident CTAs of one
+ * launch per SM (1..3, default 2; 3 applies to batch 1). */
 void mrs_set_mmvq_flags(int flags);
+void mrs_set_mmvq_ctas_per_sm(int n);
 int mrs_mmvq_has_wide(void);
 
 /* One launch for [RMSNorm ->] Q8_1 -> GEMV [-> GLU | + residual]: replaces rms_norm +
@@ -84,6 +86,32 @@ void mrs_mmq_set_weight_format(int32_t fmt);
 int32_t mrs_gptq_gemm(const void *x, const int32_t *qweight, const void *scales, const int32_t *qzeros,
                       const int32_t *g_idx, void *y, int32_t M, int32_t K, int32_t N, int32_t group_size,
                       int32_t is_awq, void *stream);
+
+/* ---- GPTQ / AWQ through the reference's Marlin symbols — REF mistralrs-quant/src/gptq/marlin_ffi.rs:6-81
+ * (same names, argument order and return convention: 0 ok, cudaError or -1 otherwise).  `weight` of
+ * the matmuls is the buffer our own *_marlin_repack filled (opaque to the Rust side, same byte
+ * count as the reference's [k/16, n*16/8] i32 result); `scales` arrive permuted by
+ * marlin_permute_scales (gptq_cuda.rs:542-565) in the activation dtype; `zeros`: raw AWQ qzeros
+ * (ignored for GPTQ: symmetric, w = (q-8)*s); `workspace` is unused (no global locks: split-K is
+ * reduced inside a thread-block cluster).  Kernel: csrc/w4a16.cu, any m >= 1. */
+int marlin_gptq_4bit_f16(const void *inputs, const int32_t *weight, const void *scales, const void *zeros,
+                         const void *out, int m, int k, int n, const void *workspace, int groupsize, int64_t stream);
+int marlin_gptq_4bit_bf16(const void *inputs, const int32_t *weight, const void *scales, const void *zeros,
+                          const void *out, int m, int k, int n, const void *workspace, int groupsize, int64_t stream);
+int marlin_awq_4bit_f16(const void *inputs, const int32_t *weight, const void *scales, const void *zeros,
+                        const void *out, int m, int k, int n, const void *workspace, int groupsize, int64_t stream);
+int marlin_awq_4bit_bf16(const void *inputs, const int32_t *weight, const void *scales, const void *zeros,
+                         const void *out, int m, int k, int n, const void *workspace, int groupsize, int64_t stream);
+/* weight: GPTQ [k/8, n] i32 / AWQ [k, n] i32 with n = out_dim/8; perm: argsort(g_idx) [k] i32 (GPTQ;
+ * NULL = identity); bits must be 4 — REF kernels/marlin/marlin_repack.cu:255,473 */
+void gptq_marlin_repack(const void *weight, const void *perm, const void *result, int k, int n, int bits, int64_t stream);
+void awq_marlin_repack(const void *weight, const void *perm, const void *result, int k, int n, int bits, int64_t stream);
+
+/* B200-native forms of the same kernel: explicit dtype / scale-column convention, and the dense
+ * 16-bit linear (lm_head of GPTQ/AWQ checkpoints at decode batch; REF kernels/gemv/gemv.cu). */
+int32_t mrs_w4a16_gemm(const void *x, const void *w_tiles, const void *scales, const int32_t *qzeros, void *y, int32_t M,
+                       int32_t K, int32_t N, int32_t group, int32_t dtype, int32_t scale_perm, void *stream);
+int32_t mrs_dense_linear(const void *x, const void *w, void *y, int32_t M, int32_t K, int32_t N, int32_t dtype, void *stream);
 
 #ifdef __cplusplus
 }

@@ -21,8 +21,8 @@
 // activations are used as they are (bf16/f16) — no activation quantisation — f32 accumulation
 // in TMEM.  This is closer to the exact product than the reference's int8-activation MMQ.
 #include "dequant.cuh"
+#include "tc_common.cuh"
 
-#include <cuda.h>
 #include <stdio.h>
 
 namespace mrs {
@@ -37,54 +37,6 @@ constexpr int TC_THREADS = 64 + TC_DQ_WARPS * 32;
 constexpr int A_STAGE_BYTES = TC_MT * TC_BM * TC_BK * 2;   // 32 KB
 constexpr int B_STAGE_BYTES = TC_BN * TC_BK * 2;           // 32 KB
 constexpr int TC_SMEM = 1024 + TC_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
-
-// ---- tcgen05 / TMA wrappers ---------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
-          "r"(smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (f16/bf16 inputs, f32 accumulate)
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, SWIZZLE_128B operand descriptor (REF layout: cute/atom/mma_traits_sm100.hpp
-// make_umma_desc<Major::K>): start>>4 | LBO=1 | SBO=1024B>>4 | version 1 | layout 2
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem_ptr) {
-  const uint64_t addr = (uint64_t)(smem_u32(smem_ptr) >> 4) & 0x3FFF;
-  return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// 32 lanes x 32 columns of f32 accumulators -> 32 registers per thread (lane == TMEM lane)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t *r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ---- exact block decoders: 64 consecutive weights of one row -> f16 ------------------------
 // (formulas identical to oracle/mrs_oracle.c unpack_block; REF layouts mmvq_gguf.cu:134-225)
@@ -498,21 +450,6 @@ mmq_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const TcParams p) {
 }
 
 // ---- host -----------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-  static PFN_encodeTiled fn = nullptr;
-  if (fn == nullptr) {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)p;
-  }
-  return fn;
-}
-
 template <int TYPE>
 static cudaError_t launch_tc(const TcParams &p, const CUtensorMap &tmap, cudaStream_t st) {
   auto kern = mmq_tc_kernel<TYPE>;
@@ -546,7 +483,7 @@ extern "C" int32_t mrs_mmq_gguf(int32_t ggml_type, const void *w, const void *x,
   const int rb = tc_row_bytes(ggml_type, K);
   if (rb == 0 || K % 64 != 0 || (dtype != 0 && dtype != 1)) return (int32_t)cudaErrorInvalidValue;
   if (ggml_type >= MRS_Q2_K && K % 256 != 0) return (int32_t)cudaErrorInvalidValue;
-  PFN_encodeTiled enc = get_encode();
+  PFN_encodeTiled enc = tc_get_encode();
   if (enc == nullptr) return (int32_t)cudaErrorNotSupported;
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
@@ -585,7 +522,7 @@ extern "C" int32_t mrs_gptq_gemm(const void *x, const int32_t *qweight, const vo
   if (M <= 0 || N <= 0) return 0;
   if (K % 64 != 0 || N % 8 != 0 || group_size <= 0 || K % group_size != 0) return (int32_t)cudaErrorInvalidValue;
   if (is_awq && qzeros == nullptr) return (int32_t)cudaErrorInvalidValue;
-  PFN_encodeTiled enc = get_encode();
+  PFN_encodeTiled enc = tc_get_encode();
   if (enc == nullptr) return (int32_t)cudaErrorNotSupported;
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};

@@ -256,32 +256,40 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
   if (p.pdl) pdl_wait();  // activations come from the upstream kernel
   if (tid == 0) MRS_STAMP(3);
   if (p.xkind == X_Q8_1) {
-    // gather pre-quantised Q8_1 blocks straight into consumption order
+    // pre-quantised Q8_1 blocks (the reference's two-call form): every thread moves 8-byte chunks of
+    // qs plus its block's (d, s) straight to their consumption-order position — the same scatter as
+    // the fused prologue below, with loads in place of the quantiser (all loads independent: one
+    // global latency instead of a chain of 4-byte gathers)
     const block_q8_1 *y = (const block_q8_1 *)p.x;
-    for (int idx = ctid; idx < NCOLS * npos; idx += NCT) {
-      const int col = idx / npos, pos = idx - col * npos;
-      int blk, c;
-      pos_to_unit<T, UPL>(pos, blk, c);
-      int q[8];
-      float a[Q::AUX];
-      if (col < p.ncols && blk < nblocks) {
-        const block_q8_1 *yb = y + (size_t)col * p.stride_col_y + (size_t)blk * (Q::QK / 32);
-#pragma unroll
-        for (int w = 0; w < 8; w++) {
-          const int e = Q::x_elem(c, w);
-          q[w] = *(const int *)(yb[e >> 5].qs + (e & 31));
+    const int nchunks = p.K >> 3;
+    const int nchunks_w = (nchunks + 31) & ~31;
+    for (int col = 0; col < NCOLS; col++) {
+      const bool livec = col < p.ncols;
+      int4 *c0 = xq0 + (size_t)col * npos, *c1 = xq1 + (size_t)col * npos;
+      float *ca = xa + (size_t)col * npos * Q::AUX;
+      for (int ch = ctid; ch < nchunks_w; ch += NCT) {
+        const bool ok = ch < nchunks;
+        int2 qv = make_int2(0, 0);
+        float d = 0.f, sm = 0.f;
+        if (ok && livec) {
+          const block_q8_1 *yb = y + (size_t)col * p.stride_col_y + (ch >> 2);
+          const int *qp = (const int *)(yb->qs + 8 * (ch & 3));
+          qv = make_int2(qp[0], qp[1]);
+          const float2 ds = __half22float2(yb->ds);
+          d = ds.x; sm = ds.y;
         }
-        Q::aux(q, c, YGlobal{yb}, a);
-      } else {
-#pragma unroll
-        for (int w = 0; w < 8; w++) q[w] = 0;
-#pragma unroll
-        for (int i = 0; i < Q::AUX; i++) a[i] = 0.f;
+        const int isum8 = __dp4a(qv.x, 0x01010101, __dp4a(qv.y, 0x01010101, 0));
+        const int isum16 = isum8 + __shfl_xor_sync(0xffffffffu, isum8, 1);
+        if (ok) {
+          const int e0 = ch * 8;
+          const int blk = e0 / Q::QK, e = e0 - blk * Q::QK;
+          int c, hi, w8;
+          Q::chunk_dest(e, c, hi, w8);
+          const int pos = unit_to_pos<T, UPL>(blk, c);
+          *((int2 *)((hi ? c1 : c0) + pos) + w8) = qv;
+          Q::chunk_aux(e, d, sm, isum8, isum16, ca + (size_t)pos * Q::AUX);
+        }
       }
-      xq0[idx] = make_int4(q[0], q[1], q[2], q[3]);
-      xq1[idx] = make_int4(q[4], q[5], q[6], q[7]);
-#pragma unroll
-      for (int i = 0; i < Q::AUX; i++) xa[(size_t)idx * Q::AUX + i] = a[i];
     }
   } else {
     // fused prologue: (optional RMSNorm) -> round to activation dtype -> Q8_1 -> consumption
@@ -424,6 +432,18 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
     for (int r = 0; r < 2; r++)
 #pragma unroll
       for (int j = 0; j < NCOLS; j++) acc[r][j] = 0.f;
+    // the residual (lane 0 adds it in the epilogue) is fetched now, not after the reduction: one
+    // global latency less on the tail of every o_proj / down_proj launch
+    float resv[2][NCOLS];
+    if (p.residual != nullptr && lane == 0 && p.mode != MODE_GLU) {
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const int64_t cs = (p.mode == MODE_QKV) ? p.nrows[mm[r]] : p.stride_col_dst;
+#pragma unroll
+        for (int j = 0; j < NCOLS; j++)
+          resv[r][j] = (valid[r] && j < p.ncols) ? load_act(p.residual, (int64_t)j * cs + rr[r], p.dst_dtype) : 0.f;
+      }
+    }
 
     for (int s = 0; s < nseg; s++) {
       mbar_wait(&full[stage], phase);
@@ -507,7 +527,7 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
               float v = acc[r][j];
               if (p.residual != nullptr) {
                 // y materialised in dtype, then residual add rounded again (candle `+`)
-                v = round_act(v, p.dst_dtype) + load_act(p.residual, (int64_t)j * cs + rr[r], p.dst_dtype);
+                v = round_act(v, p.dst_dtype) + resv[r][j];
               }
               store_act(p.dst[mm[r]], (int64_t)j * cs + rr[r], v, p.dst_dtype);
             }

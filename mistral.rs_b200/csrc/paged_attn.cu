@@ -239,7 +239,10 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
     for (int g = 0; g < G; g++) {
       float x = s[g];
       if (p.softcap > 0.f) x = p.softcap * tanhf(x / p.softcap);
-      x += slope[g] * (float)(t - kv_len + 1);
+      // REF pagedattention.cuh:138,283: `context_len` is a uint32_t there, so `token_idx - context_len + 1`
+      // is evaluated in unsigned arithmetic and wraps for every token but the last; restated as is
+      // (tests/golden pins it against the reference kernel's output)
+      if (slope[g] != 0.f) x += slope[g] * (float)(uint32_t)(t - kv_len + 1);
       if (!in_window) x = -INFINITY;
       const float mn = fmaxf(m[g], x);
       if (mn > -INFINITY) {
@@ -709,7 +712,9 @@ MRS_PAGED(bf16, __nv_bfloat16)
 // [B * KVH * ceil(group/8)] scratch (left zero).  `pdl`: bit 0 = launched with programmatic stream
 // serialisation, bit 1 = interleaved RoPE pairing (GGUF llama files; default rotate-half).  Same arithmetic as the separate
 // rotary_embedding_positions -> reshape_and_cache_flashinfer -> flashinfer_decode chain.
-extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, void *key_cache, void *value_cache,
+// q rows are q_stride_n elements apart, k_new / v_new rows kv_new_stride (a fused QKV GEMM writes
+// [B, (H + 2 KVH) D] and hands three pointers into it)
+extern "C" int32_t mrs_paged_decode_fused_strided(void *q, void *k_new, void *v_new, void *key_cache, void *value_cache,
                                           const void *rope_cos, const void *rope_sin, const int32_t *positions,
                                           const int64_t *slot_mapping, const int32_t *kv_indptr,
                                           const int32_t *kv_indices, const int32_t *kv_last_page_len,
@@ -719,7 +724,7 @@ extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, voi
                                           int32_t *counters, int32_t batch_size, int32_t padded_batch_size,
                                           int32_t num_qo_heads, int32_t num_kv_heads, int32_t head_size,
                                           int32_t page_size, float sm_scale, uint32_t dtype, int32_t pdl,
-                                          void *stream) {
+                                          int64_t q_stride_n, int64_t kv_new_stride, void *stream) {
   if (dtype != 0 && dtype != 1) return (int32_t)cudaErrorInvalidValue;
   PagedParams p = {};
   p.q = q; p.kc = key_cache; p.vc = value_cache; p.out = o;
@@ -732,9 +737,9 @@ extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, voi
   p.kv_indptr = kv_indptr; p.kv_indices = kv_indices; p.kv_last_page_len = kv_last_page_len;
   p.kv_block_stride = (int64_t)num_kv_heads * page_size * head_size; p.kv_head_stride = (int64_t)page_size * head_size;
   p.num_heads = num_qo_heads; p.num_kv_heads = num_kv_heads; p.page_size = page_size;
-  p.q_stride_n = (int64_t)num_qo_heads * head_size; p.q_stride_h = head_size; p.sm_scale = sm_scale;
+  p.q_stride_n = q_stride_n; p.q_stride_h = head_size; p.sm_scale = sm_scale;
   p.window_left = -1; p.pdl = pdl & 1; p.rope_interleaved = (pdl >> 1) & 1;
-  p.k_new = k_new; p.v_new = v_new; p.kv_new_stride = (int64_t)num_kv_heads * head_size;
+  p.k_new = k_new; p.v_new = v_new; p.kv_new_stride = kv_new_stride;
   p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.positions = positions; p.slot_mapping = slot_mapping;
   p.o_indptr = o_indptr; p.counters = counters;
   const int tiles = split ? padded_batch_size : batch_size;
@@ -742,4 +747,22 @@ extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, voi
                                      : launch_decode<__nv_bfloat16, 1, true>(p, head_size, tiles, (cudaStream_t)stream);
   if (e != cudaSuccess) fprintf(stderr, "mrs_b200: mrs_paged_decode_fused failed: %s\n", cudaGetErrorString(e));
   return (int32_t)e;
+}
+
+extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, void *key_cache, void *value_cache,
+                                          const void *rope_cos, const void *rope_sin, const int32_t *positions,
+                                          const int64_t *slot_mapping, const int32_t *kv_indptr,
+                                          const int32_t *kv_indices, const int32_t *kv_last_page_len,
+                                          const int32_t *request_indices, const int32_t *kv_tile_indices,
+                                          const int32_t *o_indptr, const int32_t *kv_chunk_size_ptr,
+                                          const uint8_t *block_valid_mask, void *o, void *tmp_v, float *tmp_s,
+                                          int32_t *counters, int32_t batch_size, int32_t padded_batch_size,
+                                          int32_t num_qo_heads, int32_t num_kv_heads, int32_t head_size,
+                                          int32_t page_size, float sm_scale, uint32_t dtype, int32_t pdl,
+                                          void *stream) {
+  return mrs_paged_decode_fused_strided(q, k_new, v_new, key_cache, value_cache, rope_cos, rope_sin, positions, slot_mapping,
+                                        kv_indptr, kv_indices, kv_last_page_len, request_indices, kv_tile_indices, o_indptr,
+                                        kv_chunk_size_ptr, block_valid_mask, o, tmp_v, tmp_s, counters, batch_size,
+                                        padded_batch_size, num_qo_heads, num_kv_heads, head_size, page_size, sm_scale, dtype,
+                                        pdl, (int64_t)num_qo_heads * head_size, (int64_t)num_kv_heads * head_size, stream);
 }

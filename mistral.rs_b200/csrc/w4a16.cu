@@ -1,0 +1,501 @@
+// w4a16.cu — small-batch W4A16 (GPTQ / AWQ int4) and dense f16/bf16 linear on the 5th-gen tensor
+// cores, "swap-AB": the WEIGHT rows are the MMA's M = 128 and the tokens its N (32 … 256), so a
+// decode batch of 32 fills the tensor core instead of 25 % of a 128-token tile.
+//
+// Replaces the reference's Marlin path behind its own symbols
+//   marlin_{gptq,awq}_4bit_{f16,bf16}, {gptq,awq}_marlin_repack     REF mistralrs-quant/src/gptq/marlin_ffi.rs:6-81,
+//   kernels/marlin/marlin_kernel.cuh (one kernel for every m), marlin_repack.cu:255,473
+// and the dense small-batch lm_head of GPTQ checkpoints (REF kernels/gemv/gemv.cu, candle matmul).
+//
+// HBM-bound at m <= 64 (Mistral-7B g128: 3.6 GB of packed weights per step), so the design is a
+// streaming one (per CTA = one 128-row weight tile x one K split, 320 threads, 2 CTAs/SM):
+//   warp 0      producer: cp.async.bulk of the packed int4 rows of the K-step (4 KB, contiguous in the
+//               repacked layout) + TMA tensor load of the activation tile X[NT x 64] (SWIZZLE_128B)
+//   warps 2..9  dequantisers: thread = (weight row, 32-weight half): one LDS.128 of packed nibbles ->
+//               exact (q - 8) [(q - z) for AWQ] in the activation format via the magic-number trick
+//               -> x scale (one rounding, = the reference's dequant) -> K-major 128B-swizzled A tile
+//   warp 1      MMA issuer: tcgen05.mma.cta_group::1.kind::f16, M=128 x N=NT x K=16, D in TMEM
+//   epilogue    (the dequant warps) tcgen05.ld -> [cluster/DSMEM split-K reduction in rank order] ->
+//               y[token][row] in the activation dtype
+// Split-K CTAs of one tile form a thread-block cluster (<= 4): partial accumulators go to the leader's
+// shared memory through DSMEM and are summed in a fixed order — deterministic, no global scratch.
+//
+// Repacked weight layout ("mrs int4 tiles", same byte count as the checkpoint tensor so the
+// reference's result buffer [K/16, N*16/8] i32 fits): [K/64][N][32 B]; the 32 bytes of (k-step, row)
+// hold 64 nibbles, word w = k 8w..8w+7 with nibble j < 4 <-> k = 2j and nibble 4+j <-> k = 2j+1 (so
+// that `q & 0x000f000f` yields the f16x2 pair (k, k+1)).
+#include "tc_common.cuh"
+
+#include <stdio.h>
+
+namespace mrs {
+
+constexpr int WA_BM = 128;      // weight rows per CTA (UMMA M)
+constexpr int WA_BK = 64;       // K per stage
+constexpr int WA_STAGES = 4;
+constexpr int WA_DQ_WARPS = 8;
+constexpr int WA_THREADS = 64 + WA_DQ_WARPS * 32;
+constexpr int WA_A_BYTES = WA_BM * WA_BK * 2;   // 16 KB
+constexpr int WA_RAW_BYTES = WA_BM * 32;        // 4 KB
+
+enum { WA_SRC_INT4 = 0, WA_SRC_DENSE = 1 };
+
+struct WaParams {
+  const uint8_t *wq;       // repacked int4 [K/64][N][32 B]
+  const void *scales;      // [K/group, N] in the activation dtype (columns possibly Marlin-permuted)
+  const int32_t *qzeros;   // AWQ: raw [K/group, N/8] (nibbles in AWQ order) or nullptr
+  void *y;                 // [M, N]
+  int M, N, K, group, dtype;
+  int scale_perm;          // 0: plain columns, 1: Marlin 64-wide permutation, 2: Marlin "single" (32-wide)
+  int m0;                  // first token of this pass
+  int ksteps_per_split;    // K-steps (of 64) per split CTA
+};
+
+// Inverses of the reference's scale-column permutations (REF gptq_cuda.rs:530-540 get_scale_perms):
+// permuted[j] = original[perm[j]], so original column r of a 64- (32-) wide chunk sits at inv(r).
+//   64-wide: perm[8i + j] = i + 8j                          -> inv(r) = 8 (r % 8) + r / 8
+//   32-wide: perm[8i + j] = 2i + {0,1,8,9,16,17,24,25}[j]   -> inv(r) = 8 ((r % 8) / 2) + 2 (r / 8) + r % 2
+__host__ __device__ __forceinline__ int inv_scale_perm64(int r) { return 8 * (r & 7) + (r >> 3); }
+__host__ __device__ __forceinline__ int inv_scale_perm32(int r) { return 8 * ((r & 7) >> 1) + 2 * (r >> 3) + (r & 1); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_t rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+// 8 packed nibbles (layout above) -> four 16-bit pairs of (q - zp) * s in the activation format
+template <bool BF16>
+__device__ __forceinline__ void dequant_word(uint32_t q, int zp, float s_f, uint32_t s2, uint32_t *out) {
+  if constexpr (!BF16) {
+    // f16: (q & 0xf) | 0x6400 = 1024 + q exactly; the nibble at bits 4..7 gives 1024 + 16 q, and
+    // fma(x, 1/16, -(64 + zp)) is exact — REF marlin dequant (kU4B8 / kU4), then one rounding in x s
+    const uint32_t sub_lo = 0x64006400u + (uint32_t)zp * 0x00010001u;                   // 1024 + zp (exact: < 2048)
+    const __half hz = __int2half_rn(-(64 + zp));
+    const uint32_t sub_hi = (uint32_t)__half_as_ushort(hz) * 0x00010001u;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const uint32_t lo = (q & 0x000f000fu) | 0x64006400u;
+      const uint32_t hi = (q & 0x00f000f0u) | 0x64006400u;
+      __half2 a = __hsub2(*(const __half2 *)&lo, *(const __half2 *)&sub_lo);
+      const uint32_t sixteenth = 0x2c002c00u;
+      __half2 b = __hfma2(*(const __half2 *)&hi, *(const __half2 *)&sixteenth, *(const __half2 *)&sub_hi);
+      a = __hmul2(a, *(const __half2 *)&s2);
+      b = __hmul2(b, *(const __half2 *)&s2);
+      out[2 * i] = *(const uint32_t *)&a;
+      out[2 * i + 1] = *(const uint32_t *)&b;
+      q >>= 8;
+    }
+  } else {
+    // bf16: (q - zp) is a small integer, its product with the bf16 scale is exact in f32 -> one rounding
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int a = (int)((q >> (4 * j)) & 0xF) - zp, b = (int)((q >> (4 * j + 16)) & 0xF) - zp;
+      const __nv_bfloat162 h = __floats2bfloat162_rn((float)a * s_f, (float)b * s_f);
+      out[j] = *(const uint32_t *)&h;
+    }
+    (void)s2;
+  }
+}
+
+template <int NT, int SRC>
+__global__ void __launch_bounds__(WA_THREADS, NT <= 64 ? 2 : 1)
+w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const WaParams p) {
+  constexpr int X_BYTES = NT * 128;
+  constexpr int STAGE = WA_A_BYTES + X_BYTES + (SRC == WA_SRC_INT4 ? WA_RAW_BYTES : 0);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = (uint64_t *)(smem + WA_STAGES * STAGE);
+  uint64_t *in_full = bars, *a_full = bars + WA_STAGES, *empty = bars + 2 * WA_STAGES, *acc_full = bars + 3 * WA_STAGES;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 3 * WA_STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * WA_BM;
+  const int ksplit = gridDim.y;
+  const uint32_t rank = (ksplit > 1) ? cluster_ctarank() : 0u;
+  const int nk_total = p.K / WA_BK;
+  const int kb0 = (int)rank * p.ksteps_per_split;
+  const int nk = max(0, min(p.ksteps_per_split, nk_total - kb0));
+  const int rows_valid = min(WA_BM, p.N - n0);
+
+  if (tid == 0) {
+    for (int s = 0; s < WA_STAGES; s++) { mbar_init(&in_full[s], 1); mbar_init(&a_full[s], WA_DQ_WARPS); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  constexpr uint32_t TCOLS = NT < 32 ? 32 : NT;
+  if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int i = 0; i < nk; i++) {
+        const int kb = kb0 + i;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t *st = smem + (size_t)stage * STAGE;
+        if constexpr (SRC == WA_SRC_INT4) {
+          const uint32_t raw_bytes = (uint32_t)rows_valid * 32u;
+          mbar_arrive_expect_tx(&in_full[stage], X_BYTES + raw_bytes);
+          bulk_g2s(st + WA_A_BYTES + X_BYTES, p.wq + ((size_t)kb * p.N + n0) * 32, raw_bytes, &in_full[stage]);
+        } else {
+          mbar_arrive_expect_tx(&in_full[stage], X_BYTES + WA_A_BYTES);
+          tma_load_2d(st, &tmap_w, kb * WA_BK, n0, &in_full[stage]);
+        }
+        tma_load_2d(st + WA_A_BYTES, &tmap_x, kb * WA_BK, p.m0, &in_full[stage]);
+        if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t fmt = (p.dtype == MRS_BF16) ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(WA_BM >> 4) << 24);
+    int stage = 0, phase = 0;
+    for (int i = 0; i < nk; i++) {
+      mbar_wait(&in_full[stage], phase);
+      if constexpr (SRC == WA_SRC_INT4) mbar_wait(&a_full[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint8_t *as = smem + (size_t)stage * STAGE, *xs = as + WA_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WA_BK / 16; k++)
+          umma_f16(tmem_base, umma_desc_sw128(as) + (uint64_t)(2 * k), umma_desc_sw128(xs) + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        if (i == nk - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================== dequantisers, then epilogue =====================
+    const int dt_ = tid - 64;              // 0..255
+    const int r = dt_ >> 1, hf = dt_ & 1;  // weight row in the tile, which 32-weight half of the K-step
+    const int n = n0 + r;
+    const bool live = r < rows_valid;
+    if constexpr (SRC == WA_SRC_INT4) {
+      const bool bf = p.dtype == MRS_BF16;
+      int scol = n;
+      if (p.scale_perm == 1) scol = (n & ~63) + inv_scale_perm64(n & 63);
+      else if (p.scale_perm == 2) scol = (n & ~31) + inv_scale_perm32(n & 31);
+      const int zsh = 4 * ((n & 7) == 0 ? 0 : (n & 7) == 1 ? 4 : (n & 7) == 2 ? 1 : (n & 7) == 3 ? 5 : (n & 7) == 4 ? 2 : (n & 7) == 5 ? 6 : (n & 7) == 6 ? 3 : 7);
+      auto load_scale = [&](int kb) -> uint32_t {   // 16-bit scale | zero point << 16 of this thread's half of K-step kb
+        if (!live || kb >= nk_total) return 0u;
+        const int g = (kb * WA_BK + 32 * hf) / p.group;
+        uint32_t v = ((const uint16_t *)p.scales)[(size_t)g * p.N + scol];
+        uint32_t z = 8u;
+        if (p.qzeros != nullptr) z = ((uint32_t)p.qzeros[(size_t)g * (p.N >> 3) + (n >> 3)] >> zsh) & 0xFu;
+        return v | (z << 16);
+      };
+      uint32_t sz = load_scale(kb0);
+      int stage = 0, phase = 0;
+      for (int i = 0; i < nk; i++) {
+        const int kb = kb0 + i;
+        const uint32_t sz_next = load_scale(kb + 1);   // next K-step's scale in flight during this one
+        mbar_wait(&in_full[stage], phase);
+        uint8_t *st = smem + (size_t)stage * STAGE;
+        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+        if (live) raw = *(const uint4 *)(st + WA_A_BYTES + X_BYTES + r * 32 + hf * 16);
+        const uint32_t s16 = sz & 0xFFFFu;
+        const int zp = (int)(sz >> 16);
+        const uint32_t s2 = s16 * 0x00010001u;
+        float s_f = 0.f;
+        if (bf) s_f = __bfloat162float(__ushort_as_bfloat16((unsigned short)s16));
+        uint8_t *dst = st + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+          uint32_t o[4];
+          if (bf) dequant_word<true>(w[c4], zp, s_f, s2, o);
+          else dequant_word<false>(w[c4], zp, s_f, s2, o);
+          const int c = 4 * hf + c4;
+          *(uint4 *)(dst + ((c ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[stage]);
+        sz = sz_next;
+        if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  // ===================== epilogue (all threads take part in the cluster barriers) =====================
+  constexpr int CPW = NT / 2;              // columns (tokens) per epilogue warp: two warps share a lane quarter
+  const bool epi = warp >= 2;
+  const int q = warp & 3, half = (warp - 2) >> 2;
+  const int row = q * 32 + lane;           // TMEM lane = weight row inside the tile
+  auto ld16 = [&](int col, float *dstv) {
+    uint32_t v[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) dstv[i] = __uint_as_float(v[i]);
+  };
+  __syncwarp();
+  if constexpr (NT <= 64) {
+    float acc[CPW];
+    if (epi) {
+      if (nk > 0) {
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < CPW; c0 += 16) ld16(half * CPW + c0, acc + c0);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CPW; i++) acc[i] = 0.f;
+      }
+    }
+    if (ksplit > 1) {
+      // deterministic split-K reduction through the leader's shared memory (stage memory is free once
+      // every CTA of the cluster has drained its pipeline): red[rank-1][token][row]
+      float *red = (float *)smem;
+      cluster_sync_all();
+      if (epi && rank != 0) {
+#pragma unroll
+        for (int i = 0; i < CPW; i++)
+          st_cluster_f32(smem_u32(red + ((size_t)(rank - 1) * NT + half * CPW + i) * WA_BM + row), 0u, acc[i]);
+      }
+      cluster_sync_all();
+      if (epi && rank == 0) {
+        for (int s = 1; s < ksplit; s++)
+#pragma unroll
+          for (int i = 0; i < CPW; i++) acc[i] += red[((size_t)(s - 1) * NT + half * CPW + i) * WA_BM + row];
+      }
+    }
+    if (epi && rank == 0 && row < rows_valid) {
+      const int nrow = n0 + row;
+#pragma unroll
+      for (int i = 0; i < CPW; i++) {
+        const int tok = p.m0 + half * CPW + i;
+        if (tok < p.M) store_act(p.y, (int64_t)tok * p.N + nrow, acc[i], p.dtype);
+      }
+    }
+  } else {
+    // large token tiles (no split-K): stream the accumulators out 16 columns at a time
+    if (epi && nk > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < CPW; c0 += 16) {
+        float v[16];
+        ld16(half * CPW + c0, v);
+        if (row < rows_valid) {
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            const int tok = p.m0 + half * CPW + c0 + i;
+            if (tok < p.M) store_act(p.y, (int64_t)tok * p.N + n0 + row, v[i], p.dtype);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
+}
+
+// ---------------------------------------------------------------- repack kernels
+// GPTQ checkpoint [K/8, N] i32 (nibble j of word (k8, n) = k 8*k8 + j) -> mrs int4 tiles; `perm`
+// (argsort of g_idx, REF gptq_cuda.rs:573-583) gathers source rows exactly like
+// gptq_marlin_repack does: packed row k' takes checkpoint row perm[k'].
+__global__ void repack_gptq_kernel(const uint32_t *__restrict__ qw, const int32_t *__restrict__ perm, uint32_t *__restrict__ out,
+                                   int K, int N) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one output word: (ks, n, w)
+  const int64_t total = (int64_t)(K / 64) * N * 8;
+  if (idx >= total) return;
+  const int w = (int)(idx & 7);
+  const int n = (int)((idx >> 3) % N);
+  const int ks = (int)((idx >> 3) / N);
+  uint32_t o = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int kdst = ks * 64 + w * 8 + j;
+    const int ksrc = perm ? perm[kdst] : kdst;
+    const uint32_t nib = (qw[(size_t)(ksrc >> 3) * N + n] >> (4 * (ksrc & 7))) & 0xFu;
+    const int pos = (j & 1) ? 4 + (j >> 1) : (j >> 1);
+    o |= nib << (4 * pos);
+  }
+  out[idx] = o;
+}
+// AWQ checkpoint [K, N/8] i32 (nibble i of word (k, c) = column 8c + {0,2,4,6,1,3,5,7}[i]) -> mrs int4 tiles
+__global__ void repack_awq_kernel(const uint32_t *__restrict__ qw, uint32_t *__restrict__ out, int K, int N) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)(K / 64) * N * 8;
+  if (idx >= total) return;
+  const int w = (int)(idx & 7);
+  const int n = (int)((idx >> 3) % N);
+  const int ks = (int)((idx >> 3) / N);
+  const int c7 = n & 7;
+  const int ipos = (c7 & 1) ? 4 + (c7 >> 1) : (c7 >> 1);   // inverse of {0,2,4,6,1,3,5,7}
+  uint32_t o = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int k = ks * 64 + w * 8 + j;
+    const uint32_t nib = (qw[(size_t)k * (N >> 3) + (n >> 3)] >> (4 * ipos)) & 0xFu;
+    const int pos = (j & 1) ? 4 + (j >> 1) : (j >> 1);
+    o |= nib << (4 * pos);
+  }
+  out[idx] = o;
+}
+
+// ---------------------------------------------------------------- host
+template <int NT, int SRC>
+static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaParams p, int ksplit, cudaStream_t st) {
+  auto kern = w4a16_kernel<NT, SRC>;
+  constexpr int STAGE = WA_A_BYTES + NT * 128 + (SRC == WA_SRC_INT4 ? WA_RAW_BYTES : 0);
+  const size_t smem = 1024 + (size_t)WA_STAGES * STAGE + 256;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((p.N + WA_BM - 1) / WA_BM, ksplit);
+  cfg.blockDim = dim3(WA_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = ksplit; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ksplit > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, tx, tw, p);
+}
+
+// split K over a cluster when the row tiles alone leave SMs idle (two CTAs per SM are resident)
+static int pick_ksplit(int N, int K, int NT) {
+  if (NT > 64) return 1;   // large token tiles stream their epilogue; compute-bound anyway
+  int sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = (N + WA_BM - 1) / WA_BM, nk = K / WA_BK;
+  const int slots = (NT <= 64 ? 2 : 1) * sms;
+  int ks = 1;
+  for (int c = 2; c <= 4; c *= 2) {
+    const int per = (nk + c - 1) / c;
+    // the reduction buffer (c-1 partials of NT x 128 f32) lives in the pipeline's stage memory
+    const size_t red = (size_t)(c - 1) * NT * WA_BM * 4, stages = (size_t)WA_STAGES * (WA_A_BYTES + NT * 128);
+    if (tiles * c <= slots && per >= 4 && red <= stages) ks = c;
+  }
+  return ks;
+}
+
+static cudaError_t run_wa(int src, const void *x, const void *w, const void *scales, const int32_t *qzeros, void *y, int M,
+                          int K, int N, int group, int dtype, int scale_perm, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (K % WA_BK != 0 || (dtype != MRS_F16 && dtype != MRS_BF16)) return cudaErrorInvalidValue;
+  if (group <= 0) group = K;
+  if (src == WA_SRC_INT4 && (group % 32 != 0 || K % group != 0)) return cudaErrorInvalidValue;
+  if (((uintptr_t)x & 15) || ((uintptr_t)w & 15)) return cudaErrorMisalignedAddress;
+  CUtensorMap tx, tw;
+  memset(&tw, 0, sizeof tw);
+  for (int m0 = 0; m0 < M; m0 += 256) {
+    const int mt = M - m0 < 256 ? M - m0 : 256;
+    const int NT = mt <= 32 ? 32 : mt <= 64 ? 64 : mt <= 128 ? 128 : 256;
+    if (!tc_make_map_2d(&tx, x, (uint64_t)M, (uint64_t)K, WA_BK, (uint32_t)NT, dtype)) return cudaErrorInvalidValue;
+    if (src == WA_SRC_DENSE && !tc_make_map_2d(&tw, w, (uint64_t)N, (uint64_t)K, WA_BK, WA_BM, dtype)) return cudaErrorInvalidValue;
+    WaParams p = {};
+    p.wq = (const uint8_t *)w; p.scales = scales; p.qzeros = qzeros; p.y = y;
+    p.M = M; p.N = N; p.K = K; p.group = group; p.dtype = dtype; p.scale_perm = scale_perm; p.m0 = m0;
+    const int ks = pick_ksplit(N, K, NT);
+    p.ksteps_per_split = (K / WA_BK + ks - 1) / ks;
+    cudaError_t e;
+#define MRS_WA(NTV)                                                                                   \
+  e = (src == WA_SRC_INT4) ? launch_wa<NTV, WA_SRC_INT4>(tx, tw, p, ks, st) : launch_wa<NTV, WA_SRC_DENSE>(tx, tw, p, ks, st)
+    if (NT == 32) MRS_WA(32); else if (NT == 64) MRS_WA(64); else if (NT == 128) MRS_WA(128); else MRS_WA(256);
+#undef MRS_WA
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace mrs
+
+using namespace mrs;
+
+// ---- B200-native entries ---------------------------------------------------------------------
+// Y[M,N] = X[M,K] . W^T, W = repacked int4 (mrs tiles, see gptq_marlin_repack below); scales
+// [K/group, N] in dtype (0 f16 / 1 bf16), group <= 0: one group; qzeros: AWQ raw zero points or NULL
+// (symmetric, zero point 8); scale_perm: 0 plain, 1/2 Marlin-permuted scale columns.
+extern "C" int32_t mrs_w4a16_gemm(const void *x, const void *w_tiles, const void *scales, const int32_t *qzeros, void *y,
+                                  int32_t M, int32_t K, int32_t N, int32_t group, int32_t dtype, int32_t scale_perm,
+                                  void *stream) {
+  return (int32_t)run_wa(WA_SRC_INT4, x, w_tiles, scales, qzeros, y, M, K, N, group, dtype, scale_perm, (cudaStream_t)stream);
+}
+// Y[M,N] = X[M,K] . W[N,K]^T with dense 16-bit W (the lm_head of GPTQ/AWQ checkpoints at decode batch)
+extern "C" int32_t mrs_dense_linear(const void *x, const void *w, void *y, int32_t M, int32_t K, int32_t N, int32_t dtype,
+                                    void *stream) {
+  return (int32_t)run_wa(WA_SRC_DENSE, x, w, nullptr, nullptr, y, M, K, N, 0, dtype, 0, (cudaStream_t)stream);
+}
+
+// ---- the reference's Marlin symbols (REF mistralrs-quant/src/gptq/marlin_ffi.rs:6-81) ----------
+// `weight` of the matmuls is what our own *_marlin_repack wrote (the Rust side treats it as opaque);
+// `scales` arrive column-permuted by marlin_permute_scales (REF gptq_cuda.rs:542-565): the 64-wide
+// permutation when group < K/8 (the reference passes in_dim / pack_factor as size_k), else the
+// 32-wide one; `workspace` (Marlin's lock array) is not needed.
+static int marlin_common(const void *inputs, const int32_t *weight, const void *scales, const void *zeros, void *out, int m,
+                         int k, int n, int groupsize, int dtype, int is_awq, int64_t stream) {
+  cudaError_t status = cudaGetLastError();
+  if (status != cudaSuccess) return (int)status;
+  const int group = groupsize <= 0 ? k : groupsize;
+  const int perm_kind = (groupsize > 0 && groupsize < k / 8) ? 1 : 2;
+  const cudaError_t e = run_wa(WA_SRC_INT4, inputs, weight, scales, is_awq ? (const int32_t *)zeros : nullptr, out, m, k, n, group,
+                               dtype, perm_kind, (cudaStream_t)stream);
+  return e == cudaSuccess ? (int)cudaGetLastError() : (int)e;
+}
+extern "C" int marlin_gptq_4bit_f16(const void *inputs, const int32_t *weight, const void *scales, const void *zeros,
+                                    const void *out, int m, int k, int n, const void *workspace, int groupsize, int64_t stream) {
+  (void)workspace;
+  return marlin_common(inputs, weight, scales, zeros, (void *)out, m, k, n, groupsize, MRS_F16, 0, stream);
+}
+extern "C" int marlin_gptq_4bit_bf16(const void *inputs, const int32_t *weight, const void *scales, const void *zeros,
+                                     const void *out, int m, int k, int n, const void *workspace, int groupsize, int64_t stream) {
+  (void)workspace;
+  return marlin_common(inputs, weight, scales, zeros, (void *)out, m, k, n, groupsize, MRS_BF16, 0, stream);
+}
+extern "C" int marlin_awq_4bit_f16(const void *inputs, const int32_t *weight, const void *scales, const void *zeros,
+                                   const void *out, int m, int k, int n, const void *workspace, int groupsize, int64_t stream) {
+  (void)workspace;
+  return marlin_common(inputs, weight, scales, zeros, (void *)out, m, k, n, groupsize, MRS_F16, 1, stream);
+}
+extern "C" int marlin_awq_4bit_bf16(const void *inputs, const int32_t *weight, const void *scales, const void *zeros,
+                                    const void *out, int m, int k, int n, const void *workspace, int groupsize, int64_t stream) {
+  (void)workspace;
+  return marlin_common(inputs, weight, scales, zeros, (void *)out, m, k, n, groupsize, MRS_BF16, 1, stream);
+}
+
+// weight [k/8, n] i32, perm [k] i32 (argsort of g_idx; the reference always passes one), result: k*n/2 bytes
+extern "C" void gptq_marlin_repack(const void *weight, const void *perm, const void *result, int k, int n, int bits,
+                                   int64_t stream) {
+  if (bits != 4 || k % 64 != 0 || n % 8 != 0) {
+    fprintf(stderr, "mrs_b200: gptq_marlin_repack supports 4-bit weights with k %% 64 == 0 (got bits %d, k %d, n %d)\n", bits, k, n);
+    return;
+  }
+  const int64_t total = (int64_t)(k / 64) * n * 8;
+  repack_gptq_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)weight, (const int32_t *)perm,
+                                                                                    (uint32_t *)result, k, n);
+}
+// in [k, n] i32 with n = out_dim / 8 (REF marlin_repack.cu:473-483), perm unused
+extern "C" void awq_marlin_repack(const void *in, const void *perm, const void *out, int k, int n, int bits, int64_t stream) {
+  (void)perm;
+  const int size_n = n * 8;
+  if (bits != 4 || k % 64 != 0) {
+    fprintf(stderr, "mrs_b200: awq_marlin_repack supports 4-bit weights with k %% 64 == 0 (got bits %d, k %d)\n", bits, k);
+    return;
+  }
+  const int64_t total = (int64_t)(k / 64) * size_n * 8;
+  repack_awq_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)in, (uint32_t *)out, k, size_n);
+}

@@ -39,6 +39,7 @@ class LlamaConfig:
     name: str = "llama-3-8b"
     rope_neox: bool = True     # rotate-half pairing; GGUF llama files use the interleaved pairing (False)
     rope_freq_factors: object = None   # optional per-frequency divisors (GGUF `rope_freqs.weight`, Llama-3.1 scaling)
+    synth_scale_exp: tuple = (-9, -7)  # synthetic weights: block scales d = 2^U(lo, hi)
 
     @staticmethod
     def llama3_8b(**kw):
@@ -78,13 +79,13 @@ TENSOR_IDS = {"attn_q": 0, "attn_k": 1, "attn_v": 2, "attn_output": 3, "ffn_gate
               "attn_norm": 7, "ffn_norm": 8, "token_embd": 9, "output": 10, "output_norm": 11}
 
 
-def synth_blocks(dtype: str, nblocks: int, seed: int) -> np.ndarray:
+def synth_blocks(dtype: str, nblocks: int, seed: int, scale_exp=(-9, -7)) -> np.ndarray:
     """uint8 [nblocks, block_bytes] per SURVEY §8(d), numpy PCG64(seed)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     bb = BLOCK_BYTES[dtype]
     raw = rng.integers(0, 256, size=(nblocks, bb), dtype=np.uint8)
     f = F16_FIELDS[dtype]
-    d = np.exp2(rng.uniform(-9, -7, size=nblocks)).astype(np.float16)
+    d = np.exp2(rng.uniform(scale_exp[0], scale_exp[1], size=nblocks)).astype(np.float16)
     raw[:, f[0]:f[0] + 2] = d.view(np.uint8).reshape(nblocks, 2)
     if len(f) > 1:
         m = (d.astype(np.float32) * rng.uniform(0, 0.5, size=nblocks)).astype(np.float16)
@@ -374,7 +375,7 @@ class LlamaWeights:
         :695-975 (row), gguf/weight_source.rs:809-818 (block-aligned K slices)."""
         dt = tensor_type(self.cfg, name, layer)
         be, bb = BLOCK_ELEMS[dt], BLOCK_BYTES[dt]
-        full = synth_blocks(dt, rows * cols // be, tensor_seed(layer, name)).reshape(rows, cols // be, bb)
+        full = synth_blocks(dt, rows * cols // be, tensor_seed(layer, name), self.cfg.synth_scale_exp).reshape(rows, cols // be, bb)
         r, w = self.tp_rank, self.tp_size
         if kind == "col" and w > 1:
             full = full[r * rows // w:(r + 1) * rows // w]
