@@ -107,6 +107,17 @@ int32_t mrs_paged_decode_fused_strided(void *q, void *k_new, void *v_new, void *
                                int32_t num_qo_heads, int32_t num_kv_heads, int32_t head_size, int32_t page_size,
                                float sm_scale, uint32_t dtype, int32_t pdl, int64_t q_stride_n, int64_t kv_new_stride,
                                void *stream);
+/* ---- prompt attention over fresh q/k/v (REF paged_attention.rs:1413-1475 ->
+ * flash_attn_varlen): causal [+ sliding window / soft-cap], GQA, var-len batches via cu_seqlens
+ * (device i32 [batch+1], or NULL for one sequence).  q [total,H,D], k/v [total,KVH,D], strides in
+ * elements between tokens; head_dim 64 | 128; dtype 0 f16 / 1 bf16.  csrc/prefill_attn.cu. */
+int32_t mrs_prefill_attention(const void *q, const void *k, const void *v, void *out, const int32_t *cu_seqlens,
+                              int32_t batch, int32_t total_tokens, int32_t max_seqlen, int32_t num_heads,
+                              int32_t num_kv_heads, int32_t head_dim, int64_t q_stride, int64_t kv_stride, int64_t o_stride,
+                              float softmax_scale, int32_t causal, int32_t window_left, float softcap, uint32_t dtype,
+                              void *stream);
+/* diagnostics: bit 0 keeps HND decode attention on the SIMT kernel instead of the tensor-core one */
+void mrs_set_attn_flags(int32_t flags);
 #ifdef __cplusplus
 }
 #endif

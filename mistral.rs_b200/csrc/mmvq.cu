@@ -267,27 +267,39 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
       const bool livec = col < p.ncols;
       int4 *c0 = xq0 + (size_t)col * npos, *c1 = xq1 + (size_t)col * npos;
       float *ca = xa + (size_t)col * npos * Q::AUX;
-      for (int ch = ctid; ch < nchunks_w; ch += NCT) {
-        const bool ok = ch < nchunks;
-        int2 qv = make_int2(0, 0);
-        float d = 0.f, sm = 0.f;
-        if (ok && livec) {
-          const block_q8_1 *yb = y + (size_t)col * p.stride_col_y + (ch >> 2);
-          const int *qp = (const int *)(yb->qs + 8 * (ch & 3));
-          qv = make_int2(qp[0], qp[1]);
-          const float2 ds = __half22float2(yb->ds);
-          d = ds.x; sm = ds.y;
+      constexpr int CB = 4;
+#pragma unroll 1
+      for (int ch0 = ctid; ch0 < nchunks_w; ch0 += CB * NCT) {
+        int2 qv[CB];
+        __half2 dsv[CB];
+#pragma unroll
+        for (int u = 0; u < CB; u++) {     // all loads of four chunks in flight together
+          const int ch = ch0 + u * NCT;
+          qv[u] = make_int2(0, 0);
+          dsv[u] = __floats2half2_rn(0.f, 0.f);
+          if (ch < nchunks && livec) {
+            const block_q8_1 *yb = y + (size_t)col * p.stride_col_y + (ch >> 2);
+            const int *qp = (const int *)(yb->qs + 8 * (ch & 3));
+            qv[u] = make_int2(qp[0], qp[1]);
+            dsv[u] = yb->ds;
+          }
         }
-        const int isum8 = __dp4a(qv.x, 0x01010101, __dp4a(qv.y, 0x01010101, 0));
-        const int isum16 = isum8 + __shfl_xor_sync(0xffffffffu, isum8, 1);
-        if (ok) {
-          const int e0 = ch * 8;
-          const int blk = e0 / Q::QK, e = e0 - blk * Q::QK;
-          int c, hi, w8;
-          Q::chunk_dest(e, c, hi, w8);
-          const int pos = unit_to_pos<T, UPL>(blk, c);
-          *((int2 *)((hi ? c1 : c0) + pos) + w8) = qv;
-          Q::chunk_aux(e, d, sm, isum8, isum16, ca + (size_t)pos * Q::AUX);
+#pragma unroll
+        for (int u = 0; u < CB; u++) {
+          const int ch = ch0 + u * NCT;
+          if (ch >= nchunks_w) break;          // warp-uniform
+          const float2 ds = __half22float2(dsv[u]);
+          const int isum8 = __dp4a(qv[u].x, 0x01010101, __dp4a(qv[u].y, 0x01010101, 0));
+          const int isum16 = isum8 + __shfl_xor_sync(0xffffffffu, isum8, 1);
+          if (ch < nchunks) {
+            const int e0 = ch * 8;
+            const int blk = e0 / Q::QK, e = e0 - blk * Q::QK;
+            int c, hi, w8;
+            Q::chunk_dest(e, c, hi, w8);
+            const int pos = unit_to_pos<T, UPL>(blk, c);
+            *((int2 *)((hi ? c1 : c0) + pos) + w8) = qv[u];
+            Q::chunk_aux(e, ds.x, ds.y, isum8, isum16, ca + (size_t)pos * Q::AUX);
+          }
         }
       }
     }
@@ -345,63 +357,82 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
       if (tid == 0) MRS_STAMP(4);
       int4 *c0 = xq0 + (size_t)col * npos, *c1 = xq1 + (size_t)col * npos;
       float *ca = xa + (size_t)col * npos * Q::AUX;
-      int it = 0;
+      // chunks are taken four at a time: the four activation (and norm-weight) loads are issued
+      // together, so a long K (down_proj: 7 chunks per thread) pays two cache latencies, not seven
+      // (the shuffles inside the per-chunk work keep the compiler from hoisting loads itself)
+      constexpr int CB = 4;
 #pragma unroll 1
-      for (int ch = ctid; ch < nchunks_w; ch += NCT, it++) {
-        const bool ok = ch < nchunks;
-        const bool inreg = reg16 && (it == 0 || (it == 1 && NCW == SSW));
-        float v[8];
-        if (ok && live) {
-          if (inreg) unpack_act8(sel_u4(it == 0, xr0, xr1), p.xdtype, v);
-          else load_act8(p.x, (int64_t)col * p.K + ch * 8, p.xdtype, v);
-          if (p.norm_w != nullptr) {
-            float wv[8];
-            if (inreg) unpack_act8(sel_u4(it == 0, nwr0, nwr1), p.xdtype, wv);
-            else load_act8(p.norm_w, ch * 8, p.xdtype, wv);
+      for (int ch0 = ctid, it0 = 0; ch0 < nchunks_w; ch0 += CB * NCT, it0 += CB) {
+        uint4 xr[CB], wr[CB];   // (f32 activations are not batched: loaded chunk by chunk below)
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = round_act(v[i] * inv_rms * wv[i], p.xdtype);
+        for (int u = 0; u < CB; u++) {
+          const int ch = ch0 + u * NCT;
+          const bool ok = ch < nchunks && live;
+          if (reg16) {
+            const bool in0 = (it0 + u) == 0, in1 = (it0 + u) == 1 && NCW == SSW;
+            xr[u] = in0 ? xr0 : (in1 ? xr1 : (ok ? *((const uint4 *)((const uint16_t *)p.x + (int64_t)col * p.K) + ch) : make_uint4(0u, 0u, 0u, 0u)));
+            if (p.norm_w != nullptr)
+              wr[u] = in0 ? nwr0 : (in1 ? nwr1 : (ok ? __ldg((const uint4 *)p.norm_w + ch) : make_uint4(0u, 0u, 0u, 0u)));
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; i++) v[i] = 0.f;
         }
-        float am = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; i++) am = fmaxf(am, fabsf(v[i]));
-        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
-        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
-        float bsum = 0.f;
-        if constexpr (Q::NEEDS_SUM) {
-          // the reference's butterfly sum of the 32 block elements (i+16, i+8, then 4/2/1)
-          float t[8];
+        for (int u = 0; u < CB; u++) {
+          const int ch = ch0 + u * NCT;
+          if (ch >= nchunks_w) break;          // warp-uniform: whole warps iterate together
+          const bool ok = ch < nchunks;
+          float v[8];
+          if (ok && live) {
+            if (reg16) unpack_act8(xr[u], p.xdtype, v);
+            else load_act8(p.x, (int64_t)col * p.K + ch * 8, p.xdtype, v);
+            if (p.norm_w != nullptr) {
+              float wv[8];
+              if (reg16) unpack_act8(wr[u], p.xdtype, wv);
+              else load_act8(p.norm_w, ch * 8, p.xdtype, wv);
 #pragma unroll
-          for (int i = 0; i < 8; i++) t[i] = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 2);
+              for (int i = 0; i < 8; i++) v[i] = round_act(v[i] * inv_rms * wv[i], p.xdtype);
+            }
+          } else {
 #pragma unroll
-          for (int i = 0; i < 8; i++) t[i] = t[i] + __shfl_xor_sync(0xffffffffu, t[i], 1);
-#pragma unroll
-          for (int m = 4; m > 0; m >>= 1) {
-#pragma unroll
-            for (int i = 0; i < m; i++) t[i] = t[i] + t[i + m];
+            for (int i = 0; i < 8; i++) v[i] = 0.f;
           }
-          bsum = __half2float(__float2half_rn(t[0]));
-        }
-        const float d = __fdividef(am, 127.0f);
-        uint32_t wq[2] = {0u, 0u};
+          float am = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int qi = (am == 0.0f) ? 0 : (int)(int8_t)roundf(__fdividef(v[i], d));
-          wq[i >> 2] |= (uint32_t)(qi & 0xff) << (8 * (i & 3));
-        }
-        const int isum8 = __dp4a((int)wq[0], 0x01010101, __dp4a((int)wq[1], 0x01010101, 0));
-        const int isum16 = isum8 + __shfl_xor_sync(0xffffffffu, isum8, 1);
-        if (ok) {
-          const int e0 = ch * 8;
-          const int blk = e0 / Q::QK, e = e0 - blk * Q::QK;
-          int c, hi, w8;
-          Q::chunk_dest(e, c, hi, w8);
-          const int pos = unit_to_pos<T, UPL>(blk, c);
-          *((int2 *)((hi ? c1 : c0) + pos) + w8) = make_int2((int)wq[0], (int)wq[1]);
-          Q::chunk_aux(e, __half2float(__float2half_rn(d)), bsum, isum8, isum16, ca + (size_t)pos * Q::AUX);
+          for (int i = 0; i < 8; i++) am = fmaxf(am, fabsf(v[i]));
+          am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+          am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+          float bsum = 0.f;
+          if constexpr (Q::NEEDS_SUM) {
+            // the reference's butterfly sum of the 32 block elements (i+16, i+8, then 4/2/1)
+            float t[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 2);
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = t[i] + __shfl_xor_sync(0xffffffffu, t[i], 1);
+#pragma unroll
+            for (int m = 4; m > 0; m >>= 1) {
+#pragma unroll
+              for (int i = 0; i < m; i++) t[i] = t[i] + t[i + m];
+            }
+            bsum = __half2float(__float2half_rn(t[0]));
+          }
+          const float d = __fdividef(am, 127.0f);
+          uint32_t wq[2] = {0u, 0u};
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int qi = (am == 0.0f) ? 0 : (int)(int8_t)roundf(__fdividef(v[i], d));
+            wq[i >> 2] |= (uint32_t)(qi & 0xff) << (8 * (i & 3));
+          }
+          const int isum8 = __dp4a((int)wq[0], 0x01010101, __dp4a((int)wq[1], 0x01010101, 0));
+          const int isum16 = isum8 + __shfl_xor_sync(0xffffffffu, isum8, 1);
+          if (ok) {
+            const int e0 = ch * 8;
+            const int blk = e0 / Q::QK, e = e0 - blk * Q::QK;
+            int c, hi, w8;
+            Q::chunk_dest(e, c, hi, w8);
+            const int pos = unit_to_pos<T, UPL>(blk, c);
+            *((int2 *)((hi ? c1 : c0) + pos) + w8) = make_int2((int)wq[0], (int)wq[1]);
+            Q::chunk_aux(e, __half2float(__float2half_rn(d)), bsum, isum8, isum16, ca + (size_t)pos * Q::AUX);
+          }
         }
       }
     }
@@ -435,7 +466,8 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
     // the residual (lane 0 adds it in the epilogue) is fetched now, not after the reduction: one
     // global latency less on the tail of every o_proj / down_proj launch
     float resv[2][NCOLS];
-    if (p.residual != nullptr && lane == 0 && p.mode != MODE_GLU) {
+    const bool res_early = !(p.flags & 16);
+    if (p.residual != nullptr && lane == 0 && p.mode != MODE_GLU && res_early) {
 #pragma unroll
       for (int r = 0; r < 2; r++) {
         const int64_t cs = (p.mode == MODE_QKV) ? p.nrows[mm[r]] : p.stride_col_dst;
@@ -527,7 +559,7 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
               float v = acc[r][j];
               if (p.residual != nullptr) {
                 // y materialised in dtype, then residual add rounded again (candle `+`)
-                v = round_act(v, p.dst_dtype) + resv[r][j];
+                v = round_act(v, p.dst_dtype) + (res_early ? resv[r][j] : load_act(p.residual, (int64_t)j * cs + rr[r], p.dst_dtype));
               }
               store_act(p.dst[mm[r]], (int64_t)j * cs + rr[r], v, p.dst_dtype);
             }
@@ -545,7 +577,7 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
 }
 
 template <int T, int NCOLS, bool FAST, int NCW, int UPL>
-__global__ void __launch_bounds__((NCW + 1) * 32, NCOLS == 1 ? 3 : 2) mmvq_stream_kernel(const MmvqParams p) {
+__global__ void __launch_bounds__((NCW + 1) * 32, 2) mmvq_stream_kernel(const MmvqParams p) {
   mmvq_body<T, NCOLS, FAST, NCW, UPL>(p, (int)blockIdx.x, (int)gridDim.x);
 }
 
@@ -794,7 +826,9 @@ extern "C" void mrs_set_pdl(int enabled) { g_mrs_pdl = enabled; }
 // flags: bit 3 = never use the long-segment variant; bits 8.. = long-segment threshold in MiB
 extern "C" void mrs_set_mmvq_flags(int f) { g_flags = f & 0xff; if (f >> 8) g_long_min_bytes = (long long)(f >> 8) << 20; }
 extern "C" int mrs_mmvq_has_wide(void) { return 0; }
-extern "C" void mrs_set_mmvq_ctas_per_sm(int n) { g_ctas_per_sm = n < 1 ? 1 : (n > 3 ? 3 : n); }
+// (three CTAs per SM — 72-register kernels, 24 consumer warps — measured 9 % slower end to end than two:
+// profiles/r02_experiments.md; the kernels are compiled for two)
+extern "C" void mrs_set_mmvq_ctas_per_sm(int n) { g_ctas_per_sm = n < 1 ? 1 : (n > 2 ? 2 : n); }
 
 static inline void report(cudaError_t e, const char *what) {
   if (e != cudaSuccess) fprintf(stderr, "mrs_b200: %s failed: %s\n", what, cudaGetErrorString(e));

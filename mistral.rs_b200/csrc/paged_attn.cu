@@ -525,11 +525,17 @@ __global__ void merge_partials_kernel(const T *__restrict__ tmp_o, const float *
   }
 }
 
+}  // namespace mrs
+#include "paged_attn_mma.cuh"
+namespace mrs {
+
+static int g_pa_flags = 0;   // bit 0: keep HND decode on the SIMT kernel (A/B, debugging)
+
 template <typename K>
-static cudaError_t launch_pa(K kern, dim3 grid, const PagedParams &p, cudaStream_t st, size_t dyn_smem) {
+static cudaError_t launch_pa(K kern, dim3 grid, const PagedParams &p, cudaStream_t st, size_t dyn_smem, int threads = PA_THREADS) {
   if (dyn_smem > 0) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(PA_THREADS); cfg.dynamicSmemBytes = dyn_smem; cfg.stream = st;
+  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = dyn_smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -540,6 +546,16 @@ static cudaError_t launch_pa(K kern, dim3 grid, const PagedParams &p, cudaStream
 template <typename T, int D, int LAYOUT, bool FUSED>
 static cudaError_t launch_decode_g(PagedParams p, int tiles, cudaStream_t st) {
   const int group = p.num_heads / p.num_kv_heads;
+  if constexpr (LAYOUT == 1 && D <= 128) {
+    // HND cache: the GQA group is an MMA tile (paged_attn_mma.cuh); ALiBi / sinks are vLLM-layout features
+    if (!(g_pa_flags & 1) && p.alibi_slopes == nullptr && p.sinks == nullptr && p.kv_indptr != nullptr && !p.tiles_are_partitions) {
+      const int nsub = (group + 15) / 16;
+      p.heads_per_cta = (group + nsub - 1) / nsub;
+      dim3 grid(tiles, p.num_kv_heads, nsub);
+      const size_t dyn = (size_t)4 * PM_BN * D * sizeof(T) + (size_t)16 * D * sizeof(T);
+      return launch_pa(paged_decode_mma_kernel<T, D, FUSED>, grid, p, st, dyn, PM_THREADS);
+    }
+  }
   constexpr int GMAX = (D <= 128) ? 8 : 4;  // static smem budget: 8 states x G x D floats
   const int nsub = (group + GMAX - 1) / GMAX;
   const int per = (group + nsub - 1) / nsub;
@@ -766,3 +782,6 @@ extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, voi
                                         padded_batch_size, num_qo_heads, num_kv_heads, head_size, page_size, sm_scale, dtype,
                                         pdl, (int64_t)num_qo_heads * head_size, (int64_t)num_kv_heads * head_size, stream);
 }
+
+// bit 0: keep HND decode attention on the SIMT kernel instead of the tensor-core one (A/B, debugging)
+extern "C" void mrs_set_attn_flags(int32_t flags) { mrs::g_pa_flags = flags; }

@@ -49,6 +49,7 @@ struct WaParams {
   int scale_perm;          // 0: plain columns, 1: Marlin 64-wide permutation, 2: Marlin "single" (32-wide)
   int m0;                  // first token of this pass
   int ksteps_per_split;    // K-steps (of 64) per split CTA
+  int groups_per_cta;      // scale groups a CTA's K range can touch (sizes the shared scale table)
 };
 
 // Inverses of the reference's scale-column permutations (REF gptq_cuda.rs:530-540 get_scale_perms):
@@ -116,6 +117,7 @@ w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
   uint64_t *bars = (uint64_t *)(smem + WA_STAGES * STAGE);
   uint64_t *in_full = bars, *a_full = bars + WA_STAGES, *empty = bars + 2 * WA_STAGES, *acc_full = bars + 3 * WA_STAGES;
   uint32_t *tmem_slot = (uint32_t *)(bars + 3 * WA_STAGES + 1);
+  uint32_t *sc_tab = (uint32_t *)(smem + WA_STAGES * STAGE + 256);   // [groups_per_cta][128]: f16/bf16 scale | zero point << 16
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * WA_BM;
@@ -190,19 +192,27 @@ w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
       if (p.scale_perm == 1) scol = (n & ~63) + inv_scale_perm64(n & 63);
       else if (p.scale_perm == 2) scol = (n & ~31) + inv_scale_perm32(n & 31);
       const int zsh = 4 * ((n & 7) == 0 ? 0 : (n & 7) == 1 ? 4 : (n & 7) == 2 ? 1 : (n & 7) == 3 ? 5 : (n & 7) == 4 ? 2 : (n & 7) == 5 ? 6 : (n & 7) == 6 ? 3 : 7);
-      auto load_scale = [&](int kb) -> uint32_t {   // 16-bit scale | zero point << 16 of this thread's half of K-step kb
-        if (!live || kb >= nk_total) return 0u;
-        const int g = (kb * WA_BK + 32 * hf) / p.group;
-        uint32_t v = ((const uint16_t *)p.scales)[(size_t)g * p.N + scol];
-        uint32_t z = 8u;
-        if (p.qzeros != nullptr) z = ((uint32_t)p.qzeros[(size_t)g * (p.N >> 3) + (n >> 3)] >> zsh) & 0xFu;
-        return v | (z << 16);
-      };
-      uint32_t sz = load_scale(kb0);
+      // scales (+ AWQ zero points) of this CTA's K range go to shared memory once: a per-K-step global
+      // load in the loop would bound every iteration by an L2 round trip (measured: 1 us per K-step)
+      const int g_first = (kb0 * WA_BK) / p.group;
+      {
+        const int g_last = nk > 0 ? ((kb0 + nk) * WA_BK - 1) / p.group : g_first - 1;
+        for (int g = g_first + hf; g <= g_last; g += 2) {
+          uint32_t v = 0u;
+          if (live) {
+            v = ((const uint16_t *)p.scales)[(size_t)g * p.N + scol];
+            uint32_t z = 8u;
+            if (p.qzeros != nullptr) z = ((uint32_t)p.qzeros[(size_t)g * (p.N >> 3) + (n >> 3)] >> zsh) & 0xFu;
+            v |= z << 16;
+          }
+          sc_tab[(g - g_first) * WA_BM + r] = v;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(WA_DQ_WARPS * 32));
+      }
       int stage = 0, phase = 0;
       for (int i = 0; i < nk; i++) {
         const int kb = kb0 + i;
-        const uint32_t sz_next = load_scale(kb + 1);   // next K-step's scale in flight during this one
+        const uint32_t sz = sc_tab[((kb * WA_BK + 32 * hf) / p.group - g_first) * WA_BM + r];
         mbar_wait(&in_full[stage], phase);
         uint8_t *st = smem + (size_t)stage * STAGE;
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);
@@ -225,7 +235,6 @@ w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[stage]);
-        sz = sz_next;
         if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -359,7 +368,8 @@ template <int NT, int SRC>
 static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaParams p, int ksplit, cudaStream_t st) {
   auto kern = w4a16_kernel<NT, SRC>;
   constexpr int STAGE = WA_A_BYTES + NT * 128 + (SRC == WA_SRC_INT4 ? WA_RAW_BYTES : 0);
-  const size_t smem = 1024 + (size_t)WA_STAGES * STAGE + 256;
+  const size_t smem = 1024 + (size_t)WA_STAGES * STAGE + 256 + (SRC == WA_SRC_INT4 ? (size_t)p.groups_per_cta * WA_BM * 4 : 0);
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((p.N + WA_BM - 1) / WA_BM, ksplit);
@@ -412,6 +422,7 @@ static cudaError_t run_wa(int src, const void *x, const void *w, const void *sca
     p.M = M; p.N = N; p.K = K; p.group = group; p.dtype = dtype; p.scale_perm = scale_perm; p.m0 = m0;
     const int ks = pick_ksplit(N, K, NT);
     p.ksteps_per_split = (K / WA_BK + ks - 1) / ks;
+    p.groups_per_cta = (p.ksteps_per_split * WA_BK + group - 1) / group + 1;
     cudaError_t e;
 #define MRS_WA(NTV)                                                                                   \
   e = (src == WA_SRC_INT4) ? launch_wa<NTV, WA_SRC_INT4>(tx, tw, p, ks, st) : launch_wa<NTV, WA_SRC_DENSE>(tx, tw, p, ks, st)

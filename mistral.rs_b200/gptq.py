@@ -98,7 +98,7 @@ class GptqMarlinLayer:
         else:
             self.k, self.n = qweight.shape[0] * 8, qweight.shape[1]
             if g_idx is None:
-                g_idx = torch.arange(self.k, device=dev, dtype=torch.int32) // group_size
+                g_idx = torch.arange(self.k, device=dev, dtype=torch.int32) // (group_size if group_size > 0 else self.k)
             perm = torch.argsort(g_idx.cpu(), stable=True).to(torch.int32).to(dev)   # REF gptq_cuda.rs:578-582
             self.q_weight = torch.empty(self.k // 16, self.n * 16 // 8, dtype=torch.int32, device=dev)
             lib().gptq_marlin_repack(P(qweight.contiguous()), P(perm), P(self.q_weight), ctypes.c_int(self.k),

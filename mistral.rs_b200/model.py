@@ -546,14 +546,10 @@ class LlamaRunner:
 class LlamaPrefill:
     """Prompt processing (one sequence, positions 0..T-1) composed from the C-ABI ops, in the order
     of the reference's prefill forward (`models/llama.rs` Block::forward with seq_len > 1):
-    RMSNorm -> tcgen05 dequant-GEMMs (`mmq.forward`, the `fast_mmq` path) -> RoPE -> KV scatter into
-    the paged HND cache -> causal attention -> o_proj -> add+RMSNorm -> GLU -> down -> add.
-
-    Causal attention is computed by the paged DECODE kernel with one virtual request per prompt token
-    (request i attends the first i+1 cache rows through a shared page list): exact, and built only
-    from the already-measured kernels — but it re-reads the KV cache once per token, O(T^2) traffic.
-    It is the correctness path for prefill until the tcgen05 prefill-attention kernel (SURVEY §8(f)
-    rank 1) replaces it; `bench.py`'s prefill block therefore still reports the linears separately."""
+    RMSNorm -> tcgen05 dequant-GEMMs (`mmq.forward`, the `fast_mmq` path) -> RoPE -> causal prompt
+    attention over the fresh q/k/v (`paged_attn.prefill_attention`, the reference's flash-attn call,
+    paged_attention.rs:1413-1475) -> KV scatter into the paged HND cache -> o_proj -> add+RMSNorm ->
+    GLU -> down -> add.  TTFT of BASELINE config 3 is the time of `forward` on a 4096-token prompt."""
 
     def __init__(self, weights: "LlamaWeights", max_tokens=4096):
         from . import ops, paged_attn, quant  # noqa: F401  (fail early when the extension is missing)
@@ -569,31 +565,17 @@ class LlamaPrefill:
         self.k_cache = [torch.zeros(nb, cfg.n_kv_heads, bs, cfg.head_dim, dtype=dt, device=dev) for _ in range(cfg.n_layers)]
         self.v_cache = [torch.zeros(nb, cfg.n_kv_heads, bs, cfg.head_dim, dtype=dt, device=dev) for _ in range(cfg.n_layers)]
 
-    def _plan(self, T):
-        """CSR page lists of T virtual requests (request i: context i+1) + the unsplit tile plan."""
-        bs, dev = self.cfg.block_size, self.dev
-        pages = np.asarray(self.table, dtype=np.int32)
-        counts = (np.arange(T) + bs) // bs                       # ceil((i+1)/bs)
-        indptr = np.zeros(T + 1, dtype=np.int32)
-        np.cumsum(counts, out=indptr[1:])
-        indices = np.concatenate([pages[:c] for c in counts]).astype(np.int32)
-        last = (np.arange(T) % bs + 1).astype(np.int32)
-        i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
-        slots = np.asarray([self.table[i // bs] * bs + i % bs for i in range(T)], dtype=np.int64)
-        return dict(indptr=i32(indptr), indices=i32(indices), last=i32(last), req=i32(np.arange(T)), tile=i32(np.zeros(T)),
-                    o_indptr=i32(np.arange(T + 1)), chunk=i32(np.array([bs])),
-                    mask=torch.ones(T, dtype=torch.uint8, device=dev), slots=torch.from_numpy(slots).to(dev))
-
     def forward(self, tokens, all_logits=False):
         """tokens: list[int] (1 < len <= max_tokens).  Returns logits [vocab] of the last token, or
         [T, vocab] with all_logits=True.  The KV cache of every layer holds rows 0..T-1 afterwards."""
         from . import mmq, ops, paged_attn, quant
         cfg, dev, dt, w = self.cfg, self.dev, self.dt, self.w
         T = len(tokens)
-        if not 1 < T <= self.max_tokens:
-            raise ValueError(f"LlamaPrefill.forward: need 1 < tokens <= {self.max_tokens}, got {T}")
+        if not 1 < T <= min(self.max_tokens, cfg.max_pos):
+            raise ValueError(f"LlamaPrefill.forward: need 1 < tokens <= {min(self.max_tokens, cfg.max_pos)}, got {T}")
         H, KVH, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
-        plan = self._plan(T)
+        bs = cfg.block_size
+        slots = torch.tensor([self.table[i // bs] * bs + i % bs for i in range(T)], dtype=torch.int64, device=dev)
         ids = torch.tensor(tokens, dtype=torch.int32, device=dev)
         x = torch.empty(T, cfg.hidden, dtype=dt, device=dev)
         t, ty, rows, cols = w.tok_embd
@@ -611,10 +593,8 @@ class LlamaPrefill:
             k = mmq.forward(qt(L["attn_k"]), h).view(T, KVH, D)
             v = mmq.forward(qt(L["attn_v"]), h).view(T, KVH, D)
             ops.apply_rotary_qk(q, k, w.rope_cos, w.rope_sin, None, is_neox=cfg.rope_neox)
-            paged_attn.reshape_and_cache_flashinfer(k, v, self.k_cache[l], self.v_cache[l], plan["slots"])
-            attn = paged_attn.flashinfer_decode(q, self.k_cache[l], self.v_cache[l], plan["indptr"], plan["indices"],
-                                                plan["last"], plan["req"], plan["tile"], plan["o_indptr"], plan["chunk"],
-                                                plan["mask"], scale)
+            attn = paged_attn.prefill_attention(q, k, v, scale)
+            paged_attn.reshape_and_cache_flashinfer(k, v, self.k_cache[l], self.v_cache[l], slots)
             o = mmq.forward(qt(L["attn_output"]), attn.view(T, H * D))
             x, h2 = ops.add_rms_norm(o, x, L["ffn_norm"], cfg.rms_eps)       # x = o + x ; h2 = norm(x)
             gate = mmq.forward(qt(L["ffn_gate"]), h2)

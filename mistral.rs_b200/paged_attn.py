@@ -249,3 +249,33 @@ def kv_scale_update(key: torch.Tensor, value: torch.Tensor, k_scales: torch.Tens
     key, value = key.contiguous(), value.contiguous()
     getattr(lib(), f"update_kv_scales_{tag}")(_p(key), _p(value), ctypes.c_long(key.numel()), _p(k_scales), _p(v_scales),
                                               ctypes.c_int64(torch.cuda.current_stream(key.device).cuda_stream))
+
+
+def prefill_attention(q, k, v, softmax_scale, causal=True, cu_seqlens=None, max_seqlen=None, window_left=None,
+                      softcap=None):
+    """Prompt attention over fresh q/k/v (the reference's flash-attn call on a fresh prompt,
+    paged_attention.rs:1413-1475; `flash_attn_varlen` signature when cu_seqlens is given).
+    q [T, H, D], k/v [T, KVH, D] (last dim contiguous, heads dense), f16/bf16 -> out [T, H, D]."""
+    if q.dtype not in _TAG:
+        raise ValueError(f"prefill_attention: unsupported dtype {q.dtype}")
+    T, H, D = q.shape
+    KVH = k.shape[1]
+    if D not in (64, 128):
+        raise ValueError("prefill_attention: head_dim must be 64 or 128")
+    if k.shape != v.shape or k.shape[0] != T or k.shape[2] != D or H % KVH:
+        raise ValueError("prefill_attention: q/k/v shapes do not agree")
+    for t, name in ((q, "q"), (k, "k"), (v, "v")):
+        if t.stride(2) != 1 or t.stride(1) != D:
+            raise ValueError(f"prefill_attention: {name} must have dense heads")
+    out = torch.empty(T, H, D, dtype=q.dtype, device=q.device)
+    batch = 0 if cu_seqlens is None else cu_seqlens.numel() - 1
+    rc = lib().mrs_prefill_attention(_p(q), _p(k), _p(v), _p(out), _p(cu_seqlens), ctypes.c_int(batch), ctypes.c_int(T),
+                                     ctypes.c_int(max_seqlen or T), ctypes.c_int(H), ctypes.c_int(KVH), ctypes.c_int(D),
+                                     ctypes.c_int64(q.stride(0)), ctypes.c_int64(k.stride(0)), ctypes.c_int64(out.stride(0)),
+                                     ctypes.c_float(softmax_scale), ctypes.c_int(int(causal)),
+                                     ctypes.c_int(-1 if window_left is None else window_left),
+                                     ctypes.c_float(0.0 if softcap is None else softcap),
+                                     ctypes.c_uint32({torch.float16: 0, torch.bfloat16: 1}[q.dtype]), _stream(q.device))
+    if rc != 0:
+        raise RuntimeError(f"mrs_prefill_attention failed with cudaError {rc}")
+    return out

@@ -43,7 +43,19 @@ class OracleLlama:
             y = oracle.qmatmul_cpu(ty, w, x, cols, rows, self.threads)
         else:
             xq, stride = oracle.quantize_q8_1(x)
-            y = oracle.mmvq_q8_1(ty, w, xq, cols, rows, stride, x.shape[0]).astype(np.float32)
+            if self.threads > 1 and rows >= 4 * self.threads:
+                # row slices on a thread pool (ctypes drops the GIL): same arithmetic, row by row
+                from concurrent.futures import ThreadPoolExecutor
+                rb = oracle.BLOCK_BYTES[ty] * cols // oracle.BLOCK_ELEMS[ty]
+                wv = np.asarray(w).reshape(-1)
+                cuts = [rows * i // self.threads for i in range(self.threads + 1)]
+                def part(i):
+                    r0, r1 = cuts[i], cuts[i + 1]
+                    return oracle.mmvq_q8_1(ty, wv[r0 * rb:r1 * rb], xq, cols, r1 - r0, stride, x.shape[0])
+                with ThreadPoolExecutor(self.threads) as ex:
+                    y = np.concatenate(list(ex.map(part, range(self.threads))), axis=1).astype(np.float32)
+            else:
+                y = oracle.mmvq_q8_1(ty, w, xq, cols, rows, stride, x.shape[0]).astype(np.float32)
         return oracle.round_dtype(y.astype(np.float32), self.dt)
 
     def embed(self, tokens):

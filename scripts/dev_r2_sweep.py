@@ -32,12 +32,10 @@ def timed(run, mask, reps=30):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-for ctas in (2, 3):
-    for flags in (128 << 8, 8 | (128 << 8)):
-        L.mrs_set_mmvq_ctas_per_sm(ctypes.c_int(ctas))
-        L.mrs_set_mmvq_flags(ctypes.c_int(flags))
-        run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=True)
-        full, gemv, attn = timed(run, 0), timed(run, 1), timed(run, 2)
-        print(f"layers={layers} ctas/SM={ctas} long={'off' if flags & 8 else 'on'}: full {full:8.1f} us  gemv-only {gemv:8.1f} us  "
-              f"attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)
-L.mrs_set_mmvq_ctas_per_sm(ctypes.c_int(2)); L.mrs_set_mmvq_flags(ctypes.c_int(128 << 8))
+for name, mflags, aflags in (("default", 128 << 8, 0), ("late-residual", 16 | (128 << 8), 0), ("simt-attention", 128 << 8, 1)):
+    L.mrs_set_mmvq_flags(ctypes.c_int(mflags))
+    L.mrs_set_attn_flags(ctypes.c_int(aflags))
+    run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=True)
+    full, gemv, attn = timed(run, 0), timed(run, 1), timed(run, 2)
+    print(f"layers={layers} {name}: full {full:8.1f} us  gemv-only {gemv:8.1f} us  attn-only {attn:8.1f} us  -> {1e6/full:6.1f} tok/s", flush=True)
+L.mrs_set_mmvq_flags(ctypes.c_int(128 << 8)); L.mrs_set_attn_flags(ctypes.c_int(0))
