@@ -1,20 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — decode tok/s of the quantized-linear + paged-attention hot path on B200.
+"""bench.py — the quantized-linear + paged-attention hot path of mistral.rs on B200.
 
-Workload (BASELINE.json configs[1]): Llama-3-8B, GGUF Q4_K_M tensor types, decode batch=1,
-128-token prompt -> +256 generated tokens, synthetic weights/prompts, paged KV
-cache block_size=16 in the FlashInfer HND layout.  Metric definitions follow the reference's
-`mistralrs bench` (mistralrs-cli/src/commands/bench.rs:269-296): decode tok/s =
-(gen_len - 1) / (t_last_token - t_first_token).
+Headline (BASELINE.json configs[1], `--config 2`, the default): Llama-3-8B, GGUF Q4_K_M tensor types,
+decode batch 1, 128-token prompt -> +256 generated tokens, synthetic weights / prompts,
+paged KV cache block_size 16 (FlashInfer HND layout).  Metric definitions follow the reference's
+`mistralrs bench` (mistralrs-cli/src/commands/bench.rs:269-296): prefill tok/s = L / TTFT, decode
+tok/s = (G - 1) / (t_last_token - t_first_token).
 
-A "step" is one full generation (prompt + 256 tokens); the timed region of a step is its decode
-phase, bracketed by CUDA events on the launching stream (max over ranks).  `value` replays the
-per-token CUDA graph with every input resident in HBM (the sampled token feeds the next step on
-the device); `e2e` drives the same graph the way a serving engine does: the token id is copied
-from pinned host memory before every step and the sampled id is read back after it.
+A "step" is one full generation; its timed region is the decode phase, bracketed by CUDA events on
+the launching stream (max over ranks).  `value` replays the per-token CUDA graph with every input
+resident in HBM; `e2e` drives the same graph the way a serving engine does (token id copied from
+pinned host memory before every step, sampled id read back after it).  The same JSON line carries
+`roofline` (dominant kernel, measured live), `cpu_baseline` (the reference's CPU arithmetic, whole
+tokens on all host cores), `prefill` (BASELINE config 3: 4096-token prompt on Q8_0 weights, TTFT
+including prompt attention) and `config4` (Mistral-7B GPTQ int4 decode at batch 32, both KV layouts).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   (tensor parallel, NCCL)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N      (tensor parallel)
 """
 import argparse
 import ctypes
@@ -22,6 +24,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -29,6 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 PROMPT_LEN, GEN_LEN = 128, 256
+GGML = {"q4_0": 2, "q4_1": 3, "q5_0": 6, "q5_1": 7, "q8_0": 8, "q2_k": 10, "q3_k": 11, "q4_k": 12, "q5_k": 13, "q6_k": 14}
 
 
 def prompt_tokens(it, case=0, n=PROMPT_LEN):
@@ -97,86 +101,266 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline_sample(cfg, M, threads, layers=2):
-    """The reference's CPU path restated (oracle/: Q8_K/Q8_0 activations + integer block dots,
-    candle QMatMul algorithm) timed on a bounded sample of the SAME workload: the seven GEMVs of
-    `layers` decoder layers + the lm_head of this model, batch 1; extrapolated to a full token."""
-    import numpy as np
-    import oracle
-    rng = np.random.default_rng(0)
-    H, I = cfg.hidden, cfg.inter
-    nq, nkv = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
-    shapes = [("attn_q", nq, H), ("attn_k", nkv, H), ("attn_v", nkv, H), ("attn_output", H, nq), ("ffn_gate", I, H),
-              ("ffn_up", I, H), ("ffn_down", H, I)]
-    ws = {}
-    for l in range(layers):
-        for name, rows, cols in shapes:
-            t = M.tensor_type(cfg, name, l)
-            ws[(l, name)] = (t, M.synth_blocks(t, rows * cols // oracle.BLOCK_ELEMS[t], M.tensor_seed(l, name)), rows, cols)
-    t = M.tensor_type(cfg, "output", 0)
-    head = (t, M.synth_blocks(t, cfg.vocab * H // oracle.BLOCK_ELEMS[t], M.tensor_seed(0, "output")), cfg.vocab, H)
-    xs = {c: rng.standard_normal((1, c)).astype(np.float32) for c in (H, I, nq)}
-
-    def once():
-        t0 = time.perf_counter()
-        for (l, name), (ty, w, rows, cols) in ws.items():
-            oracle.qmatmul_cpu(ty, w, xs[cols], cols, rows, threads)
-        t_layers = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        oracle.qmatmul_cpu(head[0], head[1], xs[H], H, cfg.vocab, threads)
-        return t_layers, time.perf_counter() - t0
-
-    once()
-    reps, tl, th = 0, 0.0, 0.0
-    t_start = time.perf_counter()
-    while reps < 3 or (time.perf_counter() - t_start < 8.0 and reps < 50):
-        a, b = once()
-        tl += a; th += b; reps += 1
-    per_token = tl / reps / layers * cfg.n_layers + th / reps
-    return 1.0 / per_token, f"{layers} of {cfg.n_layers} layers' GEMVs + lm_head, batch 1, x{reps} (GEMV-only: attention/norm/rope excluded; the sampled weights stay partly cache-resident across repetitions, which favours the CPU)"
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_decode_tokens_per_s(cfg, M, seconds=10.0, min_tokens=2, threads=0):
+    """The reference's CPU arithmetic (oracle/mrs_oracle.c: Q8_K / Q8_0 activations + integer block dots,
+    the candle QMatMul algorithm) on WHOLE tokens of this model: all layers, every weight byte streamed
+    from DRAM each token, attention / norms / GLU included, one pinned thread per host core
+    (oracle/cpu_decode_bench.c).  Compiled here, on the box that runs it, with -O3 -march=native."""
+    src = os.path.join(ROOT, "oracle", "cpu_decode_bench.c")
+    out_dir = os.path.join(tempfile.gettempdir(), f"mrs_cpu_bench_{os.getuid()}")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libcpu_decode_bench.so")
+    subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-pthread", "-Wno-unused-function", "-I",
+                           os.path.join(ROOT, "oracle"), "-o", so, src, "-lm"])
+    # a short-lived child: the benchmark allocates the whole model (4.6 GB) and pins its threads
+    code = (
+        "import ctypes, json, sys\n"
+        f"L = ctypes.CDLL({so!r}); L.mrs_cpu_decode_bench.restype = ctypes.c_double\n"
+        "a = json.loads(sys.argv[1])\n"
+        "types = (ctypes.c_int * len(a['types']))(*a['types'])\n"
+        "tok, wb, tu = ctypes.c_int(), ctypes.c_double(), ctypes.c_int()\n"
+        "r = L.mrs_cpu_decode_bench(a['layers'], a['hidden'], a['inter'], a['heads'], a['kv_heads'], a['head_dim'], a['vocab'], types,\n"
+        "                           a['head_type'], a['ctx'], a['threads'], ctypes.c_double(a['seconds']), a['min_tokens'],\n"
+        "                           ctypes.byref(tok), ctypes.byref(wb), ctypes.byref(tu))\n"
+        "print(json.dumps({'tok_s': r, 'tokens': tok.value, 'weight_bytes': wb.value, 'threads': tu.value}))\n")
+    types = []
+    for l in range(cfg.n_layers):
+        types += [GGML[M.tensor_type(cfg, n, l)] for n in ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")]
+    arg = dict(layers=cfg.n_layers, hidden=cfg.hidden, inter=cfg.inter, heads=cfg.n_heads, kv_heads=cfg.n_kv_heads,
+               head_dim=cfg.head_dim, vocab=cfg.vocab, types=types, head_type=GGML[M.tensor_type(cfg, "output", 0)],
+               ctx=PROMPT_LEN + GEN_LEN // 2, threads=threads, seconds=seconds, min_tokens=min_tokens)
+    r = json.loads(subprocess.check_output([sys.executable, "-c", code, json.dumps(arg)], text=True).strip().splitlines()[-1])
+    sample = (f"{r['tokens']} whole tokens (all {cfg.n_layers} layers + lm_head, {r['weight_bytes'] / 1e9:.2f} GB of weights streamed "
+              f"from DRAM per token, attention over {arg['ctx']} cached tokens, norms and GLU included), decode batch 1, "
+              f"-O3 -march=native, {r['threads']} pinned threads")
+    return r["tok_s"], r["threads"], sample
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (candle QMatMul is not
-    buildable here: no Rust, candle un-vendored — so the C restatement in oracle/, kind 'port'),
-    all host threads, same metric/config; each step = one bounded sample."""
+    """--impl reference: the reference's CPU implementation of the path (candle QMatMul cannot be built
+    here: no Rust toolchain, candle un-vendored — the C restatement in oracle/, kind "port"), all host
+    threads, same metric and workload; each step is one bounded sample of whole decode tokens."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, ROOT)
     import __graft_entry__ as g
     g.load_package()
     from mistralrs_b200 import model as M
     cfg = M.LlamaConfig.llama3_8b()
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    vals = []
-    for _ in range(max(args.warmup, 0)):
-        pass  # cpu_baseline_sample warms itself
-    sample = ""
+    if args.layers:
+        cfg.n_layers = args.layers
     t0 = time.perf_counter()
-    for _ in range(max(1, min(args.steps, 3))):
-        v, sample = cpu_baseline_sample(cfg, M, threads)
-        vals.append(v)
+    steps = max(1, args.steps)
+    budget = max(4.0, min(20.0, 150.0 / (steps + max(args.warmup, 0))))
+    vals, threads, sample = [], 0, ""
+    for i in range(max(args.warmup, 0) + steps):
+        v, threads, sample = cpu_decode_tokens_per_s(cfg, M, seconds=budget if i >= args.warmup else 2.0)
+        if i >= args.warmup:
+            vals.append(v)
     value = sum(vals) / len(vals)
     print(json.dumps({
         "impl": "reference", "metric": "decode_tok_s", "value": value, "unit": "tok/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value * (GEN_LEN - 1), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4/6 block dots, f32 accumulate", "data": "synthetic",
-        "config": {"workload": "Llama-3-8B GGUF Q4_K_M decode batch=1 128->+256 (CPU sample)"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "int8 (Q8_K / Q8_0) activations x ggml block dots, f32 accumulate", "data": "synthetic",
+        "config": {"workload": "Llama-3-8B GGUF Q4_K_M decode batch=1 (CPU, whole tokens; each step a bounded sample)"},
         "cpu_baseline": {"value": value, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0}))
 
 
+# ------------------------------------------------------------------------------------------- helpers
+def count_graph_kernels(graph):
+    """kernel nodes of a captured CUDA graph (= our launches per replay), read back from the driver"""
+    try:
+        cu = ctypes.CDLL("libcuda.so.1")
+        raw = ctypes.c_void_p(int(graph.raw_cuda_graph()))
+        n = ctypes.c_size_t(0)
+        if cu.cuGraphGetNodes(raw, None, ctypes.byref(n)) != 0:
+            return None
+        nodes = (ctypes.c_void_p * n.value)()
+        if cu.cuGraphGetNodes(raw, nodes, ctypes.byref(n)) != 0:
+            return None
+        k = 0
+        for i in range(n.value):
+            ty = ctypes.c_int(-1)
+            cu.cuGraphNodeGetType(ctypes.c_void_p(nodes[i]), ctypes.byref(ty))
+            k += int(ty.value == 0)      # CU_GRAPH_NODE_TYPE_KERNEL
+        return k
+    except Exception:
+        return None
+
+
+def timed_graph(graph, reps, torch):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 1e3 / reps
+
+
+def validate_first_tokens(weights, M, torch, n_tokens=6):
+    """The benchmarked 32-layer model against the CPU oracle (thread-pooled over rows): one prompt token,
+    then greedy decoding; logits compared on every step, sampled ids must agree off ties."""
+    import numpy as np
+    from oracle.model import OracleLlama
+    cfg = weights.cfg
+    threads = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 1))
+    run = M.LlamaRunner(weights, batch=1, max_ctx=32, pdl=True)
+    cos, sin = M.rope_tables(cfg)
+    ref = OracleLlama(cfg, weights.host, M.tensor_type, cos, sin, "bf16", threads=threads)
+    toks, worst, same = [prompt_tokens(0)[0]], 0.0, 0
+    run.set_tokens(toks)
+    t0 = time.perf_counter()
+    for pos in range(n_tokens):
+        run.step()
+        torch.cuda.synchronize()
+        got = run.logits().float().cpu().numpy()
+        want = ref.step(toks, pos)
+        scale = float(np.abs(want).max())
+        worst = max(worst, float(np.abs(got - want).max()) / scale)
+        top2 = np.sort(want[0])[-2:]
+        tie = (top2[1] - top2[0]) <= 8 * 2.0 ** -8 * scale
+        g_tok, w_tok = int(run.meta["token_ids"][0]), int(np.argmax(want[0]))
+        if g_tok != w_tok and not tie:
+            raise AssertionError(f"bench validation: sampled token {g_tok} != oracle {w_tok} at position {pos}")
+        same += int(g_tok == w_tok)
+        toks = [w_tok]
+        run.set_tokens(toks)
+    if not worst <= 4.1 * 2.0 ** -7:
+        raise AssertionError(f"bench validation: logits differ from the oracle by {worst:.3e} of the logit scale")
+    del run
+    return {"tokens_checked": n_tokens, "tokens_equal": same, "worst_logit_err_ulp_bf16": worst / 2.0 ** -8,
+            "oracle_threads": threads, "seconds": time.perf_counter() - t0,
+            "what": f"all {cfg.n_layers} layers + lm_head of the benchmarked weights vs oracle/ (CPU), greedy from one prompt token"}
+
+
+# ------------------------------------------------------------------------------------------- config 3
+def bench_prefill_q8(M, torch, dev, peaks, prompt=4096, layers=0):
+    """BASELINE config 3: Llama-3-8B with Q8_0 blocks everywhere (UQFF q8), one 4096-token prompt.
+    TTFT = embedding -> 32 x (norm, tcgen05 dequant-GEMMs, RoPE, causal prompt attention, KV scatter, GLU) ->
+    lm_head on the last row -> argmax; prefill tok/s = L / TTFT (bench.rs:269-271)."""
+    cfg = M.LlamaConfig.llama3_8b(quant="q8_0")
+    if layers:
+        cfg.n_layers = layers
+    w = M.LlamaWeights(cfg, dev, fast_synth=True)
+    pre = M.LlamaPrefill(w, max_tokens=prompt)
+    toks = prompt_tokens(0, n=prompt)
+    pre.forward(toks)
+    torch.cuda.synchronize()
+    ts = []
+    for it in range(3):
+        toks = prompt_tokens(it + 1, n=prompt)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        logits = pre.forward(toks)
+        first = torch.argmax(logits)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / 1e3)
+    ttft = sorted(ts)[len(ts) // 2]
+    # attention share, timed alone on the same shapes
+    H, KVH, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
+    from mistralrs_b200 import paged_attn
+    q = torch.randn(prompt, H, D, device=dev).to(w.dtype)
+    k = torch.randn(prompt, KVH, D, device=dev).to(w.dtype)
+    v = torch.randn(prompt, KVH, D, device=dev).to(w.dtype)
+    paged_attn.prefill_attention(q, k, v, D ** -0.5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(cfg.n_layers):
+        paged_attn.prefill_attention(q, k, v, D ** -0.5)
+    e1.record()
+    torch.cuda.synchronize()
+    attn_s = e0.elapsed_time(e1) / 1e3
+    lin_params = cfg.n_layers * (2 * cfg.hidden * H * D + 2 * cfg.hidden * KVH * D + 3 * cfg.hidden * cfg.inter)
+    flop = 2.0 * prompt * lin_params + cfg.n_layers * 2.0 * prompt * prompt * H * D + 2.0 * cfg.vocab * cfg.hidden
+    attn_flop = cfg.n_layers * 2.0 * prompt * prompt * H * D
+    tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+    out = {"workload": "Llama-3-8B Q8_0 (UQFF q8) prefill, 1 x %d tokens, incl. prompt attention, lm_head on the last row" % prompt,
+           "prompt_tokens": prompt, "layers": cfg.n_layers, "ttft_ms": ttft * 1e3, "prefill_tok_s": prompt / ttft,
+           "tflops": flop / ttft / 1e12, "tensor_peak_tflops": tpeak, "tensor_frac": flop / ttft / 1e12 / tpeak,
+           "attention_ms": attn_s * 1e3, "attention_tflops": attn_flop / attn_s / 1e12,
+           "linears_ms_est": (ttft - attn_s) * 1e3, "linears_tflops_est": 2.0 * prompt * lin_params / max(ttft - attn_s, 1e-9) / 1e12,
+           "weights": "synthetic Q8_0 blocks generated on the device", "first_token": int(first)}
+    del pre, w
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------- config 4
+def bench_gptq_batch32(torch, dev, peaks, steps=2, layers=0, batch=32):
+    """BASELINE config 4: Mistral-7B GPTQ int4 (g128, symmetric) decode at batch 32, paged KV block 16,
+    128-token prompts -> +256 tokens, in the HND (FlashInfer) and vLLM cache layouts."""
+    from mistralrs_b200 import gptq_model as G
+    cfg = G.GptqConfig.mistral_7b()
+    if layers:
+        cfg.n_layers = layers
+    w = G.GptqWeights(cfg, dev)
+    peak = peaks.get("hbm_gbs", 6650.0)
+    kv_mean = batch * 2 * cfg.n_kv_heads * cfg.head_dim * 2 * cfg.n_layers * (PROMPT_LEN + GEN_LEN // 2)
+    res = {"workload": f"Mistral-7B GPTQ int4 g128 decode batch={batch}, 128-token prompts -> +256 tokens, paged KV block_size=16",
+           "layers": cfg.n_layers, "weight_bytes_per_step": w.nbytes, "kv_bytes_per_step_mean": kv_mean}
+    for layout in ("hnd", "vllm"):
+        run = G.GptqRunner(w, batch=batch, max_ctx=PROMPT_LEN + GEN_LEN + 16, cache_layout=layout)
+        graph = run.capture()
+        vals = []
+        for it in range(steps + 1):
+            run.reset()
+            ptoks = [prompt_tokens(it, case=b) for b in range(batch)]
+            for i in range(PROMPT_LEN):
+                run.set_tokens([p[i] for p in ptoks])
+                graph.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(GEN_LEN - 1):
+                graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            if it > 0:
+                vals.append(e0.elapsed_time(e1) / 1e3)
+        sec = sum(vals) / len(vals)
+        step_s = sec / (GEN_LEN - 1)
+        res[layout] = {"decode_tok_s": batch * (GEN_LEN - 1) / sec, "ms_per_decode_step": step_s * 1e3,
+                       "hbm_frac": (w.nbytes + kv_mean) / step_s / 1e9 / peak, "launches_per_step": count_graph_kernels(graph)}
+        # the W4A16 + dense linears alone (attention-side kernels skipped): roofline of the dominant kernel
+        if layout == "hnd":
+            run.step_struct.skip_mask = 1
+            gg = torch.cuda.CUDAGraph()
+            run.reset(PROMPT_LEN + GEN_LEN // 2); run.step(); torch.cuda.synchronize()
+            with torch.cuda.graph(gg):
+                run.step()
+            lin_s = timed_graph(gg, 10, torch)
+            run.step_struct.skip_mask = 0
+            res["linears"] = {"ms_per_step": lin_s * 1e3, "achieved_gbs": w.nbytes / lin_s / 1e9, "hbm_frac": w.nbytes / lin_s / 1e9 / peak,
+                              "kernel": "w4a16_kernel<32> (swap-AB tcgen05) + dense lm_head"}
+        del run, graph
+    del w
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="headline workload: 2 = 8B Q4_K_M decode b=1 (default), 3 = 8B Q8_0 prefill 4096, 4 = Mistral-7B GPTQ b=32, "
+                         "5 = Llama-3-70B Q4_K_M tensor parallel (needs --gpus 8)")
     ap.add_argument("--layers", type=int, default=0, help="debug: truncate the model")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("MRS_PDL", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3 / config 4 blocks of the default line")
+    ap.add_argument("--no-validate", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -196,46 +380,89 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib()  # fail loudly if the CUDA extension is missing
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
 
-    cfg = M.LlamaConfig.llama3_8b()
+    if args.config == 3 and world == 1:
+        pf = bench_prefill_q8(M, torch, dev, peaks, layers=args.layers)
+        print(json.dumps({"metric": "prefill_tok_s", "value": pf["prefill_tok_s"], "unit": "tok/s", "n_gpus": 1, "steps": 3, "warmup": 1,
+                          "ms_per_step": pf["ttft_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "bf16 activations x Q8_0 blocks dequantised to bf16 (tcgen05), f32 accumulate", "data": "synthetic",
+                          "config": {"workload": pf["workload"]}, "prefill": pf,
+                          "roofline": {"bound": "tensor", "achieved": pf["tflops"], "peak": pf["tensor_peak_tflops"], "unit": "TFLOP/s",
+                                       "frac": pf["tensor_frac"], "traffic": None}}))
+        return
+    if args.config == 4 and world == 1:
+        c4 = bench_gptq_batch32(torch, dev, peaks, steps=max(1, min(args.steps, 3)), layers=args.layers)
+        print(json.dumps({"metric": "decode_tok_s", "value": c4["hnd"]["decode_tok_s"], "unit": "tok/s", "n_gpus": 1, "steps": args.steps,
+                          "warmup": 1, "ms_per_step": c4["hnd"]["ms_per_decode_step"] * (GEN_LEN - 1), "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f16 activations x int4 (q-8)*s dequantised to f16 (tcgen05), f32 accumulate",
+                          "data": "synthetic", "config": {"workload": c4["workload"]}, "config4": c4,
+                          "roofline": {"bound": "hbm", "achieved": c4["linears"]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                                       "frac": c4["linears"]["hbm_frac"], "traffic": None, "peak_source": peak_src}}))
+        return
+
+    # ---------------------------------------------------------------- configs 2 / 5: decode batch 1 (TP = world)
+    big = args.config == 5
+    cfg = M.LlamaConfig.llama3_70b() if big else M.LlamaConfig.llama3_8b()
     if args.layers:
         cfg.n_layers = args.layers
-    weights = M.LlamaWeights(cfg, dev, tp_rank=rank, tp_size=world)
-    comm = None
-    if world > 1:
-        bufs = {}
-
-        def comm(buf, count, dtype, stream, user):  # row-parallel sum all-reduce (NCCL over NVLink)
-            t = bufs.get(buf)
-            if t is None:
-                raise RuntimeError("unknown all-reduce buffer")
-            dist.all_reduce(t)
-    runner = M.LlamaRunner(weights, batch=1, max_ctx=PROMPT_LEN + GEN_LEN + 16, pdl=bool(args.pdl), comm=comm)
-    if world > 1:
+    validate = (not args.no_validate) and world == 1 and not big
+    weights = M.LlamaWeights(cfg, dev, tp_rank=rank, tp_size=world, keep_host=validate, fast_synth=big)
+    peer, comm, bufs = None, None, {}
+    if world > 1 and os.environ.get("MRS_TP_NCCL", "0") != "1":
+        peer = M.PeerAllReduce(cfg.hidden, weights.dtype, dev)       # in-graph peer-memory sum (product path)
+    elif world > 1:
+        def comm(buf, count, dtype, stream, user):                   # A/B: NCCL all-reduce through torch.distributed
+            dist.all_reduce(bufs[buf])
+    runner = M.LlamaRunner(weights, batch=1, max_ctx=PROMPT_LEN + GEN_LEN + 16, pdl=bool(args.pdl), comm=comm, peer_allreduce=peer)
+    if comm is not None:
         bufs[runner.buf["x"].data_ptr()] = runner.buf["x"]
         bufs[runner.buf["x2"].data_ptr()] = runner.buf["x2"]
+    validation = validate_first_tokens(weights, M, torch) if validate else None
+    weights.host = None
     runner.capture()
     graph = runner.graph
+    launches_per_token = count_graph_kernels(graph)
     tok_dev = runner.meta["token_ids"]
     pinned_in = torch.zeros(1, dtype=torch.int32).pin_memory()
     pinned_out = torch.zeros(1, dtype=torch.int32).pin_memory()
+    prefill_runner = M.LlamaPrefill(weights, max_tokens=PROMPT_LEN, runner=runner) if world == 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    ttfts = []
+
     def generation(it, e2e):
-        """one step: prompt (token-by-token through the decode graph), then GEN_LEN tokens.
-        Returns device-timed seconds of the decode phase (first generated token -> last)."""
+        """one step: the prompt (one prefill pass on a single GPU; token by token through the decode graph
+        under TP), then GEN_LEN tokens.  Returns device-timed seconds of the decode phase."""
         runner.reset()
-        for t in prompt_tokens(it):
-            pinned_in[0] = t
-            tok_dev.copy_(pinned_in, non_blocking=True)
-            graph.replay()
-        # the last prompt replay produced generated token #1 in tok_dev
+        toks = prompt_tokens(it)
+        if prefill_runner is not None:
+            if e2e:
+                hp = torch.tensor(toks, dtype=torch.int32).pin_memory()   # prompt ids cross PCIe inside the timed TTFT
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            logits = prefill_runner.forward(hp if e2e else toks)
+            tok_dev.copy_(torch.argmax(logits).to(torch.int32).reshape(1))
+            runner.reset(PROMPT_LEN)
+            p1.record()
+        else:
+            for t in toks:
+                pinned_in[0] = t
+                tok_dev.copy_(pinned_in, non_blocking=True)
+                graph.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        if prefill_runner is not None:
+            ttfts.append(p0.elapsed_time(p1) / 1e3)
         e0.record()
         if not e2e:
             for _ in range(GEN_LEN - 1):
@@ -259,8 +486,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    for w in range(args.warmup):
-        generation(w, False)
+    for w_ in range(args.warmup):
+        generation(w_, False)
+    ttfts.clear()
+
     def timed_steps():
         sampler = ClockSampler(local)
         if rank == 0:
@@ -269,122 +498,112 @@ def main():
         return ts, (sampler.stop() if rank == 0 else None)
 
     times, clocks = timed_steps()
-    # a run that saw a hardware / thermal slowdown is discarded and measured once more (all ranks
-    # follow rank 0's verdict); sw_power_cap is kept and reported
     bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     redo = torch.tensor([1 if (rank == 0 and bad & set(clocks.get("reasons", []))) else 0], device=dev)
     if world > 1:
         dist.broadcast(redo, src=0)
-    remeasured = bool(redo.item())
-    if remeasured:
+    if bool(redo.item()):
         first = clocks
+        ttfts.clear()
         times, clocks = timed_steps()
         if rank == 0:
             clocks["remeasured_after"] = first.get("reasons", [])
+    ttft_dev = sorted(ttfts)[len(ttfts) // 2] if ttfts else None
+    ttfts.clear()
     e2e_times = [max_over_ranks(generation(args.warmup + i, True)) for i in range(max(1, min(args.steps, 2)))]
+    ttft_e2e = sorted(ttfts)[len(ttfts) // 2] if ttfts else None
     ntok = GEN_LEN - 1
     value = ntok * len(times) / sum(times)
     e2e_value = ntok * len(e2e_times) / sum(e2e_times)
 
-    # ---- roofline of the dominant kernel (mmvq_stream_kernel: every quantized GEMV of a token) ----
-    # measured live: a CUDA graph of ONE token's GEMV chain only (attention-side kernels skipped),
-    # CUDA events on the launching stream; weights (4.6 GB) >> L2 so every launch streams from HBM.
+    # ---- roofline of the dominant kernel (mmvq_stream_kernel: every quantized GEMV of a token), measured live:
+    # a CUDA graph of ONE token's GEMV chain only (attention-side kernels skipped), CUDA events on the launching
+    # stream; weights (4.6 GB) >> L2 so every launch streams from HBM.  Under TP the chain includes the all-reduces.
     runner.step_struct.skip_mask = 1
-    gg = torch.cuda.CUDAGraph()
+    gg = torch.cuda.CUDAGraph(keep_graph=True)
+    runner.reset(PROMPT_LEN + GEN_LEN // 2)
     runner.forward(); torch.cuda.synchronize()
     with torch.cuda.graph(gg):
         runner.forward()
-    for _ in range(3):
-        gg.replay()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
-    e0.record()
-    for _ in range(reps):
-        gg.replay()
-    e1.record()
-    torch.cuda.synchronize()
+    gemv_s = max_over_ranks(timed_graph(gg, 20, torch))
+    runner.step_struct.skip_mask = 2
+    ga = torch.cuda.CUDAGraph()
+    runner.forward(); torch.cuda.synchronize()
+    with torch.cuda.graph(ga):
+        runner.forward()
+    barrier()
+    attn_s = max_over_ranks(timed_graph(ga, 20, torch))
     runner.step_struct.skip_mask = 0
-    gemv_s = e0.elapsed_time(e1) / 1e3 / reps
     total_bytes, weight_bytes = algorithmic_bytes_per_token(cfg, M, world)
+    if world > 1:   # replicated lm_head: every rank streams all of it
+        t = M.tensor_type(cfg, "output", 0)
+        from mistralrs_b200 import BLOCK_BYTES, BLOCK_ELEMS
+        head = cfg.vocab * cfg.hidden * BLOCK_BYTES[t] // BLOCK_ELEMS[t]
+        weight_bytes = (weight_bytes - head) + head   # algorithmic_bytes_per_token already keeps the head whole per rank
     n_gemv = sum(4 if M.tensor_type(cfg, "attn_v", l) == M.tensor_type(cfg, "attn_q", l) else 5 for l in range(cfg.n_layers)) + 1
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     achieved = weight_bytes / gemv_s / 1e9
-    # DRAM traffic per GEMV launch from the committed ncu --set full capture (dram__bytes_read+write
-    # over algorithmic bytes of the same launches), applied to this run's average launch
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))
-        traffic = tr["dram_bytes_over_algorithmic"] * weight_bytes / n_gemv
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
-    # our kernels per token: per layer qkv (1, or 2 where attn_v has its own ggml type) + fused
-    # rope/cache/attention/merge (1) + o_proj + gate_up + down (+2 residual adds under TP), plus
-    # advance + embedding + lm_head + argmax
-    per_layer_launches = [(1 if M.tensor_type(cfg, "attn_v", l) == M.tensor_type(cfg, "attn_q", l) else 2) + 1 + 3 +
-                          (2 if world > 1 else 0) for l in range(cfg.n_layers)]
-    launches_per_token = 2 + sum(per_layer_launches) + 2
 
-    # ---- prefill (BASELINE configs[2] shape, same Q4_K_M weights): the seven linear GEMMs of
-    # every layer for a 4096-token prompt on the tcgen05 dequant-GEMM (prefill attention is a
-    # SURVEY §8(f) "next" row and is not included) ------------------------------------------------
-    prefill = None
-    if world == 1:
-        from mistralrs_b200 import mmq, quant
-        PT = 4096
-        xs = {c: torch.randn(PT, c, device=dev).to(weights.dtype) for c in (cfg.hidden, cfg.inter, cfg.n_heads * cfg.head_dim)}
-        mats = []
-        for L in weights.layers:
-            for name in ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down"):
-                t, ty, rows, cols = L[name]
-                mats.append(quant.QTensor(t, ty, (rows, cols)))
-
-        def prefill_pass():
-            for w_ in mats:
-                mmq.forward(w_, xs[w_.shape[1]])
-        prefill_pass(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); prefill_pass(); e1.record(); torch.cuda.synchronize()
-        pf_s = e0.elapsed_time(e1) / 1e3
-        pf_flop = 2.0 * PT * sum(m.shape[0] * m.shape[1] for m in mats)
-        tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
-        prefill = {"prompt_tokens": PT, "linears_tok_s": PT / pf_s, "linears_ms": pf_s * 1e3, "tflops": pf_flop / pf_s / 1e12,
-                   "tensor_peak_tflops": tpeak, "tensor_frac": pf_flop / pf_s / 1e12 / tpeak,
-                   "note": "linear layers only (7 GEMMs x layers, tcgen05 dequant-GEMM); prefill attention not included"}
-        del xs
+    prefill = c4 = None
+    if world == 1 and not args.no_extras and not big and not args.layers:
+        del prefill_runner
+        try:
+            prefill = bench_prefill_q8(M, torch, dev, peaks)
+        except Exception as e:   # the extras must never take the headline line down
+            prefill = {"error": repr(e)}
+        try:
+            c4 = bench_gptq_batch32(torch, dev, peaks, steps=1)
+        except Exception as e:
+            c4 = {"error": repr(e)}
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            v, sample = cpu_baseline_sample(cfg, M, threads)
-            cpu = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample}
+        if not args.no_cpu_baseline and world == 1 and not big:
+            try:
+                v, threads, sample = cpu_decode_tokens_per_s(cfg, M, seconds=12.0)
+                cpu = {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample}
+            except Exception as e:
+                cpu = {"value": None, "unit": "tok/s", "cores": 0, "kind": "port", "sample": f"failed: {e!r}"}
+        name = "Llama-3-70B" if big else "Llama-3-8B"
         out = {
             "metric": "decode_tok_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "int8 activations x 4/6-bit ggml blocks (dp4a), f32 accumulate, bf16 I/O",
             "data": "synthetic",
-            "config": {"workload": "Llama-3-8B GGUF Q4_K_M decode batch=1, 128-token prompt -> +256 tokens, paged KV block_size=16 (HND)",
-                       "parallelism": f"tp{world}", "l2": "inputs larger than L2 (4.6 GB of weights streamed per token)",
+            "config": {"workload": f"{name} GGUF Q4_K_M decode batch=1, 128-token prompt -> +256 tokens, paged KV block_size=16 (HND)",
+                       "parallelism": f"tp{world}", "l2": "inputs larger than L2 (weights streamed once per token)",
                        "layers": cfg.n_layers, "pdl": bool(args.pdl),
+                       "all_reduce": None if world == 1 else ("peer-memory one-shot sum + residual, in-graph (mrs_tp_allreduce_residual)" if peer is not None else "NCCL via torch.distributed, captured"),
                        "kv_split": f"{runner.split_pages * cfg.block_size}-token chunks, {runner.padded_tiles} tiles (SM-filling plan)"},
-            "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": 4 * ntok, "d2h_bytes_per_step": 4 * ntok},
-            "gpu_launches": launches_per_token * ntok,
+            "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": 4 * ntok + 4 * PROMPT_LEN, "d2h_bytes_per_step": 4 * ntok,
+                    "ttft_ms": None if ttft_e2e is None else ttft_e2e * 1e3},
+            "gpu_launches": None if launches_per_token is None else launches_per_token * ntok,
+            "launches_per_token": launches_per_token,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": weight_bytes / n_gemv, "peak_source": peak_src, "kernel": "mmvq_stream_kernel (all quantized GEMVs of one token)",
+                         "traffic": traffic, "algorithmic_bytes_per_launch": weight_bytes / n_gemv, "peak_source": peak_src,
+                         "kernel": "mmvq_stream_kernel (all quantized GEMVs of one token" + (", incl. the in-graph all-reduces)" if world > 1 else ")"),
                          "launches": n_gemv, "avg_launch_us": gemv_s / n_gemv * 1e6, "bytes_per_token": weight_bytes},
+            "breakdown_us_per_token": {"gemv_chain": gemv_s * 1e6, "attention_chain": attn_s * 1e6, "whole_token": 1e6 / value},
             "step_hbm_frac": total_bytes * value / 1e9 / peak,
             "clocks": clocks,
         }
+        if ttft_dev is not None:
+            out["prompt"] = {"tokens": PROMPT_LEN, "ttft_ms": ttft_dev * 1e3, "prefill_tok_s": PROMPT_LEN / ttft_dev,
+                             "note": "the 128-token prompt of this workload: one prefill pass (tcgen05 dequant-GEMMs + prompt attention + KV scatter) + first sample"}
+        if validation:
+            out["validation"] = validation
         if cpu:
             out["cpu_baseline"] = cpu
         if prefill:
             out["prefill"] = prefill
+        if c4:
+            out["config4"] = c4
         print(json.dumps(out))
     if world > 1:
         # NCCL teardown with captured collectives still alive can hang: synchronise and leave

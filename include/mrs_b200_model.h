@@ -25,6 +25,21 @@ typedef struct {
   void *k_cache, *v_cache;                           /* HND [num_blocks, kv_heads, block_size, head_dim] */
 } mrs_llama_layer;
 
+/* Tensor-parallel context of the peer-memory all-reduce (one process per GPU; the buffers are
+ * symmetric allocations whose peer mappings the host obtained by rendezvous, e.g.
+ * torch.distributed._symmetric_memory): every rank owns [flags | slot 0 | slot 1] at the same offsets. */
+typedef struct {
+  int32_t world, rank;
+  void *peer_base[8];            /* base of rank r's buffer as mapped in THIS process (own included) */
+  int64_t flags_offset;          /* >= world uint32 flag words, zero-initialised */
+  int64_t slot_offset[2];        /* two partial buffers of >= batch * hidden activation elements each */
+  void *seq_counter;             /* local device uint32, zero-initialised */
+} mrs_tp_ctx;
+/* out = T(T(sum over ranks of slot partials, rank order, f32) + residual); count % 8 == 0; one CTA, in-graph,
+ * PDL-chained.  Stands in for SumAllReduce::sum_all_reduce + the residual add (REF distributed/mod.rs:436-453). */
+int32_t mrs_tp_allreduce_residual(const mrs_tp_ctx *ctx, int32_t slot, const void *residual, void *out, int32_t count,
+                                  int32_t dtype, int32_t pdl, void *stream);
+
 typedef struct {
   int32_t hidden, n_layers, n_heads, n_kv_heads, head_dim, vocab; /* heads are LOCAL counts under TP */
   int32_t block_size, act_dtype;   /* act_dtype: 0 f16, 1 bf16 */
@@ -53,6 +68,7 @@ typedef struct {
   /* tensor parallel: called after the row-parallel projections when non-NULL */
   void (*all_reduce)(void *buf, int64_t count, int32_t dtype, void *stream, void *user);
   void *all_reduce_user;
+  const mrs_tp_ctx *tp;      /* non-NULL with world > 1: peer-memory sum (takes precedence over all_reduce) */
 } mrs_llama_step;
 
 /* Enqueue one decode step (all layers + lm_head + argmax) on `stream`. Returns cudaError. */

@@ -116,7 +116,8 @@ int32_t mrs_prefill_attention(const void *q, const void *k, const void *v, void 
                               int32_t num_kv_heads, int32_t head_dim, int64_t q_stride, int64_t kv_stride, int64_t o_stride,
                               float softmax_scale, int32_t causal, int32_t window_left, float softcap, uint32_t dtype,
                               void *stream);
-/* diagnostics: bit 0 keeps HND decode attention on the SIMT kernel instead of the tensor-core one */
+/* diagnostics: bit 0 keeps HND decode attention on the SIMT kernel instead of the tensor-core one;
+ * bit 1 disables the cluster/DSMEM merge of split-KV tiles (global partials + counter instead) */
 void mrs_set_attn_flags(int32_t flags);
 #ifdef __cplusplus
 }

@@ -114,6 +114,63 @@ __global__ void add_residual_kernel(void *__restrict__ dst, const void *__restri
   if (i < n) store_act(dst, i, load_act(dst, i, dt) + load_act(res, i, dt), dt);
 }
 
+// ---- tensor-parallel sum of the row-parallel partials (REF SumAllReduce::sum_all_reduce,
+// mistralrs-quant/src/distributed/mod.rs:436-453: ncclAllReduce(sum) in the activation dtype, then the
+// residual add of the decoder layer) as ONE small kernel over NVLink peer memory, in the CUDA graph and
+// on the PDL chain — a latency-bound 8-16 KB message does not need a collective library:
+//   every rank's row-parallel GEMV wrote its partial [count] (activation dtype) into ITS slot buffer;
+//   thread 0 publishes "rank r reached all-reduce #seq" into every peer's flag word r (system-scope
+//   release), waits until its own flag words show every peer at #seq (acquire), then all threads pull
+//   the peers' partials with 16-byte loads (ld.volatile: the same addresses are reused every second
+//   all-reduce), sum them in f32 IN RANK ORDER (every rank computes bit-identical sums), round to the
+//   dtype like the collective's output, add the residual, round again.
+// Two slot buffers alternate: a rank can only overwrite slot s two all-reduces later, after a barrier
+// every peer reaches only once it has finished reading s.
+struct ArCtxDev {
+  int world, rank;
+  const uint8_t *peer_base[8];     // peers' symmetric buffers (own included), mapped into this process
+  uint32_t *flags_local;           // [world] flag words in the own buffer
+  unsigned long long flags_off, slot_off[2];
+  uint32_t *seq;                   // device counter of all-reduces done (graph replays continue it)
+};
+__global__ void __launch_bounds__(1024) tp_allreduce_residual_kernel(const ArCtxDev c, int slot, const void *__restrict__ residual,
+                                                                     void *__restrict__ out, int count, int dt, int pdl) {
+  __shared__ uint32_t s_seq;
+  if (pdl && threadIdx.x == 0) pdl_launch_dependents();
+  if (pdl) pdl_wait();                       // the own partial is complete and flushed
+  if (threadIdx.x == 0) {
+    const uint32_t seq = *c.seq + 1u;
+    *c.seq = seq;
+    __threadfence_system();
+    for (int r = 0; r < c.world; r++) {
+      uint32_t *flag = (uint32_t *)(c.peer_base[r] + c.flags_off) + c.rank;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+    }
+    for (int r = 0; r < c.world; r++) {
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(c.flags_local + r) : "memory");
+      } while ((int32_t)(v - seq) < 0);
+    }
+    s_seq = seq;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x * 8; i < count; i += blockDim.x * 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < c.world; r++) {
+      const uint4 raw = __ldcv((const uint4 *)(c.peer_base[r] + c.slot_off[slot]) + (i >> 3));
+      float v[8];
+      unpack_act8(raw, dt, v);
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] += v[k];
+    }
+    float res[8];
+    load_act8(residual, i, dt, res);
+#pragma unroll
+    for (int k = 0; k < 8; k++) store_act(out, (int64_t)i + k, round_act(acc[k], dt) + res[k], dt);
+  }
+}
+
 // one CTA: integers only, must match the host producers.  Thread b owns sequence b (lengths, slot,
 // chunk count), thread 0 turns the per-sequence counts into the two prefix sums, then all threads
 // fill the tile list and the page indices.  A sequence that has used up its block table or the RoPE
@@ -213,6 +270,29 @@ extern "C" int32_t mrs_decode_advance(const int32_t *block_tables, int32_t max_b
   return (int32_t)cudaGetLastError();
 }
 
+extern "C" int32_t mrs_tp_allreduce_residual(const mrs_tp_ctx *ctx, int32_t slot, const void *residual, void *out,
+                                             int32_t count, int32_t dtype, int32_t pdl, void *stream) {
+  if (ctx == nullptr || ctx->world < 1 || ctx->world > 8 || (slot & ~1) || count % 8 || (dtype != MRS_F16 && dtype != MRS_BF16))
+    return (int32_t)cudaErrorInvalidValue;
+  ArCtxDev c = {};
+  c.world = ctx->world; c.rank = ctx->rank;
+  for (int r = 0; r < ctx->world; r++) c.peer_base[r] = (const uint8_t *)ctx->peer_base[r];
+  c.flags_off = (unsigned long long)ctx->flags_offset;
+  c.slot_off[0] = (unsigned long long)ctx->slot_offset[0]; c.slot_off[1] = (unsigned long long)ctx->slot_offset[1];
+  c.flags_local = (uint32_t *)((uint8_t *)ctx->peer_base[ctx->rank] + ctx->flags_offset);
+  c.seq = (uint32_t *)ctx->seq_counter;
+  int threads = (count / 8 + 31) / 32 * 32;
+  if (threads > 1024) threads = 1024;
+  if (threads < 32) threads = 32;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1); cfg.blockDim = dim3(threads); cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return (int32_t)cudaLaunchKernelEx(&cfg, tp_allreduce_residual_kernel, c, (int)slot, residual, out, (int)count, (int)dtype, (int)pdl);
+}
+
 #define MRS_TRY(expr)                                  \
   do {                                                 \
     const int _e = (int)(expr);                        \
@@ -278,7 +358,13 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
                               (uint32_t)dt, (uint32_t)dt, st));
     }
     if (!do_gemv) continue;
-    if (s->all_reduce == nullptr) {
+    if (s->tp != nullptr && s->tp->world > 1) {
+      // row-parallel partial -> this rank's slot buffer -> peer-memory sum + residual (one kernel, on the PDL chain)
+      void *part = (uint8_t *)s->tp->peer_base[s->tp->rank] + s->tp->slot_offset[0];
+      MRS_TRY(mrs_mmvq_fused(L.wo.ggml_type, 0, dt, L.wo.data, nullptr, nullptr, s->attn_out, nullptr, 0.f, nullptr,
+                             part, nullptr, nullptr, nq, H, 0, 0, B, 0, pdl, stream));
+      MRS_TRY(mrs_tp_allreduce_residual(s->tp, 0, hidden, hidden2, B * H, dt, pdl, stream));
+    } else if (s->all_reduce == nullptr) {
       MRS_TRY(mrs_mmvq_fused(L.wo.ggml_type, 0, dt, L.wo.data, nullptr, nullptr, s->attn_out, nullptr, 0.f, hidden,
                              hidden2, nullptr, nullptr, nq, H, 0, 0, B, 0, pdl, stream));
     } else {  // row-parallel: partial sums -> all-reduce -> residual add (REF distributed/layers.rs:965-975)
@@ -292,7 +378,12 @@ extern "C" int32_t mrs_llama_decode_step(const mrs_llama_step *s, void *stream) 
     MRS_TRY(mrs_mmvq_fused(L.w_gate.ggml_type, 1, dt, L.w_gate.data, L.w_up.data, nullptr, hidden2, L.ffn_norm,
                            s->rms_eps, nullptr, s->act, nullptr, nullptr, H, L.w_gate.rows, L.w_gate.rows, 0, B, 0,
                            pdl, stream));
-    if (s->all_reduce == nullptr) {
+    if (s->tp != nullptr && s->tp->world > 1) {
+      void *part = (uint8_t *)s->tp->peer_base[s->tp->rank] + s->tp->slot_offset[1];
+      MRS_TRY(mrs_mmvq_fused(L.w_down.ggml_type, 0, dt, L.w_down.data, nullptr, nullptr, s->act, nullptr, 0.f, nullptr,
+                             part, nullptr, nullptr, L.w_down.cols, H, 0, 0, B, 0, pdl, stream));
+      MRS_TRY(mrs_tp_allreduce_residual(s->tp, 1, hidden2, hidden, B * H, dt, pdl, stream));
+    } else if (s->all_reduce == nullptr) {
       MRS_TRY(mrs_mmvq_fused(L.w_down.ggml_type, 0, dt, L.w_down.data, nullptr, nullptr, s->act, nullptr, 0.f, hidden2,
                              hidden, nullptr, nullptr, L.w_down.cols, H, 0, 0, B, 0, pdl, stream));
     } else {

@@ -50,6 +50,7 @@ struct PagedParams {
   int tiles_are_partitions; // vLLM v2: tile index = seq * num_partitions + partition
   int num_partitions;
   int heads_per_cta;        // GQA group may be processed in sub-groups (blockIdx.z)
+  int batch_size;           // sequences in this launch (0: unknown)
   int pdl;                  // launched with programmatic stream serialisation
   // FUSED (mrs_paged_decode_fused): un-rotated new-token K/V, RoPE tables, slots, merge counters
   const void *k_new, *v_new;
@@ -552,8 +553,37 @@ static cudaError_t launch_decode_g(PagedParams p, int tiles, cudaStream_t st) {
       const int nsub = (group + 15) / 16;
       p.heads_per_cta = (group + nsub - 1) / nsub;
       dim3 grid(tiles, p.num_kv_heads, nsub);
-      const size_t dyn = (size_t)4 * PM_BN * D * sizeof(T) + (size_t)16 * D * sizeof(T);
-      return launch_pa(paged_decode_mma_kernel<T, D, FUSED>, grid, p, st, dyn, PM_THREADS);
+      if constexpr (FUSED) {
+        // one sequence split into <= 8 tiles: the tiles form a cluster and merge through DSMEM
+        // (batch > 1 plans are compacted per sequence, so a fixed cluster size would straddle sequences)
+        if (!(g_pa_flags & 2) && p.tmp_o != nullptr && p.batch_size == 1 && tiles <= PM_CL_MAX && nsub == 1 && p.heads_per_cta <= PM_CL_G) {
+          auto kern = paged_decode_mma_kernel<T, D, true, true>;
+          const size_t dyn = pm_smem_bytes<D>(true, true);
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = grid; cfg.blockDim = dim3(PM_THREADS); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
+          cudaLaunchAttribute attr[2];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = tiles; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+          attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[1].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = attr; cfg.numAttrs = 1;
+          // is this cluster shape schedulable on the device?  (asked once per shape; a failed launch inside a
+          // stream capture would poison the capture, so never find out by trying)
+          static int feasible[PM_CL_MAX + 1] = {};   // 0 unknown, 1 yes, -1 no
+          if (feasible[tiles] == 0) {
+            int ncl = 0;
+            const cudaError_t qe = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+            feasible[tiles] = (qe == cudaSuccess && ncl >= 1) ? 1 : -1;
+            if (qe != cudaSuccess) (void)cudaGetLastError();
+          }
+          if (feasible[tiles] == 1) {
+            cfg.numAttrs = p.pdl ? 2 : 1;
+            return cudaLaunchKernelEx(&cfg, kern, p);
+          }
+        }
+      }
+      return launch_pa(paged_decode_mma_kernel<T, D, FUSED, false>, grid, p, st, pm_smem_bytes<D>(FUSED, false), PM_THREADS);
     }
   }
   constexpr int GMAX = (D <= 128) ? 8 : 4;  // static smem budget: 8 states x G x D floats
@@ -757,7 +787,7 @@ extern "C" int32_t mrs_paged_decode_fused_strided(void *q, void *k_new, void *v_
   p.window_left = -1; p.pdl = pdl & 1; p.rope_interleaved = (pdl >> 1) & 1;
   p.k_new = k_new; p.v_new = v_new; p.kv_new_stride = kv_new_stride;
   p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.positions = positions; p.slot_mapping = slot_mapping;
-  p.o_indptr = o_indptr; p.counters = counters;
+  p.o_indptr = o_indptr; p.counters = counters; p.batch_size = batch_size;
   const int tiles = split ? padded_batch_size : batch_size;
   const cudaError_t e = (dtype == 0) ? launch_decode<__half, 1, true>(p, head_size, tiles, (cudaStream_t)stream)
                                      : launch_decode<__nv_bfloat16, 1, true>(p, head_size, tiles, (cudaStream_t)stream);
@@ -783,5 +813,6 @@ extern "C" int32_t mrs_paged_decode_fused(void *q, void *k_new, void *v_new, voi
                                         pdl, (int64_t)num_qo_heads * head_size, (int64_t)num_kv_heads * head_size, stream);
 }
 
-// bit 0: keep HND decode attention on the SIMT kernel instead of the tensor-core one (A/B, debugging)
+// bit 0: keep HND decode attention on the SIMT kernel instead of the tensor-core one; bit 1: no cluster/DSMEM
+// merge of split-KV tiles (A/B, debugging)
 extern "C" void mrs_set_attn_flags(int32_t flags) { mrs::g_pa_flags = flags; }

@@ -50,6 +50,7 @@ struct WaParams {
   int m0;                  // first token of this pass
   int ksteps_per_split;    // K-steps (of 64) per split CTA
   int groups_per_cta;      // scale groups a CTA's K range can touch (sizes the shared scale table)
+  int raw_stages;          // depth of the packed-weight ring (int4 kernel)
 };
 
 // Inverses of the reference's scale-column permutations (REF gptq_cuda.rs:530-540 get_scale_perms):
@@ -107,142 +108,15 @@ __device__ __forceinline__ void dequant_word(uint32_t q, int zp, float s_f, uint
   }
 }
 
-template <int NT, int SRC>
-__global__ void __launch_bounds__(WA_THREADS, NT <= 64 ? 2 : 1)
-w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const WaParams p) {
-  constexpr int X_BYTES = NT * 128;
-  constexpr int STAGE = WA_A_BYTES + X_BYTES + (SRC == WA_SRC_INT4 ? WA_RAW_BYTES : 0);
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t *bars = (uint64_t *)(smem + WA_STAGES * STAGE);
-  uint64_t *in_full = bars, *a_full = bars + WA_STAGES, *empty = bars + 2 * WA_STAGES, *acc_full = bars + 3 * WA_STAGES;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 3 * WA_STAGES + 1);
-  uint32_t *sc_tab = (uint32_t *)(smem + WA_STAGES * STAGE + 256);   // [groups_per_cta][128]: f16/bf16 scale | zero point << 16
-
+// ---- shared epilogue: TMEM -> registers -> [cluster split-K reduction] -> y ----------------------
+// Called by ALL threads of the CTA (the cluster barriers are CTA-wide); `epi` marks the 8 epilogue
+// warps (warp ids 2..9), two per TMEM lane quarter.
+template <int NT>
+__device__ __forceinline__ void wa_epilogue(const WaParams &p, uint8_t *smem, uint64_t *acc_full, uint32_t tmem_base, int nk,
+                                            int ksplit, uint32_t rank, int n0, int rows_valid) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * WA_BM;
-  const int ksplit = gridDim.y;
-  const uint32_t rank = (ksplit > 1) ? cluster_ctarank() : 0u;
-  const int nk_total = p.K / WA_BK;
-  const int kb0 = (int)rank * p.ksteps_per_split;
-  const int nk = max(0, min(p.ksteps_per_split, nk_total - kb0));
-  const int rows_valid = min(WA_BM, p.N - n0);
-
-  if (tid == 0) {
-    for (int s = 0; s < WA_STAGES; s++) { mbar_init(&in_full[s], 1); mbar_init(&a_full[s], WA_DQ_WARPS); mbar_init(&empty[s], 1); }
-    mbar_init(acc_full, 1);
-    fence_mbar_init();
-  }
-  constexpr uint32_t TCOLS = NT < 32 ? 32 : NT;
-  if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
-      int stage = 0, phase = 0;
-      for (int i = 0; i < nk; i++) {
-        const int kb = kb0 + i;
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t *st = smem + (size_t)stage * STAGE;
-        if constexpr (SRC == WA_SRC_INT4) {
-          const uint32_t raw_bytes = (uint32_t)rows_valid * 32u;
-          mbar_arrive_expect_tx(&in_full[stage], X_BYTES + raw_bytes);
-          bulk_g2s(st + WA_A_BYTES + X_BYTES, p.wq + ((size_t)kb * p.N + n0) * 32, raw_bytes, &in_full[stage]);
-        } else {
-          mbar_arrive_expect_tx(&in_full[stage], X_BYTES + WA_A_BYTES);
-          tma_load_2d(st, &tmap_w, kb * WA_BK, n0, &in_full[stage]);
-        }
-        tma_load_2d(st + WA_A_BYTES, &tmap_x, kb * WA_BK, p.m0, &in_full[stage]);
-        if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t fmt = (p.dtype == MRS_BF16) ? 1u : 0u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(WA_BM >> 4) << 24);
-    int stage = 0, phase = 0;
-    for (int i = 0; i < nk; i++) {
-      mbar_wait(&in_full[stage], phase);
-      if constexpr (SRC == WA_SRC_INT4) mbar_wait(&a_full[stage], phase);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint8_t *as = smem + (size_t)stage * STAGE, *xs = as + WA_A_BYTES;
-#pragma unroll
-        for (int k = 0; k < WA_BK / 16; k++)
-          umma_f16(tmem_base, umma_desc_sw128(as) + (uint64_t)(2 * k), umma_desc_sw128(xs) + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
-        umma_commit(&empty[stage]);
-        if (i == nk - 1) umma_commit(acc_full);
-      }
-      __syncwarp();
-      if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
-    }
-  } else {
-    // ===================== dequantisers, then epilogue =====================
-    const int dt_ = tid - 64;              // 0..255
-    const int r = dt_ >> 1, hf = dt_ & 1;  // weight row in the tile, which 32-weight half of the K-step
-    const int n = n0 + r;
-    const bool live = r < rows_valid;
-    if constexpr (SRC == WA_SRC_INT4) {
-      const bool bf = p.dtype == MRS_BF16;
-      int scol = n;
-      if (p.scale_perm == 1) scol = (n & ~63) + inv_scale_perm64(n & 63);
-      else if (p.scale_perm == 2) scol = (n & ~31) + inv_scale_perm32(n & 31);
-      const int zsh = 4 * ((n & 7) == 0 ? 0 : (n & 7) == 1 ? 4 : (n & 7) == 2 ? 1 : (n & 7) == 3 ? 5 : (n & 7) == 4 ? 2 : (n & 7) == 5 ? 6 : (n & 7) == 6 ? 3 : 7);
-      // scales (+ AWQ zero points) of this CTA's K range go to shared memory once: a per-K-step global
-      // load in the loop would bound every iteration by an L2 round trip (measured: 1 us per K-step)
-      const int g_first = (kb0 * WA_BK) / p.group;
-      {
-        const int g_last = nk > 0 ? ((kb0 + nk) * WA_BK - 1) / p.group : g_first - 1;
-        for (int g = g_first + hf; g <= g_last; g += 2) {
-          uint32_t v = 0u;
-          if (live) {
-            v = ((const uint16_t *)p.scales)[(size_t)g * p.N + scol];
-            uint32_t z = 8u;
-            if (p.qzeros != nullptr) z = ((uint32_t)p.qzeros[(size_t)g * (p.N >> 3) + (n >> 3)] >> zsh) & 0xFu;
-            v |= z << 16;
-          }
-          sc_tab[(g - g_first) * WA_BM + r] = v;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(WA_DQ_WARPS * 32));
-      }
-      int stage = 0, phase = 0;
-      for (int i = 0; i < nk; i++) {
-        const int kb = kb0 + i;
-        const uint32_t sz = sc_tab[((kb * WA_BK + 32 * hf) / p.group - g_first) * WA_BM + r];
-        mbar_wait(&in_full[stage], phase);
-        uint8_t *st = smem + (size_t)stage * STAGE;
-        uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-        if (live) raw = *(const uint4 *)(st + WA_A_BYTES + X_BYTES + r * 32 + hf * 16);
-        const uint32_t s16 = sz & 0xFFFFu;
-        const int zp = (int)(sz >> 16);
-        const uint32_t s2 = s16 * 0x00010001u;
-        float s_f = 0.f;
-        if (bf) s_f = __bfloat162float(__ushort_as_bfloat16((unsigned short)s16));
-        uint8_t *dst = st + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
-        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int c4 = 0; c4 < 4; c4++) {
-          uint32_t o[4];
-          if (bf) dequant_word<true>(w[c4], zp, s_f, s2, o);
-          else dequant_word<false>(w[c4], zp, s_f, s2, o);
-          const int c = 4 * hf + c4;
-          *(uint4 *)(dst + ((c ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[stage]);
-        if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  }
-
-  // ===================== epilogue (all threads take part in the cluster barriers) =====================
   constexpr int CPW = NT / 2;              // columns (tokens) per epilogue warp: two warps share a lane quarter
-  const bool epi = warp >= 2;
+  const bool epi = warp >= 2 && warp < 2 + WA_DQ_WARPS;
   const int q = warp & 3, half = (warp - 2) >> 2;
   const int row = q * 32 + lane;           // TMEM lane = weight row inside the tile
   auto ld16 = [&](int col, float *dstv) {
@@ -271,7 +145,7 @@ w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
       }
     }
     if (ksplit > 1) {
-      // deterministic split-K reduction through the leader's shared memory (stage memory is free once
+      // deterministic split-K reduction through the leader's shared memory (the operand rings are free once
       // every CTA of the cluster has drained its pipeline): red[rank-1][token][row]
       float *red = (float *)smem;
       cluster_sync_all();
@@ -314,6 +188,229 @@ w4a16_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
       }
     }
   }
+}
+
+// ---- dense 16-bit weights: A tiles straight from TMA, one ring -------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(WA_THREADS, NT <= 64 ? 2 : 1)
+w16_dense_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const WaParams p) {
+  constexpr int X_BYTES = NT * 128;
+  constexpr int STAGE = WA_A_BYTES + X_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = (uint64_t *)(smem + WA_STAGES * STAGE);
+  uint64_t *in_full = bars, *empty = bars + WA_STAGES, *acc_full = bars + 2 * WA_STAGES;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * WA_STAGES + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * WA_BM;
+  const int ksplit = gridDim.y;
+  const uint32_t rank = (ksplit > 1) ? cluster_ctarank() : 0u;
+  const int nk_total = p.K / WA_BK;
+  const int kb0 = (int)rank * p.ksteps_per_split;
+  const int nk = max(0, min(p.ksteps_per_split, nk_total - kb0));
+  const int rows_valid = min(WA_BM, p.N - n0);
+  if (tid == 0) {
+    for (int s = 0; s < WA_STAGES; s++) { mbar_init(&in_full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  constexpr uint32_t TCOLS = NT < 32 ? 32 : NT;
+  if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int i = 0; i < nk; i++) {
+        const int kb = kb0 + i;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t *st = smem + (size_t)stage * STAGE;
+        mbar_arrive_expect_tx(&in_full[stage], X_BYTES + WA_A_BYTES);
+        tma_load_2d(st, &tmap_w, kb * WA_BK, n0, &in_full[stage]);
+        tma_load_2d(st + WA_A_BYTES, &tmap_x, kb * WA_BK, p.m0, &in_full[stage]);
+        if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t fmt = (p.dtype == MRS_BF16) ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(WA_BM >> 4) << 24);
+    int stage = 0, phase = 0;
+    for (int i = 0; i < nk; i++) {
+      mbar_wait(&in_full[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint8_t *as = smem + (size_t)stage * STAGE, *xs = as + WA_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < WA_BK / 16; k++)
+          umma_f16(tmem_base, umma_desc_sw128(as) + (uint64_t)(2 * k), umma_desc_sw128(xs) + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        if (i == nk - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
+    }
+  }
+  wa_epilogue<NT>(p, smem, acc_full, tmem_base, nk, ksplit, rank, n0, rows_valid);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
+}
+
+// ---- int4 weights: three decoupled rings ------------------------------------------------------------
+//   RAW ring (deep: up to 16 x 4 KB of packed nibbles in flight per CTA — the HBM stream; a k-step's raw
+//   bytes are only 4 KB, so the depth of THIS ring is what keeps enough bytes in flight to cover the
+//   loaded HBM latency), X ring (activation tiles, L2-resident), A ring (dequantised 16 KB tiles).
+//   warp 0 raw producer | warp 1 MMA | warps 2..9 dequantisers + epilogue | warp 10 X producer
+constexpr int WA_AS = 2, WA_XS = 4, WA_RS_MAX = 16;
+constexpr int WA4_THREADS = 64 + WA_DQ_WARPS * 32 + 32;
+
+template <int NT>
+__global__ void __launch_bounds__(WA4_THREADS, NT <= 64 ? 2 : 1)
+w4a16_int4_kernel(const __grid_constant__ CUtensorMap tmap_x, const WaParams p) {
+  constexpr int X_BYTES = NT * 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int RS = p.raw_stages;
+  uint8_t *a_ring = smem, *x_ring = smem + WA_AS * WA_A_BYTES, *r_ring = x_ring + WA_XS * X_BYTES;
+  uint64_t *bars = (uint64_t *)(r_ring + (size_t)RS * WA_RAW_BYTES);
+  uint64_t *raw_full = bars, *raw_empty = bars + WA_RS_MAX, *x_full = bars + 2 * WA_RS_MAX, *x_empty = x_full + WA_XS,
+           *a_full = x_empty + WA_XS, *a_empty = a_full + WA_AS, *acc_full = a_empty + WA_AS;
+  uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
+  uint32_t *sc_tab = (uint32_t *)((uint8_t *)bars + 512);   // [groups_per_cta][128]: 16-bit scale | zero point << 16
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * WA_BM;
+  const int ksplit = gridDim.y;
+  const uint32_t rank = (ksplit > 1) ? cluster_ctarank() : 0u;
+  const int nk_total = p.K / WA_BK;
+  const int kb0 = (int)rank * p.ksteps_per_split;
+  const int nk = max(0, min(p.ksteps_per_split, nk_total - kb0));
+  const int rows_valid = min(WA_BM, p.N - n0);
+
+  if (tid == 0) {
+    for (int s = 0; s < RS; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], WA_DQ_WARPS); }
+    for (int s = 0; s < WA_XS; s++) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
+    for (int s = 0; s < WA_AS; s++) { mbar_init(&a_full[s], WA_DQ_WARPS); mbar_init(&a_empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  constexpr uint32_t TCOLS = NT < 32 ? 32 : NT;
+  if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== raw producer: the HBM stream =====================
+    if (lane == 0) {
+      const uint32_t raw_bytes = (uint32_t)rows_valid * 32u;
+      int stage = 0, phase = 0;
+      for (int i = 0; i < nk; i++) {
+        mbar_wait(&raw_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&raw_full[stage], raw_bytes);
+        bulk_g2s(r_ring + (size_t)stage * WA_RAW_BYTES, p.wq + ((size_t)(kb0 + i) * p.N + n0) * 32, raw_bytes, &raw_full[stage]);
+        if (++stage == RS) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== X producer (activation tiles, L2) =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int i = 0; i < nk; i++) {
+        mbar_wait(&x_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&x_full[stage], X_BYTES);
+        tma_load_2d(x_ring + (size_t)stage * X_BYTES, &tmap_x, (kb0 + i) * WA_BK, p.m0, &x_full[stage]);
+        if (++stage == WA_XS) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t fmt = (p.dtype == MRS_BF16) ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(WA_BM >> 4) << 24);
+    int xs_ = 0, xph = 0, as_ = 0, aph = 0;
+    for (int i = 0; i < nk; i++) {
+      mbar_wait(&x_full[xs_], xph);
+      mbar_wait(&a_full[as_], aph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint8_t *as = a_ring + (size_t)as_ * WA_A_BYTES, *xs = x_ring + (size_t)xs_ * X_BYTES;
+#pragma unroll
+        for (int k = 0; k < WA_BK / 16; k++)
+          umma_f16(tmem_base, umma_desc_sw128(as) + (uint64_t)(2 * k), umma_desc_sw128(xs) + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+        umma_commit(&a_empty[as_]);
+        umma_commit(&x_empty[xs_]);
+        if (i == nk - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+      if (++xs_ == WA_XS) { xs_ = 0; xph ^= 1; }
+      if (++as_ == WA_AS) { as_ = 0; aph ^= 1; }
+    }
+  } else {
+    // ===================== dequantisers =====================
+    const int dt_ = tid - 64;              // 0..255
+    const int r = dt_ >> 1, hf = dt_ & 1;  // weight row in the tile, which 32-weight half of the K-step
+    const int n = n0 + r;
+    const bool live = r < rows_valid;
+    const bool bf = p.dtype == MRS_BF16;
+    int scol = n;
+    if (p.scale_perm == 1) scol = (n & ~63) + inv_scale_perm64(n & 63);
+    else if (p.scale_perm == 2) scol = (n & ~31) + inv_scale_perm32(n & 31);
+    const int zsh = 4 * ((n & 7) == 0 ? 0 : (n & 7) == 1 ? 4 : (n & 7) == 2 ? 1 : (n & 7) == 3 ? 5 : (n & 7) == 4 ? 2 : (n & 7) == 5 ? 6 : (n & 7) == 6 ? 3 : 7);
+    // scales (+ AWQ zero points) of this CTA's K range go to shared memory once
+    const int g_first = (kb0 * WA_BK) / p.group;
+    {
+      const int g_last = nk > 0 ? ((kb0 + nk) * WA_BK - 1) / p.group : g_first - 1;
+      for (int g = g_first + hf; g <= g_last; g += 2) {
+        uint32_t v = 0u;
+        if (live) {
+          v = ((const uint16_t *)p.scales)[(size_t)g * p.N + scol];
+          uint32_t z = 8u;
+          if (p.qzeros != nullptr) z = ((uint32_t)p.qzeros[(size_t)g * (p.N >> 3) + (n >> 3)] >> zsh) & 0xFu;
+          v |= z << 16;
+        }
+        sc_tab[(g - g_first) * WA_BM + r] = v;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(WA_DQ_WARPS * 32));
+    }
+    int rs_ = 0, rph = 0, as_ = 0, aph = 0;
+    for (int i = 0; i < nk; i++) {
+      const int kb = kb0 + i;
+      const uint32_t sz = sc_tab[((kb * WA_BK + 32 * hf) / p.group - g_first) * WA_BM + r];
+      mbar_wait(&raw_full[rs_], rph);
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (live) raw = *(const uint4 *)(r_ring + (size_t)rs_ * WA_RAW_BYTES + r * 32 + hf * 16);
+      const uint32_t s16 = sz & 0xFFFFu;
+      const int zp = (int)(sz >> 16);
+      const uint32_t s2 = s16 * 0x00010001u;
+      float s_f = 0.f;
+      if (bf) s_f = __bfloat162float(__ushort_as_bfloat16((unsigned short)s16));
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t o[4][4];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4++) {
+        if (bf) dequant_word<true>(w[c4], zp, s_f, s2, o[c4]);
+        else dequant_word<false>(w[c4], zp, s_f, s2, o[c4]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[rs_]);       // the packed bytes have been consumed into registers: free the raw slot
+      mbar_wait(&a_empty[as_], aph ^ 1);                 // the MMA that read this A slot has retired
+      uint8_t *dst = a_ring + (size_t)as_ * WA_A_BYTES + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; c4++) {
+        const int c = 4 * hf + c4;
+        *(uint4 *)(dst + ((c ^ (r & 7)) << 4)) = make_uint4(o[c4][0], o[c4][1], o[c4][2], o[c4][3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[as_]);
+      if (++rs_ == RS) { rs_ = 0; rph ^= 1; }
+      if (++as_ == WA_AS) { as_ = 0; aph ^= 1; }
+    }
+  }
+  wa_epilogue<NT>(p, smem, acc_full, tmem_base, nk, ksplit, rank, n0, rows_valid);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
@@ -364,24 +461,43 @@ __global__ void repack_awq_kernel(const uint32_t *__restrict__ qw, uint32_t *__r
 }
 
 // ---------------------------------------------------------------- host
+static size_t wa4_fixed_bytes(int NT, int groups) {
+  return 1024 + (size_t)WA_AS * WA_A_BYTES + (size_t)WA_XS * NT * 128 + 512 + (size_t)groups * WA_BM * 4;
+}
+
 template <int NT, int SRC>
 static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaParams p, int ksplit, cudaStream_t st) {
-  auto kern = w4a16_kernel<NT, SRC>;
-  constexpr int STAGE = WA_A_BYTES + NT * 128 + (SRC == WA_SRC_INT4 ? WA_RAW_BYTES : 0);
-  const size_t smem = 1024 + (size_t)WA_STAGES * STAGE + 256 + (SRC == WA_SRC_INT4 ? (size_t)p.groups_per_cta * WA_BM * 4 : 0);
-  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((p.N + WA_BM - 1) / WA_BM, ksplit);
-  cfg.blockDim = dim3(WA_THREADS);
-  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = ksplit; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ksplit > 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, tx, tw, p);
+  if constexpr (SRC == WA_SRC_INT4) {
+    auto kern = w4a16_int4_kernel<NT>;
+    // two CTAs per SM for the decode tiles: the raw ring takes what is left of half an SM's shared memory
+    const size_t budget = (NT <= 64) ? (size_t)(227 * 1024) / 2 - 1024 : (size_t)200 * 1024;
+    const size_t fixed = wa4_fixed_bytes(NT, p.groups_per_cta);
+    int rs = fixed < budget ? (int)((budget - fixed) / WA_RAW_BYTES) : 0;
+    if (rs > WA_RS_MAX) rs = WA_RS_MAX;
+    if (rs < 2) rs = 2;
+    p.raw_stages = rs;
+    const size_t smem = fixed + (size_t)rs * WA_RAW_BYTES;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cfg.blockDim = dim3(WA4_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    return cudaLaunchKernelEx(&cfg, kern, tx, p);
+  } else {
+    auto kern = w16_dense_kernel<NT>;
+    const size_t smem = 1024 + (size_t)WA_STAGES * (WA_A_BYTES + NT * 128) + 256;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cfg.blockDim = dim3(WA_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    return cudaLaunchKernelEx(&cfg, kern, tx, tw, p);
+  }
 }
 
 // split K over a cluster when the row tiles alone leave SMs idle (two CTAs per SM are resident)
@@ -392,13 +508,13 @@ static int pick_ksplit(int N, int K, int NT) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = (N + WA_BM - 1) / WA_BM, nk = K / WA_BK;
-  const int slots = (NT <= 64 ? 2 : 1) * sms;
+  const int slots = 2 * sms;
   int ks = 1;
   for (int c = 2; c <= 4; c *= 2) {
     const int per = (nk + c - 1) / c;
-    // the reduction buffer (c-1 partials of NT x 128 f32) lives in the pipeline's stage memory
-    const size_t red = (size_t)(c - 1) * NT * WA_BM * 4, stages = (size_t)WA_STAGES * (WA_A_BYTES + NT * 128);
-    if (tiles * c <= slots && per >= 4 && red <= stages) ks = c;
+    // the reduction buffer (c-1 partials of NT x 128 f32) aliases the operand rings (A + X + >= 2 raw stages)
+    const size_t red = (size_t)(c - 1) * NT * WA_BM * 4, rings = (size_t)WA_AS * WA_A_BYTES + (size_t)WA_XS * NT * 128 + 2 * WA_RAW_BYTES;
+    if (tiles * c <= slots && per >= 4 && red <= rings) ks = c;
   }
   return ks;
 }

@@ -124,7 +124,43 @@ class _Step(ctypes.Structure):
                                                "kv_chunk_size", "block_valid_mask", "x", "x2", "q", "k", "v",
                                                "attn_out", "act", "logits", "tmp_v", "tmp_s", "out_token",
                                                "attn_counters", "argmax_scratch")] + \
-               [("all_reduce", _AR_FN), ("all_reduce_user", ctypes.c_void_p)]
+               [("all_reduce", _AR_FN), ("all_reduce_user", ctypes.c_void_p), ("tp", ctypes.c_void_p)]
+
+
+class _TpCtx(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("peer_base", ctypes.c_void_p * 8),
+                ("flags_offset", ctypes.c_int64), ("slot_offset", ctypes.c_int64 * 2), ("seq_counter", ctypes.c_void_p)]
+
+
+class PeerAllReduce:
+    """Symmetric buffer + peer mappings for the in-graph peer-memory all-reduce (`mrs_tp_ctx`).
+    One process per GPU; the rendezvous goes through torch.distributed._symmetric_memory (plumbing:
+    allocation + IPC handle exchange), the data path is our own kernel over NVLink loads."""
+
+    def __init__(self, elems: int, dtype, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("peer-memory all-reduce supports up to 8 ranks (one NVSwitch domain)")
+        slot = (elems * torch.empty(0, dtype=dtype).element_size() + 255) // 256 * 256
+        self.buf = symm.empty(256 + 2 * slot, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm.rendezvous(self.buf, group)
+        self.seq = torch.zeros(1, dtype=torch.int32, device=device)
+        c = _TpCtx()
+        c.world, c.rank = self.world, self.rank
+        for r in range(self.world):
+            c.peer_base[r] = int(self.handle.buffer_ptrs[r])
+        c.flags_offset, c.slot_offset[0], c.slot_offset[1] = 0, 256, 256 + slot
+        c.seq_counter = self.seq.data_ptr()
+        self.ctx = c
+        dist.barrier(group)
+
+    def pointer(self):
+        return ctypes.addressof(self.ctx)
 
 
 def rope_tables(cfg: LlamaConfig):
@@ -157,9 +193,15 @@ def rope_tables(cfg: LlamaConfig):
 class LlamaWeights:
     """Synthetic device-resident weights (optionally one tensor-parallel shard)."""
 
-    def __init__(self, cfg: LlamaConfig, device, dtype=torch.bfloat16, tp_rank=0, tp_size=1, keep_host=False):
+    def __init__(self, cfg: LlamaConfig, device, dtype=torch.bfloat16, tp_rank=0, tp_size=1, keep_host=False, fast_synth=False):
+        """fast_synth: generate the (shard-shaped) blocks on the device with torch's RNG instead of numpy
+        PCG64 on the host — same distribution, not the SURVEY §8(d) byte stream; for throughput runs of
+        large models (config 3's 8 GB, config 5's 40 GB) where no oracle comparison is made."""
         self.cfg, self.device, self.dtype = cfg, device, dtype
         self.tp_rank, self.tp_size = tp_rank, tp_size
+        self.fast_synth = bool(fast_synth)
+        if fast_synth and keep_host:
+            raise ValueError("fast_synth weights have no host copy")
         self.host = {} if keep_host else None
         H, I = cfg.hidden, cfg.inter
         nq, nkv = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
@@ -375,6 +417,26 @@ class LlamaWeights:
         :695-975 (row), gguf/weight_source.rs:809-818 (block-aligned K slices)."""
         dt = tensor_type(self.cfg, name, layer)
         be, bb = BLOCK_ELEMS[dt], BLOCK_BYTES[dt]
+        if self.fast_synth:
+            w = self.tp_size
+            if kind == "col" and w > 1:
+                rows //= w
+            elif kind == "row" and w > 1:
+                assert (cols // be) % w == 0
+                cols //= w
+            nblocks = rows * cols // be
+            gen = torch.Generator(device=self.device).manual_seed(tensor_seed(layer, name) * 64 + self.tp_rank)
+            raw = torch.randint(0, 256, (nblocks, bb), dtype=torch.uint8, device=self.device, generator=gen)
+            lo, hi = self.cfg.synth_scale_exp
+            f = F16_FIELDS[dt]
+            d = torch.exp2(torch.empty(nblocks, device=self.device).uniform_(lo, hi, generator=gen)).to(torch.float16)
+            raw[:, f[0]:f[0] + 2] = d.view(torch.uint8).reshape(nblocks, 2)
+            if len(f) > 1:
+                m = (d.float() * torch.empty(nblocks, device=self.device).uniform_(0, 0.5, generator=gen)).to(torch.float16)
+                raw[:, f[1]:f[1] + 2] = m.view(torch.uint8).reshape(nblocks, 2)
+            t = raw.reshape(-1)
+            self.nbytes += t.numel()
+            return (t, dt, rows, cols)
         full = synth_blocks(dt, rows * cols // be, tensor_seed(layer, name), self.cfg.synth_scale_exp).reshape(rows, cols // be, bb)
         r, w = self.tp_rank, self.tp_size
         if kind == "col" and w > 1:
@@ -409,7 +471,7 @@ class LlamaRunner:
     mrs_llama_decode_step / mrs_decode_advance (eagerly or as a captured CUDA graph)."""
 
     def __init__(self, weights: LlamaWeights, batch=1, max_ctx=512, pdl=False, sm_count=148, comm=None,
-                 fused_attention=True, split_policy="sm_fill", split_min_tokens=64):
+                 fused_attention=True, split_policy="sm_fill", split_min_tokens=64, peer_allreduce=None):
         cfg, dev, dt = weights.cfg, weights.device, weights.dtype
         self.w, self.cfg, self.dev, self.dt, self.B = weights, cfg, dev, dt, batch
         tp = weights.tp_size
@@ -473,7 +535,9 @@ class LlamaRunner:
             setattr(s, n, t.data_ptr())
         for n, t in self.buf.items():
             setattr(s, n, t.data_ptr())
-        self._ar_cb = None
+        self._ar_cb, self._peer = None, peer_allreduce
+        if peer_allreduce is not None:     # in-graph peer-memory sum (takes precedence over the callback)
+            s.tp = peer_allreduce.pointer()
         if comm is not None:
             self._ar_cb = _AR_FN(comm)
             s.all_reduce = self._ar_cb
@@ -529,7 +593,7 @@ class LlamaRunner:
     def capture(self):
         self.step(); self.reset()  # warm-up outside capture (module load, attributes)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
+        g = torch.cuda.CUDAGraph(keep_graph=True)   # keep_graph: the kernel nodes can be counted afterwards
         with torch.cuda.graph(g):
             self.step()
         self.reset()
@@ -551,7 +615,9 @@ class LlamaPrefill:
     paged_attention.rs:1413-1475) -> KV scatter into the paged HND cache -> o_proj -> add+RMSNorm ->
     GLU -> down -> add.  TTFT of BASELINE config 3 is the time of `forward` on a 4096-token prompt."""
 
-    def __init__(self, weights: "LlamaWeights", max_tokens=4096):
+    def __init__(self, weights: "LlamaWeights", max_tokens=4096, runner: "LlamaRunner" = None):
+        """runner: write the prompt's K/V into sequence 0 of this decode runner's paged cache (its block
+        table), so a generation is prefill -> `runner.reset(T)` -> decode-graph replays."""
         from . import ops, paged_attn, quant  # noqa: F401  (fail early when the extension is missing)
         cfg, dev, dt = weights.cfg, weights.device, weights.dtype
         if weights.tp_size != 1:
@@ -560,10 +626,16 @@ class LlamaPrefill:
         bs = cfg.block_size
         self.max_tokens = int(max_tokens)
         self.nblocks = -(-self.max_tokens // bs)
-        nb = self.nblocks + 1                                   # block 0 stays the null block
-        self.table = list(range(1, self.nblocks + 1))
-        self.k_cache = [torch.zeros(nb, cfg.n_kv_heads, bs, cfg.head_dim, dtype=dt, device=dev) for _ in range(cfg.n_layers)]
-        self.v_cache = [torch.zeros(nb, cfg.n_kv_heads, bs, cfg.head_dim, dtype=dt, device=dev) for _ in range(cfg.n_layers)]
+        if runner is not None:
+            if runner.max_blocks < self.nblocks:
+                raise ValueError("LlamaPrefill: the runner's block table is shorter than max_tokens")
+            self.table, self.k_cache, self.v_cache = list(runner.tables[0]), runner.k_cache, runner.v_cache
+        else:
+            nb = self.nblocks + 1                                   # block 0 stays the null block
+            self.table = list(range(1, self.nblocks + 1))
+            self.k_cache = [torch.zeros(nb, cfg.n_kv_heads, bs, cfg.head_dim, dtype=dt, device=dev) for _ in range(cfg.n_layers)]
+            self.v_cache = [torch.zeros(nb, cfg.n_kv_heads, bs, cfg.head_dim, dtype=dt, device=dev) for _ in range(cfg.n_layers)]
+        self._slots = torch.tensor([self.table[i // bs] * bs + i % bs for i in range(self.max_tokens)], dtype=torch.int64, device=dev)
 
     def forward(self, tokens, all_logits=False):
         """tokens: list[int] (1 < len <= max_tokens).  Returns logits [vocab] of the last token, or
@@ -574,9 +646,11 @@ class LlamaPrefill:
         if not 1 < T <= min(self.max_tokens, cfg.max_pos):
             raise ValueError(f"LlamaPrefill.forward: need 1 < tokens <= {min(self.max_tokens, cfg.max_pos)}, got {T}")
         H, KVH, D = cfg.n_heads, cfg.n_kv_heads, cfg.head_dim
-        bs = cfg.block_size
-        slots = torch.tensor([self.table[i // bs] * bs + i % bs for i in range(T)], dtype=torch.int64, device=dev)
-        ids = torch.tensor(tokens, dtype=torch.int32, device=dev)
+        slots = self._slots[:T]
+        if torch.is_tensor(tokens):      # e.g. pinned host ids: the H2D copy is part of the call
+            ids = tokens.to(device=dev, dtype=torch.int32, non_blocking=True)
+        else:
+            ids = torch.tensor(tokens, dtype=torch.int32, device=dev)
         x = torch.empty(T, cfg.hidden, dtype=dt, device=dev)
         t, ty, rows, cols = w.tok_embd
         rc = lib().mrs_embedding_gather(ctypes.c_int32(GGML[ty]), ctypes.c_void_p(t.data_ptr()), ctypes.c_int32(cols),

@@ -32,7 +32,8 @@ def timed(run, mask, reps=30):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-for name, mflags, aflags in (("default", 128 << 8, 0), ("late-residual", 16 | (128 << 8), 0), ("simt-attention", 128 << 8, 1)):
+for name, mflags, aflags in (("default (mma attention, cluster merge)", 128 << 8, 0), ("mma attention, counter merge", 128 << 8, 2),
+                             ("simt attention", 128 << 8, 1)):
     L.mrs_set_mmvq_flags(ctypes.c_int(mflags))
     L.mrs_set_attn_flags(ctypes.c_int(aflags))
     run = M.LlamaRunner(w, batch=1, max_ctx=400, pdl=True)

@@ -148,6 +148,22 @@ def test_reference_signatures_match_ffi_rs():
     assert not bad, bad[:5]
 
 
+def test_rust_ffi_source_matches_headers():
+    """rust/mrs_b200_ffi.rs (the `extern "C"` block a maintainer adds for the mrs_* entry points) is
+    generated from include/*.h; re-parse the committed file with the same parser used on the
+    reference's ffi.rs and compare arity / argument classes / return with the headers."""
+    rust = _rust_signatures(open(os.path.join(ROOT, "rust", "mrs_b200_ffi.rs")).read())
+    ours = {n: v for n, v in _c_signatures().items() if n.startswith("mrs_")}
+    assert set(rust) == set(ours), sorted(set(rust) ^ set(ours))
+    for n, (cargs, cret) in ours.items():
+        rargs, rret = rust[n]
+        cargs = ["ptr" if c.startswith("?") else c for c in cargs]     # structs / callbacks cross as opaque pointers
+        assert cargs == rargs and cret == rret, (n, cargs, rargs)
+    shim = open(os.path.join(ROOT, "rust", "b200_quant_method.rs")).read()
+    for name in re.findall(r"ffi::(mrs_[a-z0-9_]+)", shim):
+        assert name in ours, name
+
+
 def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
     import mistralrs_b200 as pkg
     monkeypatch.setattr(pkg, "_lib", None)

@@ -33,19 +33,33 @@ def main():
     for n in ("x", "x2"):
         bufs[tp.buf[n].data_ptr()] = tp.buf[n]
     tp.capture()   # exercises NCCL inside CUDA-graph capture
-    ref.set_tokens([11, 400]); tp.set_tokens([11, 400])
-    worst = 0.0
-    for step in range(8):
-        ref.step(); tp.graph.replay()
-        torch.cuda.synchronize()
-        a, b = ref.logits().float(), tp.logits().float()
-        worst = max(worst, ((a - b).abs().max() / a.abs().max()).item())
-        tp.set_tokens(ref.meta["token_ids"].cpu().tolist())
-    ok = worst <= 4 * 2.0 ** -7
+    # the product path: in-graph peer-memory all-reduce fused with the residual add, PDL chain intact
+    peer = M.PeerAllReduce(2 * cfg.hidden, torch.bfloat16, dev)
+    tp2 = M.LlamaRunner(shard, batch=2, max_ctx=64, pdl=True, peer_allreduce=peer)
+    tp2.capture()
+    results = {}
+    for name, runner in (("nccl", tp), ("peer", tp2)):
+        ref.reset(); runner.reset()
+        ref.set_tokens([11, 400]); runner.set_tokens([11, 400])
+        worst = 0.0
+        for step in range(8):
+            ref.step(); runner.graph.replay()
+            torch.cuda.synchronize()
+            a, b = ref.logits().float(), runner.logits().float()
+            worst = max(worst, ((a - b).abs().max() / a.abs().max()).item())
+            runner.set_tokens(ref.meta["token_ids"].cpu().tolist())
+        results[name] = worst
+    # every rank must hold identical logits on the peer path (rank-ordered f32 sums)
+    mine = tp2.logits().float().clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    same = bool(torch.equal(mine, other))
+    ok = max(results.values()) <= 4 * 2.0 ** -7 and same
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"TP{world} vs TP1 worst rel logit diff {worst:.3e} -> {'OK' if t.item() == 1.0 else 'FAIL'}", flush=True)
+        print(f"TP{world} vs TP1 worst rel logit diff: nccl {results['nccl']:.3e}, peer-memory {results['peer']:.3e}, "
+              f"ranks bit-identical: {same} -> {'OK' if t.item() == 1.0 else 'FAIL'}", flush=True)
     rc = 0 if t.item() == 1.0 else 1
     dist.barrier()
     torch.cuda.synchronize()
