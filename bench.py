@@ -223,6 +223,8 @@ def validate_first_tokens(weights, M, torch, n_tokens=6):
         got = run.logits().float().cpu().numpy()
         want = ref.step(toks, pos)
         scale = float(np.abs(want).max())
+        if not (np.isfinite(want).all() and np.isfinite(got).all() and scale > 0):
+            raise AssertionError("bench validation: non-finite or degenerate logits")
         worst = max(worst, float(np.abs(got - want).max()) / scale)
         top2 = np.sort(want[0])[-2:]
         tie = (top2[1] - top2[0]) <= 8 * 2.0 ** -8 * scale

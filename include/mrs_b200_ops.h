@@ -41,6 +41,25 @@ MRS_RMS_DECL(f16) MRS_RMS_DECL(bf16) MRS_RMS_DECL(f32)
                                int64_t stride_s, int64_t stride_d, int32_t batch, int32_t heads, int32_t seq_len, \
                                int32_t head_dim, float eps, int64_t stream);
 MRS_RMS4D_DECL(f16) MRS_RMS4D_DECL(bf16) MRS_RMS4D_DECL(f32)
+/* ---- sampling tail — REF mistralrs-core/src/cuda/ffi.rs:581-665, sort.cu:1503-2262 (csrc/sampler.cu).
+ * top-k of raw f32 logits in (value desc, index asc) order + softmax statistics at inv_temperature:
+ * packed_out = [values k | indices as f32 k | denom | global_max]; scratch arrays as the Rust callers
+ * size them (block_values / block_indices: nblocks*k per row, block_maxes / block_sums: nblocks per row);
+ * chunk_size <= 2048, nblocks * k <= 47 * 1024.  top-1: packed [value, token id] and / or token ids;
+ * a NaN logit poisons the row (NaN / UINT32_MAX). */
+void topk_large_f32(const float *input, float *block_values, uint32_t *block_indices, float *block_maxes, float *block_sums,
+                    float *values_out, uint32_t *indices_out, float *softmax_info_out, int ncols, int k, int chunk_size,
+                    int nblocks, float inv_temperature, int64_t stream);
+void topk_large_f32_packed(const float *input, float *block_values, uint32_t *block_indices, float *block_maxes,
+                           float *block_sums, float *packed_out, int ncols, int k, int chunk_size, int nblocks,
+                           float inv_temperature, int64_t stream);
+void topk_large_f32_packed_batched(const float *input, const float *inv_temperatures, float *block_values,
+                                   uint32_t *block_indices, float *block_maxes, float *block_sums, float *packed_out,
+                                   int nrows, int ncols, int k, int chunk_size, int nblocks, int64_t stream);
+void top1_large_f32_packed(const float *input, float *block_values, uint32_t *block_indices, float *packed_out,
+                           uint32_t *token_ids_out, int ncols, int chunk_size, int nblocks, int64_t stream);
+void top1_large_f32_packed_batched(const float *input, float *block_values, uint32_t *block_indices, float *packed_out,
+                                   uint32_t *token_ids_out, int nrows, int ncols, int chunk_size, int nblocks, int64_t stream);
 #ifdef __cplusplus
 }
 #endif

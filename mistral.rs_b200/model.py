@@ -41,12 +41,18 @@ class LlamaConfig:
     rope_freq_factors: object = None   # optional per-frequency divisors (GGUF `rope_freqs.weight`, Llama-3.1 scaling)
     synth_scale_exp: tuple = (-9, -7)  # synthetic weights: block scales d = 2^U(lo, hi)
 
+    # Real-size models take block super-scales 2^U(-15,-13): with the 6-bit sub-scales (1..63) and 4-bit
+    # quants of the k-quants that gives |w| ~ 0.016, i.e. unit-scale activations at K = 4096 .. 28672.
+    # SURVEY §8(d)'s 2^U(-9,-7) (|w| ~ 1) sends the 14336-wide down projection past f16's range, and the
+    # Q8_1 block scale is a half (REF mmvq_gguf.cu:146-152): the reference itself would produce NaN.
     @staticmethod
     def llama3_8b(**kw):
+        kw.setdefault("synth_scale_exp", (-15, -13))
         return LlamaConfig(rope_scaling=None, **kw)
 
     @staticmethod
     def llama3_70b(**kw):
+        kw.setdefault("synth_scale_exp", (-15, -13))
         return LlamaConfig(hidden=8192, inter=28672, n_layers=80, n_heads=64, n_kv_heads=8, name="llama-3-70b", **kw)
 
     @staticmethod

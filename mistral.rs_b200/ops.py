@@ -120,3 +120,51 @@ def add_rms_norm(x, residual, weight, eps):
                                                      ctypes.c_int(x.numel() // cols), ctypes.c_int(cols),
                                                      ctypes.c_float(eps), ctypes.c_int64(_stream(x.device)))
     return s, n
+
+
+CUDA_TOPK_CHUNK_SIZE, CUDA_TOPK_MAX_K = 2048, 128   # REF mistralrs-core/src/ops.rs:12,18
+
+
+def cuda_topk_logits_f32_packed(logits: torch.Tensor, k: int, temperature: float):
+    """Mirror of `cuda_topk_logits_f32_packed[_batched]` (REF mistralrs-core/src/ops.rs:690-830): f32 logits
+    [vocab] or [rows, vocab] -> (values [.., k], indices [.., k] i64, denom [..], global_max [..])."""
+    if temperature <= 0.0 or not np.isfinite(temperature):
+        raise ValueError("cuda_topk_logits_f32_packed requires a positive finite temperature")
+    if logits.dtype != torch.float32:
+        raise ValueError("cuda_topk_logits_f32_packed requires F32 logits")
+    x = logits.contiguous().reshape(-1, logits.shape[-1])
+    rows, ncols = x.shape
+    k = min(k, ncols)
+    if k == 0 or k > CUDA_TOPK_MAX_K:
+        raise ValueError(f"cuda_topk_logits_f32_packed k={k} must be in [1, {CUDA_TOPK_MAX_K}]")
+    nblocks = -(-ncols // CUDA_TOPK_CHUNK_SIZE)
+    dev = x.device
+    bv = torch.empty(rows * nblocks * k, dtype=torch.float32, device=dev)
+    bi = torch.empty(rows * nblocks * k, dtype=torch.int32, device=dev)
+    bm = torch.empty(rows * nblocks, dtype=torch.float32, device=dev)
+    bs = torch.empty(rows * nblocks, dtype=torch.float32, device=dev)
+    packed = torch.empty(rows, 2 * k + 2, dtype=torch.float32, device=dev)
+    it = torch.full((rows,), 1.0 / temperature, dtype=torch.float32, device=dev)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    lib().topk_large_f32_packed_batched(P(x), P(it), P(bv), P(bi), P(bm), P(bs), P(packed), ctypes.c_int(rows), ctypes.c_int(ncols),
+                                        ctypes.c_int(k), ctypes.c_int(CUDA_TOPK_CHUNK_SIZE), ctypes.c_int(nblocks),
+                                        ctypes.c_int64(torch.cuda.current_stream(dev).cuda_stream))
+    shape = logits.shape[:-1]
+    return (packed[:, :k].reshape(*shape, k), packed[:, k:2 * k].to(torch.int64).reshape(*shape, k),
+            packed[:, 2 * k].reshape(shape), packed[:, 2 * k + 1].reshape(shape))
+
+
+def cuda_top1_logits_f32(logits: torch.Tensor) -> torch.Tensor:
+    """greedy token ids [rows] (u32 as i64) of f32 logits [rows, vocab] — `top1_large_f32_packed_batched`."""
+    x = logits.contiguous().reshape(-1, logits.shape[-1])
+    rows, ncols = x.shape
+    nblocks = -(-ncols // CUDA_TOPK_CHUNK_SIZE)
+    dev = x.device
+    bv = torch.empty(rows * nblocks, dtype=torch.float32, device=dev)
+    bi = torch.empty(rows * nblocks, dtype=torch.int32, device=dev)
+    out = torch.empty(rows, dtype=torch.int32, device=dev)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    lib().top1_large_f32_packed_batched(P(x), P(bv), P(bi), ctypes.c_void_p(0), P(out), ctypes.c_int(rows), ctypes.c_int(ncols),
+                                        ctypes.c_int(CUDA_TOPK_CHUNK_SIZE), ctypes.c_int(nblocks),
+                                        ctypes.c_int64(torch.cuda.current_stream(dev).cuda_stream))
+    return out.to(torch.int64) & 0xFFFFFFFF

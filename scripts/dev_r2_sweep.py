@@ -6,6 +6,8 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
 import __graft_entry__ as g
 pkg = g.load_package()
+if os.environ.get("MRS_DEV_LIB"):
+    pkg.LIB_PATH = os.environ["MRS_DEV_LIB"]     # A/B another build of libmrs_b200.so
 from mistralrs_b200 import model as M
 dev = torch.device("cuda:0")
 layers = int(sys.argv[1]) if len(sys.argv) > 1 else 32
