@@ -169,6 +169,27 @@ def run_reference(args):
         "wall_s": time.perf_counter() - t0}))
 
 
+def run_config1(args):
+    """BASELINE config 1: TinyLlama-1.1B GGUF Q4_K_M on the CPU, 128-token prompt + 64 decode tokens — plumbing
+    only (no GPU): the CPU port of the reference's arithmetic through every layer (oracle/cpu_decode_bench.c),
+    the prompt fed token by token like the decode steps."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import __graft_entry__ as g
+    g.load_package()
+    from mistralrs_b200 import model as M
+    cfg = M.LlamaConfig.tinyllama()
+    t0 = time.perf_counter()
+    v, threads, sample = cpu_decode_tokens_per_s(cfg, M, seconds=0.0, min_tokens=128 + 64)
+    print(json.dumps({"metric": "decode_tok_s", "value": v, "unit": "tok/s", "n_gpus": 0, "steps": 1, "warmup": 1,
+                      "ms_per_step": 1e3 * (128 + 64) / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "int8 (Q8_K / Q8_0) activations x ggml block dots, f32 accumulate", "data": "synthetic",
+                      "config": {"workload": "TinyLlama-1.1B GGUF Q4_K_M on CPU, 128-token prompt + 64 decode tokens (192 token steps, plumbing)"},
+                      "cpu_baseline": {"value": v, "unit": "tok/s", "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0, "wall_s": time.perf_counter() - t0}))
+
+
 # ------------------------------------------------------------------------------------------- helpers
 def count_graph_kernels(graph):
     """kernel nodes of a captured CUDA graph (= our launches per replay), read back from the driver"""
@@ -355,9 +376,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
-                    help="headline workload: 2 = 8B Q4_K_M decode b=1 (default), 3 = 8B Q8_0 prefill 4096, 4 = Mistral-7B GPTQ b=32, "
-                         "5 = Llama-3-70B Q4_K_M tensor parallel (needs --gpus 8)")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="headline workload: 1 = TinyLlama-1.1B Q4_K_M on the CPU (plumbing, no GPU), 2 = 8B Q4_K_M decode b=1 (default), "
+                         "3 = 8B Q8_0 prefill 4096, 4 = Mistral-7B GPTQ b=32, 5 = Llama-3-70B Q4_K_M tensor parallel (needs --gpus 8)")
     ap.add_argument("--layers", type=int, default=0, help="debug: truncate the model")
     ap.add_argument("--pdl", type=int, default=int(os.environ.get("MRS_PDL", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -366,6 +387,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 1:
+        return run_config1(args)
 
     import numpy as np
     import torch

@@ -59,7 +59,7 @@ void gather_kv_cache(void *key_cache, void *value_cache, void *k_out, void *v_ou
                               int32_t head_size, int32_t max_num_blocks_per_seq, int32_t q_stride,                 \
                               int32_t kv_block_stride, int32_t kv_head_stride, mrs_stream_t stream,                \
                               uint32_t cache_dtype, float *k_scale, float *v_scale, const float *sinks);
-MRS_PAGED_DECL(f16) MRS_PAGED_DECL(bf16)
+MRS_PAGED_DECL(f16) MRS_PAGED_DECL(bf16) MRS_PAGED_DECL(f32)
 
 /* REF ffi.rs:440-482 / copy_blocks_kernel.cu */
 #define MRS_COPY_DECL(t)                                                                                     \

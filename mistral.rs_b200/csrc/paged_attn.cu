@@ -16,6 +16,7 @@
 // reference's formulas.
 #include "common.cuh"
 
+#include <cuda_fp8.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -45,6 +46,8 @@ struct PagedParams {
   int num_heads, num_kv_heads, page_size;
   int64_t q_stride_n, q_stride_h;
   float sm_scale, softcap;  // softcap <= 0: disabled
+  float k_scale, v_scale;   // FP8 cache: per-tensor dequantisation scales (1 for 16/32-bit caches)
+  const float *k_scale_ptr, *v_scale_ptr;   // the same as device scalars (vLLM-style API); override the values
   int window_left;          // < 0: disabled
   const float *alibi_slopes, *sinks;
   int tiles_are_partitions; // vLLM v2: tile index = seq * num_partitions + partition
@@ -96,11 +99,43 @@ template <> struct Vec8<__nv_bfloat16> {
     *(uint4 *)p = v;
   }
 };
+template <> struct Vec8<float> {
+  __device__ static __forceinline__ void load(const float *p, float *f) {
+    const float4 a = *(const float4 *)p, b = *(const float4 *)(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  __device__ static __forceinline__ float one(const float *p) { return *p; }
+  __device__ static __forceinline__ void store(float *p, const float *f) {
+    *(float4 *)p = make_float4(f[0], f[1], f[2], f[3]);
+    *(float4 *)(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+// FP8-E4M3 cache bytes (cache_dtype 3, REF mistralrs-paged-attn/src/cuda/ffi.rs dtype codes): value = float(e4m3);
+// the per-tensor scales are folded into the logits (k_scale) and the output (v_scale)
+struct fp8_t { uint8_t b; };
+__device__ __forceinline__ float fp8_to_float(uint8_t b) {
+  const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3);
+  return __half2float(*(const __half *)&h);
+}
+template <> struct Vec8<fp8_t> {
+  __device__ static __forceinline__ void load(const fp8_t *p, float *f) {
+    const uint2 v = *(const uint2 *)p;
+    const uint8_t *b = (const uint8_t *)&v;
+#pragma unroll
+    for (int i = 0; i < 8; i++) f[i] = fp8_to_float(b[i]);
+  }
+  __device__ static __forceinline__ float one(const fp8_t *p) { return fp8_to_float(p->b); }
+};
 
 // round through T (what storing a tensor of dtype T would do)
 template <typename T> __device__ __forceinline__ float rnd(float v);
 template <> __device__ __forceinline__ float rnd<__half>(float v) { return __half2float(__float2half_rn(v)); }
 template <> __device__ __forceinline__ float rnd<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+template <> __device__ __forceinline__ float rnd<float>(float v) { return v; }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ __half from_float<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
 
 // NeoX RoPE of the 8-element slice held by lane `gl` (elements d0..d0+7 of a head), with the
 // reference kernel's per-operation rounding in T (rotary.cu:10-34).  The partner slice
@@ -122,7 +157,6 @@ __device__ __forceinline__ void rope_slice(float *x, const T *cosp, const T *sin
     x[i] = (float)__hfma((T)x[i], (T)c[i], (T)(upper ? b : -b));
   }
 }
-
 // GPT-J / GGUF-llama pairing: (x[2i], x[2i+1]) rotate together and both live in this lane's slice;
 // cos/sin index d/2.  Same per-operation rounding as rope_slice (REF rotary.cu:10-34, is_neox = 0).
 template <typename T, int D>
@@ -143,36 +177,30 @@ __device__ __forceinline__ void rope_any(float *x, const T *cosp, const T *sinp,
   else rope_slice<T, D>(x, cosp, sinp, gl);
 }
 
-#define MRS_LOAD_Q \
-  if (p.pdl) pdl_wait(); \
-    if constexpr (FUSED) { \
-      const int64_t pos = p.positions[seq]; \
-      cosp = (const T *)p.rope_cos + pos * (D / 2); \
-      sinp = (const T *)p.rope_sin + pos * (D / 2); \
-    } \
-   \
-    for (int g = 0; g < G; g++) { \
-      if (g < gsize) { \
-        Vec8<T>::load((const T *)p.q + (int64_t)seq * p.q_stride_n + (int64_t)(h0 + g) * p.q_stride_h + d0, qf[g]); \
-      } else { \
-        for (int i = 0; i < 8; i++) qf[g][i] = 0.f; \
-      } \
-      if constexpr (FUSED) rope_any<T, D>(qf[g], cosp, sinp, gl, p.rope_interleaved != 0); \
-      for (int i = 0; i < 8; i++) qf[g][i] *= p.sm_scale; \
-    } \
+constexpr int pa_next_pow2(int v) { return v <= 8 ? 8 : (v <= 16 ? 16 : 32); }
 
-// LAYOUT 0: vLLM (K [NB,KVH,D/8,BS,8], V [NB,KVH,D,BS]); 1: HND ([NB,KVH,BS,D])
-// FUSED: q/k/v of the new token arrive un-rotated; the kernel applies RoPE, writes the new K/V
-// row into the cache (the tile that owns the last position) and merges split-KV partials itself
-// ("last tile done" counter) — one launch instead of rope + reshape_and_cache + decode + merge.
-template <typename T, int D, int G, int LAYOUT, bool FUSED>
+// LAYOUT 0: vLLM (K [NB,KVH,D/x,BS,x] with x = 16 / sizeof(cache element), V [NB,KVH,D,BS]); 1: HND ([NB,KVH,BS,D])
+// T: query / output dtype; CT: cache element (T, or fp8_t for the FP8-E4M3 cache).
+// Head sizes that are not 8 x a power of two (80, 96, 112, 192) run with the next power-of-two lane count and
+// idle lanes; 512 gives every lane 16 elements.
+// FUSED (16-bit caches, D in {64,128,256}): q/k/v of the new token arrive un-rotated; the kernel applies RoPE,
+// writes the new K/V row into the cache (the tile that owns the last position) and merges split-KV partials
+// itself ("last tile done" counter) — one launch instead of rope + reshape_and_cache + decode + merge.
+template <typename T, typename CT, int D, int G, int LAYOUT, bool FUSED>
 __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedParams p) {
-  constexpr int LPT = D / 8;               // lanes per token
-  constexpr int NGRP = PA_THREADS / LPT;   // token groups per CTA
+  constexpr int EPL = (D > 256) ? 16 : 8;              // elements per lane
+  constexpr int NV = EPL / 8;                          // 8-element vectors per lane
+  constexpr int LPT_RAW = (D + EPL - 1) / EPL;         // lanes that hold data
+  constexpr int LPT = pa_next_pow2(LPT_RAW);           // lanes per token (power of two: shuffle reductions)
+  constexpr int NGRP = PA_THREADS / LPT;               // token groups per CTA
+  constexpr int UNROLL = (EPL == 16) ? 1 : PA_UNROLL;
+  constexpr int XK = 16 / (int)sizeof(CT);             // vLLM K-cache inner width
+  static_assert(!FUSED || (EPL == 8 && LPT_RAW == LPT && sizeof(CT) == sizeof(T)), "fused path: plain 16-bit heads");
   const int tile = blockIdx.x, kvh = blockIdx.y;
   const int tid = threadIdx.x;
   const int grp = tid / LPT, gl = tid % LPT;  // group, lane within group
-  const int d0 = gl * 8;
+  const int d0 = gl * EPL;
+  const bool act = gl < LPT_RAW;              // lane holds elements d0 .. d0+EPL-1 (all < D: D % EPL == 0)
 
   if (p.pdl && tid == 0) pdl_launch_dependents();  // downstream GEMV may start prefetching its weights
   if (p.block_valid_mask != nullptr && p.block_valid_mask[tile] == 0) return;
@@ -202,24 +230,47 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   const int h0 = kvh * group + blockIdx.z * p.heads_per_cta;      // first query head of this CTA
   const int gsize = min(p.heads_per_cta, group - (int)blockIdx.z * p.heads_per_cta);  // heads here (<= G)
 
-  // q slice of this lane for all heads of the group; filled by MRS_LOAD_Q after the page copies
-  // are in flight and after griddepcontrol.wait (q/k_new/v_new come from the upstream kernel)
-  float qf[G][8];
+  // q slice of this lane for all heads of the group; filled after the page copies are in flight and after
+  // griddepcontrol.wait (q/k_new/v_new come from the upstream kernel)
+  float qf[G][EPL];
   const T *cosp = nullptr, *sinp = nullptr;
   float slope[G];
 #pragma unroll
   for (int g = 0; g < G; g++) slope[g] = (p.alibi_slopes != nullptr && g < gsize) ? p.alibi_slopes[h0 + g] : 0.f;
 
-  float m[G], l[G], o[G][8];
+  float m[G], l[G], o[G][EPL];
 #pragma unroll
   for (int g = 0; g < G; g++) {
     m[g] = -INFINITY; l[g] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; i++) o[g][i] = 0.f;
+    for (int i = 0; i < EPL; i++) o[g][i] = 0.f;
   }
 
-  const T *kc = (const T *)p.kc, *vc = (const T *)p.vc;
+  const CT *kc = (const CT *)p.kc, *vc = (const CT *)p.vc;
   const int win_lo = (p.window_left >= 0) ? max(0, kv_len - 1 - p.window_left) : 0;
+
+  auto load_q = [&]() {
+    if (p.pdl) pdl_wait();
+    if constexpr (FUSED) {
+      const int64_t pos = p.positions[seq];
+      cosp = (const T *)p.rope_cos + pos * (D / 2);
+      sinp = (const T *)p.rope_sin + pos * (D / 2);
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (g < gsize && act) {
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+          Vec8<T>::load((const T *)p.q + (int64_t)seq * p.q_stride_n + (int64_t)(h0 + g) * p.q_stride_h + d0 + 8 * v, qf[g] + 8 * v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < EPL; i++) qf[g][i] = 0.f;
+      }
+      if constexpr (FUSED) rope_any<T, D>(qf[g], cosp, sinp, gl, p.rope_interleaved != 0);
+#pragma unroll
+      for (int i = 0; i < EPL; i++) qf[g][i] *= p.sm_scale * (p.k_scale_ptr ? *p.k_scale_ptr : p.k_scale);
+    }
+  };
 
   // one token's contribution to the running softmax state of this token group
   auto update = [&](const float *kf, const float *vf, int t, bool live) {
@@ -228,7 +279,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
     for (int g = 0; g < G; g++) {
       float a = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; i++) a = fmaf(qf[g][i], kf[i], a);
+      for (int i = 0; i < EPL; i++) a = fmaf(qf[g][i], kf[i], a);
       s[g] = a;
     }
 #pragma unroll
@@ -251,7 +302,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
         const float pv = __expf(x - mn);
         l[g] = l[g] * corr + pv;
 #pragma unroll
-        for (int i = 0; i < 8; i++) o[g][i] = fmaf(pv, vf[i], o[g][i] * corr);
+        for (int i = 0; i < EPL; i++) o[g][i] = fmaf(pv, vf[i], o[g][i] * corr);
         m[g] = mn;
       }
     }
@@ -267,14 +318,15 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
   if constexpr (LAYOUT == 1) {
     // ---- HND: stage the chunk's pages through shared memory with the TMA engine.  A page is a
     // contiguous [page_size, D] slab per KV head, so one cp.async.bulk per (page, K|V) moves it;
-    // all copies of a 128-token sub-chunk are in flight at once (one HBM latency per sub-chunk
+    // all copies of a sub-chunk are in flight at once (one HBM latency per sub-chunk
     // instead of one per 4 tokens), double buffered.
     extern __shared__ __align__(128) uint8_t pa_stage[];
-    constexpr int SUB = (D <= 128) ? 128 : 64;          // tokens per sub-chunk
-    constexpr int SUB_BYTES = SUB * D * (int)sizeof(T);  // per K or V buffer
+    constexpr int ROWB = D * (int)sizeof(CT);                         // bytes per cached row
+    constexpr int SUB = (ROWB <= 256) ? 128 : (ROWB <= 512 ? 64 : 32);  // tokens per sub-chunk
+    constexpr int SUB_BYTES = SUB * ROWB;                              // per K or V buffer
     __shared__ __align__(8) uint64_t st_full[2];
-    T *st_k[2] = {(T *)pa_stage, (T *)(pa_stage + 2 * SUB_BYTES)};
-    T *st_v[2] = {(T *)(pa_stage + SUB_BYTES), (T *)(pa_stage + 3 * SUB_BYTES)};
+    CT *st_k[2] = {(CT *)pa_stage, (CT *)(pa_stage + 2 * SUB_BYTES)};
+    CT *st_v[2] = {(CT *)(pa_stage + SUB_BYTES), (CT *)(pa_stage + 3 * SUB_BYTES)};
     if (tid == 0) { mbar_init(&st_full[0], 1); mbar_init(&st_full[1], 1); fence_mbar_init(); }
     __syncthreads();
     const int nsub = (t_end > t_begin) ? (t_end - t_begin + SUB - 1) / SUB : 0;
@@ -289,71 +341,87 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
     auto issue = [&](int si) {  // thread 0 only
       const int s0 = t_begin + si * SUB, s1 = min(t_end, s0 + SUB);
       const int b = si & 1;
-      mbar_arrive_expect_tx(&st_full[b], (uint32_t)(2 * (s1 - s0) * D * (int)sizeof(T)));
+      mbar_arrive_expect_tx(&st_full[b], (uint32_t)(2 * (s1 - s0) * ROWB));
       for (int t = s0; t < s1;) {
         const int off = t % p.page_size;
         const int n = min(p.page_size - off, s1 - t);   // tokens of this page inside the sub-chunk
         const int pgi = t / p.page_size;
         const int64_t pg = pages_in_smem ? st_pages[pgi - pg0] : pages[pgi];
         const int64_t base = pg * p.kv_block_stride + (int64_t)kvh * p.kv_head_stride + (int64_t)off * D;
-        const uint32_t bytes = (uint32_t)(n * D * (int)sizeof(T));
+        const uint32_t bytes = (uint32_t)(n * ROWB);
         bulk_g2s(st_k[b] + (size_t)(t - s0) * D, kc + base, bytes, &st_full[b]);
         bulk_g2s(st_v[b] + (size_t)(t - s0) * D, vc + base, bytes, &st_full[b]);
         t += n;
       }
     };
     if (tid == 0 && nsub > 0) issue(0);
-    MRS_LOAD_Q
+    load_q();
     for (int si = 0; si < nsub; si++) {
       const int b = si & 1;
       if (tid == 0 && si + 1 < nsub) issue(si + 1);   // buffer (si+1)&1 was released by the barrier below
       mbar_wait(&st_full[b], (uint32_t)((si >> 1) & 1));
       const int s0 = t_begin + si * SUB, s1 = min(t_end, s0 + SUB);
       // trip count is uniform across the CTA (the shuffles need every lane of the warp)
-      for (int tb0 = s0; tb0 < s1; tb0 += NGRP * PA_UNROLL) {
+      for (int tb0 = s0; tb0 < s1; tb0 += NGRP * UNROLL) {
         const int tb = tb0 + grp;
-        float kf[PA_UNROLL][8], vf[PA_UNROLL][8];
-        bool ok[PA_UNROLL];
+        float kf[UNROLL][EPL], vf[UNROLL][EPL];
+        bool ok[UNROLL];
 #pragma unroll
-        for (int u = 0; u < PA_UNROLL; u++) {
+        for (int u = 0; u < UNROLL; u++) {
           const int t = tb + u * NGRP;
           ok[u] = t < s1;
 #pragma unroll
-          for (int i = 0; i < 8; i++) { kf[u][i] = 0.f; vf[u][i] = 0.f; }
-          if (ok[u]) {
-            Vec8<T>::load(st_k[b] + (size_t)(t - s0) * D + d0, kf[u]);
-            Vec8<T>::load(st_v[b] + (size_t)(t - s0) * D + d0, vf[u]);
+          for (int i = 0; i < EPL; i++) { kf[u][i] = 0.f; vf[u][i] = 0.f; }
+          if (ok[u] && act) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+              Vec8<CT>::load(st_k[b] + (size_t)(t - s0) * D + d0 + 8 * v, kf[u] + 8 * v);
+              Vec8<CT>::load(st_v[b] + (size_t)(t - s0) * D + d0 + 8 * v, vf[u] + 8 * v);
+            }
           }
         }
 #pragma unroll
-        for (int u = 0; u < PA_UNROLL; u++) update(kf[u], vf[u], tb + u * NGRP, ok[u]);
+        for (int u = 0; u < UNROLL; u++) update(kf[u], vf[u], tb + u * NGRP, ok[u]);
       }
       __syncthreads();  // everyone is done with buffer b before it is refilled
     }
   } else {
-  MRS_LOAD_Q
+  load_q();
   // trip count is uniform across the CTA (the shuffles need every lane of the warp)
-  for (int tb0 = t_begin; tb0 < t_end; tb0 += NGRP * PA_UNROLL) {
+  for (int tb0 = t_begin; tb0 < t_end; tb0 += NGRP * UNROLL) {
     const int tb = tb0 + grp;
-    float kf[PA_UNROLL][8], vf[PA_UNROLL][8];
-    bool ok[PA_UNROLL];
+    float kf[UNROLL][EPL], vf[UNROLL][EPL];
+    bool ok[UNROLL];
 #pragma unroll
-    for (int u = 0; u < PA_UNROLL; u++) {
+    for (int u = 0; u < UNROLL; u++) {
       const int t = tb + u * NGRP;
       ok[u] = t < t_end;
 #pragma unroll
-      for (int i = 0; i < 8; i++) { kf[u][i] = 0.f; vf[u][i] = 0.f; }
-      if (ok[u]) {
+      for (int i = 0; i < EPL; i++) { kf[u][i] = 0.f; vf[u][i] = 0.f; }
+      if (ok[u] && act) {
         const int64_t page = pages[t / p.page_size];
         const int off = t % p.page_size;
         const int64_t base = page * p.kv_block_stride + (int64_t)kvh * p.kv_head_stride;
-        Vec8<T>::load(kc + base + ((int64_t)gl * p.page_size + off) * 8, kf[u]);
+        // K [D/XK][BS][XK]: this lane's EPL consecutive d's are EPL/XK whole groups, or part of one group
+        if constexpr (EPL >= XK) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) vf[u][i] = Vec8<T>::one(vc + base + (int64_t)(d0 + i) * p.page_size + off);
+          for (int c = 0; c < EPL / XK; c++) {
+            const CT *src = kc + base + ((int64_t)(d0 / XK + c) * p.page_size + off) * XK;
+            if constexpr (XK == 8) Vec8<CT>::load(src, kf[u] + 8 * c);
+            else {                                       // XK == 4 (f32 cache)
+#pragma unroll
+              for (int i = 0; i < XK; i++) kf[u][XK * c + i] = Vec8<CT>::one(src + i);
+            }
+          }
+        } else {                                          // XK == 16 (fp8 cache), EPL == 8
+          Vec8<CT>::load(kc + base + ((int64_t)(d0 / XK) * p.page_size + off) * XK + (d0 % XK), kf[u]);
+        }
+#pragma unroll
+        for (int i = 0; i < EPL; i++) vf[u][i] = Vec8<CT>::one(vc + base + (int64_t)(d0 + i) * p.page_size + off);
       }
     }
 #pragma unroll
-    for (int u = 0; u < PA_UNROLL; u++) update(kf[u], vf[u], tb + u * NGRP, ok[u]);
+    for (int u = 0; u < UNROLL; u++) update(kf[u], vf[u], tb + u * NGRP, ok[u]);
   }
   }
 
@@ -378,7 +446,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
         } else {
           Vec8<T>::store(kcw + base + ((int64_t)gl * p.page_size + off) * 8, kn);
 #pragma unroll
-          for (int i = 0; i < 8; i++) vcw[base + (int64_t)(d0 + i) * p.page_size + off] = (T)vn[i];
+          for (int i = 0; i < 8; i++) vcw[base + (int64_t)(d0 + i) * p.page_size + off] = from_float<T>(vn[i]);
         }
       }
     }
@@ -402,7 +470,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
         const float ca = (mn > -INFINITY) ? __expf(m[g] - mn) : 0.f;
         const float cb = (mn > -INFINITY) ? __expf(mo - mn) : 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < EPL; i++) {
           const float oo = __shfl_xor_sync(0xffffffffu, o[g][i], mask);
           o[g][i] = o[g][i] * ca + oo * cb;
         }
@@ -419,8 +487,10 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
 #pragma unroll
     for (int g = 0; g < G; g++) {
       if (gl == 0) { sm_m[sidx][g] = m[g]; sm_l[sidx][g] = l[g]; }
+      if (act) {
 #pragma unroll
-      for (int i = 0; i < 8; i++) sm_o[sidx][g][d0 + i] = o[g][i];
+        for (int i = 0; i < EPL; i++) sm_o[sidx][g][d0 + i] = o[g][i];
+      }
     }
   }
   __syncthreads();
@@ -443,12 +513,12 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
       }
     }
     if (use_sink) L += __expf(p.sinks[h0 + g] - M);
-    const float val = (L > 0.f) ? acc / L : 0.f;
+    const float val = (L > 0.f) ? acc / L * (p.v_scale_ptr ? *p.v_scale_ptr : p.v_scale) : 0.f;
     if (partial) {
-      ((T *)p.tmp_o)[((int64_t)tile * p.num_heads + h0 + g) * D + d] = (T)val;
+      ((T *)p.tmp_o)[((int64_t)tile * p.num_heads + h0 + g) * D + d] = from_float<T>(val);
       if (d == 0) p.tmp_lse[(int64_t)tile * p.num_heads + h0 + g] = (L > 0.f) ? M + __logf(L) : -INFINITY;
     } else {
-      ((T *)p.out)[((int64_t)seq * p.num_heads + h0 + g) * D + d] = (T)val;
+      ((T *)p.out)[((int64_t)seq * p.num_heads + h0 + g) * D + d] = from_float<T>(val);
     }
   }
 
@@ -487,7 +557,7 @@ __global__ void __launch_bounds__(PA_THREADS) paged_decode_kernel(const PagedPar
               acc += w * (float)tv;
             }
           }
-          ((T *)p.out)[((int64_t)seq * p.num_heads + h) * D + d] = (T)((W > 0.f) ? acc / W : 0.f);
+          ((T *)p.out)[((int64_t)seq * p.num_heads + h) * D + d] = from_float<T>((W > 0.f) ? acc / W : 0.f);
         }
       }
     }
@@ -544,11 +614,11 @@ static cudaError_t launch_pa(K kern, dim3 grid, const PagedParams &p, cudaStream
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-template <typename T, int D, int LAYOUT, bool FUSED>
+template <typename T, typename CT, int D, int LAYOUT, bool FUSED>
 static cudaError_t launch_decode_g(PagedParams p, int tiles, cudaStream_t st) {
   const int group = p.num_heads / p.num_kv_heads;
-  if constexpr (LAYOUT == 1 && D <= 128) {
-    // HND cache: the GQA group is an MMA tile (paged_attn_mma.cuh); ALiBi / sinks are vLLM-layout features
+  if constexpr (LAYOUT == 1 && (D == 64 || D == 128) && sizeof(T) == 2 && sizeof(CT) == 2) {
+    // HND 16-bit cache: the GQA group is an MMA tile (paged_attn_mma.cuh); ALiBi / sinks are vLLM-layout features
     if (!(g_pa_flags & 1) && p.alibi_slopes == nullptr && p.sinks == nullptr && p.kv_indptr != nullptr && !p.tiles_are_partitions) {
       const int nsub = (group + 15) / 16;
       p.heads_per_cta = (group + nsub - 1) / nsub;
@@ -586,30 +656,62 @@ static cudaError_t launch_decode_g(PagedParams p, int tiles, cudaStream_t st) {
       return launch_pa(paged_decode_mma_kernel<T, D, FUSED, false>, grid, p, st, pm_smem_bytes<D>(FUSED, false), PM_THREADS);
     }
   }
-  constexpr int GMAX = (D <= 128) ? 8 : 4;  // static smem budget: 8 states x G x D floats
+  constexpr int GMAX = (D <= 128) ? 8 : (D <= 256 ? 4 : 2);  // static smem budget: 8 states x G x D floats
   const int nsub = (group + GMAX - 1) / GMAX;
   const int per = (group + nsub - 1) / nsub;
   p.heads_per_cta = per;
   dim3 grid(tiles, p.num_kv_heads, nsub);
-  // HND: two double-buffered (K, V) sub-chunk stages of 128 (D<=128) / 64 tokens
-  const size_t dyn = (LAYOUT == 1) ? (size_t)4 * ((D <= 128) ? 128 : 64) * D * sizeof(T) : 0;
-  if (per <= 1) return launch_pa(paged_decode_kernel<T, D, 1, LAYOUT, FUSED>, grid, p, st, dyn);
-  if (per <= 2) return launch_pa(paged_decode_kernel<T, D, 2, LAYOUT, FUSED>, grid, p, st, dyn);
-  if (per <= 4) return launch_pa(paged_decode_kernel<T, D, 4, LAYOUT, FUSED>, grid, p, st, dyn);
-  if constexpr (D <= 128) return launch_pa(paged_decode_kernel<T, D, 8, LAYOUT, FUSED>, grid, p, st, dyn);
+  // HND: two double-buffered (K, V) sub-chunk stages sized by the cached row (see the kernel)
+  constexpr int ROWB = D * (int)sizeof(CT);
+  constexpr int SUB = (ROWB <= 256) ? 128 : (ROWB <= 512 ? 64 : 32);
+  const size_t dyn = (LAYOUT == 1) ? (size_t)4 * SUB * ROWB : 0;
+  if (per <= 1) return launch_pa(paged_decode_kernel<T, CT, D, 1, LAYOUT, FUSED>, grid, p, st, dyn);
+  if (per <= 2) return launch_pa(paged_decode_kernel<T, CT, D, 2, LAYOUT, FUSED>, grid, p, st, dyn);
+  if constexpr (D <= 256) {
+    if (per <= 4) return launch_pa(paged_decode_kernel<T, CT, D, 4, LAYOUT, FUSED>, grid, p, st, dyn);
+  }
+  if constexpr (D <= 128) return launch_pa(paged_decode_kernel<T, CT, D, 8, LAYOUT, FUSED>, grid, p, st, dyn);
   return cudaErrorInvalidValue;
 }
 
-template <typename T, int LAYOUT, bool FUSED = false>
+// head sizes: REF pagedattention.cuh:718-739 (64, 80, 96, 112, 128, 192, 256) + 512 (flashinfer/mod.rs:262)
+template <typename T, typename CT, int LAYOUT, bool FUSED = false>
 static cudaError_t launch_decode(const PagedParams &p, int head_size, int tiles, cudaStream_t st) {
   if (tiles <= 0) return cudaSuccess;
   if (p.num_heads % p.num_kv_heads) return cudaErrorInvalidValue;
   switch (head_size) {
-  case 64: return launch_decode_g<T, 64, LAYOUT, FUSED>(p, tiles, st);
-  case 128: return launch_decode_g<T, 128, LAYOUT, FUSED>(p, tiles, st);
-  case 256: return launch_decode_g<T, 256, LAYOUT, FUSED>(p, tiles, st);
-  default: return cudaErrorInvalidValue;
+  case 64: return launch_decode_g<T, CT, 64, LAYOUT, FUSED>(p, tiles, st);
+  case 128: return launch_decode_g<T, CT, 128, LAYOUT, FUSED>(p, tiles, st);
+  case 256: return launch_decode_g<T, CT, 256, LAYOUT, FUSED>(p, tiles, st);
+  default: break;
   }
+  if constexpr (!FUSED) {
+    switch (head_size) {
+    case 80: return launch_decode_g<T, CT, 80, LAYOUT, false>(p, tiles, st);
+    case 96: return launch_decode_g<T, CT, 96, LAYOUT, false>(p, tiles, st);
+    case 112: return launch_decode_g<T, CT, 112, LAYOUT, false>(p, tiles, st);
+    case 192: return launch_decode_g<T, CT, 192, LAYOUT, false>(p, tiles, st);
+    case 512: return launch_decode_g<T, CT, 512, LAYOUT, false>(p, tiles, st);
+    default: break;
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+// dtype: 0 f16, 1 bf16, 2 f32; cache_dtype: same codes, or 3 = FP8-E4M3 bytes (REF ffi.rs dtype codes)
+template <int LAYOUT>
+static cudaError_t launch_decode_any(const PagedParams &p, uint32_t dtype, uint32_t cache_dtype, int head_size, int tiles, cudaStream_t st) {
+  if (cache_dtype == 3) {
+    if (dtype == 0) return launch_decode<__half, fp8_t, LAYOUT>(p, head_size, tiles, st);
+    if (dtype == 1) return launch_decode<__nv_bfloat16, fp8_t, LAYOUT>(p, head_size, tiles, st);
+    if (dtype == 2) return launch_decode<float, fp8_t, LAYOUT>(p, head_size, tiles, st);
+    return cudaErrorInvalidValue;
+  }
+  if (cache_dtype != dtype) return cudaErrorInvalidValue;
+  if (dtype == 0) return launch_decode<__half, __half, LAYOUT>(p, head_size, tiles, st);
+  if (dtype == 1) return launch_decode<__nv_bfloat16, __nv_bfloat16, LAYOUT>(p, head_size, tiles, st);
+  if (dtype == 2) return launch_decode<float, float, LAYOUT>(p, head_size, tiles, st);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace mrs
@@ -627,12 +729,14 @@ extern "C" int32_t flashinfer_decode(void *q, void *key_cache, void *value_cache
                                      int32_t q_stride_h, float sm_scale, int32_t window_left, float logits_soft_cap,
                                      float k_scale, float v_scale, uint32_t dtype, uint32_t cache_dtype,
                                      cudaStream_t stream) {
-  if (dtype != cache_dtype || (dtype != 0 && dtype != 1)) {
-    fprintf(stderr, "mrs_b200: flashinfer_decode supports f16/bf16 caches matching the query dtype (got %u/%u)\n", dtype, cache_dtype);
+  if (dtype > 2 || (cache_dtype != dtype && cache_dtype != 3)) {
+    fprintf(stderr, "mrs_b200: flashinfer_decode: unsupported query / cache dtype codes %u / %u\n", dtype, cache_dtype);
     return (int32_t)cudaErrorInvalidValue;
   }
-  (void)k_scale; (void)v_scale;
   PagedParams p = {};
+  // FP8-E4M3 cache: k_scale folds into the logits, v_scale into the output (REF flashinfer_decode.cu: sm_scale * k_scale, v_scale)
+  p.k_scale = (cache_dtype == 3) ? k_scale : 1.f; p.v_scale = (cache_dtype == 3) ? v_scale : 1.f;
+  p.batch_size = batch_size;
   p.q = q; p.kc = key_cache; p.vc = value_cache; p.out = o;
   const bool split = tmp_v != nullptr && padded_batch_size > batch_size;
   p.tmp_o = split ? tmp_v : nullptr; p.tmp_lse = split ? (float *)tmp_s : nullptr;
@@ -650,13 +754,13 @@ extern "C" int32_t flashinfer_decode(void *q, void *key_cache, void *value_cache
     p.request_indices = nullptr; p.kv_tile_indices = nullptr; p.block_valid_mask = nullptr;
   }
   const int tiles = split ? padded_batch_size : batch_size;
-  cudaError_t e = (dtype == 0) ? launch_decode<__half, 1>(p, head_size, tiles, stream)
-                               : launch_decode<__nv_bfloat16, 1>(p, head_size, tiles, stream);
+  cudaError_t e = launch_decode_any<1>(p, dtype, cache_dtype, head_size, tiles, stream);
   if (e != cudaSuccess) { fprintf(stderr, "mrs_b200: flashinfer_decode failed: %s\n", cudaGetErrorString(e)); return (int32_t)e; }
   if (split) {
     dim3 grid(batch_size, num_qo_heads);
     if (dtype == 0) merge_partials_kernel<__half><<<grid, 128, 0, stream>>>((const __half *)tmp_v, (const float *)tmp_s, (__half *)o, o_indptr, 0, num_qo_heads, head_size, nullptr, nullptr, 0);
-    else merge_partials_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16 *)tmp_v, (const float *)tmp_s, (__nv_bfloat16 *)o, o_indptr, 0, num_qo_heads, head_size, nullptr, nullptr, 0);
+    else if (dtype == 1) merge_partials_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16 *)tmp_v, (const float *)tmp_s, (__nv_bfloat16 *)o, o_indptr, 0, num_qo_heads, head_size, nullptr, nullptr, 0);
+    else merge_partials_kernel<float><<<grid, 128, 0, stream>>>((const float *)tmp_v, (const float *)tmp_s, (float *)o, o_indptr, 0, num_qo_heads, head_size, nullptr, nullptr, 0);
     e = cudaGetLastError();
   }
   return (int32_t)e;
@@ -675,6 +779,13 @@ static void vllm_common(PagedParams &p, void *out, void *query, void *key_cache,
   p.q_stride_n = q_stride; p.q_stride_h = head_size; p.sm_scale = scale;
   p.softcap = (softcapping != 1.0f) ? softcapping : 0.f;  // REF pagedattention.cuh:276-279
   p.window_left = -1; p.alibi_slopes = (const float *)alibi; p.sinks = sinks;
+  p.k_scale = 1.f; p.v_scale = 1.f;
+}
+// FP8 cache: the vLLM-style API hands the per-tensor scales as DEVICE pointers (REF pagedattention.cuh
+// `*k_scale`); a one-thread kernel would cost a launch, so the attention kernel reads them itself
+static void vllm_scales(PagedParams &p, uint32_t cache_dtype, const float *k_scale, const float *v_scale) {
+  p.k_scale_ptr = (cache_dtype == 3) ? k_scale : nullptr;
+  p.v_scale_ptr = (cache_dtype == 3) ? v_scale : nullptr;
 }
 
 static void die_if(cudaError_t e, const char *what) {
@@ -684,28 +795,25 @@ static void die_if(cudaError_t e, const char *what) {
   }
 }
 
-template <typename T>
-static void paged_v1(void *out, void *query, void *key_cache, void *value_cache, void *alibi, int num_kv_heads,
+static void paged_v1(uint32_t dtype, void *out, void *query, void *key_cache, void *value_cache, void *alibi, int num_kv_heads,
                      float scale, float softcapping, const int32_t *block_tables, const int32_t *context_lens,
                      int block_size, int num_seqs, int num_heads, int head_size, int max_num_blocks_per_seq,
                      int q_stride, int kv_block_stride, int kv_head_stride, cudaStream_t stream, uint32_t cache_dtype,
-                     const float *sinks) {
-  if (cache_dtype == 3) die_if(cudaErrorInvalidValue, "paged_attention_v1 (FP8 cache not implemented)");
+                     const float *k_scale, const float *v_scale, const float *sinks) {
   PagedParams p = {};
   vllm_common(p, out, query, key_cache, value_cache, alibi, num_kv_heads, scale, softcapping, block_tables,
               context_lens, block_size, num_heads, head_size, max_num_blocks_per_seq, q_stride, kv_block_stride,
               kv_head_stride, sinks);
-  die_if(launch_decode<T, 0>(p, head_size, num_seqs, stream), "paged_attention_v1");
+  vllm_scales(p, cache_dtype, k_scale, v_scale);
+  die_if(launch_decode_any<0>(p, dtype, cache_dtype, head_size, num_seqs, stream), "paged_attention_v1");
 }
 
-template <typename T>
-static void paged_v2(void *out, float *exp_sums, float *max_logits, void *tmp_out, void *query, void *key_cache,
+static void paged_v2(uint32_t dtype, void *out, float *exp_sums, float *max_logits, void *tmp_out, void *query, void *key_cache,
                      void *value_cache, void *alibi, int num_kv_heads, float scale, float softcapping,
                      const int32_t *block_tables, const int32_t *context_lens, int block_size, int max_context_len,
                      int num_seqs, int num_heads, int head_size, int max_num_blocks_per_seq, int q_stride,
                      int kv_block_stride, int kv_head_stride, cudaStream_t stream, uint32_t cache_dtype,
-                     const float *sinks) {
-  if (cache_dtype == 3) die_if(cudaErrorInvalidValue, "paged_attention_v2 (FP8 cache not implemented)");
+                     const float *k_scale, const float *v_scale, const float *sinks) {
   (void)exp_sums;
   constexpr int PARTITION = 512;  // REF backend/paged_attention.rs:302
   const int num_partitions = (max_context_len + PARTITION - 1) / PARTITION;
@@ -713,28 +821,29 @@ static void paged_v2(void *out, float *exp_sums, float *max_logits, void *tmp_ou
   vllm_common(p, out, query, key_cache, value_cache, alibi, num_kv_heads, scale, softcapping, block_tables,
               context_lens, block_size, num_heads, head_size, max_num_blocks_per_seq, q_stride, kv_block_stride,
               kv_head_stride, nullptr);
+  vllm_scales(p, cache_dtype, k_scale, v_scale);
   p.tmp_o = tmp_out; p.tmp_lse = max_logits;  // scratch is opaque to the caller: lse lives in max_logits
   p.kv_chunk_size = PARTITION; p.tiles_are_partitions = 1; p.num_partitions = num_partitions;
-  die_if(launch_decode<T, 0>(p, head_size, num_seqs * num_partitions, stream), "paged_attention_v2");
+  die_if(launch_decode_any<0>(p, dtype, cache_dtype, head_size, num_seqs * num_partitions, stream), "paged_attention_v2");
   dim3 grid(num_seqs, num_heads);
-  merge_partials_kernel<T><<<grid, 128, 0, stream>>>((const T *)tmp_out, max_logits, (T *)out, nullptr,
-                                                     num_partitions, num_heads, head_size, sinks, context_lens,
-                                                     PARTITION);
+  if (dtype == 0) merge_partials_kernel<__half><<<grid, 128, 0, stream>>>((const __half *)tmp_out, max_logits, (__half *)out, nullptr, num_partitions, num_heads, head_size, sinks, context_lens, PARTITION);
+  else if (dtype == 1) merge_partials_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16 *)tmp_out, max_logits, (__nv_bfloat16 *)out, nullptr, num_partitions, num_heads, head_size, sinks, context_lens, PARTITION);
+  else merge_partials_kernel<float><<<grid, 128, 0, stream>>>((const float *)tmp_out, max_logits, (float *)out, nullptr, num_partitions, num_heads, head_size, sinks, context_lens, PARTITION);
   die_if(cudaGetLastError(), "paged_attention_v2 reduce");
 }
 
-#define MRS_PAGED(tag, T)                                                                                       \
+#define MRS_PAGED(tag, DT)                                                                                      \
   extern "C" void paged_attention_v1_##tag(void *out, void *query, void *key_cache, void *value_cache,          \
       void *alibi_slopes, int32_t num_kv_heads, float scale, float softcapping, uint32_t *block_tables,         \
       uint32_t *context_lens, int32_t block_size, int32_t max_context_len, int32_t num_seqs, int32_t num_heads, \
       int32_t head_size, int32_t max_num_blocks_per_seq, int32_t q_stride, int32_t kv_block_stride,             \
       int32_t kv_head_stride, cudaStream_t stream, uint32_t cache_dtype, float *k_scale, float *v_scale,        \
       const float *sinks) {                                                                                     \
-    (void)max_context_len; (void)k_scale; (void)v_scale;                                                        \
-    paged_v1<T>(out, query, key_cache, value_cache, alibi_slopes, num_kv_heads, scale, softcapping,             \
-                (const int32_t *)block_tables, (const int32_t *)context_lens, block_size, num_seqs, num_heads,  \
-                head_size, max_num_blocks_per_seq, q_stride, kv_block_stride, kv_head_stride, stream,           \
-                cache_dtype, sinks);                                                                            \
+    (void)max_context_len;                                                                                      \
+    paged_v1(DT, out, query, key_cache, value_cache, alibi_slopes, num_kv_heads, scale, softcapping,            \
+             (const int32_t *)block_tables, (const int32_t *)context_lens, block_size, num_seqs, num_heads,     \
+             head_size, max_num_blocks_per_seq, q_stride, kv_block_stride, kv_head_stride, stream,              \
+             cache_dtype, k_scale, v_scale, sinks);                                                             \
   }                                                                                                             \
   extern "C" void paged_attention_v2_##tag(void *out, float *exp_sums, float *max_logits, void *tmp_out,        \
       void *query, void *key_cache, void *value_cache, void *alibi_slopes, int32_t num_kv_heads, float scale,   \
@@ -742,14 +851,14 @@ static void paged_v2(void *out, float *exp_sums, float *max_logits, void *tmp_ou
       int32_t max_context_len, int32_t num_seqs, int32_t num_heads, int32_t head_size,                          \
       int32_t max_num_blocks_per_seq, int32_t q_stride, int32_t kv_block_stride, int32_t kv_head_stride,        \
       cudaStream_t stream, uint32_t cache_dtype, float *k_scale, float *v_scale, const float *sinks) {          \
-    (void)k_scale; (void)v_scale;                                                                               \
-    paged_v2<T>(out, exp_sums, max_logits, tmp_out, query, key_cache, value_cache, alibi_slopes, num_kv_heads,  \
-                scale, softcapping, (const int32_t *)block_tables, (const int32_t *)context_lens, block_size,   \
-                max_context_len, num_seqs, num_heads, head_size, max_num_blocks_per_seq, q_stride,              \
-                kv_block_stride, kv_head_stride, stream, cache_dtype, sinks);                                   \
+    paged_v2(DT, out, exp_sums, max_logits, tmp_out, query, key_cache, value_cache, alibi_slopes, num_kv_heads, \
+             scale, softcapping, (const int32_t *)block_tables, (const int32_t *)context_lens, block_size,      \
+             max_context_len, num_seqs, num_heads, head_size, max_num_blocks_per_seq, q_stride,                 \
+             kv_block_stride, kv_head_stride, stream, cache_dtype, k_scale, v_scale, sinks);                    \
   }
-MRS_PAGED(f16, __half)
-MRS_PAGED(bf16, __nv_bfloat16)
+MRS_PAGED(f16, 0u)
+MRS_PAGED(bf16, 1u)
+MRS_PAGED(f32, 2u)
 
 // ---------------------------------------------------------------- B200-native fused decode attention
 // RoPE(q, k_new) + KV-cache write + paged decode attention + split-KV merge in ONE launch over
@@ -788,9 +897,10 @@ extern "C" int32_t mrs_paged_decode_fused_strided(void *q, void *k_new, void *v_
   p.k_new = k_new; p.v_new = v_new; p.kv_new_stride = kv_new_stride;
   p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.positions = positions; p.slot_mapping = slot_mapping;
   p.o_indptr = o_indptr; p.counters = counters; p.batch_size = batch_size;
+  p.k_scale = 1.f; p.v_scale = 1.f;
   const int tiles = split ? padded_batch_size : batch_size;
-  const cudaError_t e = (dtype == 0) ? launch_decode<__half, 1, true>(p, head_size, tiles, (cudaStream_t)stream)
-                                     : launch_decode<__nv_bfloat16, 1, true>(p, head_size, tiles, (cudaStream_t)stream);
+  const cudaError_t e = (dtype == 0) ? launch_decode<__half, __half, 1, true>(p, head_size, tiles, (cudaStream_t)stream)
+                                     : launch_decode<__nv_bfloat16, __nv_bfloat16, 1, true>(p, head_size, tiles, (cudaStream_t)stream);
   if (e != cudaSuccess) fprintf(stderr, "mrs_b200: mrs_paged_decode_fused failed: %s\n", cudaGetErrorString(e));
   return (int32_t)e;
 }

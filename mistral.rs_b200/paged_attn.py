@@ -14,8 +14,8 @@ import torch
 from . import lib
 
 _DT_CODE = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}
-_TAG = {torch.float16: "f16", torch.bfloat16: "bf16"}
-_SUPPORTED_HEAD_SIZES = (64, 128, 256)
+_TAG = {torch.float16: "f16", torch.bfloat16: "bf16", torch.float32: "f32"}
+_SUPPORTED_HEAD_SIZES = (64, 80, 96, 112, 128, 192, 256)      # backend/paged_attention.rs:251-261
 PARTITION_SIZE = 512  # backend/paged_attention.rs:302
 
 
