@@ -156,6 +156,26 @@ __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// explicit shared-space accesses through 32-bit shared addresses: a pointer derived from a kernel's dynamic
+// shared memory by byte arithmetic is "generic" to the compiler (SASS LD.E / ST.E with an address-space
+// check, accounted as long-scoreboard traffic); these force LDS / STS
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 // unaligned 32-bit read from shared memory (addr has any byte alignment)
 __device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *p) {
   const uintptr_t a = (uintptr_t)p;

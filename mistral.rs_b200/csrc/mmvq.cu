@@ -256,52 +256,32 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
   if (p.pdl) pdl_wait();  // activations come from the upstream kernel
   if (tid == 0) MRS_STAMP(3);
   if (p.xkind == X_Q8_1) {
-    // pre-quantised Q8_1 blocks (the reference's two-call form): every thread moves 8-byte chunks of
-    // qs plus its block's (d, s) straight to their consumption-order position — the same scatter as
-    // the fused prologue below, with loads in place of the quantiser (all loads independent: one
-    // global latency instead of a chain of 4-byte gathers)
+    // gather pre-quantised Q8_1 blocks straight into consumption order
     const block_q8_1 *y = (const block_q8_1 *)p.x;
-    const int nchunks = p.K >> 3;
-    const int nchunks_w = (nchunks + 31) & ~31;
-    for (int col = 0; col < NCOLS; col++) {
-      const bool livec = col < p.ncols;
-      int4 *c0 = xq0 + (size_t)col * npos, *c1 = xq1 + (size_t)col * npos;
-      float *ca = xa + (size_t)col * npos * Q::AUX;
-      constexpr int CB = 4;
-#pragma unroll 1
-      for (int ch0 = ctid; ch0 < nchunks_w; ch0 += CB * NCT) {
-        int2 qv[CB];
-        __half2 dsv[CB];
+    for (int idx = ctid; idx < NCOLS * npos; idx += NCT) {
+      const int col = idx / npos, pos = idx - col * npos;
+      int blk, c;
+      pos_to_unit<T, UPL>(pos, blk, c);
+      int q[8];
+      float a[Q::AUX];
+      if (col < p.ncols && blk < nblocks) {
+        const block_q8_1 *yb = y + (size_t)col * p.stride_col_y + (size_t)blk * (Q::QK / 32);
 #pragma unroll
-        for (int u = 0; u < CB; u++) {     // all loads of four chunks in flight together
-          const int ch = ch0 + u * NCT;
-          qv[u] = make_int2(0, 0);
-          dsv[u] = __floats2half2_rn(0.f, 0.f);
-          if (ch < nchunks && livec) {
-            const block_q8_1 *yb = y + (size_t)col * p.stride_col_y + (ch >> 2);
-            const int *qp = (const int *)(yb->qs + 8 * (ch & 3));
-            qv[u] = make_int2(qp[0], qp[1]);
-            dsv[u] = yb->ds;
-          }
+        for (int w = 0; w < 8; w++) {
+          const int e = Q::x_elem(c, w);
+          q[w] = *(const int *)(yb[e >> 5].qs + (e & 31));
         }
+        Q::aux(q, c, YGlobal{yb}, a);
+      } else {
 #pragma unroll
-        for (int u = 0; u < CB; u++) {
-          const int ch = ch0 + u * NCT;
-          if (ch >= nchunks_w) break;          // warp-uniform
-          const float2 ds = __half22float2(dsv[u]);
-          const int isum8 = __dp4a(qv[u].x, 0x01010101, __dp4a(qv[u].y, 0x01010101, 0));
-          const int isum16 = isum8 + __shfl_xor_sync(0xffffffffu, isum8, 1);
-          if (ch < nchunks) {
-            const int e0 = ch * 8;
-            const int blk = e0 / Q::QK, e = e0 - blk * Q::QK;
-            int c, hi, w8;
-            Q::chunk_dest(e, c, hi, w8);
-            const int pos = unit_to_pos<T, UPL>(blk, c);
-            *((int2 *)((hi ? c1 : c0) + pos) + w8) = qv[u];
-            Q::chunk_aux(e, ds.x, ds.y, isum8, isum16, ca + (size_t)pos * Q::AUX);
-          }
-        }
+        for (int w = 0; w < 8; w++) q[w] = 0;
+#pragma unroll
+        for (int i = 0; i < Q::AUX; i++) a[i] = 0.f;
       }
+      xq0[idx] = make_int4(q[0], q[1], q[2], q[3]);
+      xq1[idx] = make_int4(q[4], q[5], q[6], q[7]);
+#pragma unroll
+      for (int i = 0; i < Q::AUX; i++) xa[(size_t)idx * Q::AUX + i] = a[i];
     }
   } else {
     // fused prologue: (optional RMSNorm) -> round to activation dtype -> Q8_1 -> consumption
@@ -357,82 +337,63 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
       if (tid == 0) MRS_STAMP(4);
       int4 *c0 = xq0 + (size_t)col * npos, *c1 = xq1 + (size_t)col * npos;
       float *ca = xa + (size_t)col * npos * Q::AUX;
-      // chunks are taken four at a time: the four activation (and norm-weight) loads are issued
-      // together, so a long K (down_proj: 7 chunks per thread) pays two cache latencies, not seven
-      // (the shuffles inside the per-chunk work keep the compiler from hoisting loads itself)
-      constexpr int CB = 4;
+      int it = 0;
 #pragma unroll 1
-      for (int ch0 = ctid, it0 = 0; ch0 < nchunks_w; ch0 += CB * NCT, it0 += CB) {
-        uint4 xr[CB], wr[CB];   // (f32 activations are not batched: loaded chunk by chunk below)
+      for (int ch = ctid; ch < nchunks_w; ch += NCT, it++) {
+        const bool ok = ch < nchunks;
+        const bool inreg = reg16 && (it == 0 || (it == 1 && NCW == SSW));
+        float v[8];
+        if (ok && live) {
+          if (inreg) unpack_act8(sel_u4(it == 0, xr0, xr1), p.xdtype, v);
+          else load_act8(p.x, (int64_t)col * p.K + ch * 8, p.xdtype, v);
+          if (p.norm_w != nullptr) {
+            float wv[8];
+            if (inreg) unpack_act8(sel_u4(it == 0, nwr0, nwr1), p.xdtype, wv);
+            else load_act8(p.norm_w, ch * 8, p.xdtype, wv);
 #pragma unroll
-        for (int u = 0; u < CB; u++) {
-          const int ch = ch0 + u * NCT;
-          const bool ok = ch < nchunks && live;
-          if (reg16) {
-            const bool in0 = (it0 + u) == 0, in1 = (it0 + u) == 1 && NCW == SSW;
-            xr[u] = in0 ? xr0 : (in1 ? xr1 : (ok ? *((const uint4 *)((const uint16_t *)p.x + (int64_t)col * p.K) + ch) : make_uint4(0u, 0u, 0u, 0u)));
-            if (p.norm_w != nullptr)
-              wr[u] = in0 ? nwr0 : (in1 ? nwr1 : (ok ? __ldg((const uint4 *)p.norm_w + ch) : make_uint4(0u, 0u, 0u, 0u)));
+            for (int i = 0; i < 8; i++) v[i] = round_act(v[i] * inv_rms * wv[i], p.xdtype);
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = 0.f;
         }
+        float am = 0.f;
 #pragma unroll
-        for (int u = 0; u < CB; u++) {
-          const int ch = ch0 + u * NCT;
-          if (ch >= nchunks_w) break;          // warp-uniform: whole warps iterate together
-          const bool ok = ch < nchunks;
-          float v[8];
-          if (ok && live) {
-            if (reg16) unpack_act8(xr[u], p.xdtype, v);
-            else load_act8(p.x, (int64_t)col * p.K + ch * 8, p.xdtype, v);
-            if (p.norm_w != nullptr) {
-              float wv[8];
-              if (reg16) unpack_act8(wr[u], p.xdtype, wv);
-              else load_act8(p.norm_w, ch * 8, p.xdtype, wv);
+        for (int i = 0; i < 8; i++) am = fmaxf(am, fabsf(v[i]));
+        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+        float bsum = 0.f;
+        if constexpr (Q::NEEDS_SUM) {
+          // the reference's butterfly sum of the 32 block elements (i+16, i+8, then 4/2/1)
+          float t[8];
 #pragma unroll
-              for (int i = 0; i < 8; i++) v[i] = round_act(v[i] * inv_rms * wv[i], p.xdtype);
-            }
-          } else {
+          for (int i = 0; i < 8; i++) t[i] = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 2);
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = 0.f;
+          for (int i = 0; i < 8; i++) t[i] = t[i] + __shfl_xor_sync(0xffffffffu, t[i], 1);
+#pragma unroll
+          for (int m = 4; m > 0; m >>= 1) {
+#pragma unroll
+            for (int i = 0; i < m; i++) t[i] = t[i] + t[i + m];
           }
-          float am = 0.f;
+          bsum = __half2float(__float2half_rn(t[0]));
+        }
+        const float d = __fdividef(am, 127.0f);
+        uint32_t wq[2] = {0u, 0u};
 #pragma unroll
-          for (int i = 0; i < 8; i++) am = fmaxf(am, fabsf(v[i]));
-          am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
-          am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
-          float bsum = 0.f;
-          if constexpr (Q::NEEDS_SUM) {
-            // the reference's butterfly sum of the 32 block elements (i+16, i+8, then 4/2/1)
-            float t[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 2);
-#pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = t[i] + __shfl_xor_sync(0xffffffffu, t[i], 1);
-#pragma unroll
-            for (int m = 4; m > 0; m >>= 1) {
-#pragma unroll
-              for (int i = 0; i < m; i++) t[i] = t[i] + t[i + m];
-            }
-            bsum = __half2float(__float2half_rn(t[0]));
-          }
-          const float d = __fdividef(am, 127.0f);
-          uint32_t wq[2] = {0u, 0u};
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const int qi = (am == 0.0f) ? 0 : (int)(int8_t)roundf(__fdividef(v[i], d));
-            wq[i >> 2] |= (uint32_t)(qi & 0xff) << (8 * (i & 3));
-          }
-          const int isum8 = __dp4a((int)wq[0], 0x01010101, __dp4a((int)wq[1], 0x01010101, 0));
-          const int isum16 = isum8 + __shfl_xor_sync(0xffffffffu, isum8, 1);
-          if (ok) {
-            const int e0 = ch * 8;
-            const int blk = e0 / Q::QK, e = e0 - blk * Q::QK;
-            int c, hi, w8;
-            Q::chunk_dest(e, c, hi, w8);
-            const int pos = unit_to_pos<T, UPL>(blk, c);
-            *((int2 *)((hi ? c1 : c0) + pos) + w8) = make_int2((int)wq[0], (int)wq[1]);
-            Q::chunk_aux(e, __half2float(__float2half_rn(d)), bsum, isum8, isum16, ca + (size_t)pos * Q::AUX);
-          }
+        for (int i = 0; i < 8; i++) {
+          const int qi = (am == 0.0f) ? 0 : (int)(int8_t)roundf(__fdividef(v[i], d));
+          wq[i >> 2] |= (uint32_t)(qi & 0xff) << (8 * (i & 3));
+        }
+        const int isum8 = __dp4a((int)wq[0], 0x01010101, __dp4a((int)wq[1], 0x01010101, 0));
+        const int isum16 = isum8 + __shfl_xor_sync(0xffffffffu, isum8, 1);
+        if (ok) {
+          const int e0 = ch * 8;
+          const int blk = e0 / Q::QK, e = e0 - blk * Q::QK;
+          int c, hi, w8;
+          Q::chunk_dest(e, c, hi, w8);
+          const int pos = unit_to_pos<T, UPL>(blk, c);
+          *((int2 *)((hi ? c1 : c0) + pos) + w8) = make_int2((int)wq[0], (int)wq[1]);
+          Q::chunk_aux(e, __half2float(__float2half_rn(d)), bsum, isum8, isum16, ca + (size_t)pos * Q::AUX);
         }
       }
     }
@@ -463,19 +424,6 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
     for (int r = 0; r < 2; r++)
 #pragma unroll
       for (int j = 0; j < NCOLS; j++) acc[r][j] = 0.f;
-    // the residual (lane 0 adds it in the epilogue) is fetched now, not after the reduction: one
-    // global latency less on the tail of every o_proj / down_proj launch
-    float resv[2][NCOLS];
-    const bool res_early = !(p.flags & 16);
-    if (p.residual != nullptr && lane == 0 && p.mode != MODE_GLU && res_early) {
-#pragma unroll
-      for (int r = 0; r < 2; r++) {
-        const int64_t cs = (p.mode == MODE_QKV) ? p.nrows[mm[r]] : p.stride_col_dst;
-#pragma unroll
-        for (int j = 0; j < NCOLS; j++)
-          resv[r][j] = (valid[r] && j < p.ncols) ? load_act(p.residual, (int64_t)j * cs + rr[r], p.dst_dtype) : 0.f;
-      }
-    }
 
     for (int s = 0; s < nseg; s++) {
       mbar_wait(&full[stage], phase);
@@ -559,7 +507,7 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
               float v = acc[r][j];
               if (p.residual != nullptr) {
                 // y materialised in dtype, then residual add rounded again (candle `+`)
-                v = round_act(v, p.dst_dtype) + (res_early ? resv[r][j] : load_act(p.residual, (int64_t)j * cs + rr[r], p.dst_dtype));
+                v = round_act(v, p.dst_dtype) + load_act(p.residual, (int64_t)j * cs + rr[r], p.dst_dtype);
               }
               store_act(p.dst[mm[r]], (int64_t)j * cs + rr[r], v, p.dst_dtype);
             }
@@ -577,7 +525,7 @@ __device__ __forceinline__ void mmvq_body(const MmvqParams &p, const int cta, co
 }
 
 template <int T, int NCOLS, bool FAST, int NCW, int UPL>
-__global__ void __launch_bounds__((NCW + 1) * 32, 2) mmvq_stream_kernel(const MmvqParams p) {
+__global__ void __launch_bounds__((NCW + 1) * 32, NCOLS == 1 ? 3 : 2) mmvq_stream_kernel(const MmvqParams p) {
   mmvq_body<T, NCOLS, FAST, NCW, UPL>(p, (int)blockIdx.x, (int)gridDim.x);
 }
 
@@ -826,9 +774,7 @@ extern "C" void mrs_set_pdl(int enabled) { g_mrs_pdl = enabled; }
 // flags: bit 3 = never use the long-segment variant; bits 8.. = long-segment threshold in MiB
 extern "C" void mrs_set_mmvq_flags(int f) { g_flags = f & 0xff; if (f >> 8) g_long_min_bytes = (long long)(f >> 8) << 20; }
 extern "C" int mrs_mmvq_has_wide(void) { return 0; }
-// (three CTAs per SM — 72-register kernels, 24 consumer warps — measured 9 % slower end to end than two:
-// profiles/r02_experiments.md; the kernels are compiled for two)
-extern "C" void mrs_set_mmvq_ctas_per_sm(int n) { g_ctas_per_sm = n < 1 ? 1 : (n > 2 ? 2 : n); }
+extern "C" void mrs_set_mmvq_ctas_per_sm(int n) { g_ctas_per_sm = n < 1 ? 1 : (n > 3 ? 3 : n); }
 
 static inline void report(cudaError_t e, const char *what) {
   if (e != cudaSuccess) fprintf(stderr, "mrs_b200: %s failed: %s\n", what, cudaGetErrorString(e));

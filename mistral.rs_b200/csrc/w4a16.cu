@@ -74,40 +74,26 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
 }
 
-// 8 packed nibbles (layout above) -> four 16-bit pairs of (q - zp) * s in the activation format
-template <bool BF16>
-__device__ __forceinline__ void dequant_word(uint32_t q, int zp, float s_f, uint32_t s2, uint32_t *out) {
-  if constexpr (!BF16) {
-    // f16: (q & 0xf) | 0x6400 = 1024 + q exactly; the nibble at bits 4..7 gives 1024 + 16 q, and
-    // fma(x, 1/16, -(64 + zp)) is exact — REF marlin dequant (kU4B8 / kU4), then one rounding in x s
-    const uint32_t sub_lo = 0x64006400u + (uint32_t)zp * 0x00010001u;                   // 1024 + zp (exact: < 2048)
-    const __half hz = __int2half_rn(-(64 + zp));
-    const uint32_t sub_hi = (uint32_t)__half_as_ushort(hz) * 0x00010001u;
+// 8 packed nibbles (layout above) -> four 16-bit pairs of (q - zp) * s in the activation format.
+// f16: (q & 0xf) | 0x6400 = 1024 + q exactly; the nibble at bits 4..7 gives 1024 + 16 q, and
+// fma(x, 1/16, -(64 + zp)) is exact — REF marlin dequant (kU4B8 / kU4) — then one rounding in x s.
+// sub_lo = f16x2(1024 + zp), sub_hi = f16x2(-(64 + zp)) are per-(row, group) constants of the caller.
+__device__ __forceinline__ void dequant_word_f16(uint32_t q, uint32_t sub_lo, uint32_t sub_hi, uint32_t s2, uint32_t *out) {
+  const uint32_t sixteenth = 0x2c002c00u;
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const uint32_t lo = (q & 0x000f000fu) | 0x64006400u;
-      const uint32_t hi = (q & 0x00f000f0u) | 0x64006400u;
-      __half2 a = __hsub2(*(const __half2 *)&lo, *(const __half2 *)&sub_lo);
-      const uint32_t sixteenth = 0x2c002c00u;
-      __half2 b = __hfma2(*(const __half2 *)&hi, *(const __half2 *)&sixteenth, *(const __half2 *)&sub_hi);
-      a = __hmul2(a, *(const __half2 *)&s2);
-      b = __hmul2(b, *(const __half2 *)&s2);
-      out[2 * i] = *(const uint32_t *)&a;
-      out[2 * i + 1] = *(const uint32_t *)&b;
-      q >>= 8;
-    }
-  } else {
-    // bf16: (q - zp) is a small integer, its product with the bf16 scale is exact in f32 -> one rounding
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int a = (int)((q >> (4 * j)) & 0xF) - zp, b = (int)((q >> (4 * j + 16)) & 0xF) - zp;
-      const __nv_bfloat162 h = __floats2bfloat162_rn((float)a * s_f, (float)b * s_f);
-      out[j] = *(const uint32_t *)&h;
-    }
-    (void)s2;
+  for (int i = 0; i < 2; i++) {
+    uint32_t lo, hi;
+    asm("lop3.b32 %0, %1, 0x000f000f, 0x64006400, 0xea;" : "=r"(lo) : "r"(q));   // (q & mask) | magic
+    asm("lop3.b32 %0, %1, 0x00f000f0, 0x64006400, 0xea;" : "=r"(hi) : "r"(q));
+    __half2 a = __hsub2(*(const __half2 *)&lo, *(const __half2 *)&sub_lo);
+    __half2 b = __hfma2(*(const __half2 *)&hi, *(const __half2 *)&sixteenth, *(const __half2 *)&sub_hi);
+    a = __hmul2(a, *(const __half2 *)&s2);
+    b = __hmul2(b, *(const __half2 *)&s2);
+    out[2 * i] = *(const uint32_t *)&a;
+    out[2 * i + 1] = *(const uint32_t *)&b;
+    q >>= 8;
   }
 }
-
 // ---- shared epilogue: TMEM -> registers -> [cluster split-K reduction] -> y ----------------------
 // Called by ALL threads of the CTA (the cluster barriers are CTA-wide); `epi` marks the 8 epilogue
 // warps (warp ids 2..9), two per TMEM lane quarter.
@@ -258,25 +244,52 @@ w16_dense_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
 }
 
-// ---- int4 weights: three decoupled rings ------------------------------------------------------------
-//   RAW ring (deep: up to 16 x 4 KB of packed nibbles in flight per CTA — the HBM stream; a k-step's raw
-//   bytes are only 4 KB, so the depth of THIS ring is what keeps enough bytes in flight to cover the
-//   loaded HBM latency), X ring (activation tiles, L2-resident), A ring (dequantised 16 KB tiles).
+// ---- int4 weights: three decoupled rings, A operand in tensor memory --------------------------------
+//   RAW ring (deep: 8 KB stages of packed nibbles, the HBM stream — its depth is what keeps enough bytes in
+//   flight to cover the loaded HBM latency), X ring (activation tiles, L2-resident) and the A ring, which
+//   lives in TENSOR MEMORY: the dequantisers write their 16-bit pairs with tcgen05.st (lane = weight row,
+//   two consecutive-k values per 32-bit column) and the MMA reads A from TMEM (TS form).  No shared-memory
+//   round trip for the dequantised tile: no STS, no generic->async proxy fence (MEMBAR.ALL.CTA), no A bytes
+//   competing with the raw stream for shared memory.
+//   One iteration = 128 k (two 64-k chunks of the repacked layout): dequantiser warp w owns TMEM lane
+//   quarter w & 3 (rows 32 (w & 3) + lane) and chunk (w - 2) >> 2 of the iteration.
 //   warp 0 raw producer | warp 1 MMA | warps 2..9 dequantisers + epilogue | warp 10 X producer
-constexpr int WA_AS = 2, WA_XS = 4, WA_RS_MAX = 16;
+constexpr int WA_XS = 3, WA_RS_MAX = 12;
+constexpr int WA4_BK = 128;                       // k per iteration
+constexpr int WA4_RAW_BYTES = 2 * WA_RAW_BYTES;   // 8 KB
 constexpr int WA4_THREADS = 64 + WA_DQ_WARPS * 32 + 32;
+template <int NT> struct Wa4Tmem {
+  static constexpr uint32_t COLS = NT <= 64 ? 256u : 512u;        // two CTAs per SM share the 512 columns when NT <= 64
+  static constexpr int AS = (int)((COLS - NT) / 64u) > 6 ? 6 : (int)((COLS - NT) / 64u);   // A stages of 64 columns
+};
+
+// bf16: (q & 0xf) | 0x4300 = 128 + q exactly (the 7-bit mantissa holds the nibble); the subtraction of 128 + zp is
+// exact and the product with the bf16 scale rounds once — the same value as (float)(q - zp) * s rounded to bf16
+__device__ __forceinline__ void dequant_word_bf16_m(uint32_t q, uint32_t sub2, uint32_t s2, uint32_t *out) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    uint32_t v;
+    asm("lop3.b32 %0, %1, 0x000f000f, 0x43004300, 0xea;" : "=r"(v) : "r"(q));
+    __nv_bfloat162 a = __hsub2(*(const __nv_bfloat162 *)&v, *(const __nv_bfloat162 *)&sub2);
+    a = __hmul2(a, *(const __nv_bfloat162 *)&s2);
+    out[j] = *(const uint32_t *)&a;
+    q >>= 4;
+  }
+}
 
 template <int NT>
 __global__ void __launch_bounds__(WA4_THREADS, NT <= 64 ? 2 : 1)
 w4a16_int4_kernel(const __grid_constant__ CUtensorMap tmap_x, const WaParams p) {
-  constexpr int X_BYTES = NT * 128;
+  constexpr int X_BYTES = NT * 256;                 // two SW128 sub-tiles [NT][64 k]
+  constexpr int AS = Wa4Tmem<NT>::AS;
+  constexpr uint32_t TCOLS = Wa4Tmem<NT>::COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int RS = p.raw_stages;
-  uint8_t *a_ring = smem, *x_ring = smem + WA_AS * WA_A_BYTES, *r_ring = x_ring + WA_XS * X_BYTES;
-  uint64_t *bars = (uint64_t *)(r_ring + (size_t)RS * WA_RAW_BYTES);
+  uint8_t *x_ring = smem, *r_ring = x_ring + WA_XS * X_BYTES;
+  uint64_t *bars = (uint64_t *)(r_ring + (size_t)RS * WA4_RAW_BYTES);
   uint64_t *raw_full = bars, *raw_empty = bars + WA_RS_MAX, *x_full = bars + 2 * WA_RS_MAX, *x_empty = x_full + WA_XS,
-           *a_full = x_empty + WA_XS, *a_empty = a_full + WA_AS, *acc_full = a_empty + WA_AS;
+           *a_full = x_empty + WA_XS, *a_empty = a_full + 8, *acc_full = a_empty + 8;
   uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
   uint32_t *sc_tab = (uint32_t *)((uint8_t *)bars + 512);   // [groups_per_cta][128]: 16-bit scale | zero point << 16
 
@@ -284,74 +297,82 @@ w4a16_int4_kernel(const __grid_constant__ CUtensorMap tmap_x, const WaParams p) 
   const int n0 = blockIdx.x * WA_BM;
   const int ksplit = gridDim.y;
   const uint32_t rank = (ksplit > 1) ? cluster_ctarank() : 0u;
-  const int nk_total = p.K / WA_BK;
-  const int kb0 = (int)rank * p.ksteps_per_split;
+  const int nk_total = p.K / WA_BK;                       // 64-k chunks
+  const int kb0 = (int)rank * p.ksteps_per_split;         // first chunk of this split (even)
   const int nk = max(0, min(p.ksteps_per_split, nk_total - kb0));
+  const int nit = (nk + 1) >> 1;                          // iterations of two chunks; only the global K tail is half-filled
   const int rows_valid = min(WA_BM, p.N - n0);
 
   if (tid == 0) {
     for (int s = 0; s < RS; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], WA_DQ_WARPS); }
     for (int s = 0; s < WA_XS; s++) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
-    for (int s = 0; s < WA_AS; s++) { mbar_init(&a_full[s], WA_DQ_WARPS); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < AS; s++) { mbar_init(&a_full[s], WA_DQ_WARPS); mbar_init(&a_empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  constexpr uint32_t TCOLS = NT < 32 ? 32 : NT;
   if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a = tmem_base + (uint32_t)NT;       // A ring: AS stages of 64 columns after the accumulator
 
   if (warp == 0) {
     // ===================== raw producer: the HBM stream =====================
     if (lane == 0) {
       const uint32_t raw_bytes = (uint32_t)rows_valid * 32u;
       int stage = 0, phase = 0;
-      for (int i = 0; i < nk; i++) {
+      for (int i = 0; i < nit; i++) {
+        const int nc = min(2, nk - 2 * i);
         mbar_wait(&raw_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&raw_full[stage], raw_bytes);
-        bulk_g2s(r_ring + (size_t)stage * WA_RAW_BYTES, p.wq + ((size_t)(kb0 + i) * p.N + n0) * 32, raw_bytes, &raw_full[stage]);
+        mbar_arrive_expect_tx(&raw_full[stage], raw_bytes * (uint32_t)nc);
+        for (int c = 0; c < nc; c++)
+          bulk_g2s(r_ring + (size_t)stage * WA4_RAW_BYTES + (size_t)c * WA_RAW_BYTES,
+                   p.wq + ((size_t)(kb0 + 2 * i + c) * p.N + n0) * 32, raw_bytes, &raw_full[stage]);
         if (++stage == RS) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 10) {
-    // ===================== X producer (activation tiles, L2) =====================
+    // ===================== X producer (activation tiles, L2; k beyond K is zero-filled by TMA) =====================
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int i = 0; i < nk; i++) {
+      for (int i = 0; i < nit; i++) {
         mbar_wait(&x_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&x_full[stage], X_BYTES);
-        tma_load_2d(x_ring + (size_t)stage * X_BYTES, &tmap_x, (kb0 + i) * WA_BK, p.m0, &x_full[stage]);
+        uint8_t *xs = x_ring + (size_t)stage * X_BYTES;
+        tma_load_2d(xs, &tmap_x, (kb0 + 2 * i) * WA_BK, p.m0, &x_full[stage]);
+        tma_load_2d(xs + NT * 128, &tmap_x, (kb0 + 2 * i + 1) * WA_BK, p.m0, &x_full[stage]);
         if (++stage == WA_XS) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer: D[128 rows, NT tokens] += A[tmem] . X[smem]^T =====================
     const uint32_t fmt = (p.dtype == MRS_BF16) ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(WA_BM >> 4) << 24);
     int xs_ = 0, xph = 0, as_ = 0, aph = 0;
-    for (int i = 0; i < nk; i++) {
+    for (int i = 0; i < nit; i++) {
       mbar_wait(&x_full[xs_], xph);
       mbar_wait(&a_full[as_], aph);
       tc_fence_after();
       if (lane == 0) {
-        const uint8_t *as = a_ring + (size_t)as_ * WA_A_BYTES, *xs = x_ring + (size_t)xs_ * X_BYTES;
+        const uint8_t *xs = x_ring + (size_t)xs_ * X_BYTES;
+        const uint64_t d0 = umma_desc_sw128(xs), d1 = umma_desc_sw128(xs + NT * 128);
+        const uint32_t ta = tmem_a + (uint32_t)as_ * 64u;
 #pragma unroll
-        for (int k = 0; k < WA_BK / 16; k++)
-          umma_f16(tmem_base, umma_desc_sw128(as) + (uint64_t)(2 * k), umma_desc_sw128(xs) + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+        for (int j = 0; j < 8; j++)
+          umma_f16_ts(tmem_base, ta + (uint32_t)(8 * j), (j < 4 ? d0 : d1) + (uint64_t)(2 * (j & 3)), idesc, (i | j) ? 1u : 0u);
         umma_commit(&a_empty[as_]);
         umma_commit(&x_empty[xs_]);
-        if (i == nk - 1) umma_commit(acc_full);
+        if (i == nit - 1) umma_commit(acc_full);
       }
       __syncwarp();
       if (++xs_ == WA_XS) { xs_ = 0; xph ^= 1; }
-      if (++as_ == WA_AS) { as_ = 0; aph ^= 1; }
+      if (++as_ == AS) { as_ = 0; aph ^= 1; }
     }
   } else {
     // ===================== dequantisers =====================
-    const int dt_ = tid - 64;              // 0..255
-    const int r = dt_ >> 1, hf = dt_ & 1;  // weight row in the tile, which 32-weight half of the K-step
+    const int q4 = warp & 3, hf = (warp - 2) >> 2;   // TMEM lane quarter, which 64-k chunk of the iteration
+    const int r = q4 * 32 + lane;                    // weight row in the tile == TMEM lane
     const int n = n0 + r;
     const bool live = r < rows_valid;
     const bool bf = p.dtype == MRS_BF16;
@@ -375,39 +396,57 @@ w4a16_int4_kernel(const __grid_constant__ CUtensorMap tmap_x, const WaParams p) 
       }
       asm volatile("bar.sync 1, %0;" ::"n"(WA_DQ_WARPS * 32));
     }
+    // shared-space addresses (LDS, not generic loads) and an incremental group index (no division in the loop)
+    const uint32_t sc_base = smem_u32(sc_tab) + (uint32_t)r * 4u;
+    const uint32_t raw_base = smem_u32(r_ring) + (uint32_t)(hf * WA_RAW_BYTES + r * 32);
+    const uint32_t ta_base = tmem_a + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(hf * 32);
+    const int k_first = (kb0 + hf) * WA_BK;
+    int g_rel = k_first / p.group - g_first, k_in_g = k_first % p.group;
     int rs_ = 0, rph = 0, as_ = 0, aph = 0;
-    for (int i = 0; i < nk; i++) {
-      const int kb = kb0 + i;
-      const uint32_t sz = sc_tab[((kb * WA_BK + 32 * hf) / p.group - g_first) * WA_BM + r];
+    for (int i = 0; i < nit; i++) {
+      // the thread's 64 weights are two 32-weight halves, each inside one scale group (group % 32 == 0)
+      const uint32_t sz0 = lds32(sc_base + (uint32_t)g_rel * (WA_BM * 4));
+      const uint32_t sz1 = lds32(sc_base + (uint32_t)(g_rel + (k_in_g + 32 >= p.group ? 1 : 0)) * (WA_BM * 4));
+      k_in_g += WA4_BK;
+      while (k_in_g >= p.group) { k_in_g -= p.group; g_rel++; }
+      uint32_t o[32];
       mbar_wait(&raw_full[rs_], rph);
-      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-      if (live) raw = *(const uint4 *)(r_ring + (size_t)rs_ * WA_RAW_BYTES + r * 32 + hf * 16);
-      const uint32_t s16 = sz & 0xFFFFu;
-      const int zp = (int)(sz >> 16);
-      const uint32_t s2 = s16 * 0x00010001u;
-      float s_f = 0.f;
-      if (bf) s_f = __bfloat162float(__ushort_as_bfloat16((unsigned short)s16));
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-      uint32_t o[4][4];
+      if (2 * i + hf < nk) {
+        const uint32_t ra = raw_base + (uint32_t)rs_ * WA4_RAW_BYTES;
+        const uint4 raw0 = lds128(ra), raw1 = lds128(ra + 16);
+        const uint32_t w[8] = {raw0.x, raw0.y, raw0.z, raw0.w, raw1.x, raw1.y, raw1.z, raw1.w};
 #pragma unroll
-      for (int c4 = 0; c4 < 4; c4++) {
-        if (bf) dequant_word<true>(w[c4], zp, s_f, s2, o[c4]);
-        else dequant_word<false>(w[c4], zp, s_f, s2, o[c4]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[rs_]);       // the packed bytes have been consumed into registers: free the raw slot
-      mbar_wait(&a_empty[as_], aph ^ 1);                 // the MMA that read this A slot has retired
-      uint8_t *dst = a_ring + (size_t)as_ * WA_A_BYTES + (size_t)(r >> 3) * 1024 + (size_t)(r & 7) * 128;
+        for (int h = 0; h < 2; h++) {
+          const uint32_t sz = h ? sz1 : sz0;
+          const uint32_t s2 = (sz & 0xFFFFu) * 0x00010001u, zp = sz >> 16;
+          if (bf) {
+            const uint32_t sub2 = 0x43004300u + zp * 0x00010001u;                                  // bf16x2(128 + zp)
 #pragma unroll
-      for (int c4 = 0; c4 < 4; c4++) {
-        const int c = 4 * hf + c4;
-        *(uint4 *)(dst + ((c ^ (r & 7)) << 4)) = make_uint4(o[c4][0], o[c4][1], o[c4][2], o[c4][3]);
+            for (int c4 = 0; c4 < 4; c4++) dequant_word_bf16_m(w[4 * h + c4], sub2, s2, o + 16 * h + 4 * c4);
+          } else {
+            const uint32_t sub_lo = 0x64006400u + zp * 0x00010001u;                                // f16x2(1024 + zp)
+            const uint32_t sub_hi = (0xD400u + (zp << 4)) * 0x00010001u;                           // f16x2(-(64 + zp)): ulp 1/16 in [64, 128)
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++) dequant_word_f16(w[4 * h + c4], sub_lo, sub_hi, s2, o + 16 * h + 4 * c4);
+          }
+        }
+      } else {
+        // half-filled last iteration (K % 128 == 64): this chunk lies beyond K — zero A against TMA's zero X
+#pragma unroll
+        for (int j = 0; j < 32; j++) o[j] = 0u;
       }
-      fence_proxy_async();
+      mbar_wait(&a_empty[as_], aph ^ 1);                 // the MMAs that read this A stage have retired
+      tc_fence_after();
+      tmem_st_32x32(ta_base + (uint32_t)as_ * 64u, o);
+      tmem_wait_st();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[as_]);
+      if (lane == 0) {
+        mbar_arrive(&raw_empty[rs_]);                    // the packed bytes are in registers (and past them): free the raw slot
+        mbar_arrive(&a_full[as_]);
+      }
       if (++rs_ == RS) { rs_ = 0; rph ^= 1; }
-      if (++as_ == WA_AS) { as_ = 0; aph ^= 1; }
+      if (++as_ == AS) { as_ = 0; aph ^= 1; }
     }
   }
   wa_epilogue<NT>(p, smem, acc_full, tmem_base, nk, ksplit, rank, n0, rows_valid);
@@ -461,9 +500,22 @@ __global__ void repack_awq_kernel(const uint32_t *__restrict__ qw, uint32_t *__r
 }
 
 // ---------------------------------------------------------------- host
-static size_t wa4_fixed_bytes(int NT, int groups) {
-  return 1024 + (size_t)WA_AS * WA_A_BYTES + (size_t)WA_XS * NT * 128 + 512 + (size_t)groups * WA_BM * 4;
+// shared-memory plan of the int4 kernel for one (NT, groups) choice: raw stages take what is left of the budget
+struct Wa4Plan { int rs; size_t smem, rings; };
+static Wa4Plan wa4_plan(int NT, int groups) {
+  const size_t budget = (NT <= 64) ? (size_t)(227 * 1024) / 2 - 1024 : (size_t)200 * 1024;   // two CTAs per SM for the decode tiles
+  const size_t xring = (size_t)WA_XS * NT * 256;
+  const size_t fixed = 1024 + xring + 512 + (size_t)groups * WA_BM * 4;
+  int rs = fixed < budget ? (int)((budget - fixed) / WA4_RAW_BYTES) : 0;
+  if (rs > WA_RS_MAX) rs = WA_RS_MAX;
+  if (rs < 2) rs = 2;
+  Wa4Plan pl;
+  pl.rs = rs;
+  pl.smem = fixed + (size_t)rs * WA4_RAW_BYTES;
+  pl.rings = xring + (size_t)rs * WA4_RAW_BYTES;
+  return pl;
 }
+static int wa_groups_per_cta(int ksteps_per_split, int group) { return (ksteps_per_split * WA_BK + group - 1) / group + 1; }
 
 template <int NT, int SRC>
 static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaParams p, int ksplit, cudaStream_t st) {
@@ -477,18 +529,12 @@ static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaPar
   cfg.numAttrs = ksplit > 1 ? 1 : 0;
   if constexpr (SRC == WA_SRC_INT4) {
     auto kern = w4a16_int4_kernel<NT>;
-    // two CTAs per SM for the decode tiles: the raw ring takes what is left of half an SM's shared memory
-    const size_t budget = (NT <= 64) ? (size_t)(227 * 1024) / 2 - 1024 : (size_t)200 * 1024;
-    const size_t fixed = wa4_fixed_bytes(NT, p.groups_per_cta);
-    int rs = fixed < budget ? (int)((budget - fixed) / WA_RAW_BYTES) : 0;
-    if (rs > WA_RS_MAX) rs = WA_RS_MAX;
-    if (rs < 2) rs = 2;
-    p.raw_stages = rs;
-    const size_t smem = fixed + (size_t)rs * WA_RAW_BYTES;
-    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const Wa4Plan pl = wa4_plan(NT, p.groups_per_cta);
+    p.raw_stages = pl.rs;
+    if (pl.smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     cfg.blockDim = dim3(WA4_THREADS);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = pl.smem;
     return cudaLaunchKernelEx(&cfg, kern, tx, p);
   } else {
     auto kern = w16_dense_kernel<NT>;
@@ -500,8 +546,9 @@ static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaPar
   }
 }
 
-// split K over a cluster when the row tiles alone leave SMs idle (two CTAs per SM are resident)
-static int pick_ksplit(int N, int K, int NT) {
+// split K over a cluster when the row tiles alone leave SMs idle (two CTAs per SM are resident).  Splits are
+// whole 128-k iterations (an even number of 64-k chunks) so that only the global K tail can be half-filled.
+static int pick_ksplit(int src, int N, int K, int NT, int group) {
   if (NT > 64) return 1;   // large token tiles stream their epilogue; compute-bound anyway
   int sms = 148;
   int dev = 0;
@@ -511,10 +558,12 @@ static int pick_ksplit(int N, int K, int NT) {
   const int slots = 2 * sms;
   int ks = 1;
   for (int c = 2; c <= 4; c *= 2) {
-    const int per = (nk + c - 1) / c;
-    // the reduction buffer (c-1 partials of NT x 128 f32) aliases the operand rings (A + X + >= 2 raw stages)
-    const size_t red = (size_t)(c - 1) * NT * WA_BM * 4, rings = (size_t)WA_AS * WA_A_BYTES + (size_t)WA_XS * NT * 128 + 2 * WA_RAW_BYTES;
-    if (tiles * c <= slots && per >= 4 && red <= rings) ks = c;
+    const int per = ((nk + c - 1) / c + 1) & ~1;
+    // the reduction buffer (c-1 partials of NT x 128 f32) aliases the operand rings
+    const size_t red = (size_t)(c - 1) * NT * WA_BM * 4;
+    const size_t rings = (src == WA_SRC_INT4) ? wa4_plan(NT, wa_groups_per_cta(per, group)).rings
+                                              : (size_t)WA_STAGES * (WA_A_BYTES + NT * 128);
+    if (tiles * c <= slots && per >= 4 && per * (c - 1) < nk && red <= rings) ks = c;
   }
   return ks;
 }
@@ -536,9 +585,9 @@ static cudaError_t run_wa(int src, const void *x, const void *w, const void *sca
     WaParams p = {};
     p.wq = (const uint8_t *)w; p.scales = scales; p.qzeros = qzeros; p.y = y;
     p.M = M; p.N = N; p.K = K; p.group = group; p.dtype = dtype; p.scale_perm = scale_perm; p.m0 = m0;
-    const int ks = pick_ksplit(N, K, NT);
-    p.ksteps_per_split = (K / WA_BK + ks - 1) / ks;
-    p.groups_per_cta = (p.ksteps_per_split * WA_BK + group - 1) / group + 1;
+    const int ks = pick_ksplit(src, N, K, NT, group);
+    p.ksteps_per_split = ks > 1 ? (((K / WA_BK + ks - 1) / ks + 1) & ~1) : K / WA_BK;
+    p.groups_per_cta = wa_groups_per_cta(p.ksteps_per_split, group);
     cudaError_t e;
 #define MRS_WA(NTV)                                                                                   \
   e = (src == WA_SRC_INT4) ? launch_wa<NTV, WA_SRC_INT4>(tx, tw, p, ks, st) : launch_wa<NTV, WA_SRC_DENSE>(tx, tw, p, ks, st)

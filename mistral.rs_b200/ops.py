@@ -4,6 +4,8 @@
 `forward_add_rms_norm` (mistralrs-core/src/layers.rs:328-413 -> core/src/cuda/ffi.rs)."""
 import ctypes
 
+import numpy as np
+
 import torch
 
 from . import lib

@@ -99,6 +99,7 @@ static void attn_heads(int layer, int h0, int h1) {
 }
 
 enum { JOB_GEMV = 1, JOB_ATTN = 2, JOB_GLU = 3 };
+#define MRS_SPIN_LIMIT 20000
 
 static void run_share(int tid) {
   const int nt = G.nthreads;
@@ -133,9 +134,9 @@ static void *worker(void *arg) {
   pin_to(tid);
   int seen = 0;
   for (;;) {
-    while (atomic_load_explicit(&G.phase, memory_order_acquire) == seen) {
+    for (int spins = 0; atomic_load_explicit(&G.phase, memory_order_acquire) == seen; spins++) {
       if (atomic_load_explicit(&G.stop, memory_order_relaxed)) return NULL;
-      MRS_CPU_RELAX();
+      if (spins < MRS_SPIN_LIMIT) MRS_CPU_RELAX(); else sched_yield();   /* a CPU quota below the thread count must not starve the pool */
     }
     seen = atomic_load_explicit(&G.phase, memory_order_acquire);
     run_share(tid);
@@ -148,7 +149,9 @@ static void dispatch(int kind, const cpu_mat_t *m, const float *in, float *out, 
   atomic_store_explicit(&G.arrived, 0, memory_order_relaxed);
   atomic_fetch_add_explicit(&G.phase, 1, memory_order_release);
   run_share(0);
-  while (atomic_load_explicit(&G.arrived, memory_order_acquire) < G.nthreads - 1) MRS_CPU_RELAX();
+  for (int spins = 0; atomic_load_explicit(&G.arrived, memory_order_acquire) < G.nthreads - 1; spins++) {
+    if (spins < MRS_SPIN_LIMIT) MRS_CPU_RELAX(); else sched_yield();
+  }
 }
 
 static void quantize_act(const float *x, int cols, int be) {
