@@ -169,6 +169,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds_u16s(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return (uint32_t)v;
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, const uint4 &v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

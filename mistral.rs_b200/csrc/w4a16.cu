@@ -49,7 +49,6 @@ struct WaParams {
   int scale_perm;          // 0: plain columns, 1: Marlin 64-wide permutation, 2: Marlin "single" (32-wide)
   int m0;                  // first token of this pass
   int ksteps_per_split;    // K-steps (of 64) per split CTA
-  int groups_per_cta;      // scale groups a CTA's K range can touch (sizes the shared scale table)
   int raw_stages;          // depth of the packed-weight ring (int4 kernel)
 };
 
@@ -68,10 +67,27 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_t rank, float v) {
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+  return remote;
+}
+__device__ __forceinline__ void st_cluster_f32_at(uint32_t remote_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote_addr), "f"(v) : "memory");
+}
+// arrive on another CTA's mbarrier; release at cluster scope orders this thread's earlier remote stores before it
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra.uni WAITC_DONE;\n\tbra.uni WAITC_LOOP;\n\tWAITC_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
 }
 
 // 8 packed nibbles (layout above) -> four 16-bit pairs of (q - zp) * s in the activation format.
@@ -95,11 +111,16 @@ __device__ __forceinline__ void dequant_word_f16(uint32_t q, uint32_t sub_lo, ui
   }
 }
 // ---- shared epilogue: TMEM -> registers -> [cluster split-K reduction] -> y ----------------------
-// Called by ALL threads of the CTA (the cluster barriers are CTA-wide); `epi` marks the 8 epilogue
-// warps (warp ids 2..9), two per TMEM lane quarter.
+// Called by ALL threads of the CTA; `epi` marks the 8 epilogue warps (warp ids 2..9), two per TMEM lane
+// quarter.  Split-K: the non-leader CTAs push their partial tile straight into a DEDICATED region of the
+// leader's shared memory (red[rank-1][token][row], never aliased with the operand rings, so no "rings drained"
+// rendezvous is needed) and then arrive, thread by thread with release.cluster, on the leader's `red_bar`;
+// the leader adds the partials in rank order (deterministic).  The only cluster barrier is the start-up one
+// (arrive right after the mbarrier init in the kernel prologue, wait here, long since complete), which
+// guarantees the leader's barrier exists before anybody arrives on it.
 template <int NT>
-__device__ __forceinline__ void wa_epilogue(const WaParams &p, uint8_t *smem, uint64_t *acc_full, uint32_t tmem_base, int nk,
-                                            int ksplit, uint32_t rank, int n0, int rows_valid) {
+__device__ __forceinline__ void wa_epilogue(const WaParams &p, float *red, uint64_t *red_bar, uint64_t *acc_full, uint32_t tmem_base,
+                                            int nk, int ksplit, uint32_t rank, int n0, int rows_valid) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int CPW = NT / 2;              // columns (tokens) per epilogue warp: two warps share a lane quarter
   const bool epi = warp >= 2 && warp < 2 + WA_DQ_WARPS;
@@ -131,17 +152,15 @@ __device__ __forceinline__ void wa_epilogue(const WaParams &p, uint8_t *smem, ui
       }
     }
     if (ksplit > 1) {
-      // deterministic split-K reduction through the leader's shared memory (the operand rings are free once
-      // every CTA of the cluster has drained its pipeline): red[rank-1][token][row]
-      float *red = (float *)smem;
-      cluster_sync_all();
+      cluster_wait_acquire();              // start-up barrier (every thread of every CTA arrived in the prologue)
       if (epi && rank != 0) {
+        const uint32_t rbase = map_to_rank(smem_u32(red + ((size_t)(rank - 1) * NT + half * CPW) * WA_BM + row), 0u);
 #pragma unroll
-        for (int i = 0; i < CPW; i++)
-          st_cluster_f32(smem_u32(red + ((size_t)(rank - 1) * NT + half * CPW + i) * WA_BM + row), 0u, acc[i]);
+        for (int i = 0; i < CPW; i++) st_cluster_f32_at(rbase + (uint32_t)i * (WA_BM * 4), acc[i]);
+        mbar_arrive_remote(map_to_rank(smem_u32(red_bar), 0u));
       }
-      cluster_sync_all();
       if (epi && rank == 0) {
+        mbar_wait_cluster(red_bar, 0);
         for (int s = 1; s < ksplit; s++)
 #pragma unroll
           for (int i = 0; i < CPW; i++) acc[i] += red[((size_t)(s - 1) * NT + half * CPW + i) * WA_BM + row];
@@ -185,8 +204,9 @@ w16_dense_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = (uint64_t *)(smem + WA_STAGES * STAGE);
-  uint64_t *in_full = bars, *empty = bars + WA_STAGES, *acc_full = bars + 2 * WA_STAGES;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * WA_STAGES + 1);
+  uint64_t *in_full = bars, *empty = bars + WA_STAGES, *acc_full = bars + 2 * WA_STAGES, *red_bar = acc_full + 1;
+  uint32_t *tmem_slot = (uint32_t *)(red_bar + 1);
+  float *red = (float *)((uint8_t *)bars + 256);   // split-K partials (present only when ksplit > 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * WA_BM;
   const int ksplit = gridDim.y;
@@ -198,14 +218,17 @@ w16_dense_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (tid == 0) {
     for (int s = 0; s < WA_STAGES; s++) { mbar_init(&in_full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
+    mbar_init(red_bar, (uint32_t)(ksplit - 1) * WA_DQ_WARPS * 32u);
     fence_mbar_init();
   }
   constexpr uint32_t TCOLS = NT < 32 ? 32 : NT;
   if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
   tc_fence_before();
   __syncthreads();
+  if (ksplit > 1) cluster_arrive_release();   // start-up cluster barrier; waited on in the epilogue
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // REDUX result lives in a uniform register: the MMA issue loop gets uniform operands (no per-MMA waterfall)
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
@@ -238,7 +261,7 @@ w16_dense_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (++stage == WA_STAGES) { stage = 0; phase ^= 1; }
     }
   }
-  wa_epilogue<NT>(p, smem, acc_full, tmem_base, nk, ksplit, rank, n0, rows_valid);
+  wa_epilogue<NT>(p, red, red_bar, acc_full, tmem_base, nk, ksplit, rank, n0, rows_valid);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
@@ -255,8 +278,17 @@ w16_dense_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 //   quarter w & 3 (rows 32 (w & 3) + lane) and chunk (w - 2) >> 2 of the iteration.
 //   warp 0 raw producer | warp 1 MMA | warps 2..9 dequantisers + epilogue | warp 10 X producer
 constexpr int WA_XS = 3, WA_RS_MAX = 12;
+#ifdef MRS_WA_TRACE   // dev build: SM-clock stamps of CTA (0, 0) (scripts/dev_wa_trace.py)
+__device__ long long g_wa_trace[4096];
+#define WA_T(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0) g_wa_trace[(slot)] = clock64(); } while (0)
+#else
+#define WA_T(slot) do { } while (0)
+#endif
 constexpr int WA4_BK = 128;                       // k per iteration
-constexpr int WA4_RAW_BYTES = 2 * WA_RAW_BYTES;   // 8 KB
+constexpr int WA4_RAW_BYTES = 2 * WA_RAW_BYTES;   // 8 KB of packed nibbles per stage ...
+constexpr int WA4_SC_OFF = WA4_RAW_BYTES;         // ... then up to 4 scale rows [128] of 16 bits (the groups the iteration's 128 k touch)
+constexpr int WA4_ZP_OFF = WA4_SC_OFF + 4 * 256;  // ... then up to 4 AWQ zero-point rows [16] of int32
+constexpr int WA4_STAGE = WA4_ZP_OFF + 4 * 64;    // 9472 B
 constexpr int WA4_THREADS = 64 + WA_DQ_WARPS * 32 + 32;
 template <int NT> struct Wa4Tmem {
   static constexpr uint32_t COLS = NT <= 64 ? 256u : 512u;        // two CTAs per SM share the 512 columns when NT <= 64
@@ -287,11 +319,11 @@ w4a16_int4_kernel(const __grid_constant__ CUtensorMap tmap_x, const WaParams p) 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int RS = p.raw_stages;
   uint8_t *x_ring = smem, *r_ring = x_ring + WA_XS * X_BYTES;
-  uint64_t *bars = (uint64_t *)(r_ring + (size_t)RS * WA4_RAW_BYTES);
+  uint64_t *bars = (uint64_t *)(r_ring + (size_t)RS * WA4_STAGE);
   uint64_t *raw_full = bars, *raw_empty = bars + WA_RS_MAX, *x_full = bars + 2 * WA_RS_MAX, *x_empty = x_full + WA_XS,
-           *a_full = x_empty + WA_XS, *a_empty = a_full + 8, *acc_full = a_empty + 8;
-  uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
-  uint32_t *sc_tab = (uint32_t *)((uint8_t *)bars + 512);   // [groups_per_cta][128]: 16-bit scale | zero point << 16
+           *a_full = x_empty + WA_XS, *a_empty = a_full + 8, *acc_full = a_empty + 8, *red_bar = acc_full + 1;
+  uint32_t *tmem_slot = (uint32_t *)(red_bar + 1);
+  float *red = (float *)((uint8_t *)bars + 512);            // split-K partials (present only when ksplit > 1)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * WA_BM;
@@ -303,32 +335,61 @@ w4a16_int4_kernel(const __grid_constant__ CUtensorMap tmap_x, const WaParams p) 
   const int nit = (nk + 1) >> 1;                          // iterations of two chunks; only the global K tail is half-filled
   const int rows_valid = min(WA_BM, p.N - n0);
 
+  if (warp == 0) WA_T(0);
   if (tid == 0) {
     for (int s = 0; s < RS; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], WA_DQ_WARPS); }
     for (int s = 0; s < WA_XS; s++) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
     for (int s = 0; s < AS; s++) { mbar_init(&a_full[s], WA_DQ_WARPS); mbar_init(&a_empty[s], 1); }
     mbar_init(acc_full, 1);
+    mbar_init(red_bar, (uint32_t)(ksplit - 1) * WA_DQ_WARPS * 32u);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
+
+  // dequantiser identity + the first batch of scale loads, issued before the set-up barrier (they depend on nothing)
+  const int q4 = warp & 3, hf = (warp - 2) >> 2;   // TMEM lane quarter, which 64-k chunk of the iteration
+  const int r = q4 * 32 + lane;                    // weight row in the tile == TMEM lane
+  const bool dq = warp >= 2 && warp < 2 + WA_DQ_WARPS;
+  const int n = n0 + r;
+  int scol = n;
+  if (p.scale_perm == 1) scol = (n & ~63) + inv_scale_perm64(n & 63);
+  else if (p.scale_perm == 2) scol = (n & ~31) + inv_scale_perm32(n & 31);
+  const int zsh = 4 * ((n & 7) == 0 ? 0 : (n & 7) == 1 ? 4 : (n & 7) == 2 ? 1 : (n & 7) == 3 ? 5 : (n & 7) == 4 ? 2 : (n & 7) == 5 ? 6 : (n & 7) == 6 ? 3 : 7);
   tc_fence_before();
   __syncthreads();
+  if (ksplit > 1) cluster_arrive_release();   // start-up cluster barrier; waited on in the epilogue
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // REDUX result lives in a uniform register: the MMA issue loop gets uniform operands (no per-MMA waterfall)
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
   const uint32_t tmem_a = tmem_base + (uint32_t)NT;       // A ring: AS stages of 64 columns after the accumulator
+  if (warp == 0) WA_T(1);
 
   if (warp == 0) {
     // ===================== raw producer: the HBM stream =====================
     if (lane == 0) {
-      const uint32_t raw_bytes = (uint32_t)rows_valid * 32u;
+      // per iteration: the packed nibbles of one or two 64-k chunks, plus the scale row (and AWQ zero-point row) of
+      // every group the iteration's k range touches (one row when group % 128 == 0) — the dequantisers read them
+      // from the stage with LDS; nothing on their path waits for global memory
+      const uint32_t raw_bytes = (uint32_t)rows_valid * 32u, sc_bytes = (uint32_t)rows_valid * 2u, zp_bytes = (uint32_t)rows_valid / 2u;
+      const uint16_t *sc_src = (const uint16_t *)p.scales + n0;
+      const int32_t *zp_src = p.qzeros ? p.qzeros + (n0 >> 3) : nullptr;
+      int g = (kb0 * WA_BK) / p.group, k_in_g = (kb0 * WA_BK) % p.group;
       int stage = 0, phase = 0;
       for (int i = 0; i < nit; i++) {
         const int nc = min(2, nk - 2 * i);
+        const int ng = (k_in_g + 64 * nc - 1) / p.group + 1;          // groups touched by this iteration (<= 4)
+        uint8_t *st = r_ring + (size_t)stage * WA4_STAGE;
         mbar_wait(&raw_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&raw_full[stage], raw_bytes * (uint32_t)nc);
+        WA_T(100 + i);
+        mbar_arrive_expect_tx(&raw_full[stage], raw_bytes * (uint32_t)nc + (sc_bytes + (zp_src ? zp_bytes : 0u)) * (uint32_t)ng);
         for (int c = 0; c < nc; c++)
-          bulk_g2s(r_ring + (size_t)stage * WA4_RAW_BYTES + (size_t)c * WA_RAW_BYTES,
-                   p.wq + ((size_t)(kb0 + 2 * i + c) * p.N + n0) * 32, raw_bytes, &raw_full[stage]);
+          bulk_g2s(st + (size_t)c * WA_RAW_BYTES, p.wq + ((size_t)(kb0 + 2 * i + c) * p.N + n0) * 32, raw_bytes, &raw_full[stage]);
+        for (int j = 0; j < ng; j++) {
+          bulk_g2s(st + WA4_SC_OFF + j * 256, sc_src + (size_t)(g + j) * p.N, sc_bytes, &raw_full[stage]);
+          if (zp_src) bulk_g2s(st + WA4_ZP_OFF + j * 64, zp_src + (size_t)(g + j) * (p.N >> 3), zp_bytes, &raw_full[stage]);
+        }
+        k_in_g += WA4_BK;
+        while (k_in_g >= p.group) { k_in_g -= p.group; g++; }
         if (++stage == RS) { stage = 0; phase ^= 1; }
       }
     }
@@ -354,71 +415,59 @@ w4a16_int4_kernel(const __grid_constant__ CUtensorMap tmap_x, const WaParams p) 
       mbar_wait(&x_full[xs_], xph);
       mbar_wait(&a_full[as_], aph);
       tc_fence_after();
-      if (lane == 0) {
+      WA_T(1000 + 2 * i);
+      {
         const uint8_t *xs = x_ring + (size_t)xs_ * X_BYTES;
         const uint64_t d0 = umma_desc_sw128(xs), d1 = umma_desc_sw128(xs + NT * 128);
         const uint32_t ta = tmem_a + (uint32_t)as_ * 64u;
 #pragma unroll
         for (int j = 0; j < 8; j++)
-          umma_f16_ts(tmem_base, ta + (uint32_t)(8 * j), (j < 4 ? d0 : d1) + (uint64_t)(2 * (j & 3)), idesc, (i | j) ? 1u : 0u);
-        umma_commit(&a_empty[as_]);
-        umma_commit(&x_empty[xs_]);
-        if (i == nit - 1) umma_commit(acc_full);
+          umma_f16_ts_warp(tmem_base, ta + (uint32_t)(8 * j), (j < 4 ? d0 : d1) + (uint64_t)(2 * (j & 3)), idesc, (i | j) ? 1u : 0u);
+        umma_commit_warp(&a_empty[as_]);
+        umma_commit_warp(&x_empty[xs_]);
+        if (i == nit - 1) umma_commit_warp(acc_full);
       }
-      __syncwarp();
+      WA_T(1001 + 2 * i);
       if (++xs_ == WA_XS) { xs_ = 0; xph ^= 1; }
       if (++as_ == AS) { as_ = 0; aph ^= 1; }
     }
   } else {
     // ===================== dequantisers =====================
-    const int q4 = warp & 3, hf = (warp - 2) >> 2;   // TMEM lane quarter, which 64-k chunk of the iteration
-    const int r = q4 * 32 + lane;                    // weight row in the tile == TMEM lane
-    const int n = n0 + r;
-    const bool live = r < rows_valid;
     const bool bf = p.dtype == MRS_BF16;
-    int scol = n;
-    if (p.scale_perm == 1) scol = (n & ~63) + inv_scale_perm64(n & 63);
-    else if (p.scale_perm == 2) scol = (n & ~31) + inv_scale_perm32(n & 31);
-    const int zsh = 4 * ((n & 7) == 0 ? 0 : (n & 7) == 1 ? 4 : (n & 7) == 2 ? 1 : (n & 7) == 3 ? 5 : (n & 7) == 4 ? 2 : (n & 7) == 5 ? 6 : (n & 7) == 6 ? 3 : 7);
-    // scales (+ AWQ zero points) of this CTA's K range go to shared memory once
-    const int g_first = (kb0 * WA_BK) / p.group;
-    {
-      const int g_last = nk > 0 ? ((kb0 + nk) * WA_BK - 1) / p.group : g_first - 1;
-      for (int g = g_first + hf; g <= g_last; g += 2) {
-        uint32_t v = 0u;
-        if (live) {
-          v = ((const uint16_t *)p.scales)[(size_t)g * p.N + scol];
-          uint32_t z = 8u;
-          if (p.qzeros != nullptr) z = ((uint32_t)p.qzeros[(size_t)g * (p.N >> 3) + (n >> 3)] >> zsh) & 0xFu;
-          v |= z << 16;
-        }
-        sc_tab[(g - g_first) * WA_BM + r] = v;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(WA_DQ_WARPS * 32));
-    }
-    // shared-space addresses (LDS, not generic loads) and an incremental group index (no division in the loop)
-    const uint32_t sc_base = smem_u32(sc_tab) + (uint32_t)r * 4u;
-    const uint32_t raw_base = smem_u32(r_ring) + (uint32_t)(hf * WA_RAW_BYTES + r * 32);
+    const bool has_zp = p.qzeros != nullptr;
+    if (warp == 2) WA_T(2);
+    const int tb = warp == 2 ? 200 : (warp == 9 ? 600 : 3000);
+    (void)tb;
+    // shared-space addresses (LDS, not generic loads)
+    const uint32_t st_base = smem_u32(r_ring);
+    const uint32_t raw_off = (uint32_t)(hf * WA_RAW_BYTES + r * 32);
+    const uint32_t sc_off = (uint32_t)(WA4_SC_OFF + 2 * (scol - n0)), zp_off = (uint32_t)(WA4_ZP_OFF + 4 * (r >> 3));
     const uint32_t ta_base = tmem_a + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(hf * 32);
-    const int k_first = (kb0 + hf) * WA_BK;
-    int g_rel = k_first / p.group - g_first, k_in_g = k_first % p.group;
+    // which of the iteration's scale rows each 32-weight half of this thread's chunk uses: row = group(k) - group(k_iter)
+    const int G = p.group;
+    auto row_of = [&](int x) { return (x >= G) + (x >= 2 * G) + (x >= 3 * G); };   // x < G + 128, G >= 32
+    int k_in_g = (kb0 * WA_BK) % G;                      // offset of the iteration's first k inside its group
     int rs_ = 0, rph = 0, as_ = 0, aph = 0;
     for (int i = 0; i < nit; i++) {
-      // the thread's 64 weights are two 32-weight halves, each inside one scale group (group % 32 == 0)
-      const uint32_t sz0 = lds32(sc_base + (uint32_t)g_rel * (WA_BM * 4));
-      const uint32_t sz1 = lds32(sc_base + (uint32_t)(g_rel + (k_in_g + 32 >= p.group ? 1 : 0)) * (WA_BM * 4));
-      k_in_g += WA4_BK;
-      while (k_in_g >= p.group) { k_in_g -= p.group; g_rel++; }
       uint32_t o[32];
+      const uint32_t st = st_base + (uint32_t)rs_ * WA4_STAGE;
+      const int j0 = row_of(k_in_g + 64 * hf), j1 = row_of(k_in_g + 64 * hf + 32);
+      k_in_g += WA4_BK;
+      while (k_in_g >= G) k_in_g -= G;
       mbar_wait(&raw_full[rs_], rph);
+      WA_T(tb + 4 * i);
       if (2 * i + hf < nk) {
-        const uint32_t ra = raw_base + (uint32_t)rs_ * WA4_RAW_BYTES;
-        const uint4 raw0 = lds128(ra), raw1 = lds128(ra + 16);
+        const uint4 raw0 = lds128(st + raw_off), raw1 = lds128(st + raw_off + 16);
+        const uint32_t sw0 = lds_u16s(st + sc_off + (uint32_t)j0 * 256u), sw1 = lds_u16s(st + sc_off + (uint32_t)j1 * 256u);
+        uint32_t zp0 = 8u, zp1 = 8u;
+        if (has_zp) {
+          zp0 = (lds32(st + zp_off + (uint32_t)j0 * 64u) >> zsh) & 0xFu;
+          zp1 = (lds32(st + zp_off + (uint32_t)j1 * 64u) >> zsh) & 0xFu;
+        }
         const uint32_t w[8] = {raw0.x, raw0.y, raw0.z, raw0.w, raw1.x, raw1.y, raw1.z, raw1.w};
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          const uint32_t sz = h ? sz1 : sz0;
-          const uint32_t s2 = (sz & 0xFFFFu) * 0x00010001u, zp = sz >> 16;
+          const uint32_t s2 = (h ? sw1 : sw0) * 0x00010001u, zp = h ? zp1 : zp0;
           if (bf) {
             const uint32_t sub2 = 0x43004300u + zp * 0x00010001u;                                  // bf16x2(128 + zp)
 #pragma unroll
@@ -435,21 +484,26 @@ w4a16_int4_kernel(const __grid_constant__ CUtensorMap tmap_x, const WaParams p) 
 #pragma unroll
         for (int j = 0; j < 32; j++) o[j] = 0u;
       }
+      WA_T(tb + 4 * i + 1);
       mbar_wait(&a_empty[as_], aph ^ 1);                 // the MMAs that read this A stage have retired
+      WA_T(tb + 4 * i + 2);
       tc_fence_after();
       tmem_st_32x32(ta_base + (uint32_t)as_ * 64u, o);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&raw_empty[rs_]);                    // the packed bytes are in registers (and past them): free the raw slot
+        mbar_arrive(&raw_empty[rs_]);                    // the stage's bytes are in registers (and past them): free the slot
         mbar_arrive(&a_full[as_]);
       }
+      WA_T(tb + 4 * i + 3);
       if (++rs_ == RS) { rs_ = 0; rph ^= 1; }
       if (++as_ == AS) { as_ = 0; aph ^= 1; }
     }
   }
-  wa_epilogue<NT>(p, smem, acc_full, tmem_base, nk, ksplit, rank, n0, rows_valid);
+  if (warp == 2) WA_T(3);
+  wa_epilogue<NT>(p, red, red_bar, acc_full, tmem_base, nk, ksplit, rank, n0, rows_valid);
+  if (warp == 2) WA_T(4);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
@@ -501,21 +555,19 @@ __global__ void repack_awq_kernel(const uint32_t *__restrict__ qw, uint32_t *__r
 
 // ---------------------------------------------------------------- host
 // shared-memory plan of the int4 kernel for one (NT, groups) choice: raw stages take what is left of the budget
-struct Wa4Plan { int rs; size_t smem, rings; };
-static Wa4Plan wa4_plan(int NT, int groups) {
+struct Wa4Plan { int rs; size_t smem; };
+static Wa4Plan wa4_plan(int NT, int ksplit) {
   const size_t budget = (NT <= 64) ? (size_t)(227 * 1024) / 2 - 1024 : (size_t)200 * 1024;   // two CTAs per SM for the decode tiles
   const size_t xring = (size_t)WA_XS * NT * 256;
-  const size_t fixed = 1024 + xring + 512 + (size_t)groups * WA_BM * 4;
-  int rs = fixed < budget ? (int)((budget - fixed) / WA4_RAW_BYTES) : 0;
+  const size_t fixed = 1024 + xring + 512 + (size_t)(ksplit - 1) * NT * WA_BM * 4;
+  int rs = fixed < budget ? (int)((budget - fixed) / WA4_STAGE) : 0;
   if (rs > WA_RS_MAX) rs = WA_RS_MAX;
   if (rs < 2) rs = 2;
   Wa4Plan pl;
   pl.rs = rs;
-  pl.smem = fixed + (size_t)rs * WA4_RAW_BYTES;
-  pl.rings = xring + (size_t)rs * WA4_RAW_BYTES;
+  pl.smem = fixed + (size_t)rs * WA4_STAGE;
   return pl;
 }
-static int wa_groups_per_cta(int ksteps_per_split, int group) { return (ksteps_per_split * WA_BK + group - 1) / group + 1; }
 
 template <int NT, int SRC>
 static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaParams p, int ksplit, cudaStream_t st) {
@@ -529,7 +581,7 @@ static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaPar
   cfg.numAttrs = ksplit > 1 ? 1 : 0;
   if constexpr (SRC == WA_SRC_INT4) {
     auto kern = w4a16_int4_kernel<NT>;
-    const Wa4Plan pl = wa4_plan(NT, p.groups_per_cta);
+    const Wa4Plan pl = wa4_plan(NT, ksplit);
     p.raw_stages = pl.rs;
     if (pl.smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
@@ -538,7 +590,7 @@ static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaPar
     return cudaLaunchKernelEx(&cfg, kern, tx, p);
   } else {
     auto kern = w16_dense_kernel<NT>;
-    const size_t smem = 1024 + (size_t)WA_STAGES * (WA_A_BYTES + NT * 128) + 256;
+    const size_t smem = 1024 + (size_t)WA_STAGES * (WA_A_BYTES + NT * 128) + 256 + (size_t)(ksplit - 1) * NT * WA_BM * 4;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cfg.blockDim = dim3(WA_THREADS);
     cfg.dynamicSmemBytes = smem;
@@ -559,11 +611,10 @@ static int pick_ksplit(int src, int N, int K, int NT, int group) {
   int ks = 1;
   for (int c = 2; c <= 4; c *= 2) {
     const int per = ((nk + c - 1) / c + 1) & ~1;
-    // the reduction buffer (c-1 partials of NT x 128 f32) aliases the operand rings
-    const size_t red = (size_t)(c - 1) * NT * WA_BM * 4;
-    const size_t rings = (src == WA_SRC_INT4) ? wa4_plan(NT, wa_groups_per_cta(per, group)).rings
-                                              : (size_t)WA_STAGES * (WA_A_BYTES + NT * 128);
-    if (tiles * c <= slots && per >= 4 && per * (c - 1) < nk && red <= rings) ks = c;
+    // the split-K partials (c-1 tiles of NT x 128 f32) take their own shared memory: keep >= 4 raw stages beside them
+    const bool fits = (src == WA_SRC_INT4) ? wa4_plan(NT, c).rs >= 4
+                                           : 1024 + (size_t)WA_STAGES * (WA_A_BYTES + NT * 128) + 256 + (size_t)(c - 1) * NT * WA_BM * 4 <= 227 * 1024;
+    if (tiles * c <= slots && per >= 4 && per * (c - 1) < nk && fits) ks = c;
   }
   return ks;
 }
@@ -587,7 +638,6 @@ static cudaError_t run_wa(int src, const void *x, const void *w, const void *sca
     p.M = M; p.N = N; p.K = K; p.group = group; p.dtype = dtype; p.scale_perm = scale_perm; p.m0 = m0;
     const int ks = pick_ksplit(src, N, K, NT, group);
     p.ksteps_per_split = ks > 1 ? (((K / WA_BK + ks - 1) / ks + 1) & ~1) : K / WA_BK;
-    p.groups_per_cta = wa_groups_per_cta(p.ksteps_per_split, group);
     cudaError_t e;
 #define MRS_WA(NTV)                                                                                   \
   e = (src == WA_SRC_INT4) ? launch_wa<NTV, WA_SRC_INT4>(tx, tw, p, ks, st) : launch_wa<NTV, WA_SRC_DENSE>(tx, tw, p, ks, st)
@@ -601,6 +651,12 @@ static cudaError_t run_wa(int src, const void *x, const void *w, const void *sca
 }  // namespace mrs
 
 using namespace mrs;
+
+#ifdef MRS_WA_TRACE
+extern "C" int32_t mrs_debug_wa_trace(long long *out, int32_t n) {
+  return (int32_t)cudaMemcpyFromSymbol(out, g_wa_trace, (size_t)n * sizeof(long long));
+}
+#endif
 
 // ---- B200-native entries ---------------------------------------------------------------------
 // Y[M,N] = X[M,K] . W^T, W = repacked int4 (mrs tiles, see gptq_marlin_repack below); scales

@@ -72,9 +72,11 @@ def test_gptq_act_order_follows_the_reference_flow(cuda):
     assert (np.abs(y - ref) <= tol).all(), float((np.abs(y - ref) / tol).max())
 
 
+@pytest.mark.parametrize("K,N,group,M", [(512, 384, 128, 40), (448, 160, 64, 9), (1152, 320, 32, 32), (4096, 1024, 128, 32)])
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
-def test_awq_marlin_boundary(cuda, dt):
-    K, N, group, M = 512, 384, 128, 40
+def test_awq_marlin_boundary(cuda, dt, K, N, group, M):
+    """zero points + scale rows staged per iteration: several groups per 128-k iteration (32, 64), a K tail of
+    one 64-k chunk (448, 1152 % 128 == 64... 1152 = 9 x 128), ragged last row tile (160, 320; N stays a multiple of the scale permutation width the layer applies), split-K (4096)"""
     rng, q, scales, g = _mk(K, N, group, 2)
     z = rng.integers(0, 16, size=(K // group, N))
     qweight, qzeros = og.pack_awq(q), og.pack_awq(z)
