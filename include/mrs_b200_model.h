@@ -119,7 +119,22 @@ typedef struct {
   void *x, *x2, *h, *qkv, *attn_out, *o, *gate_up, *act, *logits, *tmp_v; float *tmp_s;
   int32_t *out_token, *attn_counters; void *argmax_scratch;
 } mrs_gptq_step;
+/* skip_mask: bit0 skip rope/cache/attention, bit1 skip the linears (measurement only), bit2 plain stream order instead of
+ * the programmatic-dependent-launch chain (HND layout: every launch of the layer loop triggers its dependents at start
+ * and waits for the upstream grid before touching its inputs/outputs, so each W4A16 GEMM streams weights while the
+ * small kernel before it still runs). */
 int32_t mrs_gptq_decode_step(const mrs_gptq_step *s, void *stream);
+/* The chain's links (not reference ABI): mrs_w4a16_gemm / mrs_dense_linear / add_rms_norm / fused_split_glu with a
+ * `pdl` flag.  pdl != 0 requires that the launch before it on `stream` is also a link (or a plain kernel). */
+int32_t mrs_w4a16_gemm_pdl(const void *x, const void *w_tiles, const void *scales, const int32_t *qzeros, void *y,
+                           int32_t M, int32_t K, int32_t N, int32_t group, int32_t dtype, int32_t scale_perm,
+                           int32_t pdl, void *stream);
+int32_t mrs_dense_linear_pdl(const void *x, const void *w, void *y, int32_t M, int32_t K, int32_t N, int32_t dtype,
+                             int32_t pdl, void *stream);
+void mrs_add_rms_norm_pdl(const void *x, const void *residual, const void *weight, void *residual_dst, void *norm_dst,
+                          int32_t nrows, int32_t ncols, float eps, int32_t dtype, int32_t pdl, void *stream);
+void mrs_split_glu_pdl(const void *input, void *output, uint32_t rows, uint32_t split_size, int32_t activation,
+                       int32_t dtype, int32_t pdl, void *stream);
 
 #ifdef __cplusplus
 }

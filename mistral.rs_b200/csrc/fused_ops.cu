@@ -82,7 +82,8 @@ static void launch_rotary(void *q, void *k, void *c, void *s, void *pos, int is_
 // ------------------------------------------------------------------ GLU
 template <typename T>
 __global__ void glu_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out, uint32_t cols,
-                           uint32_t a_stride, uint32_t b_stride, uint64_t n, int act) {
+                           uint32_t a_stride, uint32_t b_stride, uint64_t n, int act, int pdl) {
+  if (pdl) { pdl_launch_dependents(); pdl_wait(); }   // inputs come from the upstream kernel; the next one may start its prologue
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t row = i / cols;
@@ -94,10 +95,19 @@ __global__ void glu_kernel(const T *__restrict__ a, const T *__restrict__ b, T *
 
 template <typename T>
 static void launch_glu(const void *a, const void *b, void *out, uint32_t rows, uint32_t cols, uint32_t as, uint32_t bs,
-                       int act, cudaStream_t st) {
+                       int act, cudaStream_t st, int pdl = 0) {
   if (rows == 0 || cols == 0) return;
   const uint64_t n = (uint64_t)rows * cols;
-  glu_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const T *)a, (const T *)b, (T *)out, cols, as, bs, n, act);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((n + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, glu_kernel<T>, (const T *)a, (const T *)b, (T *)out, cols, as, bs, n, act, pdl);
 }
 
 // ------------------------------------------------------------------ RMSNorm
@@ -116,8 +126,9 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
 // normalised from its rounded value (REF sort.cu:403-428).
 template <typename T>
 __global__ void rms_norm_kernel(const T *__restrict__ x, const T *__restrict__ res, const T *__restrict__ w,
-                                T *__restrict__ sum_out, T *__restrict__ out, int cols, float eps) {
+                                T *__restrict__ sum_out, T *__restrict__ out, int cols, float eps, int pdl) {
   __shared__ float red[32];
+  if (pdl) { pdl_launch_dependents(); pdl_wait(); }
   const int64_t off = (int64_t)blockIdx.x * cols;
   float ss = 0.f;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
@@ -139,10 +150,19 @@ __global__ void rms_norm_kernel(const T *__restrict__ x, const T *__restrict__ r
 
 template <typename T>
 static void launch_rms(const void *x, const void *res, const void *w, void *sum_out, void *out, int rows, int cols,
-                       float eps, cudaStream_t st) {
+                       float eps, cudaStream_t st, int pdl = 0) {
   if (rows <= 0 || cols <= 0) return;
   const int block = cols < 1024 ? 128 : 512;
-  rms_norm_kernel<T><<<rows, block, 0, st>>>((const T *)x, (const T *)res, (const T *)w, (T *)sum_out, (T *)out, cols, eps);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(rows);
+  cfg.blockDim = dim3(block);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, rms_norm_kernel<T>, (const T *)x, (const T *)res, (const T *)w, (T *)sum_out, (T *)out, cols, eps, pdl);
 }
 
 // Per-head RMSNorm of a strided [B, H, S, D] view into a contiguous [B, H, S, D] tensor (QK-norm of
@@ -236,6 +256,21 @@ MRS_GLU(f32, float)
 MRS_RMS(f16, __half)
 MRS_RMS(bf16, __nv_bfloat16)
 MRS_RMS(f32, float)
+
+// decode-chain forms (not in the reference's ABI): the same kernels as links of a programmatic-dependent-launch
+// chain — they let the next kernel start its prologue at once and wait for the upstream grid before reading
+extern "C" void mrs_add_rms_norm_pdl(const void *x, const void *residual, const void *weight, void *residual_dst, void *norm_dst,
+                                     int32_t nrows, int32_t ncols, float eps, int32_t dtype, int32_t pdl, void *stream) {
+  if (dtype == MRS_F16) launch_rms<__half>(x, residual, weight, residual_dst, norm_dst, nrows, ncols, eps, (cudaStream_t)stream, pdl);
+  else if (dtype == MRS_BF16) launch_rms<__nv_bfloat16>(x, residual, weight, residual_dst, norm_dst, nrows, ncols, eps, (cudaStream_t)stream, pdl);
+}
+extern "C" void mrs_split_glu_pdl(const void *input, void *output, uint32_t rows, uint32_t split_size, int32_t activation,
+                                  int32_t dtype, int32_t pdl, void *stream) {
+  if (dtype == MRS_F16)
+    launch_glu<__half>(input, (const __half *)input + split_size, output, rows, split_size, 2 * split_size, 2 * split_size, activation, (cudaStream_t)stream, pdl);
+  else if (dtype == MRS_BF16)
+    launch_glu<__nv_bfloat16>(input, (const __nv_bfloat16 *)input + split_size, output, rows, split_size, 2 * split_size, 2 * split_size, activation, (cudaStream_t)stream, pdl);
+}
 
 #define MRS_RMS4D(tag, T)                                                                                     \
   extern "C" void rms_norm_strided_4d_##tag(const void *x, const void *weight, void *dst, int64_t stride_b,   \

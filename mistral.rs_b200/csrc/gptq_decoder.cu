@@ -76,6 +76,16 @@ __global__ void dense_embedding_kernel(const uint4 *__restrict__ table, int cols
     }                                                                \
   } while (0)
 
+extern "C" int32_t mrs_w4a16_gemm_pdl(const void *x, const void *w_tiles, const void *scales, const int32_t *qzeros, void *y,
+                                      int32_t M, int32_t K, int32_t N, int32_t group, int32_t dtype, int32_t scale_perm,
+                                      int32_t pdl, void *stream);
+extern "C" int32_t mrs_dense_linear_pdl(const void *x, const void *w, void *y, int32_t M, int32_t K, int32_t N, int32_t dtype,
+                                        int32_t pdl, void *stream);
+extern "C" void mrs_add_rms_norm_pdl(const void *x, const void *residual, const void *weight, void *residual_dst, void *norm_dst,
+                                     int32_t nrows, int32_t ncols, float eps, int32_t dtype, int32_t pdl, void *stream);
+extern "C" void mrs_split_glu_pdl(const void *input, void *output, uint32_t rows, uint32_t split_size, int32_t activation,
+                                  int32_t dtype, int32_t pdl, void *stream);
+
 extern "C" int32_t mrs_gptq_decode_step(const mrs_gptq_step *s, void *stream) {
   const int dt = s->act_dtype, B = s->batch, H = s->hidden;
   const int nq = s->n_heads * s->head_dim, nkv = s->n_kv_heads * s->head_dim, nqkv = nq + 2 * nkv;
@@ -85,12 +95,17 @@ extern "C" int32_t mrs_gptq_decode_step(const mrs_gptq_step *s, void *stream) {
   auto rms = [&](const void *x, const void *w, void *dst) {
     if (f16) mrs_rms_norm_f16(x, w, dst, B, H, s->rms_eps, (int64_t)stream); else mrs_rms_norm_bf16(x, w, dst, B, H, s->rms_eps, (int64_t)stream);
   };
+  // Every launch of the layer loop is a link of ONE programmatic-dependent-launch chain (skip_mask bit 2 turns it
+  // off): each kernel triggers its dependents when it starts and waits for the upstream grid before touching its
+  // inputs / outputs, so the W4A16 GEMMs stream their weights while the small kernels before them still run.
+  // The HND attention launch is PDL-capable; the vLLM-layout chain (reference-ABI kernels, no PDL forms) is not,
+  // so that layout keeps plain stream order.
+  const int pdl = ((s->skip_mask & 4) || s->cache_layout != 1) ? 0 : 1;
   auto add_rms = [&](const void *x, const void *res, const void *w, void *res_dst, void *norm_dst) {
-    if (f16) add_rms_norm_f16(x, res, w, res_dst, norm_dst, B, H, s->rms_eps, (int64_t)stream);
-    else add_rms_norm_bf16(x, res, w, res_dst, norm_dst, B, H, s->rms_eps, (int64_t)stream);
+    mrs_add_rms_norm_pdl(x, res, w, res_dst, norm_dst, B, H, s->rms_eps, dt, pdl, stream);
   };
   auto linear = [&](const mrs_w4_weight &w, const void *x, void *y) -> int {
-    return mrs_w4a16_gemm(x, w.tiles, w.scales, (const int32_t *)w.qzeros, y, B, w.k, w.n, s->group_size, dt, 0, stream);
+    return mrs_w4a16_gemm_pdl(x, w.tiles, w.scales, (const int32_t *)w.qzeros, y, B, w.k, w.n, s->group_size, dt, 0, pdl, stream);
   };
   const bool do_attn = !(s->skip_mask & 1), do_lin = !(s->skip_mask & 2);
 
@@ -108,7 +123,7 @@ extern "C" int32_t mrs_gptq_decode_step(const mrs_gptq_step *s, void *stream) {
                                              s->block_valid_mask, s->attn_out, s->padded_tiles > B ? s->tmp_v : nullptr,
                                              s->padded_tiles > B ? s->tmp_s : nullptr, s->attn_counters, B, s->padded_tiles,
                                              s->n_heads, s->n_kv_heads, s->head_dim, s->block_size, s->sm_scale, (uint32_t)dt,
-                                             s->rope_neox ? 0 : 2, nqkv, nqkv, stream));
+                                             (s->rope_neox ? 0 : 2) | pdl, nqkv, nqkv, stream));
     } else if (do_attn) {
       // vLLM cache layout (REF MISTRALRS_FLASHINFER_DECODE=0): rotary -> reshape_and_cache -> paged_attention_v1
       rotary_embedding_positions(q, k, (void *)s->rope_cos, (void *)s->rope_sin, s->positions, s->rope_neox, s->head_dim, B,
@@ -130,12 +145,12 @@ extern "C" int32_t mrs_gptq_decode_step(const mrs_gptq_step *s, void *stream) {
     if (do_lin) MRS_TRY(linear(L.wo, s->attn_out, s->o));
     add_rms(s->o, x, L.ffn_norm, x2, s->h);                                   // x2 = o + x ; h = norm(x2)
     if (do_lin) MRS_TRY(linear(L.w_gate_up, s->h, s->gate_up));
-    if (f16) fused_split_glu_f16(s->gate_up, s->act, B, L.w_down.k, 0, st); else fused_split_glu_bf16(s->gate_up, s->act, B, L.w_down.k, 0, st);
+    mrs_split_glu_pdl(s->gate_up, s->act, B, L.w_down.k, 0, dt, pdl, stream);
     if (do_lin) MRS_TRY(linear(L.w_down, s->act, s->o));
     const void *next_norm = (l + 1 < s->n_layers) ? s->layers[l + 1].attn_norm : s->final_norm;
     add_rms(s->o, x2, next_norm, x, s->h);                                     // x = down + x2 ; h = next norm(x)
   }
-  if (do_lin) MRS_TRY(mrs_dense_linear(s->h, s->lm_head, s->logits, B, H, s->vocab, dt, stream));
+  if (do_lin) MRS_TRY(mrs_dense_linear_pdl(s->h, s->lm_head, s->logits, B, H, s->vocab, dt, pdl, stream));
   MRS_TRY(mrs_argmax(s->logits, B, s->vocab, dt, s->out_token, s->argmax_scratch, 0, stream));
   return (int32_t)cudaGetLastError();
 }

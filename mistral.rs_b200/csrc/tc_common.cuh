@@ -72,6 +72,29 @@ __device__ __forceinline__ void umma_commit_warp(uint64_t *bar) {
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_warp(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}" ::
+          "r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+// pred != 0 selects whether the elected lane issues at all (warp-uniform)
+__device__ __forceinline__ void bulk_g2s_warp(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar_smem, uint32_t pred) {
+  asm volatile(
+      "{\n\t.reg .pred e, q;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 q, %4, 0;\n\tand.pred e, e, q;\n\t"
+      "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst_smem),
+      "l"(src_gmem), "r"(bytes), "r"(bar_smem), "r"(pred)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_warp(uint64_t *bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // K-major, SWIZZLE_128B operand descriptor (REF layout: cute/atom/mma_traits_sm100.hpp
 // make_umma_desc<Major::K>): start>>4 | LBO=1 | SBO=1024B>>4 | version 1 | layout 2

@@ -50,6 +50,7 @@ struct WaParams {
   int m0;                  // first token of this pass
   int ksteps_per_split;    // K-steps (of 64) per split CTA
   int raw_stages;          // depth of the packed-weight ring (int4 kernel)
+  int pdl;                 // link of a programmatic-dependent-launch chain: x comes from the upstream grid
 };
 
 // Inverses of the reference's scale-column permutations (REF gptq_cuda.rs:530-540 get_scale_perms):
@@ -138,6 +139,9 @@ __device__ __forceinline__ void wa_epilogue(const WaParams &p, float *red, uint6
     for (int i = 0; i < 16; i++) dstv[i] = __uint_as_float(v[i]);
   };
   __syncwarp();
+  // PDL: y (and everything written two kernels ago) may only be overwritten once the upstream grid has completed;
+  // this late in the kernel the wait returns at once — and every CTA must pass it so that completion stays transitive
+  if (p.pdl) pdl_wait();
   if constexpr (NT <= 64) {
     float acc[CPW];
     if (epi) {
@@ -215,6 +219,7 @@ w16_dense_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const int kb0 = (int)rank * p.ksteps_per_split;
   const int nk = max(0, min(p.ksteps_per_split, nk_total - kb0));
   const int rows_valid = min(WA_BM, p.N - n0);
+  if (p.pdl && tid == 0) pdl_launch_dependents();
   if (tid == 0) {
     for (int s = 0; s < WA_STAGES; s++) { mbar_init(&in_full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
@@ -231,6 +236,7 @@ w16_dense_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
   if (warp == 0) {
     if (lane == 0) {
+      if (p.pdl) pdl_wait();   // (weights and activations share one stage here: the whole stream waits for the upstream grid)
       int stage = 0, phase = 0;
       for (int i = 0; i < nk; i++) {
         const int kb = kb0 + i;
@@ -336,75 +342,102 @@ w4a16_int4_kernel(const __grid_constant__ CUtensorMap tmap_x, const WaParams p) 
   const int rows_valid = min(WA_BM, p.N - n0);
 
   if (warp == 0) WA_T(0);
-  if (tid == 0) {
-    for (int s = 0; s < RS; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], WA_DQ_WARPS); }
-    for (int s = 0; s < WA_XS; s++) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 1); }
-    for (int s = 0; s < AS; s++) { mbar_init(&a_full[s], WA_DQ_WARPS); mbar_init(&a_empty[s], 1); }
-    mbar_init(acc_full, 1);
-    mbar_init(red_bar, (uint32_t)(ksplit - 1) * WA_DQ_WARPS * 32u);
+  if (p.pdl && tid == 0) pdl_launch_dependents();
+  // Set-up, split so that the weight stream starts at once: warp 0 initialises the raw ring's barriers (one per
+  // lane), signals the CTA barrier WITHOUT waiting on it (bar.arrive) and goes straight to its copy loop; warp 1
+  // initialises the rest and allocates tensor memory; warps 1..10 meet on the barrier (which also orders warp 0's
+  // initialisation before any consumer's first wait).
+  static_assert(2 * WA_RS_MAX + 2 * WA_XS + 16 + 2 <= 64, "barrier block");
+  uint32_t tmem_base = 0u;
+  if (warp == 0) {
+    if (lane < 2 * WA_RS_MAX) mbar_init(&bars[lane], lane < WA_RS_MAX ? 1u : (uint32_t)WA_DQ_WARPS);
     fence_mbar_init();
+    __syncwarp();
+    asm volatile("bar.arrive 1, %0;" ::"n"(WA4_THREADS) : "memory");
+    if (ksplit > 1) cluster_arrive_release();   // start-up cluster barrier; waited on in the epilogue
+  } else {
+    if (warp == 1) {
+      // x_full[3] x_empty[3] a_full[8] a_empty[8] acc_full red_bar, in memory order after the raw ring's 24
+      const int b = lane;
+      if (b < 2 * WA_XS + 16 + 2) {
+        uint32_t cnt = 1u;
+        if (b >= 2 * WA_XS && b < 2 * WA_XS + 8) cnt = WA_DQ_WARPS;                                       // a_full
+        if (b == 2 * WA_XS + 17) cnt = ksplit > 1 ? (uint32_t)(ksplit - 1) * WA_DQ_WARPS * 32u : 1u;      // red_bar
+        mbar_init(&x_full[b], cnt);
+      }
+      fence_mbar_init();
+      __syncwarp();
+      tmem_alloc(tmem_slot, TCOLS);
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(WA4_THREADS) : "memory");
+    if (ksplit > 1) cluster_arrive_release();
+    tc_fence_after();
+    // REDUX result lives in a uniform register: the MMA issue loop gets uniform operands (no per-MMA waterfall)
+    tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TCOLS);
+  const uint32_t tmem_a = tmem_base + (uint32_t)NT;       // A ring: AS stages of 64 columns after the accumulator
 
-  // dequantiser identity + the first batch of scale loads, issued before the set-up barrier (they depend on nothing)
+  // dequantiser identity
   const int q4 = warp & 3, hf = (warp - 2) >> 2;   // TMEM lane quarter, which 64-k chunk of the iteration
   const int r = q4 * 32 + lane;                    // weight row in the tile == TMEM lane
-  const bool dq = warp >= 2 && warp < 2 + WA_DQ_WARPS;
   const int n = n0 + r;
   int scol = n;
   if (p.scale_perm == 1) scol = (n & ~63) + inv_scale_perm64(n & 63);
   else if (p.scale_perm == 2) scol = (n & ~31) + inv_scale_perm32(n & 31);
   const int zsh = 4 * ((n & 7) == 0 ? 0 : (n & 7) == 1 ? 4 : (n & 7) == 2 ? 1 : (n & 7) == 3 ? 5 : (n & 7) == 4 ? 2 : (n & 7) == 5 ? 6 : (n & 7) == 6 ? 3 : 7);
-  tc_fence_before();
-  __syncthreads();
-  if (ksplit > 1) cluster_arrive_release();   // start-up cluster barrier; waited on in the epilogue
-  tc_fence_after();
-  // REDUX result lives in a uniform register: the MMA issue loop gets uniform operands (no per-MMA waterfall)
-  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
-  const uint32_t tmem_a = tmem_base + (uint32_t)NT;       // A ring: AS stages of 64 columns after the accumulator
   if (warp == 0) WA_T(1);
 
   if (warp == 0) {
     // ===================== raw producer: the HBM stream =====================
-    if (lane == 0) {
-      // per iteration: the packed nibbles of one or two 64-k chunks, plus the scale row (and AWQ zero-point row) of
-      // every group the iteration's k range touches (one row when group % 128 == 0) — the dequantisers read them
-      // from the stage with LDS; nothing on their path waits for global memory
-      const uint32_t raw_bytes = (uint32_t)rows_valid * 32u, sc_bytes = (uint32_t)rows_valid * 2u, zp_bytes = (uint32_t)rows_valid / 2u;
-      const uint16_t *sc_src = (const uint16_t *)p.scales + n0;
-      const int32_t *zp_src = p.qzeros ? p.qzeros + (n0 >> 3) : nullptr;
-      int g = (kb0 * WA_BK) / p.group, k_in_g = (kb0 * WA_BK) % p.group;
-      int stage = 0, phase = 0;
-      for (int i = 0; i < nit; i++) {
-        const int nc = min(2, nk - 2 * i);
-        const int ng = (k_in_g + 64 * nc - 1) / p.group + 1;          // groups touched by this iteration (<= 4)
-        uint8_t *st = r_ring + (size_t)stage * WA4_STAGE;
-        mbar_wait(&raw_empty[stage], phase ^ 1);
-        WA_T(100 + i);
-        mbar_arrive_expect_tx(&raw_full[stage], raw_bytes * (uint32_t)nc + (sc_bytes + (zp_src ? zp_bytes : 0u)) * (uint32_t)ng);
-        for (int c = 0; c < nc; c++)
-          bulk_g2s(st + (size_t)c * WA_RAW_BYTES, p.wq + ((size_t)(kb0 + 2 * i + c) * p.N + n0) * 32, raw_bytes, &raw_full[stage]);
-        for (int j = 0; j < ng; j++) {
-          bulk_g2s(st + WA4_SC_OFF + j * 256, sc_src + (size_t)(g + j) * p.N, sc_bytes, &raw_full[stage]);
-          if (zp_src) bulk_g2s(st + WA4_ZP_OFF + j * 64, zp_src + (size_t)(g + j) * (p.N >> 3), zp_bytes, &raw_full[stage]);
-        }
-        k_in_g += WA4_BK;
-        while (k_in_g >= p.group) { k_in_g -= p.group; g++; }
-        if (++stage == RS) { stage = 0; phase ^= 1; }
+    // The whole warp runs this loop convergently with warp-uniform operands; one elected lane issues each copy
+    // (inside an `if (lane == 0)` region every UBLKCP sits in an ELECT ... BRA.U.ANY loop and the address
+    // arithmetic runs through R2UR waterfalls: ~300 clocks per copy measured — the producer paced the kernel).
+    // Per iteration: the packed nibbles of one or two 64-k chunks, plus the scale row (and AWQ zero-point row) of
+    // every group the iteration's k range touches (one row when group % 128 == 0) — the dequantisers read them
+    // from the stage with LDS; nothing on their path waits for global memory.
+    const uint32_t raw_bytes = (uint32_t)rows_valid * 32u, sc_bytes = (uint32_t)rows_valid * 2u;
+    const uint32_t zp_bytes = p.qzeros ? (uint32_t)rows_valid / 2u : 0u;
+    const uint8_t *w_src = p.wq + ((size_t)kb0 * p.N + n0) * 32;
+    const size_t w_step = (size_t)p.N * 32;
+    const int G = p.group;
+    int k_in_g = (kb0 * WA_BK) % G;
+    const uint8_t *sc_src = (const uint8_t *)p.scales + ((size_t)((kb0 * WA_BK) / G) * p.N + n0) * 2;
+    const uint8_t *zp_src = p.qzeros ? (const uint8_t *)p.qzeros + ((size_t)((kb0 * WA_BK) / G) * (p.N >> 3) + (n0 >> 3)) * 4 : (const uint8_t *)p.scales;
+    const size_t sc_step = (size_t)p.N * 2, zp_step = (size_t)(p.N >> 3) * 4;
+    const uint32_t ring = smem_u32(r_ring);
+    int stage = 0, phase = 0;
+    for (int i = 0; i < nit; i++) {
+      const int nc = min(2, nk - 2 * i);
+      const int x = k_in_g + 64 * nc - 1;                             // last k of the iteration, relative to its first group
+      const int ng = 1 + (x >= G) + (x >= 2 * G) + (x >= 3 * G);      // groups touched (<= 4: 128 k over groups >= 32)
+      const uint32_t st = ring + (uint32_t)stage * WA4_STAGE, bar = smem_u32(&raw_full[stage]);
+      mbar_wait(&raw_empty[stage], phase ^ 1);
+      WA_T(100 + i);
+      mbar_arrive_expect_tx_warp(&raw_full[stage], raw_bytes * (uint32_t)nc + (sc_bytes + zp_bytes) * (uint32_t)ng);
+      bulk_g2s_warp(st, w_src, raw_bytes, bar, 1u);
+      bulk_g2s_warp(st + WA_RAW_BYTES, w_src + w_step, raw_bytes, bar, nc > 1);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        bulk_g2s_warp(st + WA4_SC_OFF + j * 256, sc_src + j * sc_step, sc_bytes, bar, j < ng);
+        bulk_g2s_warp(st + WA4_ZP_OFF + j * 64, zp_src + j * zp_step, zp_bytes, bar, (j < ng) && zp_bytes != 0u);
       }
+      w_src += 2 * w_step;
+      k_in_g += WA4_BK;
+      while (k_in_g >= G) { k_in_g -= G; sc_src += sc_step; zp_src += zp_step; }
+      if (++stage == RS) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 10) {
     // ===================== X producer (activation tiles, L2; k beyond K is zero-filled by TMA) =====================
-    if (lane == 0) {
-      int stage = 0, phase = 0;
-      for (int i = 0; i < nit; i++) {
-        mbar_wait(&x_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&x_full[stage], X_BYTES);
-        uint8_t *xs = x_ring + (size_t)stage * X_BYTES;
-        tma_load_2d(xs, &tmap_x, (kb0 + 2 * i) * WA_BK, p.m0, &x_full[stage]);
-        tma_load_2d(xs + NT * 128, &tmap_x, (kb0 + 2 * i + 1) * WA_BK, p.m0, &x_full[stage]);
-        if (++stage == WA_XS) { stage = 0; phase ^= 1; }
-      }
+    if (p.pdl) pdl_wait();   // the activations are the upstream kernel's output; the weight stream (warp 0) never waits
+    int stage = 0, phase = 0;
+    for (int i = 0; i < nit; i++) {
+      mbar_wait(&x_empty[stage], phase ^ 1);
+      mbar_arrive_expect_tx_warp(&x_full[stage], X_BYTES);
+      uint8_t *xs = x_ring + (size_t)stage * X_BYTES;
+      tma_load_2d_warp(xs, &tmap_x, (kb0 + 2 * i) * WA_BK, p.m0, &x_full[stage]);
+      tma_load_2d_warp(xs + NT * 128, &tmap_x, (kb0 + 2 * i + 1) * WA_BK, p.m0, &x_full[stage]);
+      if (++stage == WA_XS) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: D[128 rows, NT tokens] += A[tmem] . X[smem]^T =====================
@@ -574,11 +607,20 @@ static cudaError_t launch_wa(const CUtensorMap &tx, const CUtensorMap &tw, WaPar
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((p.N + WA_BM - 1) / WA_BM, ksplit);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = ksplit; attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (ksplit > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = ksplit; attr[na].val.clusterDim.z = 1;
+    na++;
+  }
+  if (p.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = ksplit > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   if constexpr (SRC == WA_SRC_INT4) {
     auto kern = w4a16_int4_kernel<NT>;
     const Wa4Plan pl = wa4_plan(NT, ksplit);
@@ -620,11 +662,12 @@ static int pick_ksplit(int src, int N, int K, int NT, int group) {
 }
 
 static cudaError_t run_wa(int src, const void *x, const void *w, const void *scales, const int32_t *qzeros, void *y, int M,
-                          int K, int N, int group, int dtype, int scale_perm, cudaStream_t st) {
+                          int K, int N, int group, int dtype, int scale_perm, cudaStream_t st, int pdl = 0) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (K % WA_BK != 0 || (dtype != MRS_F16 && dtype != MRS_BF16)) return cudaErrorInvalidValue;
   if (group <= 0) group = K;
-  if (src == WA_SRC_INT4 && (group % 32 != 0 || K % group != 0)) return cudaErrorInvalidValue;
+  if (src == WA_SRC_INT4 && (group % 32 != 0 || K % group != 0 || N % 8 != 0)) return cudaErrorInvalidValue;
+  if (src == WA_SRC_INT4 && qzeros != nullptr && N % 32 != 0) return cudaErrorInvalidValue;   // zero-point rows travel as 16-byte bulk copies
   if (((uintptr_t)x & 15) || ((uintptr_t)w & 15)) return cudaErrorMisalignedAddress;
   CUtensorMap tx, tw;
   memset(&tw, 0, sizeof tw);
@@ -636,6 +679,7 @@ static cudaError_t run_wa(int src, const void *x, const void *w, const void *sca
     WaParams p = {};
     p.wq = (const uint8_t *)w; p.scales = scales; p.qzeros = qzeros; p.y = y;
     p.M = M; p.N = N; p.K = K; p.group = group; p.dtype = dtype; p.scale_perm = scale_perm; p.m0 = m0;
+    p.pdl = (pdl && M <= 256) ? 1 : 0;   // (one pass only: a second token pass would race the first one's output)
     const int ks = pick_ksplit(src, N, K, NT, group);
     p.ksteps_per_split = ks > 1 ? (((K / WA_BK + ks - 1) / ks + 1) & ~1) : K / WA_BK;
     cudaError_t e;
@@ -671,6 +715,17 @@ extern "C" int32_t mrs_w4a16_gemm(const void *x, const void *w_tiles, const void
 extern "C" int32_t mrs_dense_linear(const void *x, const void *w, void *y, int32_t M, int32_t K, int32_t N, int32_t dtype,
                                     void *stream) {
   return (int32_t)run_wa(WA_SRC_DENSE, x, w, nullptr, nullptr, y, M, K, N, 0, dtype, 0, (cudaStream_t)stream);
+}
+// the same two as links of a programmatic-dependent-launch chain (decode layer stack): the weight stream starts while
+// the upstream kernel is still running; x is read, and y written, only after it has completed
+extern "C" int32_t mrs_w4a16_gemm_pdl(const void *x, const void *w_tiles, const void *scales, const int32_t *qzeros, void *y,
+                                      int32_t M, int32_t K, int32_t N, int32_t group, int32_t dtype, int32_t scale_perm,
+                                      int32_t pdl, void *stream) {
+  return (int32_t)run_wa(WA_SRC_INT4, x, w_tiles, scales, qzeros, y, M, K, N, group, dtype, scale_perm, (cudaStream_t)stream, pdl);
+}
+extern "C" int32_t mrs_dense_linear_pdl(const void *x, const void *w, void *y, int32_t M, int32_t K, int32_t N, int32_t dtype,
+                                        int32_t pdl, void *stream) {
+  return (int32_t)run_wa(WA_SRC_DENSE, x, w, nullptr, nullptr, y, M, K, N, 0, dtype, 0, (cudaStream_t)stream, pdl);
 }
 
 // ---- the reference's Marlin symbols (REF mistralrs-quant/src/gptq/marlin_ffi.rs:6-81) ----------
