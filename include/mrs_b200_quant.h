@@ -78,6 +78,13 @@ int mrs_mmvq_fused_qkv_mixed(int type_qk, int type_v, int dt, const void *wq, co
 int32_t mrs_mmq_gguf(int32_t ggml_type, const void *w, const void *x, void *y, int32_t M, int32_t N, int32_t K,
                      int32_t dtype, void *stream);
 void mrs_mmq_set_weight_format(int32_t fmt);
+/* mrs_mmq_gguf picks between two tcgen05 kernels: csrc/mmq_ts.cu (swap-AB, dequantised weights as the A operand in
+ * tensor memory; Q8_0 / Q4_K / Q6_K, K % 256 == 0, rows a multiple of 16 bytes) and csrc/mmq_tc.cu (everything else).
+ * path 0: automatic (default); 1: mmq_tc.cu only.  mrs_mmq_gguf_ts is the first kernel's own entry point: it returns
+ * cudaErrorNotSupported (801) when the launch does not fit it. */
+void mrs_mmq_set_path(int32_t path);
+int32_t mrs_mmq_gguf_ts(int32_t ggml_type, const void *w, const void *x, void *y, int32_t M, int32_t N, int32_t K,
+                        int32_t dtype, void *stream);
 
 /* GPTQ / AWQ int4 linear from the raw checkpoint tensors (no Marlin repack) on the same
  * tcgen05 kernel: Y[M,N] f16 = X[M,K] f16 . W; GPTQ qweight [K/8,N] (w = (q-8)*s, optional

@@ -477,9 +477,16 @@ static int tc_row_bytes(int type, int K) {
 static int g_tc_b_fmt = -1;  // -1: same 16-bit format as the activations; 0 force f16; 1 force bf16
 extern "C" void mrs_mmq_set_weight_format(int32_t fmt) { g_tc_b_fmt = fmt; }
 
+extern "C" int32_t mrs_mmq_gguf_ts(int32_t ggml_type, const void *w, const void *x, void *y, int32_t M, int32_t N, int32_t K,
+                                   int32_t dtype, void *stream);   // mmq_ts.cu
+
 extern "C" int32_t mrs_mmq_gguf(int32_t ggml_type, const void *w, const void *x, void *y, int32_t M, int32_t N,
                                 int32_t K, int32_t dtype, void *stream) {
   if (M <= 0 || N <= 0) return 0;
+  if (g_tc_b_fmt < 0) {   // the second-generation kernel (swap-AB, A operand in tensor memory) when the launch fits it
+    const int32_t e = mrs_mmq_gguf_ts(ggml_type, w, x, y, M, N, K, dtype, stream);
+    if (e != (int32_t)cudaErrorNotSupported) return e;
+  }
   const int rb = tc_row_bytes(ggml_type, K);
   if (rb == 0 || K % 64 != 0 || (dtype != 0 && dtype != 1)) return (int32_t)cudaErrorInvalidValue;
   if (ggml_type >= MRS_Q2_K && K % 256 != 0) return (int32_t)cudaErrorInvalidValue;

@@ -33,6 +33,11 @@ def forward(w, xs: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def set_path(path: str):
+    """'auto' (default): csrc/mmq_ts.cu when the launch fits it, else csrc/mmq_tc.cu; 'tc': mmq_tc.cu only (A/B, tests)."""
+    lib().mrs_mmq_set_path(ctypes.c_int({"auto": 0, "tc": 1}[path]))
+
+
 def set_weight_format(fmt: str):
     """'same' (default: the activations' 16-bit format), 'f16' or 'bf16' for the dequantised weights."""
     lib().mrs_mmq_set_weight_format(ctypes.c_int({"same": -1, "f16": 0, "bf16": 1}[fmt]))

@@ -16,8 +16,8 @@ def bench(fn, reps=10):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
-for fmt in ("same",):
-    mmq.set_weight_format(fmt)
+for fmt in ("auto", "tc"):
+    mmq.set_path(fmt)
     for dtype in ("q8_0", "q4_k", "q6_k"):
         for (M, N, K) in [(4096, 4096, 4096), (4096, 14336, 4096), (4096, 4096, 14336)]:
             rng = np.random.default_rng(0)
@@ -26,7 +26,7 @@ for fmt in ("same",):
             x = torch.randn(M, K, device=dev).to(torch.bfloat16)
             ms = bench(lambda: mmq.forward(w, x))
             wd = torch.from_numpy(oracle.dequantize(dtype, wb).reshape(N, K)).to(dev).to(torch.bfloat16)
-            ms_ref = bench(lambda: x @ wd.t())
+            ms_ref = bench(lambda: x @ wd.t()) if fmt == "auto" else float("nan")
             y = mmq.forward(w, x).float(); yr = (x.float() @ wd.float().t())
             err = ((y - yr).abs().max() / yr.abs().max()).item()
             fl = 2.0 * M * N * K

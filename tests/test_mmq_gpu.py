@@ -70,3 +70,24 @@ def test_matches_decode_path_semantics(cuda):
     scale = np.abs(ref).max()
     assert np.abs(y9 - ref).max() <= 2.0 ** -7 * scale
     assert np.abs(y8 - ref[:8]).max() <= 2e-2 * scale   # int8 activations: ~1/127 per-block noise
+
+
+@pytest.mark.parametrize("dtype", ["q8_0", "q4_k", "q6_k"])
+@pytest.mark.parametrize("dt", ["bf16", "f16"])
+@pytest.mark.parametrize("M,N,K", [(300, 520, 2048), (64, 136, 4096), (129, 128, 2048)])
+def test_second_generation_kernel(cuda, dtype, dt, M, N, K):
+    """csrc/mmq_ts.cu (swap-AB, dequantised weights as the A operand in tensor memory, raw blocks through the TMA) —
+    shapes it takes for all three types (K % 2048 == 0 keeps Q6_K rows a multiple of 16 bytes): ragged token and row
+    tiles, both token-tile widths (M <= 128 -> 128, else 256).  Against the exact product, and bit for bit against
+    csrc/mmq_tc.cu: same weight rounding, same k order of the f32 accumulation."""
+    _check(dtype, M, N, K, dt, 7)
+    wb = make_weight(dtype, N, K, 7)
+    x = to_dev(make_acts(M, K, 8, dt), cuda, dt)
+    w = quant.QTensor(to_dev(wb.reshape(-1), cuda), dtype, (N, K))
+    try:
+        mmq.set_path("tc")
+        y_tc = mmq.forward(w, x).clone()
+    finally:
+        mmq.set_path("auto")
+    y_ts = mmq.forward(w, x)
+    assert torch.equal(y_tc, y_ts), float((y_tc.float() - y_ts.float()).abs().max())
