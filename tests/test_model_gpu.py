@@ -156,7 +156,9 @@ def test_llama3_8b_shapes_two_layers(cuda, dt):
     recipe -> layer 0 all Q4_K, layer 1 attn_v / ffn_down in Q6_K, Q6_K lm_head): two real-size
     layers + lm_head through mrs_llama_decode_step vs the oracle.  Error stated in ulps of the
     logit scale; f16 must meet north_star's 1e-3 relative."""
-    cfg = M.LlamaConfig.llama3_8b(n_layers=2, max_pos=64)     # block scales 2^U(-15,-13): unit-scale activations
+    # block scales 2^U(-15,-13) (bf16) / 2^U(-17,-15) (f16): the down_proj output of the SYNTHETIC model grows with the
+    # cube of the block scale and reaches 1e6 at -15..-13 — fine in bf16, an f16 overflow (real checkpoints stay small)
+    cfg = M.LlamaConfig.llama3_8b(n_layers=2, max_pos=64, synth_scale_exp=(-15, -13) if dt == "bf16" else (-17, -15))
     tdt = {"bf16": torch.bfloat16, "f16": torch.float16}[dt]
     w = M.LlamaWeights(cfg, cuda, dtype=tdt, keep_host=True)
     run = M.LlamaRunner(w, batch=1, max_ctx=32, pdl=True)
