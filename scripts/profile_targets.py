@@ -26,3 +26,27 @@ elif what == "decode":
     for _ in range(3):
         run.step()
     torch.cuda.synchronize()
+elif what == "w4a16":
+    import ctypes
+    from mistralrs_b200 import lib
+    N, K, Mm, group = 28672, 4096, 32, 128
+    qw = torch.randint(-2**31, 2**31 - 1, (K // 8, N), dtype=torch.int32, device=dev)
+    sc = torch.rand(K // group, N, device=dev).to(torch.float16) * 0.01
+    tiles = torch.empty(K // 16, N * 2, dtype=torch.int32, device=dev)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = lambda: torch.cuda.current_stream().cuda_stream
+    lib().gptq_marlin_repack(P(qw), ctypes.c_void_p(0), P(tiles), K, N, 4, ctypes.c_int64(st()))
+    x = torch.randn(Mm, K, device=dev).to(torch.float16)
+    y = torch.empty(Mm, N, dtype=torch.float16, device=dev)
+    for _ in range(6):
+        assert lib().mrs_w4a16_gemm(P(x), P(tiles), P(sc), ctypes.c_void_p(0), P(y), Mm, K, N, group, 0, 0, ctypes.c_void_p(st())) == 0
+    torch.cuda.synchronize()
+elif what == "prefill_attn":
+    from mistralrs_b200 import paged_attn
+    T, H, KVH, D = 4096, 32, 8, 128
+    q = torch.randn(T, H, D, device=dev).to(torch.bfloat16)
+    k = torch.randn(T, KVH, D, device=dev).to(torch.bfloat16)
+    v = torch.randn(T, KVH, D, device=dev).to(torch.bfloat16)
+    for _ in range(3):
+        paged_attn.prefill_attention(q, k, v, D ** -0.5)
+    torch.cuda.synchronize()
