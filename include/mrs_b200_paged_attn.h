@@ -116,6 +116,17 @@ int32_t mrs_prefill_attention(const void *q, const void *k, const void *v, void 
                               int32_t num_kv_heads, int32_t head_dim, int64_t q_stride, int64_t kv_stride, int64_t o_stride,
                               float softmax_scale, int32_t causal, int32_t window_left, float softcap, uint32_t dtype,
                               void *stream);
+/* mrs_prefill_attention picks between csrc/prefill_attn_tc.cu (tcgen05: S and P in tensor memory, V as an MN-major
+ * shared-memory operand; head size 128, no window / softcap) and csrc/prefill_attn.cu (mma.sync; everything else).
+ * mrs_prefill_attention_tc is the first kernel's own entry: cudaErrorNotSupported (801) when the call does not fit.
+ * mrs_prefill_attn_tc_debug(enable, lbo, sbo): enable 0 keeps every call on prefill_attn.cu (A/B, tests); lbo / sbo
+ * (bytes, 0 = keep) override the V operand's descriptor strides (bring-up knob). */
+int32_t mrs_prefill_attention_tc(const void *q, const void *k, const void *v, void *out, const int32_t *cu_seqlens,
+                              int32_t batch, int32_t total_tokens, int32_t max_seqlen, int32_t num_heads,
+                              int32_t num_kv_heads, int32_t head_dim, int64_t q_stride, int64_t kv_stride, int64_t o_stride,
+                              float softmax_scale, int32_t causal, int32_t window_left, float softcap, uint32_t dtype,
+                              void *stream);
+void mrs_prefill_attn_tc_debug(int32_t enable, uint32_t lbo, uint32_t sbo);
 /* diagnostics: bit 0 keeps HND decode attention on the SIMT kernel instead of the tensor-core one;
  * bit 1 disables the cluster/DSMEM merge of split-KV tiles (global partials + counter instead) */
 void mrs_set_attn_flags(int32_t flags);

@@ -230,12 +230,24 @@ using namespace mrs;
 // [total, H, D] (o_stride); cu_seqlens [batch + 1] i32 on the device or NULL (one sequence of
 // `total` tokens; max_seqlen = longest sequence).  head_dim 64 or 128; dtype 0 f16 / 1 bf16;
 // window_left < 0: full causal; softcap <= 0: off.  Returns a cudaError_t.
+extern "C" int32_t mrs_prefill_attention_tc(const void *q, const void *k, const void *v, void *out, const int32_t *cu_seqlens,
+                                            int32_t batch, int32_t total_tokens, int32_t max_seqlen, int32_t num_heads,
+                                            int32_t num_kv_heads, int32_t head_dim, int64_t q_stride, int64_t kv_stride,
+                                            int64_t o_stride, float softmax_scale, int32_t causal, int32_t window_left,
+                                            float softcap, uint32_t dtype, void *stream);   // prefill_attn_tc.cu
+
 extern "C" int32_t mrs_prefill_attention(const void *q, const void *k, const void *v, void *out, const int32_t *cu_seqlens,
                                          int32_t batch, int32_t total_tokens, int32_t max_seqlen, int32_t num_heads,
                                          int32_t num_kv_heads, int32_t head_dim, int64_t q_stride, int64_t kv_stride,
                                          int64_t o_stride, float softmax_scale, int32_t causal, int32_t window_left,
                                          float softcap, uint32_t dtype, void *stream) {
   if (total_tokens <= 0) return 0;
+  {   // the tcgen05 kernel when the call fits it (head size 128, no window, no softcap)
+    const int32_t e = mrs_prefill_attention_tc(q, k, v, out, cu_seqlens, batch, total_tokens, max_seqlen, num_heads, num_kv_heads,
+                                               head_dim, q_stride, kv_stride, o_stride, softmax_scale, causal, window_left, softcap,
+                                               dtype, stream);
+    if (e != (int32_t)cudaErrorNotSupported) return e;
+  }
   if ((dtype != 0 && dtype != 1) || num_kv_heads <= 0 || num_heads % num_kv_heads || (q_stride | kv_stride | o_stride) % 8)
     return (int32_t)cudaErrorInvalidValue;
   if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) return (int32_t)cudaErrorMisalignedAddress;

@@ -1,0 +1,305 @@
+// prefill_attn_tc.cu — causal (var-len) prompt attention on the 5th-gen tensor cores (tcgen05 + TMEM), head size 128.
+//
+// Same contract and arithmetic class as prefill_attn.cu (REF mistralrs-core/src/paged_attention/layers/
+// paged_attention.rs:1413-1475 -> flash_attn_varlen): S = QK^T and O = PV on 16-bit MMAs with
+// f32 accumulation, online softmax in f32 (base-2 exponent, scale folded), P rounded to the activation dtype before
+// the second GEMM.  mrs_prefill_attention routes here for head_dim 128 without window / softcap; prefill_attn.cu
+// (mma.sync) keeps every other case.
+//
+// One CTA = 128 query rows of one (sequence, head), 128-token K/V tiles, 192 threads:
+//   warp 0      TMA: Q once (two SWIZZLE_128B boxes of 64 d), then K and V tiles through two 2-stage rings;
+//   warp 1      MMA issuer (one elected lane, warp-convergent):
+//                 S_j  = Q K_j^T      SS form, both operands K-major in shared memory, M128 N128 K16 x 8
+//                 O   += P_j V_j      TS form: P (16-bit pairs) is the A operand in TENSOR MEMORY, V is the B operand
+//                                     straight from its row-major [token][d] tile = MN-major SWIZZLE_128B
+//                                     (no transpose pass): M128 N128 K16 x 8
+//               S is double-buffered in TMEM, so S_{j+1} is computed while the softmax of tile j runs;
+//   warps 2..5  softmax + correction + epilogue, thread = query row = TMEM lane: tcgen05.ld the S row (two passes:
+//               max, then exp2 / sum / pack), tcgen05.st P, rescale O in TMEM only when some row's maximum moved
+//               (warp vote), finally O / l -> global.
+// TMEM columns: S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O [384,512).
+#include "tc_common.cuh"
+
+#include <math.h>
+#include <stdio.h>
+
+namespace mrs {
+
+constexpr int FT_BM = 128, FT_BN = 128, FT_D = 128;
+constexpr int FT_THREADS = 32 * 6;
+constexpr int FT_TILE_BYTES = FT_BN * FT_D * 2;                       // 32 KB: two boxes [128 rows][64 d]
+constexpr int FT_SMEM = 1024 + 5 * FT_TILE_BYTES + 256;              // Q + 2 K stages + 2 V stages + barriers
+
+struct FtParams {
+  void *o;
+  const int32_t *cu_seqlens;   // [B + 1] or nullptr (single sequence of length T)
+  int T, H, KVH;
+  int64_t o_stride;            // elements between consecutive tokens of the output
+  float scale_log2;            // softmax_scale * log2(e)
+  int causal, bf16;
+  uint32_t v_lbo, v_sbo;       // MN-major descriptor strides of the V operand, bytes
+};
+
+// shared-memory operand descriptor, SWIZZLE_128B, explicit leading / stride byte offsets
+__device__ __forceinline__ uint64_t umma_desc_sw128_ex(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint64_t addr = (uint64_t)(saddr >> 4) & 0x3FFF;
+  return addr | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_f16_ss_warp(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t *r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
+          "r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_v, const FtParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *q_s = smem, *k_ring = smem + FT_TILE_BYTES, *v_ring = smem + 3 * FT_TILE_BYTES;
+  uint64_t *bars = (uint64_t *)(smem + 5 * FT_TILE_BYTES);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 7, *s_full = bars + 9,
+           *s_free = bars + 11, *p_full = bars + 13, *pv_done = bars + 15;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 17);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int kvh = h / (p.H / p.KVH);
+  int seq0 = 0, len = p.T;
+  if (p.cu_seqlens != nullptr) { seq0 = p.cu_seqlens[b]; len = p.cu_seqlens[b + 1] - seq0; }
+  const int ntile_q = (len + FT_BM - 1) / FT_BM;
+  const int qt = ntile_q - 1 - (int)blockIdx.x;      // heavy (late) query tiles first
+  if (qt < 0) return;
+  const int q0 = qt * FT_BM;
+  const int q_hi = min(len, q0 + FT_BM) - 1;
+  const int kv_end = p.causal ? (q_hi + 1) : len;
+  const int nt = (kv_end + FT_BN - 1) / FT_BN;
+
+  if (warp == 0 && lane < 17) {
+    uint32_t cnt = 1u;
+    if (lane >= 11 && lane < 15) cnt = 4u;            // s_free, p_full: the four softmax warps
+    mbar_init(&bars[lane], cnt);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
+  const uint32_t t_s = tmem_base, t_p = tmem_base + 256u, t_o = tmem_base + 384u;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    mbar_arrive_expect_tx_warp(q_full, FT_TILE_BYTES);
+    tma_load_2d_warp(q_s, &tmap_q, h * FT_D, seq0 + q0, q_full);
+    tma_load_2d_warp(q_s + FT_TILE_BYTES / 2, &tmap_q, h * FT_D + 64, seq0 + q0, q_full);
+    for (int j = 0; j < nt; j++) {
+      const int st = j & 1, ph = (j >> 1) & 1;
+      const int row = seq0 + j * FT_BN;
+      mbar_wait(&k_empty[st], ph ^ 1);
+      mbar_arrive_expect_tx_warp(&k_full[st], FT_TILE_BYTES);
+      tma_load_2d_warp(k_ring + (size_t)st * FT_TILE_BYTES, &tmap_k, kvh * FT_D, row, &k_full[st]);
+      tma_load_2d_warp(k_ring + (size_t)st * FT_TILE_BYTES + FT_TILE_BYTES / 2, &tmap_k, kvh * FT_D + 64, row, &k_full[st]);
+      mbar_wait(&v_empty[st], ph ^ 1);
+      mbar_arrive_expect_tx_warp(&v_full[st], FT_TILE_BYTES);
+      tma_load_2d_warp(v_ring + (size_t)st * FT_TILE_BYTES, &tmap_v, kvh * FT_D, row, &v_full[st]);
+      tma_load_2d_warp(v_ring + (size_t)st * FT_TILE_BYTES + FT_TILE_BYTES / 2, &tmap_v, kvh * FT_D + 64, row, &v_full[st]);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t fmt = p.bf16 ? 1u : 0u;
+    // c = f32 (bit 4), a / b format (bits 7, 10), b_major = MN (bit 16) for the PV product, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc_s = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(FT_BN >> 3) << 17) | ((uint32_t)(FT_BM >> 4) << 24);
+    const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(FT_D >> 3) << 17) | ((uint32_t)(FT_BM >> 4) << 24);
+    auto issue_s = [&](int j) {
+      const int st = j & 1, ph = (j >> 1) & 1;
+      mbar_wait(&k_full[st], ph);
+      mbar_wait(&s_free[st], ph ^ 1);                  // the softmax has read the previous S in this buffer
+      tc_fence_after();
+      const uint8_t *ks = k_ring + (size_t)st * FT_TILE_BYTES;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint64_t ad = umma_desc_sw128(q_s + (c >> 2) * (FT_TILE_BYTES / 2)) + (uint64_t)(2 * (c & 3));
+        const uint64_t bd = umma_desc_sw128(ks + (c >> 2) * (FT_TILE_BYTES / 2)) + (uint64_t)(2 * (c & 3));
+        umma_f16_ss_warp(t_s + (uint32_t)st * 128u, ad, bd, idesc_s, c ? 1u : 0u);
+      }
+      umma_commit_warp(&s_full[st]);
+      umma_commit_warp(&k_empty[st]);
+    };
+    mbar_wait(q_full, 0);
+    if (nt > 0) issue_s(0);
+    for (int j = 0; j < nt; j++) {
+      const int st = j & 1, ph = (j >> 1) & 1;
+      if (j + 1 < nt) issue_s(j + 1);
+      mbar_wait(&p_full[st], ph);
+      mbar_wait(&v_full[st], ph);
+      tc_fence_after();
+      const uint32_t vs = smem_u32(v_ring + (size_t)st * FT_TILE_BYTES);
+#pragma unroll
+      for (int c = 0; c < 8; c++)     // 16 tokens per MMA: two 8-row groups of 1024 B
+        umma_f16_ts_warp(t_o, t_p + (uint32_t)st * 64u + (uint32_t)(8 * c), umma_desc_sw128_ex(vs + (uint32_t)c * 2048u, p.v_lbo, p.v_sbo),
+                         idesc_o, (j | c) ? 1u : 0u);
+      umma_commit_warp(&pv_done[st]);
+      umma_commit_warp(&v_empty[st]);
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: thread = query row =====================
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    const int qg = q0 + r;                                 // row index inside the sequence
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nt; j++) {
+      const int st = j & 1, ph = (j >> 1) & 1;
+      const uint32_t ts = t_s + lane_off + (uint32_t)st * 128u;
+      const int kv0 = j * FT_BN;
+      const int lim = min(p.causal ? qg : len - 1, len - 1) - kv0;   // columns > lim are masked
+      mbar_wait(&s_full[st], ph);
+      tc_fence_after();
+      // pass 1: row maximum (in scaled log2 units)
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < FT_BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(ts + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; i++) mx = fmaxf(mx, (c0 + i <= lim) ? __uint_as_float(v[i]) : -INFINITY);
+      }
+      mx *= p.scale_log2;                                   // (scale > 0: max commutes with the scaling)
+      const float m_new = fmaxf(m_run, mx);
+      const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
+      const float msub = (m_new == -INFINITY) ? 0.f : m_new;
+      // correction of O: only when some row of this warp moved its maximum; O holds tiles < j once PV_{j-1} has retired
+      if (j > 0) {
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, corr != 1.f)) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < FT_D; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_o + lane_off + (uint32_t)c0, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
+            tmem_st_32x32(t_o + lane_off + (uint32_t)c0, v);
+          }
+        }
+      }
+      // pass 2: p = 2^(s * scale - m), row sum in f32, P rounded to the activation format into TMEM
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < FT_BN; c0 += 32) {
+        uint32_t v[32], pk[16];
+        tmem_ld_32x32(ts + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = (c0 + i <= lim) ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -msub)) : 0.f;
+          const float p1 = (c0 + i + 1 <= lim) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -msub)) : 0.f;
+          rs += p0 + p1;
+          if (p.bf16) { const __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1); pk[i >> 1] = *(const uint32_t *)&hh; }
+          else { const __half2 hh = __floats2half2_rn(p0, p1); pk[i >> 1] = *(const uint32_t *)&hh; }
+        }
+        tmem_st_x16(t_p + lane_off + (uint32_t)st * 64u + (uint32_t)(c0 >> 1), pk);
+      }
+      l_run = l_run * corr + rs;
+      m_run = m_new;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&p_full[st]); mbar_arrive(&s_free[st]); }
+    }
+    // epilogue: O / l -> global, one 256-byte row per thread
+    if (nt > 0) {
+      mbar_wait(&pv_done[(nt - 1) & 1], ((nt - 1) >> 1) & 1);
+      tc_fence_after();
+    }
+    const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
+    uint8_t *orow = (uint8_t *)p.o + ((int64_t)(seq0 + qg) * p.o_stride + (int64_t)h * FT_D) * 2;
+#pragma unroll 1
+    for (int c0 = 0; c0 < FT_D; c0 += 32) {
+      uint32_t v[32];
+      if (nt > 0) tmem_ld_32x32(t_o + lane_off + (uint32_t)c0, v);
+      if (qg < len) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          uint32_t *w = (uint32_t *)&pk;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float a = (nt > 0) ? __uint_as_float(v[i + 2 * k]) * inv : 0.f, bq = (nt > 0) ? __uint_as_float(v[i + 2 * k + 1]) * inv : 0.f;
+            if (p.bf16) { const __nv_bfloat162 hh = __floats2bfloat162_rn(a, bq); w[k] = *(const uint32_t *)&hh; }
+            else { const __half2 hh = __floats2half2_rn(a, bq); w[k] = *(const uint32_t *)&hh; }
+          }
+          *(uint4 *)(orow + (size_t)(c0 + i) * 2) = pk;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace mrs
+
+using namespace mrs;
+
+static uint32_t g_ft_lbo = 16384u, g_ft_sbo = 1024u;
+static int g_ft_enable = 1;
+// dev knobs: MN-major descriptor strides of V (bytes); enable = 0 keeps mrs_prefill_attention on prefill_attn.cu
+extern "C" void mrs_prefill_attn_tc_debug(int32_t enable, uint32_t lbo, uint32_t sbo) {
+  g_ft_enable = enable;
+  if (lbo) g_ft_lbo = lbo;
+  if (sbo) g_ft_sbo = sbo;
+}
+
+// returns cudaErrorNotSupported when the call does not fit this kernel (the caller falls back to prefill_attn.cu)
+extern "C" int32_t mrs_prefill_attention_tc(const void *q, const void *k, const void *v, void *out, const int32_t *cu_seqlens,
+                                            int32_t batch, int32_t total_tokens, int32_t max_seqlen, int32_t num_heads,
+                                            int32_t num_kv_heads, int32_t head_dim, int64_t q_stride, int64_t kv_stride,
+                                            int64_t o_stride, float softmax_scale, int32_t causal, int32_t window_left,
+                                            float softcap, uint32_t dtype, void *stream) {
+  if (!g_ft_enable || head_dim != 128 || window_left >= 0 || softcap > 0.f || (dtype != 0 && dtype != 1)) return (int32_t)cudaErrorNotSupported;
+  if (total_tokens <= 0) return 0;
+  if (num_kv_heads <= 0 || num_heads % num_kv_heads || (q_stride | kv_stride | o_stride) % 8) return (int32_t)cudaErrorNotSupported;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) return (int32_t)cudaErrorNotSupported;
+  if (q_stride < (int64_t)num_heads * 128 || kv_stride < (int64_t)num_kv_heads * 128) return (int32_t)cudaErrorNotSupported;
+  PFN_encodeTiled enc = tc_get_encode();
+  if (enc == nullptr) return (int32_t)cudaErrorNotSupported;
+  auto make = [&](CUtensorMap *m, const void *base, int64_t cols, int64_t stride) -> bool {
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)total_tokens};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride * 2};
+    const cuuint32_t box[2] = {64u, 128u};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims,
+               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  CUtensorMap tq, tk, tv;
+  if (!make(&tq, q, (int64_t)num_heads * 128, q_stride) || !make(&tk, k, (int64_t)num_kv_heads * 128, kv_stride) ||
+      !make(&tv, v, (int64_t)num_kv_heads * 128, kv_stride))
+    return (int32_t)cudaErrorNotSupported;
+  FtParams p = {};
+  p.o = out; p.cu_seqlens = cu_seqlens; p.T = total_tokens; p.H = num_heads; p.KVH = num_kv_heads; p.o_stride = o_stride;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f; p.causal = causal; p.bf16 = (dtype == 1);
+  p.v_lbo = g_ft_lbo; p.v_sbo = g_ft_sbo;
+  const int nb = cu_seqlens ? batch : 1, ml = cu_seqlens ? max_seqlen : total_tokens;
+  dim3 grid((ml + FT_BM - 1) / FT_BM, num_heads, nb);
+  cudaFuncSetAttribute(prefill_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
+  prefill_attn_tc_kernel<<<grid, FT_THREADS, FT_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  return (int32_t)cudaGetLastError();
+}

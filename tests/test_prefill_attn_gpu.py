@@ -67,3 +67,27 @@ def test_varlen_batch(cuda):
         want = _ref(q[off:off + L], k[off:off + L], v[off:off + L], scale, True)
         assert (got[off:off + L] - want).abs().max().item() <= 3 * 2.0 ** -8 * want.abs().max().item()
         off += L
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_both_kernels_head_128(cuda, dt):
+    """Head size 128 without window / softcap runs on csrc/prefill_attn_tc.cu (tcgen05, S and P in tensor memory);
+    mrs_prefill_attn_tc_debug(0, ...) keeps the call on csrc/prefill_attn.cu (mma.sync).  Both against the fp64
+    reference, on a ragged multi-tile prompt, causal and not."""
+    import ctypes
+    from mistralrs_b200 import lib
+    T, H, KVH, D = 700, 8, 2, 128
+    gen = torch.Generator(device=cuda).manual_seed(9)
+    q, k, v = (torch.randn(T, h, D, device=cuda, generator=gen).to(dt) for h in (H, KVH, KVH))
+    scale = 1.0 / np.sqrt(D)
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    try:
+        for enable in (0, 1):
+            lib().mrs_prefill_attn_tc_debug(ctypes.c_int32(enable), ctypes.c_uint32(0), ctypes.c_uint32(0))
+            for causal in (True, False):
+                got = paged_attn.prefill_attention(q, k, v, scale, causal=causal).double()
+                want = _ref(q, k, v, scale, causal)
+                assert torch.isfinite(got).all()
+                assert (got - want).abs().max().item() <= 3 * ulp * want.abs().max().item() + 1e-6, (enable, causal)
+    finally:
+        lib().mrs_prefill_attn_tc_debug(ctypes.c_int32(1), ctypes.c_uint32(0), ctypes.c_uint32(0))
