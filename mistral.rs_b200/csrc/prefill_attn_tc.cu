@@ -13,11 +13,13 @@
 //                 O   += P_j V_j      TS form: P (16-bit pairs) is the A operand in TENSOR MEMORY, V is the B operand
 //                                     straight from its row-major [token][d] tile = MN-major SWIZZLE_128B
 //                                     (no transpose pass): M128 N128 K16 x 8
-//               S is double-buffered in TMEM, so S_{j+1} is computed while the softmax of tile j runs;
 //   warps 2..5  softmax + correction + epilogue, thread = query row = TMEM lane: tcgen05.ld the S row (two passes:
-//               max, then exp2 / sum / pack), tcgen05.st P, rescale O in TMEM only when some row's maximum moved
-//               (warp vote), finally O / l -> global.
-// TMEM columns: S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O [384,512).
+//               max, then exp2 / sum / pack), tcgen05.st P IN PLACE over the first 64 columns of S (a row is private
+//               to its thread, and chunk c of P lands on columns the thread has already read), rescale O in TMEM only
+//               when some row's maximum moved (warp vote), finally O / l -> global.
+// The per-tile chain S -> softmax -> PV is latency-bound (~5000 clocks for 1024 of tensor work), so the kernel is
+// laid out for TWO CTAs per SM instead of a deeper pipeline inside one: single K / V stages (96 KB of shared memory),
+// 256 TMEM columns — S / P [0,128), O [128,256) — and the other CTA's MMAs fill this one's softmax.
 #include "tc_common.cuh"
 
 #include <math.h>
@@ -28,7 +30,8 @@ namespace mrs {
 constexpr int FT_BM = 128, FT_BN = 128, FT_D = 128;
 constexpr int FT_THREADS = 32 * 6;
 constexpr int FT_TILE_BYTES = FT_BN * FT_D * 2;                       // 32 KB: two boxes [128 rows][64 d]
-constexpr int FT_SMEM = 1024 + 5 * FT_TILE_BYTES + 256;              // Q + 2 K stages + 2 V stages + barriers
+constexpr int FT_SMEM = 1024 + 3 * FT_TILE_BYTES + 256;              // Q + K + V + barriers
+constexpr uint32_t FT_TCOLS = 256;
 
 struct FtParams {
   void *o;
@@ -57,6 +60,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t *r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::
@@ -66,16 +81,16 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t *r) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 1)
+__global__ void __launch_bounds__(FT_THREADS, 2)
 prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const FtParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *q_s = smem, *k_ring = smem + FT_TILE_BYTES, *v_ring = smem + 3 * FT_TILE_BYTES;
-  uint64_t *bars = (uint64_t *)(smem + 5 * FT_TILE_BYTES);
-  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 7, *s_full = bars + 9,
-           *s_free = bars + 11, *p_full = bars + 13, *pv_done = bars + 15;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 17);
+  uint8_t *q_s = smem, *k_s = smem + FT_TILE_BYTES, *v_s = smem + 2 * FT_TILE_BYTES;
+  uint64_t *bars = (uint64_t *)(smem + 3 * FT_TILE_BYTES);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4, *s_full = bars + 5,
+           *p_full = bars + 6, *pv_done = bars + 7;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 8);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -90,18 +105,16 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   const int kv_end = p.causal ? (q_hi + 1) : len;
   const int nt = (kv_end + FT_BN - 1) / FT_BN;
 
-  if (warp == 0 && lane < 17) {
-    uint32_t cnt = 1u;
-    if (lane >= 11 && lane < 15) cnt = 4u;            // s_free, p_full: the four softmax warps
-    mbar_init(&bars[lane], cnt);
+  if (warp == 0 && lane < 8) {
+    mbar_init(&bars[lane], lane == 6 ? 4u : 1u);      // p_full: the four softmax warps
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, FT_TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, *tmem_slot);
-  const uint32_t t_s = tmem_base, t_p = tmem_base + 256u, t_o = tmem_base + 384u;
+  const uint32_t t_s = tmem_base, t_p = tmem_base, t_o = tmem_base + 128u;   // P overwrites the head of S
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -109,16 +122,16 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     tma_load_2d_warp(q_s, &tmap_q, h * FT_D, seq0 + q0, q_full);
     tma_load_2d_warp(q_s + FT_TILE_BYTES / 2, &tmap_q, h * FT_D + 64, seq0 + q0, q_full);
     for (int j = 0; j < nt; j++) {
-      const int st = j & 1, ph = (j >> 1) & 1;
+      const int ph = j & 1;
       const int row = seq0 + j * FT_BN;
-      mbar_wait(&k_empty[st], ph ^ 1);
-      mbar_arrive_expect_tx_warp(&k_full[st], FT_TILE_BYTES);
-      tma_load_2d_warp(k_ring + (size_t)st * FT_TILE_BYTES, &tmap_k, kvh * FT_D, row, &k_full[st]);
-      tma_load_2d_warp(k_ring + (size_t)st * FT_TILE_BYTES + FT_TILE_BYTES / 2, &tmap_k, kvh * FT_D + 64, row, &k_full[st]);
-      mbar_wait(&v_empty[st], ph ^ 1);
-      mbar_arrive_expect_tx_warp(&v_full[st], FT_TILE_BYTES);
-      tma_load_2d_warp(v_ring + (size_t)st * FT_TILE_BYTES, &tmap_v, kvh * FT_D, row, &v_full[st]);
-      tma_load_2d_warp(v_ring + (size_t)st * FT_TILE_BYTES + FT_TILE_BYTES / 2, &tmap_v, kvh * FT_D + 64, row, &v_full[st]);
+      mbar_wait(k_empty, ph ^ 1);
+      mbar_arrive_expect_tx_warp(k_full, FT_TILE_BYTES);
+      tma_load_2d_warp(k_s, &tmap_k, kvh * FT_D, row, k_full);
+      tma_load_2d_warp(k_s + FT_TILE_BYTES / 2, &tmap_k, kvh * FT_D + 64, row, k_full);
+      mbar_wait(v_empty, ph ^ 1);
+      mbar_arrive_expect_tx_warp(v_full, FT_TILE_BYTES);
+      tma_load_2d_warp(v_s, &tmap_v, kvh * FT_D, row, v_full);
+      tma_load_2d_warp(v_s + FT_TILE_BYTES / 2, &tmap_v, kvh * FT_D + 64, row, v_full);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -126,36 +139,30 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     // c = f32 (bit 4), a / b format (bits 7, 10), b_major = MN (bit 16) for the PV product, N >> 3 at bit 17, M >> 4 at bit 24
     const uint32_t idesc_s = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(FT_BN >> 3) << 17) | ((uint32_t)(FT_BM >> 4) << 24);
     const uint32_t idesc_o = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(FT_D >> 3) << 17) | ((uint32_t)(FT_BM >> 4) << 24);
-    auto issue_s = [&](int j) {
-      const int st = j & 1, ph = (j >> 1) & 1;
-      mbar_wait(&k_full[st], ph);
-      mbar_wait(&s_free[st], ph ^ 1);                  // the softmax has read the previous S in this buffer
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < nt; j++) {
+      const int ph = j & 1;
+      mbar_wait(k_full, ph);
+      if (j > 0) mbar_wait(pv_done, ph ^ 1);           // PV_{j-1} has read P out of the S columns S_j is about to overwrite
       tc_fence_after();
-      const uint8_t *ks = k_ring + (size_t)st * FT_TILE_BYTES;
 #pragma unroll
       for (int c = 0; c < 8; c++) {
         const uint64_t ad = umma_desc_sw128(q_s + (c >> 2) * (FT_TILE_BYTES / 2)) + (uint64_t)(2 * (c & 3));
-        const uint64_t bd = umma_desc_sw128(ks + (c >> 2) * (FT_TILE_BYTES / 2)) + (uint64_t)(2 * (c & 3));
-        umma_f16_ss_warp(t_s + (uint32_t)st * 128u, ad, bd, idesc_s, c ? 1u : 0u);
+        const uint64_t bd = umma_desc_sw128(k_s + (c >> 2) * (FT_TILE_BYTES / 2)) + (uint64_t)(2 * (c & 3));
+        umma_f16_ss_warp(t_s, ad, bd, idesc_s, c ? 1u : 0u);
       }
-      umma_commit_warp(&s_full[st]);
-      umma_commit_warp(&k_empty[st]);
-    };
-    mbar_wait(q_full, 0);
-    if (nt > 0) issue_s(0);
-    for (int j = 0; j < nt; j++) {
-      const int st = j & 1, ph = (j >> 1) & 1;
-      if (j + 1 < nt) issue_s(j + 1);
-      mbar_wait(&p_full[st], ph);
-      mbar_wait(&v_full[st], ph);
+      umma_commit_warp(s_full);
+      umma_commit_warp(k_empty);
+      mbar_wait(p_full, ph);
+      mbar_wait(v_full, ph);
       tc_fence_after();
-      const uint32_t vs = smem_u32(v_ring + (size_t)st * FT_TILE_BYTES);
+      const uint32_t vs = smem_u32(v_s);
 #pragma unroll
       for (int c = 0; c < 8; c++)     // 16 tokens per MMA: two 8-row groups of 1024 B
-        umma_f16_ts_warp(t_o, t_p + (uint32_t)st * 64u + (uint32_t)(8 * c), umma_desc_sw128_ex(vs + (uint32_t)c * 2048u, p.v_lbo, p.v_sbo),
-                         idesc_o, (j | c) ? 1u : 0u);
-      umma_commit_warp(&pv_done[st]);
-      umma_commit_warp(&v_empty[st]);
+        umma_f16_ts_warp(t_o, t_p + (uint32_t)(8 * c), umma_desc_sw128_ex(vs + (uint32_t)c * 2048u, p.v_lbo, p.v_sbo), idesc_o,
+                         (j | c) ? 1u : 0u);
+      umma_commit_warp(pv_done);
+      umma_commit_warp(v_empty);
     }
   } else {
     // ===================== softmax / correction / epilogue: thread = query row =====================
@@ -163,68 +170,70 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     const int r = q4 * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const int qg = q0 + r;                                 // row index inside the sequence
-    float m_run = -INFINITY, l_run = 0.f;
+    // m_ref is the exponent's reference point, not necessarily the running maximum: it only moves when a row's
+    // maximum outgrows it by more than 2^8 (then O and l are rescaled).  The quotient O / l does not depend on the
+    // reference, P just lives in [0, 256] instead of [0, 1] — and the O round trip through TMEM, with its wait for the
+    // previous PV, almost never happens (with a plain running maximum some row of a warp moves in most tiles).
+    float m_ref = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nt; j++) {
-      const int st = j & 1, ph = (j >> 1) & 1;
-      const uint32_t ts = t_s + lane_off + (uint32_t)st * 128u;
+      const int ph = j & 1;
+      const uint32_t ts = t_s + lane_off;
       const int kv0 = j * FT_BN;
       const int lim = min(p.causal ? qg : len - 1, len - 1) - kv0;   // columns > lim are masked
-      mbar_wait(&s_full[st], ph);
+      mbar_wait(s_full, ph);
       tc_fence_after();
-      // pass 1: row maximum (in scaled log2 units)
+      // the whole S row in registers: four loads in flight, one wait
+      uint32_t v[128];
+      tmem_ld_32x32_nowait(ts, v);
+      tmem_ld_32x32_nowait(ts + 32u, v + 32);
+      tmem_ld_32x32_nowait(ts + 64u, v + 64);
+      tmem_ld_32x32_nowait(ts + 96u, v + 96);
+      tmem_ld_wait();
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < FT_BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(ts + (uint32_t)c0, v);
 #pragma unroll
-        for (int i = 0; i < 32; i++) mx = fmaxf(mx, (c0 + i <= lim) ? __uint_as_float(v[i]) : -INFINITY);
-      }
+      for (int i = 0; i < 128; i++) mx = fmaxf(mx, (i <= lim) ? __uint_as_float(v[i]) : -INFINITY);
       mx *= p.scale_log2;                                   // (scale > 0: max commutes with the scaling)
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
-      const float msub = (m_new == -INFINITY) ? 0.f : m_new;
-      // correction of O: only when some row of this warp moved its maximum; O holds tiles < j once PV_{j-1} has retired
-      if (j > 0) {
-        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+      const bool move = (m_ref == -INFINITY) || (mx > m_ref + 8.0f);
+      const float m_use = move ? fmaxf(m_ref, mx) : m_ref;
+      const float corr = (m_use == m_ref) ? 1.f : ex2_approx(m_ref - m_use);   // (m_ref = -inf: 0, nothing accumulated yet)
+      const float msub = (m_use == -INFINITY) ? 0.f : m_use;
+      if (j > 0 && __any_sync(0xffffffffu, corr != 1.f)) {
+        mbar_wait(pv_done, ph ^ 1);                         // (already complete: S_j was issued after it)
         tc_fence_after();
-        if (__any_sync(0xffffffffu, corr != 1.f)) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < FT_D; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_o + lane_off + (uint32_t)c0, v);
+        for (int c0 = 0; c0 < FT_D; c0 += 32) {
+          uint32_t o[32];
+          tmem_ld_32x32(t_o + lane_off + (uint32_t)c0, o);
 #pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
-            tmem_st_32x32(t_o + lane_off + (uint32_t)c0, v);
-          }
+          for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+          tmem_st_32x32(t_o + lane_off + (uint32_t)c0, o);
         }
       }
-      // pass 2: p = 2^(s * scale - m), row sum in f32, P rounded to the activation format into TMEM
+      // p = 2^(s * scale - m_use), row sum in f32, P rounded to the activation format, written over the head of S
       float rs = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < FT_BN; c0 += 32) {
-        uint32_t v[32], pk[16];
-        tmem_ld_32x32(ts + (uint32_t)c0, v);
+        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = (c0 + i <= lim) ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -msub)) : 0.f;
-          const float p1 = (c0 + i + 1 <= lim) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -msub)) : 0.f;
+          const float p0 = (c0 + i <= lim) ? ex2_approx(fmaf(__uint_as_float(v[c0 + i]), p.scale_log2, -msub)) : 0.f;
+          const float p1 = (c0 + i + 1 <= lim) ? ex2_approx(fmaf(__uint_as_float(v[c0 + i + 1]), p.scale_log2, -msub)) : 0.f;
           rs += p0 + p1;
           if (p.bf16) { const __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1); pk[i >> 1] = *(const uint32_t *)&hh; }
           else { const __half2 hh = __floats2half2_rn(p0, p1); pk[i >> 1] = *(const uint32_t *)&hh; }
         }
-        tmem_st_x16(t_p + lane_off + (uint32_t)st * 64u + (uint32_t)(c0 >> 1), pk);
+        tmem_st_x16(t_p + lane_off + (uint32_t)(c0 >> 1), pk);
       }
       l_run = l_run * corr + rs;
-      m_run = m_new;
+      m_ref = m_use;
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&p_full[st]); mbar_arrive(&s_free[st]); }
+      if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue: O / l -> global, one 256-byte row per thread
     if (nt > 0) {
-      mbar_wait(&pv_done[(nt - 1) & 1], ((nt - 1) >> 1) & 1);
+      mbar_wait(pv_done, (nt - 1) & 1);
       tc_fence_after();
     }
     const float inv = (l_run > 0.f) ? 1.f / l_run : 0.f;
@@ -251,7 +260,7 @@ prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, FT_TCOLS);
 }
 
 }  // namespace mrs
