@@ -34,9 +34,16 @@ typedef struct {
   int64_t flags_offset;          /* >= world uint32 flag words, zero-initialised */
   int64_t slot_offset[2];        /* two partial buffers of >= batch * hidden activation elements each */
   void *seq_counter;             /* local device uint32, zero-initialised */
+  /* low-latency protocol (used when ll_offset != 0): every rank PUSHES its partial to every peer as 8-byte words
+   * {two activation elements, sequence number} — one NVLink store hop, no flag round trip, no fence; the receiver
+   * polls the words themselves.  Region: [2 slots][world source ranks][ll_src_stride bytes], zero-initialised,
+   * ll_src_stride >= 4 bytes per element of the largest all-reduce. */
+  int64_t ll_offset, ll_slot_stride, ll_src_stride;
 } mrs_tp_ctx;
 /* out = T(T(sum over ranks of slot partials, rank order, f32) + residual); count % 8 == 0; one CTA, in-graph,
- * PDL-chained.  Stands in for SumAllReduce::sum_all_reduce + the residual add (REF distributed/mod.rs:436-453). */
+ * PDL-chained.  Stands in for SumAllReduce::sum_all_reduce + the residual add (REF distributed/mod.rs:436-453).
+ * Two protocols, same arithmetic and bit-identical results on every rank: flags + pull (ll_offset == 0) and the
+ * low-latency push above. */
 int32_t mrs_tp_allreduce_residual(const mrs_tp_ctx *ctx, int32_t slot, const void *residual, void *out, int32_t count,
                                   int32_t dtype, int32_t pdl, void *stream);
 

@@ -132,6 +132,7 @@ struct ArCtxDev {
   uint32_t *flags_local;           // [world] flag words in the own buffer
   unsigned long long flags_off, slot_off[2];
   uint32_t *seq;                   // device counter of all-reduces done (graph replays continue it)
+  unsigned long long ll_off, ll_slot_stride, ll_src_stride;   // low-latency region (ll_off == 0: flags + pull)
 };
 __global__ void __launch_bounds__(1024) tp_allreduce_residual_kernel(const ArCtxDev c, int slot, const void *__restrict__ residual,
                                                                      void *__restrict__ out, int count, int dt, int pdl) {
@@ -168,6 +169,54 @@ __global__ void __launch_bounds__(1024) tp_allreduce_residual_kernel(const ArCtx
     load_act8(residual, i, dt, res);
 #pragma unroll
     for (int k = 0; k < 8; k++) store_act(out, (int64_t)i + k, round_act(acc[k], dt) + res[k], dt);
+  }
+}
+
+// Low-latency form (NCCL's "LL" idea on our own buffers): the partial travels as 8-byte words {two activation elements,
+// sequence number}.  An 8-byte store is delivered whole, so the receiver needs no flag and no fence — it polls the word
+// until the sequence number is the current one.  One NVLink store hop instead of flag round trip + pull round trip.
+// Thread t owns element pairs t, t + blockDim, ...: reads its own partial (local), pushes it to every peer, then collects
+// the peers' words from its own region, sums in rank order in f32, rounds, adds the residual.  Two slots alternate, the
+// sequence number grows monotonically: a word of the all-reduce two steps back can never be mistaken for the current one,
+// and a rank can only overwrite slot s after every peer has sent it the all-reduce in between, i.e. finished reading s.
+__global__ void __launch_bounds__(1024) tp_allreduce_ll_kernel(const ArCtxDev c, int slot, const void *__restrict__ partial,
+                                                               const void *__restrict__ residual, void *__restrict__ out, int count,
+                                                               int dt, int pdl) {
+  if (pdl && threadIdx.x == 0) pdl_launch_dependents();
+  if (pdl) pdl_wait();                       // the own partial is complete and flushed
+  const uint32_t seq = *(volatile const uint32_t *)c.seq + 1u;
+  __syncthreads();
+  if (threadIdx.x == 0) *(volatile uint32_t *)c.seq = seq;
+  const unsigned long long area = c.ll_off + (unsigned long long)slot * c.ll_slot_stride;
+  const int npairs = count >> 1;
+  for (int i = threadIdx.x; i < npairs; i += blockDim.x) {
+    const uint32_t mine = ((const uint32_t *)partial)[i];
+    for (int r = 0; r < c.world; r++) {
+      if (r == c.rank) continue;
+      uint2 *dst = (uint2 *)(c.peer_base[r] + area + (unsigned long long)c.rank * c.ll_src_stride) + i;
+      asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(mine), "r"(seq) : "memory");
+    }
+  }
+  for (int i = threadIdx.x; i < npairs; i += blockDim.x) {
+    const uint32_t mine = ((const uint32_t *)partial)[i];
+    float a0 = 0.f, a1 = 0.f;
+    for (int r = 0; r < c.world; r++) {
+      uint32_t w = mine;
+      if (r != c.rank) {
+        const uint2 *src = (const uint2 *)(c.peer_base[c.rank] + area + (unsigned long long)r * c.ll_src_stride) + i;
+        uint32_t fl;
+        do {
+          asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w), "=r"(fl) : "l"(src) : "memory");
+        } while (fl != seq);
+      }
+      float v0, v1;
+      if (dt == MRS_BF16) { const float2 f = __bfloat1622float2(*(const __nv_bfloat162 *)&w); v0 = f.x; v1 = f.y; }
+      else { const float2 f = __half22float2(*(const __half2 *)&w); v0 = f.x; v1 = f.y; }
+      a0 += v0; a1 += v1;
+    }
+    const float r0 = load_act(residual, 2 * (int64_t)i, dt), r1 = load_act(residual, 2 * (int64_t)i + 1, dt);
+    store_act(out, 2 * (int64_t)i, round_act(a0, dt) + r0, dt);
+    store_act(out, 2 * (int64_t)i + 1, round_act(a1, dt) + r1, dt);
   }
 }
 
@@ -281,6 +330,22 @@ extern "C" int32_t mrs_tp_allreduce_residual(const mrs_tp_ctx *ctx, int32_t slot
   c.slot_off[0] = (unsigned long long)ctx->slot_offset[0]; c.slot_off[1] = (unsigned long long)ctx->slot_offset[1];
   c.flags_local = (uint32_t *)((uint8_t *)ctx->peer_base[ctx->rank] + ctx->flags_offset);
   c.seq = (uint32_t *)ctx->seq_counter;
+  c.ll_off = (unsigned long long)ctx->ll_offset; c.ll_slot_stride = (unsigned long long)ctx->ll_slot_stride;
+  c.ll_src_stride = (unsigned long long)ctx->ll_src_stride;
+  if (ctx->ll_offset != 0) {
+    if ((int64_t)count * 4 > ctx->ll_src_stride) return (int32_t)cudaErrorInvalidValue;
+    int th = (count / 2 + 31) / 32 * 32;
+    if (th > 1024) th = 1024;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1); cfg.blockDim = dim3(th); cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    // the partial of this rank: its slot in the symmetric buffer (what the row-parallel GEMV wrote)
+    const void *partial = (const uint8_t *)ctx->peer_base[ctx->rank] + ctx->slot_offset[slot];
+    return (int32_t)cudaLaunchKernelEx(&cfg, tp_allreduce_ll_kernel, c, (int)slot, partial, residual, out, (int)count, (int)dtype, (int)pdl);
+  }
   int threads = (count / 8 + 31) / 32 * 32;
   if (threads > 1024) threads = 1024;
   if (threads < 32) threads = 32;

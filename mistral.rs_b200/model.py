@@ -10,6 +10,7 @@ llama.cpp recipe (Q4_K everywhere; Q6_K for `output`, and for attn_v + ffn_down 
 i < n/8, i >= 7n/8 or (i - n/8) % 3 == 2).
 """
 import ctypes
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -135,7 +136,8 @@ class _Step(ctypes.Structure):
 
 class _TpCtx(ctypes.Structure):
     _fields_ = [("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("peer_base", ctypes.c_void_p * 8),
-                ("flags_offset", ctypes.c_int64), ("slot_offset", ctypes.c_int64 * 2), ("seq_counter", ctypes.c_void_p)]
+                ("flags_offset", ctypes.c_int64), ("slot_offset", ctypes.c_int64 * 2), ("seq_counter", ctypes.c_void_p),
+                ("ll_offset", ctypes.c_int64), ("ll_slot_stride", ctypes.c_int64), ("ll_src_stride", ctypes.c_int64)]
 
 
 class PeerAllReduce:
@@ -143,7 +145,7 @@ class PeerAllReduce:
     One process per GPU; the rendezvous goes through torch.distributed._symmetric_memory (plumbing:
     allocation + IPC handle exchange), the data path is our own kernel over NVLink loads."""
 
-    def __init__(self, elems: int, dtype, device, group=None):
+    def __init__(self, elems: int, dtype, device, group=None, low_latency=None):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         group = group or dist.group.WORLD
@@ -151,7 +153,13 @@ class PeerAllReduce:
         if self.world > 8:
             raise ValueError("peer-memory all-reduce supports up to 8 ranks (one NVSwitch domain)")
         slot = (elems * torch.empty(0, dtype=dtype).element_size() + 255) // 256 * 256
-        self.buf = symm.empty(256 + 2 * slot, dtype=torch.uint8, device=device)
+        # low-latency region: [2 slots][world sources][4 bytes per element] of {element pair, sequence number} words
+        if low_latency is None:
+            low_latency = os.environ.get("MRS_TP_LL", "0") != "0"
+        ll_src = (elems * 4 + 255) // 256 * 256 if low_latency else 0
+        ll_slot = self.world * ll_src
+        self.low_latency = bool(low_latency)
+        self.buf = symm.empty(256 + 2 * slot + 2 * ll_slot, dtype=torch.uint8, device=device)
         self.buf.zero_()
         torch.cuda.synchronize(device)
         self.handle = symm.rendezvous(self.buf, group)
@@ -162,6 +170,8 @@ class PeerAllReduce:
             c.peer_base[r] = int(self.handle.buffer_ptrs[r])
         c.flags_offset, c.slot_offset[0], c.slot_offset[1] = 0, 256, 256 + slot
         c.seq_counter = self.seq.data_ptr()
+        if low_latency:
+            c.ll_offset, c.ll_slot_stride, c.ll_src_stride = 256 + 2 * slot, ll_slot, ll_src
         self.ctx = c
         dist.barrier(group)
 

@@ -34,11 +34,16 @@ def main():
         bufs[tp.buf[n].data_ptr()] = tp.buf[n]
     tp.capture()   # exercises NCCL inside CUDA-graph capture
     # the product path: in-graph peer-memory all-reduce fused with the residual add, PDL chain intact
-    peer = M.PeerAllReduce(2 * cfg.hidden, torch.bfloat16, dev)
+    peer = M.PeerAllReduce(2 * cfg.hidden, torch.bfloat16, dev, low_latency=True)
     tp2 = M.LlamaRunner(shard, batch=2, max_ctx=64, pdl=True, peer_allreduce=peer)
     tp2.capture()
-    results = {}
-    for name, runner in (("nccl", tp), ("peer", tp2)):
+    assert peer.low_latency
+    # the flags + pull protocol (the low-latency region switched off): same arithmetic, must give the same bits
+    peer3 = M.PeerAllReduce(2 * cfg.hidden, torch.bfloat16, dev, low_latency=False)
+    tp3 = M.LlamaRunner(shard, batch=2, max_ctx=64, pdl=True, peer_allreduce=peer3)
+    tp3.capture()
+    results, last = {}, {}
+    for name, runner in (("nccl", tp), ("peer", tp2), ("peer-pull", tp3)):
         ref.reset(); runner.reset()
         ref.set_tokens([11, 400]); runner.set_tokens([11, 400])
         worst = 0.0
@@ -49,17 +54,18 @@ def main():
             worst = max(worst, ((a - b).abs().max() / a.abs().max()).item())
             runner.set_tokens(ref.meta["token_ids"].cpu().tolist())
         results[name] = worst
+        last[name] = runner.logits().float().clone()
     # every rank must hold identical logits on the peer path (rank-ordered f32 sums)
     mine = tp2.logits().float().clone()
     other = mine.clone()
     dist.broadcast(other, src=0)
-    same = bool(torch.equal(mine, other))
+    same = bool(torch.equal(mine, other)) and bool(torch.equal(last["peer"], last["peer-pull"]))
     ok = max(results.values()) <= 4 * 2.0 ** -7 and same
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"TP{world} vs TP1 worst rel logit diff: nccl {results['nccl']:.3e}, peer-memory {results['peer']:.3e}, "
-              f"ranks bit-identical: {same} -> {'OK' if t.item() == 1.0 else 'FAIL'}", flush=True)
+        print(f"TP{world} vs TP1 worst rel logit diff: nccl {results['nccl']:.3e}, peer-memory low-latency {results['peer']:.3e} / flags+pull {results['peer-pull']:.3e}, "
+              f"ranks and both protocols bit-identical: {same} -> {'OK' if t.item() == 1.0 else 'FAIL'}", flush=True)
     rc = 0 if t.item() == 1.0 else 1
     dist.barrier()
     torch.cuda.synchronize()
