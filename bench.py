@@ -663,7 +663,7 @@ def main():
             "config": {"workload": f"{name} GGUF Q4_K_M decode batch=1, 128-token prompt -> +256 tokens, paged KV block_size=16 (HND)",
                        "parallelism": f"tp{world}", "l2": "inputs larger than L2 (weights streamed once per token)",
                        "layers": cfg.n_layers, "pdl": bool(args.pdl),
-                       "all_reduce": None if world == 1 else ("peer-memory one-shot sum + residual, in-graph (mrs_tp_allreduce_residual)" if peer is not None else "NCCL via torch.distributed, captured"),
+                       "all_reduce": None if world == 1 else (("peer-memory one-shot sum + residual, in-graph (mrs_tp_allreduce_residual; " + ("low-latency push of {data, sequence} words" if peer.low_latency else "flags + pull") + ")") if peer is not None else "NCCL via torch.distributed, captured"),
                        "kv_split": f"{runner.split_pages * cfg.block_size}-token chunks, {runner.padded_tiles} tiles (SM-filling plan)"},
             "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": 4 * ntok + 4 * PROMPT_LEN, "d2h_bytes_per_step": 4 * ntok,
                     "ttft_ms": None if ttft_e2e is None else ttft_e2e * 1e3},

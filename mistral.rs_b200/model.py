@@ -155,7 +155,7 @@ class PeerAllReduce:
         slot = (elems * torch.empty(0, dtype=dtype).element_size() + 255) // 256 * 256
         # low-latency region: [2 slots][world sources][4 bytes per element] of {element pair, sequence number} words
         if low_latency is None:
-            low_latency = os.environ.get("MRS_TP_LL", "0") != "0"
+            low_latency = os.environ.get("MRS_TP_LL", "1") != "0"
         ll_src = (elems * 4 + 255) // 256 * 256 if low_latency else 0
         ll_slot = self.world * ll_src
         self.low_latency = bool(low_latency)
