@@ -17,9 +17,12 @@
 //               128-byte-swizzled B stage; fence.proxy.async + mbarrier hand-off to the MMA
 //               warp.  After the K loop the same warps are the epilogue: tcgen05.ld -> bf16/f16
 //               -> global.
-// Numerics: weights are dequantised exactly and rounded once to f16 (11-bit mantissa),
-// activations are used as they are (bf16/f16) — no activation quantisation — f32 accumulation
-// in TMEM.  This is closer to the exact product than the reference's int8-activation MMQ.
+// Numerics: every weight is dequantised with the reference's f32 formula and rounded ONCE to the activations' 16-bit
+// format (f16 with f16 activations, bf16 with bf16 ones: the MMA takes one format for both operands); activations are
+// used as they are — no activation quantisation — f32 accumulation in TMEM.  Closer to the exact product than the
+// reference's int8-activation MMQ.
+// (Round 2: mrs_mmq_gguf sends Q8_0 / Q4_K / Q6_K launches with K % 256 == 0 to csrc/mmq_ts.cu; this kernel keeps the
+// other seven types, odd shapes and the GPTQ/AWQ checkpoint-layout GEMM, and is required to agree with it bit for bit.)
 #include "dequant.cuh"
 #include "tc_common.cuh"
 

@@ -13,7 +13,8 @@
 // ring with cp.async (16-byte copies, two tiles in flight); B fragments come from ldmatrix
 // (transposed for V).  GQA: head h reads KV head h / (H / KVH).  Causal tiles beyond the diagonal
 // are skipped, the diagonal tile is masked in registers; heavy (late) query tiles are scheduled first.
-// Legacy mma.sync path (SASS HMMA): 7 % of config 3's FLOPs; the tcgen05 version is future work.
+// Legacy mma.sync path (SASS HMMA).  Head size 128 without window / softcap now runs on prefill_attn_tc.cu (tcgen05);
+// this kernel keeps head size 64, sliding window, softcap, and is the A/B for the other one.
 #include "mma_common.cuh"
 
 #include <stdio.h>
