@@ -107,3 +107,52 @@ def test_paged_attention_vs_reference_kernels(ref):
         got = oracle.paged_attention(ref["pa_q"], ref[kn], ref[vn], ref["pa_tables"], ref["pa_ctx"], KVH, D, BS, scale, layout, "bf16")
         want = ref[on]
         assert np.abs(got - want).max() <= 2.5 * 2.0 ** -8 * np.abs(want).max(), (on, np.abs(got - want).max())
+
+
+# ---- round 2: the reference kernels' outputs for MMQ, Marlin and the paged-attention variants pin the oracle too ----
+def _need(ref, key):
+    if key not in ref.files:
+        pytest.skip(f"tests/golden/ref_golden.npz has no `{key}`")
+
+
+@pytest.mark.parametrize("t", ["q4_k", "q6_k", "q8_0"])
+def test_exact_product_vs_reference_mmq_kernel(ref, t):
+    """`oracle.matmul_exact` (f64 sum of dequantised weights x activations: the target of our prefill GEMMs) against
+    the reference's own MMQ kernels (`launch_mmq_quantize_q8_1_*` + `launch_mmq_gguf_<q>`, int8 activations): they may
+    differ by the reference's activation-quantisation noise only (its self-consistency bound, fast_mmq.rs:1583-1703)."""
+    _need(ref, f"mmq_{t}_y")
+    N, K = 256, 1024
+    exact = oracle.matmul_exact(t, ref[f"mmq_{t}_w"], ref["mmq_x"], K, N)
+    want = ref[f"mmq_{t}_y"]
+    scale = np.abs(exact).max()
+    assert np.abs(want - exact).max() <= 2e-2 * scale
+    assert np.abs(want - exact).mean() <= 3e-3 * scale
+
+
+@pytest.mark.parametrize("tag", ["m1", "m32", "m300"])
+def test_gptq_oracle_vs_reference_marlin_kernel(ref, tag):
+    """oracle/gptq.py (w = f16((q - 8) * s), f64 product) against `gptq_marlin_repack` + `marlin_gptq_4bit_f16` of the
+    reference on the same checkpoint tensors: accumulation order + one f16 output rounding apart."""
+    from oracle import gptq as og
+    _need(ref, f"marlin_{tag}_y")
+    assert int(ref[f"marlin_{tag}_rc"]) == 0
+    x, qw, sc, want = ref[f"marlin_{tag}_x"], ref[f"marlin_{tag}_qweight"], ref[f"marlin_{tag}_scales"], ref[f"marlin_{tag}_y"]
+    got = og.gemm(x, og.dequant_gptq(qw, sc, None, 128))
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 2.0 ** -10 * scale + 1e-6, float(np.abs(got - want).max() / scale)
+
+
+@pytest.mark.parametrize("name", ["plain", "alibi", "softcap", "sinks"])
+def test_paged_attention_variants_vs_reference_kernel(ref, name):
+    """oracle/paged_attn_np.py (ALiBi with the reference's unsigned wrap, soft-capping, sinks) against
+    `paged_attention_v1` of the reference (pagedattention.cuh:270-345)."""
+    from oracle import paged_attn_np
+    key = "pa_out_v1" if name == "plain" else f"pa_out_v1_{name}"
+    _need(ref, key)
+    KVH, D, BS = 2, 128, 16
+    got = paged_attn_np.paged_attention_v1(ref["pa_q"], ref["pa_k"], ref["pa_v"], ref["pa_slots"], ref["pa_tables"], ref["pa_ctx"], KVH, D,
+                                           BS, 1.0 / np.sqrt(D), "bf16", softcapping=30.0 if name == "softcap" else 1.0,
+                                           alibi_slopes=ref["pa_alibi"] if name == "alibi" else None,
+                                           sinks=ref["pa_sinks"] if name == "sinks" else None)
+    want = ref[key]
+    assert np.abs(got - want).max() <= 2.5 * 2.0 ** -8 * np.abs(want).max(), float(np.abs(got - want).max())
