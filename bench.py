@@ -469,15 +469,42 @@ def main():
     validate = (not args.no_validate) and world == 1 and not big
     weights = M.LlamaWeights(cfg, dev, tp_rank=rank, tp_size=world, keep_host=validate, fast_synth=big)
     peer, comm, bufs = None, None, {}
+    def nccl_comm(buf, count, dtype, stream, user):                   # A/B and last resort: NCCL through torch.distributed
+        dist.all_reduce(bufs[buf])
     if world > 1 and os.environ.get("MRS_TP_NCCL", "0") != "1":
-        peer = M.PeerAllReduce(cfg.hidden, weights.dtype, dev)       # in-graph peer-memory sum (product path)
-    elif world > 1:
-        def comm(buf, count, dtype, stream, user):                   # A/B: NCCL all-reduce through torch.distributed
-            dist.all_reduce(bufs[buf])
-    runner = M.LlamaRunner(weights, batch=1, max_ctx=PROMPT_LEN + GEN_LEN + 16, pdl=bool(args.pdl), comm=comm, peer_allreduce=peer)
-    if comm is not None:
-        bufs[runner.buf["x"].data_ptr()] = runner.buf["x"]
-        bufs[runner.buf["x2"].data_ptr()] = runner.buf["x2"]
+        try:
+            peer = M.PeerAllReduce(cfg.hidden, weights.dtype, dev)   # in-graph peer-memory sum (product path)
+        except Exception as e:                                        # no symmetric memory on this box: keep the run alive
+            print(f"[bench] rank {rank}: peer-memory all-reduce unavailable ({e!r}); using NCCL", file=sys.stderr, flush=True)
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                     # every rank must take the same path
+        if int(ok.item()) == 0:
+            peer = None
+    if world > 1 and peer is None:
+        comm = nccl_comm
+
+    def make_runner():
+        r = M.LlamaRunner(weights, batch=1, max_ctx=PROMPT_LEN + GEN_LEN + 16, pdl=bool(args.pdl), comm=comm, peer_allreduce=peer)
+        if comm is not None:
+            bufs[r.buf["x"].data_ptr()] = r.buf["x"]
+            bufs[r.buf["x2"].data_ptr()] = r.buf["x2"]
+        return r
+    runner = make_runner()
+    if peer is not None and peer.low_latency:
+        # the low-latency protocol polls for its peers' words with a time-out: make sure a few eager steps go through on
+        # every rank before anything is captured or timed; otherwise fall back to the flags + pull protocol
+        for _ in range(2):
+            runner.step()
+        torch.cuda.synchronize()
+        bad = torch.tensor([1 if peer.timed_out() else 0], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()) != 0:
+            print(f"[bench] rank {rank}: low-latency all-reduce timed out; falling back to flags + pull", file=sys.stderr, flush=True)
+            dist.barrier()
+            peer = M.PeerAllReduce(cfg.hidden, weights.dtype, dev, low_latency=False)
+            runner = make_runner()
+        else:
+            runner.reset()
     validation = validate_first_tokens(weights, M, torch) if validate else None
     weights.host = None
     runner.capture()

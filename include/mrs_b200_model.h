@@ -33,7 +33,8 @@ typedef struct {
   void *peer_base[8];            /* base of rank r's buffer as mapped in THIS process (own included) */
   int64_t flags_offset;          /* >= world uint32 flag words, zero-initialised */
   int64_t slot_offset[2];        /* two partial buffers of >= batch * hidden activation elements each */
-  void *seq_counter;             /* local device uint32, zero-initialised */
+  void *seq_counter;             /* local device uint32[2], zero-initialised: [0] all-reduces so far, [1] set to 1 when a
+                                  * low-latency all-reduce gave up waiting for a peer (~0.25 s): results are invalid */
   /* low-latency protocol (used when ll_offset != 0): every rank PUSHES its partial to every peer as 8-byte words
    * {two activation elements, sequence number} — one NVLink store hop, no flag round trip, no fence; the receiver
    * polls the words themselves.  Region: [2 slots][world source ranks][ll_src_stride bytes], zero-initialised,

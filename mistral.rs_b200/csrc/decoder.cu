@@ -131,7 +131,7 @@ struct ArCtxDev {
   const uint8_t *peer_base[8];     // peers' symmetric buffers (own included), mapped into this process
   uint32_t *flags_local;           // [world] flag words in the own buffer
   unsigned long long flags_off, slot_off[2];
-  uint32_t *seq;                   // device counter of all-reduces done (graph replays continue it)
+  uint32_t *seq;                   // [0] device counter of all-reduces done (graph replays continue it); [1] time-out flag
   unsigned long long ll_off, ll_slot_stride, ll_src_stride;   // low-latency region (ll_off == 0: flags + pull)
 };
 __global__ void __launch_bounds__(1024) tp_allreduce_residual_kernel(const ArCtxDev c, int slot, const void *__restrict__ residual,
@@ -204,10 +204,15 @@ __global__ void __launch_bounds__(1024) tp_allreduce_ll_kernel(const ArCtxDev c,
       uint32_t w = mine;
       if (r != c.rank) {
         const uint2 *src = (const uint2 *)(c.peer_base[c.rank] + area + (unsigned long long)r * c.ll_src_stride) + i;
-        uint32_t fl;
-        do {
+        // bounded wait: a peer that never shows up (ranks out of step) must not hang the GPU — after ~0.25 s the
+        // kernel gives up on the word, raises the flag next to the sequence counter and carries on with stale data
+        uint32_t fl, spins = 0;
+        const long long t0 = clock64();
+        for (;;) {
           asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w), "=r"(fl) : "l"(src) : "memory");
-        } while (fl != seq);
+          if (fl == seq) break;
+          if ((++spins & 1023u) == 0u && clock64() - t0 > 500000000ll) { c.seq[1] = 1u; break; }
+        }
       }
       float v0, v1;
       if (dt == MRS_BF16) { const float2 f = __bfloat1622float2(*(const __nv_bfloat162 *)&w); v0 = f.x; v1 = f.y; }

@@ -163,7 +163,7 @@ class PeerAllReduce:
         self.buf.zero_()
         torch.cuda.synchronize(device)
         self.handle = symm.rendezvous(self.buf, group)
-        self.seq = torch.zeros(1, dtype=torch.int32, device=device)
+        self.seq = torch.zeros(2, dtype=torch.int32, device=device)   # [all-reduces so far, time-out flag]
         c = _TpCtx()
         c.world, c.rank = self.world, self.rank
         for r in range(self.world):
@@ -177,6 +177,10 @@ class PeerAllReduce:
 
     def pointer(self):
         return ctypes.addressof(self.ctx)
+
+    def timed_out(self):
+        """True when a low-latency all-reduce gave up waiting for a peer (ranks out of step): results are invalid."""
+        return bool(int(self.seq[1].item()) != 0)
 
 
 def rope_tables(cfg: LlamaConfig):
