@@ -626,9 +626,9 @@ def main():
     n_gemv = sum(4 if M.tensor_type(cfg, "attn_v", l) == M.tensor_type(cfg, "attn_q", l) else 5 for l in range(cfg.n_layers)) + 1
     achieved = weight_bytes / gemv_s / 1e9
     traffic = None
-    try:
+    try:   # DRAM bytes per launch from the committed ncu --set full capture of this kernel (single-GPU shapes only)
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-        traffic = tr["dram_bytes_per_launch"]
+        traffic = tr["dram_bytes_per_launch"] if (world == 1 and not big and not args.layers) else None
     except Exception:
         pass
 
