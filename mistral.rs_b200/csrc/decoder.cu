@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(1024) tp_allreduce_ll_kernel(const ArCtxDev c,
   if (pdl && threadIdx.x == 0) pdl_launch_dependents();
   if (pdl) pdl_wait();                       // the own partial is complete and flushed
   const uint32_t seq = *(volatile const uint32_t *)c.seq + 1u;
+  const bool dead = *(volatile const uint32_t *)(c.seq + 1) != 0u;   // an earlier all-reduce gave up on a peer: never wait again
   __syncthreads();
   if (threadIdx.x == 0) *(volatile uint32_t *)c.seq = seq;
   const unsigned long long area = c.ll_off + (unsigned long long)slot * c.ll_slot_stride;
@@ -210,8 +211,9 @@ __global__ void __launch_bounds__(1024) tp_allreduce_ll_kernel(const ArCtxDev c,
         const long long t0 = clock64();
         for (;;) {
           asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(w), "=r"(fl) : "l"(src) : "memory");
-          if (fl == seq) break;
-          if ((++spins & 1023u) == 0u && clock64() - t0 > 500000000ll) { c.seq[1] = 1u; break; }
+          if (fl == seq || dead) break;
+          if ((++spins & 1023u) == 0u &&
+              (clock64() - t0 > 500000000ll || *(volatile const uint32_t *)(c.seq + 1) != 0u)) { c.seq[1] = 1u; break; }
         }
       }
       float v0, v1;
