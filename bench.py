@@ -182,7 +182,7 @@ def run_reference(args):
         cfg.n_layers = args.layers
     t0 = time.perf_counter()
     steps = max(1, args.steps)
-    budget = max(4.0, min(20.0, 150.0 / (steps + max(args.warmup, 0))))
+    budget = args.cpu_seconds if args.cpu_seconds > 0 else max(4.0, min(20.0, 150.0 / (steps + max(args.warmup, 0))))
     vals, threads, sample = [], 0, ""
     for i in range(max(args.warmup, 0) + steps):
         v, threads, sample = cpu_decode_tokens_per_s(cfg, M, seconds=budget if i >= args.warmup else 2.0)
@@ -414,6 +414,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 3 / config 4 blocks of the default line")
     ap.add_argument("--no-validate", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=0.0, help="bound of one CPU sample (tests); 0: derived from --steps")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
