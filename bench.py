@@ -117,11 +117,13 @@ def _cgroup_cpus():
         return 0
 
 
-def cpu_decode_tokens_per_s(cfg, M, seconds=10.0, min_tokens=2, threads=0):
+def cpu_decode_samples(cfg, M, seconds=10.0, min_tokens=2, threads=0, nsamples=1):
     """The reference's CPU arithmetic (oracle/mrs_oracle.c: Q8_K / Q8_0 activations + integer block dots,
     the candle QMatMul algorithm) on WHOLE tokens of this model: all layers, every weight byte streamed
-    from DRAM each token, attention / norms / GLU included, one pinned thread per host core
-    (oracle/cpu_decode_bench.c).  Compiled here, on the box that runs it, with -O3 -march=native."""
+    from DRAM each token, attention / norms / GLU included, one pinned thread per usable host core
+    (oracle/cpu_decode_bench.c).  Compiled here, on the box that runs it, with -O3 -march=native.
+    `nsamples` timed samples of about `seconds` each share ONE model allocation (one short-lived child process).
+    Returns ([tok/s per sample], threads, description)."""
     src = os.path.join(ROOT, "oracle", "cpu_decode_bench.c")
     out_dir = os.path.join(tempfile.gettempdir(), f"mrs_cpu_bench_{os.getuid()}")
     os.makedirs(out_dir, exist_ok=True)
@@ -131,20 +133,23 @@ def cpu_decode_tokens_per_s(cfg, M, seconds=10.0, min_tokens=2, threads=0):
     # a short-lived child: the benchmark allocates the whole model (4.6 GB) and pins its threads
     code = (
         "import ctypes, json, sys\n"
-        f"L = ctypes.CDLL({so!r}); L.mrs_cpu_decode_bench.restype = ctypes.c_double\n"
+        f"L = ctypes.CDLL({so!r}); L.mrs_cpu_decode_bench_samples.restype = ctypes.c_double\n"
         "a = json.loads(sys.argv[1])\n"
         "types = (ctypes.c_int * len(a['types']))(*a['types'])\n"
-        "tok, wb, tu = ctypes.c_int(), ctypes.c_double(), ctypes.c_int()\n"
-        "r = L.mrs_cpu_decode_bench(a['layers'], a['hidden'], a['inter'], a['heads'], a['kv_heads'], a['head_dim'], a['vocab'], types,\n"
-        "                           a['head_type'], a['ctx'], a['threads'], ctypes.c_double(a['seconds']), a['min_tokens'],\n"
-        "                           ctypes.byref(tok), ctypes.byref(wb), ctypes.byref(tu))\n"
-        "print(json.dumps({'tok_s': r, 'tokens': tok.value, 'weight_bytes': wb.value, 'threads': tu.value}))\n")
+        "n = a['nsamples']\n"
+        "ts, tk = (ctypes.c_double * n)(), (ctypes.c_int * n)()\n"
+        "wb, tu = ctypes.c_double(), ctypes.c_int()\n"
+        "r = L.mrs_cpu_decode_bench_samples(a['layers'], a['hidden'], a['inter'], a['heads'], a['kv_heads'], a['head_dim'], a['vocab'], types,\n"
+        "                                   a['head_type'], a['ctx'], a['threads'], ctypes.c_double(a['seconds']), a['min_tokens'], n,\n"
+        "                                   ts, tk, ctypes.byref(wb), ctypes.byref(tu))\n"
+        "print(json.dumps({'tok_s': list(ts), 'tokens': list(tk), 'weight_bytes': wb.value, 'threads': tu.value}))\n")
     types = []
     for l in range(cfg.n_layers):
         types += [GGML[M.tensor_type(cfg, n, l)] for n in ("attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up", "ffn_down")]
     arg = dict(layers=cfg.n_layers, hidden=cfg.hidden, inter=cfg.inter, heads=cfg.n_heads, kv_heads=cfg.n_kv_heads,
                head_dim=cfg.head_dim, vocab=cfg.vocab, types=types, head_type=GGML[M.tensor_type(cfg, "output", 0)],
-               ctx=PROMPT_LEN + GEN_LEN // 2, threads=threads, seconds=seconds, min_tokens=min_tokens)
+               ctx=PROMPT_LEN + GEN_LEN // 2, threads=threads, seconds=seconds, min_tokens=min_tokens, nsamples=nsamples)
+
     def run(a):
         return json.loads(subprocess.check_output([sys.executable, "-c", code, json.dumps(a)], text=True).strip().splitlines()[-1])
     if threads <= 0:
@@ -156,15 +161,20 @@ def cpu_decode_tokens_per_s(cfg, M, seconds=10.0, min_tokens=2, threads=0):
         cands = [c for c in cands if c <= ncpu]
         best = None
         for c in cands:
-            pr = run(dict(arg, threads=c, seconds=min(1.5, seconds / 4), min_tokens=1))
-            if best is None or pr["tok_s"] > best[0]:
-                best = (pr["tok_s"], c)
+            pr = run(dict(arg, threads=c, seconds=min(1.5, seconds / 4), min_tokens=1, nsamples=1))
+            if best is None or pr["tok_s"][0] > best[0]:
+                best = (pr["tok_s"][0], c)
         arg["threads"] = best[1]
     r = run(arg)
-    sample = (f"{r['tokens']} whole tokens (all {cfg.n_layers} layers + lm_head, {r['weight_bytes'] / 1e9:.2f} GB of weights streamed "
+    sample = (f"{r['tokens'][-1]} whole tokens (all {cfg.n_layers} layers + lm_head, {r['weight_bytes'] / 1e9:.2f} GB of weights streamed "
               f"from DRAM per token, attention over {arg['ctx']} cached tokens, norms and GLU included), decode batch 1, "
               f"-O3 -march=native, {r['threads']} pinned threads (pool size chosen by a short probe over {len(os.sched_getaffinity(0))} visible CPUs)")
     return r["tok_s"], r["threads"], sample
+
+
+def cpu_decode_tokens_per_s(cfg, M, seconds=10.0, min_tokens=2, threads=0):
+    vals, th, sample = cpu_decode_samples(cfg, M, seconds=seconds, min_tokens=min_tokens, threads=threads, nsamples=1)
+    return vals[0], th, sample
 
 
 def run_reference(args):
@@ -183,11 +193,11 @@ def run_reference(args):
     t0 = time.perf_counter()
     steps = max(1, args.steps)
     budget = args.cpu_seconds if args.cpu_seconds > 0 else max(4.0, min(20.0, 150.0 / (steps + max(args.warmup, 0))))
-    vals, threads, sample = [], 0, ""
-    for i in range(max(args.warmup, 0) + steps):
-        v, threads, sample = cpu_decode_tokens_per_s(cfg, M, seconds=budget if i >= args.warmup else 2.0)
-        if i >= args.warmup:
-            vals.append(v)
+    # warm-up samples and timed samples share one model allocation and one pool-size probe: the run is
+    # (warmup + steps) x budget seconds plus ~30 s of set-up, whatever --steps says
+    nw = max(args.warmup, 0)
+    allv, threads, sample = cpu_decode_samples(cfg, M, seconds=budget, nsamples=nw + steps)
+    vals = allv[nw:]
     value = sum(vals) / len(vals)
     print(json.dumps({
         "impl": "reference", "metric": "decode_tok_s", "value": value, "unit": "tok/s", "n_gpus": args.gpus,

@@ -202,9 +202,11 @@ static float *randf(size_t n, float scale) {
 /* types: per layer [q, k, v, o, gate, up, down] ggml codes (7 * n_layers ints) + lm_head type.
  * Runs whole tokens for about `seconds` (at least `min_tokens`); returns tokens/s, fills *tokens_run,
  * *weight_bytes.  threads <= 0: one per allowed CPU. */
-double mrs_cpu_decode_bench(int n_layers, int hidden, int inter, int heads, int kv_heads, int head_dim, int vocab,
-                            const int *types, int lm_head_type, int ctx, int threads, double seconds, int min_tokens,
-                            int *tokens_run, double *weight_bytes, int *threads_used) {
+/* nsamples timed samples of about `seconds` each on ONE model allocation (the weights are generated and paged in once):
+ * tok_s[i] and tokens[i] for sample i; returns the mean tokens/s. */
+double mrs_cpu_decode_bench_samples(int n_layers, int hidden, int inter, int heads, int kv_heads, int head_dim, int vocab,
+                                    const int *types, int lm_head_type, int ctx, int threads, double seconds, int min_tokens,
+                                    int nsamples, double *tok_s, int *tokens, double *weight_bytes, int *threads_used) {
   memset(&G, 0, sizeof G);
   if (threads <= 0) { cpu_set_t got; threads = (sched_getaffinity(0, sizeof got, &got) == 0) ? CPU_COUNT(&got) : 1; }
   if (threads > MRS_MAX_THREADS) threads = MRS_MAX_THREADS;
@@ -236,15 +238,31 @@ double mrs_cpu_decode_bench(int n_layers, int hidden, int inter, int heads, int 
   pin_to(0);
   for (int t = 1; t < threads; t++) pthread_create(&th[t], NULL, worker, (void *)(intptr_t)t);
   one_token();                              /* warm-up: page the weights in, wake the pool */
-  int n = 0;
-  const double t0 = now_s();
-  while (n < min_tokens || now_s() - t0 < seconds) { one_token(); n++; }
-  const double dt = now_s() - t0;
+  double mean = 0;
+  for (int s = 0; s < nsamples; s++) {
+    int n = 0;
+    const double t0 = now_s();
+    while (n < min_tokens || now_s() - t0 < seconds) { one_token(); n++; }
+    const double dt = now_s() - t0;
+    if (tok_s) tok_s[s] = n / dt;
+    if (tokens) tokens[s] = n;
+    mean += n / dt / nsamples;
+  }
   atomic_store(&G.stop, 1);
   for (int t = 1; t < threads; t++) pthread_join(th[t], NULL);
-  if (tokens_run) *tokens_run = n;
   if (weight_bytes) *weight_bytes = wb;
   if (threads_used) *threads_used = threads;
   /* (memory is released at process exit: the bench runs this once in a short-lived child) */
-  return n / dt;
+  return mean;
+}
+
+double mrs_cpu_decode_bench(int n_layers, int hidden, int inter, int heads, int kv_heads, int head_dim, int vocab,
+                            const int *types, int lm_head_type, int ctx, int threads, double seconds, int min_tokens,
+                            int *tokens_run, double *weight_bytes, int *threads_used) {
+  double ts = 0;
+  int n = 0;
+  mrs_cpu_decode_bench_samples(n_layers, hidden, inter, heads, kv_heads, head_dim, vocab, types, lm_head_type, ctx, threads, seconds,
+                               min_tokens, 1, &ts, &n, weight_bytes, threads_used);
+  if (tokens_run) *tokens_run = n;
+  return ts;
 }
