@@ -41,8 +41,10 @@ elif what == "w4a16":
     for _ in range(6):
         assert lib().mrs_w4a16_gemm(P(x), P(tiles), P(sc), ctypes.c_void_p(0), P(y), Mm, K, N, group, 0, 0, ctypes.c_void_p(st())) == 0
     torch.cuda.synchronize()
-elif what == "prefill_attn":
-    from mistralrs_b200 import paged_attn
+elif what == "prefill_attn":      # optional second argument "mma": keep the call on the mma.sync kernel
+    import ctypes
+    from mistralrs_b200 import lib, paged_attn
+    lib().mrs_prefill_attn_tc_debug(ctypes.c_int32(0 if (len(sys.argv) > 2 and sys.argv[2] == "mma") else 1), ctypes.c_uint32(0), ctypes.c_uint32(0))
     T, H, KVH, D = 4096, 32, 8, 128
     q = torch.randn(T, H, D, device=dev).to(torch.bfloat16)
     k = torch.randn(T, KVH, D, device=dev).to(torch.bfloat16)
