@@ -210,6 +210,29 @@ def rope_tables(cfg: LlamaConfig):
     return np.cos(freqs).astype(np.float32), np.sin(freqs).astype(np.float32)
 
 
+def compute_kv_shard(total_kv_heads: int, head_dim: int, rank: int, world: int):
+    """Rows of a K / V projection kept by `rank`: (first_row, rows).  REF mistralrs-quant/src/distributed/layers.rs:2692-2715
+    (`compute_kv_shard`): KV heads are split over the ranks; when there are more ranks than KV heads every head is
+    REPLICATED on world / kv_heads consecutive ranks (each rank then holds exactly one)."""
+    if world == 1:
+        return 0, total_kv_heads * head_dim
+    if world > total_kv_heads:
+        if world % total_kv_heads:
+            raise ValueError(f"tensor-parallel size {world} must be a multiple of the {total_kv_heads} KV heads to replicate them")
+        replicate = world // total_kv_heads
+        return (rank // replicate) * head_dim, head_dim
+    if total_kv_heads % world:
+        raise ValueError(f"tensor-parallel size {world} must divide the {total_kv_heads} KV heads")
+    per = total_kv_heads // world
+    return rank * per * head_dim, per * head_dim
+
+
+def compute_n_kv_groups(total_kv_heads: int, n_heads: int, world: int) -> int:
+    """Query heads per local KV head under KV-head replication.  REF distributed/layers.rs:2718-2733."""
+    replicate = world // total_kv_heads if world > total_kv_heads else 1
+    return (n_heads // total_kv_heads) // replicate if replicate else n_heads // total_kv_heads
+
+
 class LlamaWeights:
     """Synthetic device-resident weights (optionally one tensor-parallel shard)."""
 
@@ -225,12 +248,13 @@ class LlamaWeights:
         self.host = {} if keep_host else None
         H, I = cfg.hidden, cfg.inter
         nq, nkv = cfg.n_heads * cfg.head_dim, cfg.n_kv_heads * cfg.head_dim
-        assert cfg.n_heads % tp_size == 0 and cfg.n_kv_heads % tp_size == 0 and I % (tp_size * 256) == 0
+        assert cfg.n_heads % tp_size == 0 and I % (tp_size * 256) == 0
+        compute_kv_shard(cfg.n_kv_heads, cfg.head_dim, tp_rank, tp_size)      # raises on an impossible KV head layout
         self.layers = []
         self.nbytes = 0
         for l in range(cfg.n_layers):
             L = {}
-            for name, rows, cols, kind in (("attn_q", nq, H, "col"), ("attn_k", nkv, H, "col"), ("attn_v", nkv, H, "col"),
+            for name, rows, cols, kind in (("attn_q", nq, H, "col"), ("attn_k", nkv, H, "kv"), ("attn_v", nkv, H, "kv"),
                                            ("attn_output", H, nq, "row"), ("ffn_gate", I, H, "col"),
                                            ("ffn_up", I, H, "col"), ("ffn_down", H, I, "row")):
                 L[name] = self._qtensor(l, name, rows, cols, kind)
@@ -245,7 +269,7 @@ class LlamaWeights:
         self.rope_sin = torch.from_numpy(sin).to(device).to(dtype)
 
     # ---- real weights -------------------------------------------------------------------------
-    GGUF_NAMES = {"attn_q": "col", "attn_k": "col", "attn_v": "col", "attn_output": "row", "ffn_gate": "col",
+    GGUF_NAMES = {"attn_q": "col", "attn_k": "kv", "attn_v": "kv", "attn_output": "row", "ffn_gate": "col",
                   "ffn_up": "col", "ffn_down": "row"}
 
     @staticmethod
@@ -288,8 +312,9 @@ class LlamaWeights:
         self.tp_rank, self.tp_size = tp_rank, tp_size
         self.host = {} if keep_host else None
         self.layers, self.nbytes = [], 0
-        if cfg.n_heads % tp_size or cfg.n_kv_heads % tp_size:
+        if cfg.n_heads % tp_size:
             raise ValueError("tensor-parallel size must divide the head counts")
+        compute_kv_shard(cfg.n_kv_heads, cfg.head_dim, tp_rank, tp_size)      # raises on an impossible KV head layout
         for l in range(cfg.n_layers):
             L = {}
             for name, kind in cls.GGUF_NAMES.items():
@@ -345,8 +370,9 @@ class LlamaWeights:
         self.tp_rank, self.tp_size = tp_rank, tp_size
         self.host = {} if keep_host else None
         self.layers, self.nbytes = [], 0
-        if cfg.n_heads % tp_size or cfg.n_kv_heads % tp_size:
+        if cfg.n_heads % tp_size:
             raise ValueError("tensor-parallel size must divide the head counts")
+        compute_kv_shard(cfg.n_kv_heads, cfg.head_dim, tp_rank, tp_size)      # raises on an impossible KV head layout
         for l in range(cfg.n_layers):
             L = {}
             for name, kind in cls.GGUF_NAMES.items():
@@ -410,8 +436,12 @@ class LlamaWeights:
         return (t, info.dtype, rows, cols)
 
     def _shard(self, full, rows, cols, be, kind):
-        """kind: 'col' (rows sharded), 'row' (K sharded on block boundaries), 'rep' (replicated)."""
+        """kind: 'col' (rows sharded), 'kv' (rows sharded by KV head, replicated when ranks outnumber KV heads),
+        'row' (K sharded on block boundaries), 'rep' (replicated)."""
         r, w = self.tp_rank, self.tp_size
+        if kind == "kv" and w > 1:
+            first, n = compute_kv_shard(self.cfg.n_kv_heads, self.cfg.head_dim, r, w)
+            return full[first:first + n], n, cols
         if kind == "col" and w > 1:
             if rows % w:
                 raise ValueError("column-parallel rows do not divide by the tensor-parallel size")
@@ -439,7 +469,9 @@ class LlamaWeights:
         be, bb = BLOCK_ELEMS[dt], BLOCK_BYTES[dt]
         if self.fast_synth:
             w = self.tp_size
-            if kind == "col" and w > 1:
+            if kind == "kv" and w > 1:
+                rows = compute_kv_shard(self.cfg.n_kv_heads, self.cfg.head_dim, self.tp_rank, w)[1]
+            elif kind == "col" and w > 1:
                 rows //= w
             elif kind == "row" and w > 1:
                 assert (cols // be) % w == 0
@@ -458,15 +490,7 @@ class LlamaWeights:
             self.nbytes += t.numel()
             return (t, dt, rows, cols)
         full = synth_blocks(dt, rows * cols // be, tensor_seed(layer, name), self.cfg.synth_scale_exp).reshape(rows, cols // be, bb)
-        r, w = self.tp_rank, self.tp_size
-        if kind == "col" and w > 1:
-            full = full[r * rows // w:(r + 1) * rows // w]
-            rows //= w
-        elif kind == "row" and w > 1:
-            nb = cols // be
-            assert nb % w == 0
-            full = full[:, r * nb // w:(r + 1) * nb // w]
-            cols //= w
+        full, rows, cols = self._shard(full, rows, cols, be, kind)
         full = np.ascontiguousarray(full)
         t = torch.from_numpy(full.reshape(-1)).to(self.device)
         self.nbytes += t.numel()
@@ -495,7 +519,7 @@ class LlamaRunner:
         cfg, dev, dt = weights.cfg, weights.device, weights.dtype
         self.w, self.cfg, self.dev, self.dt, self.B = weights, cfg, dev, dt, batch
         tp = weights.tp_size
-        self.n_heads, self.n_kv = cfg.n_heads // tp, cfg.n_kv_heads // tp
+        self.n_heads, self.n_kv = cfg.n_heads // tp, max(1, cfg.n_kv_heads // tp)   # (KV heads are replicated when tp > kv heads)
         bs = cfg.block_size
         self.max_blocks = -(-max_ctx // bs)
         nb = batch * self.max_blocks + 1

@@ -77,3 +77,42 @@ def test_kv_head_and_block_alignment_rules():
         assert cfg.n_kv_heads % w == 0
     c70 = M.LlamaConfig.llama3_70b()
     assert (c70.inter // 8) % 256 == 0 and c70.n_kv_heads // 8 == 1
+
+
+def test_kv_head_shard_rule():
+    """`compute_kv_shard` / `compute_n_kv_groups` (REF mistralrs-quant/src/distributed/layers.rs:2692-2733): KV heads split
+    over the ranks, replicated on consecutive ranks when the ranks outnumber them."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.load_package()
+    from mistralrs_b200 import model as M
+    D = 128
+    assert M.compute_kv_shard(8, D, 0, 1) == (0, 8 * D)
+    assert [M.compute_kv_shard(8, D, r, 2) for r in range(2)] == [(0, 4 * D), (4 * D, 4 * D)]
+    assert [M.compute_kv_shard(8, D, r, 8) for r in range(8)] == [(r * D, D) for r in range(8)]
+    # 2 KV heads on 8 ranks: each head on 4 consecutive ranks
+    assert [M.compute_kv_shard(2, D, r, 8)[0] // D for r in range(8)] == [0, 0, 0, 0, 1, 1, 1, 1]
+    assert all(M.compute_kv_shard(2, D, r, 8)[1] == D for r in range(8))
+    assert M.compute_n_kv_groups(2, 32, 8) == 4 and M.compute_n_kv_groups(8, 32, 8) == 4 and M.compute_n_kv_groups(8, 32, 1) == 4
+    with pytest.raises(ValueError):
+        M.compute_kv_shard(8, D, 0, 3)          # does not divide
+    with pytest.raises(ValueError):
+        M.compute_kv_shard(3, D, 0, 8)          # cannot replicate evenly
+
+
+def test_kv_heads_replicated_when_ranks_outnumber_them():
+    """one KV head, two ranks: both ranks hold the whole K / V projection, the query heads are still split"""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.load_package()
+    from mistralrs_b200 import model as M
+    cfg = M.LlamaConfig.tiny_test(quant="q4_k_m", n_layers=1, hidden=512, inter=1024, n_heads=8, n_kv_heads=1)
+    full = M.LlamaWeights(cfg, torch.device("cpu"), keep_host=True)
+    shards = [M.LlamaWeights(cfg, torch.device("cpu"), tp_rank=r, tp_size=2, keep_host=True) for r in range(2)]
+    for name in ("attn_k", "attn_v"):
+        for sh in shards:
+            assert np.array_equal(sh.host[(0, name)], full.host[(0, name)])
+            assert sh.layers[0][name][2] == cfg.head_dim
+    q_rows = [sh.layers[0]["attn_q"][2] for sh in shards]
+    assert q_rows == [cfg.n_heads * cfg.head_dim // 2] * 2
+    assert np.array_equal(np.concatenate([sh.host[(0, "attn_q")] for sh in shards]), full.host[(0, "attn_q")])
