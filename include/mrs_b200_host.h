@@ -27,6 +27,24 @@ int mrs_block_pool_get_new_blocks(void *pool, int64_t num, int64_t *out); /* 1 o
 void mrs_block_pool_free_blocks(void *pool, const int64_t *ids, int64_t n);
 void mrs_block_pool_touch(void *pool, const int64_t *ids, int64_t n);
 
+/* ---- prefix cache: full blocks are published under a chained 64-bit hash of their prefix; a freed block keeps its
+ *      hashes until it is handed out again.  REF block_pool.rs:182-280,355-372,454-527; block_hash.rs:126-150,232-263;
+ *      kv_cache_manager.rs:129-174.  Hash VALUES are this library's own (the reference's are Rust's SipHash and never
+ *      leave its scheduler either); equal prefixes <=> equal hashes is the contract. ---- */
+void *mrs_block_pool_new_cached(int64_t num_gpu_blocks, int32_t enable_caching, int64_t hash_block_size);
+double mrs_block_pool_usage(void *pool);
+int64_t mrs_block_pool_num_cached_blocks(void *pool);
+int64_t mrs_block_pool_num_block_hashes(void *pool, int64_t block_id);
+int mrs_block_pool_get_cached_block(void *pool, uint64_t hash, const uint32_t *groups, int64_t n_groups,
+                                    int64_t *out); /* 1 hit in every group, 0 miss */
+int mrs_block_pool_cache_full_blocks(void *pool, const int64_t *ids, int64_t n_ids, const uint64_t *hashes,
+                                     int64_t n_hashes, int64_t num_cached, int64_t num_full, uint32_t group);
+int mrs_block_pool_reset_prefix_cache(void *pool); /* 1 done, 0 refused: blocks still in use */
+int64_t mrs_block_hashes(const uint32_t *tokens, int64_t n, int64_t block_size, const uint64_t *extra, int64_t n_extra,
+                         const uint64_t *prev, int64_t n_prev, uint64_t *out);
+int64_t mrs_block_pool_computed_blocks(void *pool, const uint64_t *hashes, int64_t n_hashes, int64_t num_tokens,
+                                       int64_t block_size, const uint32_t *groups, int64_t n_groups, int64_t *out);
+
 /* ---- slots / CSR / tile plans ---- */
 int mrs_slot_mapping(const int64_t *table, int64_t table_len, int64_t block_size, int64_t start, int64_t end,
                      int64_t *out);

@@ -32,6 +32,64 @@ void mrs_block_pool_touch(void *p, const int64_t *ids, int64_t n) {
   ((BlockPool *)p)->touch(v);
 }
 
+// ---- prefix cache ----
+void *mrs_block_pool_new_cached(int64_t num_gpu_blocks, int32_t enable_caching, int64_t hash_block_size) {
+  try { return new BlockPool((size_t)num_gpu_blocks, enable_caching != 0, (size_t)hash_block_size); } catch (...) { return nullptr; }
+}
+double mrs_block_pool_usage(void *p) { return ((BlockPool *)p)->usage(); }
+int64_t mrs_block_pool_num_cached_blocks(void *p) { return (int64_t)((BlockPool *)p)->num_cached_blocks(); }
+int64_t mrs_block_pool_num_block_hashes(void *p, int64_t id) { return (int64_t)((BlockPool *)p)->num_block_hashes((size_t)id); }
+// 1 and out[n_groups] when every group holds a block under this hash, else 0
+int mrs_block_pool_get_cached_block(void *p, uint64_t hash, const uint32_t *groups, int64_t n_groups, int64_t *out) {
+  std::vector<uint32_t> g(groups, groups + n_groups);
+  std::vector<size_t> v;
+  if (!((BlockPool *)p)->get_cached_block(hash, g, v)) return 0;
+  for (size_t i = 0; i < v.size(); i++) out[i] = (int64_t)v[i];
+  return 1;
+}
+// 0 ok, -1 fewer ids / hashes than num_full
+int mrs_block_pool_cache_full_blocks(void *p, const int64_t *ids, int64_t n_ids, const uint64_t *hashes, int64_t n_hashes,
+                                     int64_t num_cached, int64_t num_full, uint32_t group) {
+  try {
+    std::vector<size_t> v(ids, ids + n_ids);
+    std::vector<uint64_t> h(hashes, hashes + n_hashes);
+    ((BlockPool *)p)->cache_full_blocks(v, h, (size_t)num_cached, (size_t)num_full, group);
+    return 0;
+  } catch (...) { return -1; }
+}
+int mrs_block_pool_reset_prefix_cache(void *p) { return ((BlockPool *)p)->reset_prefix_cache() ? 1 : 0; }
+// chained hashes of the full blocks of tokens[n]; `prev` (n_prev of them) are reused, only the rest are computed.
+// Returns the number of full blocks; out holds that many.
+int64_t mrs_block_hashes(const uint32_t *tokens, int64_t n, int64_t block_size, const uint64_t *extra, int64_t n_extra,
+                         const uint64_t *prev, int64_t n_prev, uint64_t *out) {
+  if (block_size <= 0) return -1;
+  const int64_t full = n / block_size;
+  if (n_prev > full) n_prev = full;
+  for (int64_t i = 0; i < n_prev; i++) out[i] = prev[i];
+  for (int64_t i = n_prev; i < full; i++)
+    out[i] = hash_block_tokens(i > 0, i > 0 ? out[i - 1] : 0, tokens + i * block_size, (size_t)block_size, extra, (size_t)n_extra);
+  return full;
+}
+// longest cached prefix of a request: walks the hashes until a miss, never covering the last token; returns the
+// number of blocks written to out.  REF kv_cache_manager.rs:129-174
+int64_t mrs_block_pool_computed_blocks(void *p, const uint64_t *hashes, int64_t n_hashes, int64_t num_tokens, int64_t block_size,
+                                       const uint32_t *groups, int64_t n_groups, int64_t *out) {
+  BlockPool *bp = (BlockPool *)p;
+  if (!bp->caching_enabled() || block_size <= 0) return 0;
+  const int64_t cap = (num_tokens > 0 ? num_tokens - 1 : 0) / block_size;
+  std::vector<uint32_t> g(groups, groups + n_groups);
+  std::vector<size_t> v;
+  int64_t k = 0;
+  for (; k < n_hashes && k < cap; k++) {
+    if (!bp->get_cached_block(hashes[k], g, v) || v.empty()) break;
+    bool same = true;
+    for (size_t id : v) same &= (id == v[0]);
+    if (!same) break;
+    out[k] = (int64_t)v[0];
+  }
+  return k;
+}
+
 // slot mapping for tokens [start, end) of one sequence; returns 0 ok, -1 table too small
 int mrs_slot_mapping(const int64_t *table, int64_t table_len, int64_t block_size, int64_t start, int64_t end, int64_t *out) {
   try {

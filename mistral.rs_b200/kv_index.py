@@ -20,8 +20,11 @@ def host_lib():
             raise RuntimeError(f"{HOST_LIB_PATH} missing: run __graft_entry__.build()")
         L = ctypes.CDLL(HOST_LIB_PATH)
         L.mrs_block_pool_new.restype = ctypes.c_void_p
-        for f in ("null_block_id", "num_free_blocks", "ref_cnt"):
+        L.mrs_block_pool_new_cached.restype = ctypes.c_void_p
+        L.mrs_block_pool_usage.restype = ctypes.c_double
+        for f in ("null_block_id", "num_free_blocks", "ref_cnt", "num_cached_blocks", "num_block_hashes", "computed_blocks"):
             getattr(L, f"mrs_block_pool_{f}").restype = ctypes.c_int64
+        L.mrs_block_hashes.restype = ctypes.c_int64
         L.mrs_decode_split_pages.restype = ctypes.c_int64
         L.mrs_make_decode_tiles.restype = ctypes.c_int64
         _lib = L
@@ -32,11 +35,81 @@ def _i64(a):
     return np.ascontiguousarray(a, dtype=np.int64)
 
 
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def compute_block_hashes(tokens, block_size, extra_keys=(), prev=()):
+    """Chained hashes of the full blocks of `tokens` (REF block_hash.rs:232-263; with `prev`, only the blocks
+    after those already hashed are computed, :270-300)."""
+    t, e, pv = _u32(tokens), _u64(list(extra_keys)), _u64(list(prev))
+    out = np.empty(max(t.size // block_size, 1), dtype=np.uint64)
+    n = host_lib().mrs_block_hashes(ctypes.c_void_p(t.ctypes.data), ctypes.c_int64(t.size), ctypes.c_int64(block_size),
+                                    ctypes.c_void_p(e.ctypes.data), ctypes.c_int64(e.size),
+                                    ctypes.c_void_p(pv.ctypes.data), ctypes.c_int64(pv.size), ctypes.c_void_p(out.ctypes.data))
+    if n < 0:
+        raise ValueError("block_size must be positive")
+    return [int(v) for v in out[:n]]
+
+
+def hash_block_tokens(parent, tokens, extra_keys=()):
+    """One link of the chain: hash of a block given the previous block's hash (None for the first)."""
+    t = _u32(tokens)
+    if parent is None:
+        return compute_block_hashes(t, t.size, extra_keys)[0]
+    both = np.concatenate([t, t])                        # block 1 of a two-block run whose block 0 hash is `parent`
+    return compute_block_hashes(both, t.size, extra_keys, prev=[parent])[1]
+
+
 class BlockPool:
-    def __init__(self, num_gpu_blocks):
-        self._h = ctypes.c_void_p(host_lib().mrs_block_pool_new(ctypes.c_int64(num_gpu_blocks)))
+    def __init__(self, num_gpu_blocks, enable_caching=False, hash_block_size=16):
+        self._h = ctypes.c_void_p(host_lib().mrs_block_pool_new_cached(ctypes.c_int64(num_gpu_blocks), ctypes.c_int32(int(enable_caching)),
+                                                                       ctypes.c_int64(hash_block_size)))
         if not self._h:
             raise ValueError("Must have at least 1 GPU block")
+        self.enable_caching, self.hash_block_size = bool(enable_caching), hash_block_size
+
+    def usage(self):
+        return host_lib().mrs_block_pool_usage(self._h)
+
+    def num_cached_blocks(self):
+        return host_lib().mrs_block_pool_num_cached_blocks(self._h)
+
+    def num_block_hashes(self, block_id):
+        return host_lib().mrs_block_pool_num_block_hashes(self._h, ctypes.c_int64(block_id))
+
+    def get_cached_block(self, block_hash, group_ids):
+        g = _u32(group_ids)
+        out = np.empty(max(g.size, 1), dtype=np.int64)
+        ok = host_lib().mrs_block_pool_get_cached_block(self._h, ctypes.c_uint64(block_hash), ctypes.c_void_p(g.ctypes.data),
+                                                       ctypes.c_int64(g.size), ctypes.c_void_p(out.ctypes.data))
+        return [int(v) for v in out[:g.size]] if ok else None
+
+    def cache_full_blocks(self, block_ids, block_hashes, num_cached_blocks, num_full_blocks, kv_cache_group_id=0):
+        a, h = _i64(block_ids), _u64(block_hashes)
+        rc = host_lib().mrs_block_pool_cache_full_blocks(self._h, ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(a.size),
+                                                         ctypes.c_void_p(h.ctypes.data), ctypes.c_int64(h.size),
+                                                         ctypes.c_int64(num_cached_blocks), ctypes.c_int64(num_full_blocks),
+                                                         ctypes.c_uint32(kv_cache_group_id))
+        if rc != 0:
+            raise ValueError(f"Not enough block hashes ({h.size}) for {num_full_blocks} full blocks")
+
+    def reset_prefix_cache(self):
+        return bool(host_lib().mrs_block_pool_reset_prefix_cache(self._h))
+
+    def computed_blocks(self, block_hashes, num_tokens, block_size, group_ids=(0,)):
+        """Longest cached prefix of a request as block ids (REF kv_cache_manager.rs:129-174): the caller touches them
+        and starts prefill at len(result) * block_size."""
+        h, g = _u64(block_hashes), _u32(group_ids)
+        out = np.empty(max(h.size, 1), dtype=np.int64)
+        n = host_lib().mrs_block_pool_computed_blocks(self._h, ctypes.c_void_p(h.ctypes.data), ctypes.c_int64(h.size),
+                                                      ctypes.c_int64(num_tokens), ctypes.c_int64(block_size),
+                                                      ctypes.c_void_p(g.ctypes.data), ctypes.c_int64(g.size), ctypes.c_void_p(out.ctypes.data))
+        return [int(v) for v in out[:n]]
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:

@@ -1,17 +1,67 @@
 """ORACLE (test infrastructure): pure-Python restatement of the reference's KV index producers,
 written independently of the C++ host layer so the two can be diffed on random traces.
-REF: mistralrs-core/src/paged_attention/block_pool.rs:60-170,290-442;
+REF: mistralrs-core/src/paged_attention/block_pool.rs:60-170,290-442 (+ prefix cache :182-280,355-372,454-527);
+     mistralrs-core/src/paged_attention/kv_cache_manager.rs:129-174 (longest cached prefix);
      mistralrs-core/src/pipeline/inputs_processor.rs:896-923;
      mistralrs-core/src/flashinfer/metadata.rs:61-216."""
 from collections import OrderedDict
 
 
 class BlockPool:
-    def __init__(self, num_gpu_blocks):
+    def __init__(self, num_gpu_blocks, enable_caching=False, hash_block_size=16):
         assert num_gpu_blocks > 0
+        self.n = num_gpu_blocks
         self.free = OrderedDict((i, None) for i in range(num_gpu_blocks))  # FIFO free list
         self.ref = [0] * num_gpu_blocks
         self.null = self.free.popitem(last=False)[0]  # block 0 becomes the null block
+        self.caching, self.hash_block_size = enable_caching, hash_block_size
+        self.keys = [[] for _ in range(num_gpu_blocks)]   # per block: (hash, group) it is published under
+        self.cache = {}                                   # (hash, group) -> [block ids], oldest first
+
+    # ---- prefix cache (hashes are opaque integers here; the chain lives in the host layer) ----
+    def num_cached_blocks(self):
+        return len(self.cache)
+
+    def get_cached_block(self, h, groups):
+        out = []
+        for g in groups:
+            ids = self.cache.get((h, g))
+            if not ids:
+                return None
+            out.append(ids[0])
+        return out
+
+    def cache_full_blocks(self, block_ids, hashes, num_cached, num_full, group):
+        if not self.caching or num_cached >= num_full:
+            return
+        assert len(hashes) >= num_full
+        for i in range(num_cached, num_full):
+            b, k = block_ids[i], (hashes[i], group)
+            if b == self.null or k in self.keys[b]:
+                continue
+            self.keys[b].append(k)
+            self.cache.setdefault(k, []).append(b)
+
+    def reset_prefix_cache(self):
+        if self.n - len(self.free) != 1:
+            return False
+        self.cache.clear()
+        self.keys = [[] for _ in range(self.n)]
+        return True
+
+    def computed_blocks(self, hashes, num_tokens, block_size, groups=(0,)):
+        """Longest cached prefix, capped so the last token is always recomputed."""
+        if not self.caching:
+            return []
+        out = []
+        for i, h in enumerate(hashes):
+            if i >= max(num_tokens - 1, 0) // block_size:
+                break
+            ids = self.get_cached_block(h, groups)
+            if ids is None or any(b != ids[0] for b in ids):
+                break
+            out.append(ids[0])
+        return out
 
     def num_free_blocks(self):
         return len(self.free)
@@ -22,6 +72,11 @@ class BlockPool:
         out = []
         for _ in range(n):
             b = self.free.popitem(last=False)[0]
+            for k in self.keys[b]:                        # evicted only now, on reallocation
+                self.cache[k].remove(b)
+                if not self.cache[k]:
+                    del self.cache[k]
+            self.keys[b] = []
             self.ref[b] = 1
             out.append(b)
         return out

@@ -145,3 +145,186 @@ def test_runner_split_policy_fills_the_sms():
                     assert tiles * batch * kvh <= max(148, batch * kvh)
     assert M.runner_split_pages(16, 1, 8, 400) == 4          # bench shape: 64-token chunks, 7 tiles
     assert M.runner_split_pages(16, 64, 8, 400) == 25         # large batch: one chunk per request
+
+
+# ---- prefix cache: the reference's own unit tests restated (block_pool.rs:606-787, block_hash.rs tests) ----
+def _chain(*blocks):
+    out, parent = [], None
+    for b in blocks:
+        parent = kv_index.hash_block_tokens(parent, b)
+        out.append(parent)
+    return out
+
+
+def test_block_hash_chain_properties():  # block_hash.rs: deterministic, parent- and token-sensitive, extra keys matter
+    h0 = kv_index.hash_block_tokens(None, [1, 2, 3, 4])
+    assert h0 == kv_index.hash_block_tokens(None, [1, 2, 3, 4])
+    assert h0 != kv_index.hash_block_tokens(None, [1, 2, 3, 5])
+    assert kv_index.hash_block_tokens(h0, [5, 6, 7, 8]) != kv_index.hash_block_tokens(None, [5, 6, 7, 8])
+    assert kv_index.hash_block_tokens(h0, [5, 6, 7, 8]) != kv_index.hash_block_tokens(h0 ^ 1, [5, 6, 7, 8])
+    assert kv_index.hash_block_tokens(None, [1, 2, 3, 4], extra_keys=[77]) != h0
+    toks = list(range(1, 14))                                   # 13 tokens, block 4: three full blocks, the tail is not hashed
+    hs = kv_index.compute_block_hashes(toks, 4)
+    assert hs == _chain(toks[0:4], toks[4:8], toks[8:12])
+    assert kv_index.compute_block_hashes(toks[:3], 4) == []
+    # incremental: reusing the first two hashes gives the same third (block_hash.rs compute_new_block_hashes)
+    assert kv_index.compute_block_hashes(toks, 4, prev=hs[:2]) == hs
+    # no collisions over a few thousand distinct short prefixes
+    rng = np.random.default_rng(0)
+    seen = {kv_index.hash_block_tokens(None, rng.integers(0, 32000, 16)) for _ in range(4000)}
+    assert len(seen) == 4000
+
+
+def test_prefix_cache_basic_golden():  # `test_prefix_cache_basic`
+    pool = kv_index.BlockPool(8, True, 4)
+    ids = pool.get_new_blocks(3)
+    hs = _chain([1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12])
+    pool.cache_full_blocks(ids, hs, 0, 3, 0)
+    assert pool.num_cached_blocks() == 3
+    assert pool.get_cached_block(hs[0], [0]) == [ids[0]]
+    with pytest.raises(ValueError):
+        pool.cache_full_blocks(ids, hs[:1], 0, 3, 0)
+
+
+def test_prefix_cache_reuse_after_free_golden():  # `test_prefix_cache_reuse_after_free`
+    pool = kv_index.BlockPool(8, True, 4)
+    ids = pool.get_new_blocks(2)
+    hs = _chain([1, 2, 3, 4], [5, 6, 7, 8])
+    pool.cache_full_blocks(ids, hs, 0, 2, 0)
+    pool.free_blocks(ids)
+    assert pool.num_free_blocks() == 7
+    cached = pool.get_cached_block(hs[0], [0])
+    assert cached is not None
+    pool.touch(cached)
+    assert pool.block_ref_cnt(cached[0]) == 1
+    assert pool.num_free_blocks() == 6
+
+
+def test_eviction_on_reallocation_golden():  # `test_eviction_on_reallocation`
+    pool = kv_index.BlockPool(4, True, 4)
+    ids = pool.get_new_blocks(3)
+    h0 = kv_index.hash_block_tokens(None, [1, 2, 3, 4])
+    pool.cache_full_blocks(ids, [h0, h0, h0], 0, 1, 0)
+    pool.free_blocks(ids)
+    assert pool.get_cached_block(h0, [0]) == [ids[0]]            # still there while merely free
+    assert len(pool.get_new_blocks(3)) == 3
+    assert pool.get_cached_block(h0, [0]) is None and pool.num_cached_blocks() == 0
+
+
+def test_caching_disabled_is_inert():
+    pool = kv_index.BlockPool(8, False, 4)
+    ids = pool.get_new_blocks(2)
+    hs = _chain([1, 2, 3, 4], [5, 6, 7, 8])
+    pool.cache_full_blocks(ids, hs, 0, 2, 0)
+    assert pool.num_cached_blocks() == 0 and pool.get_cached_block(hs[0], [0]) is None
+    assert pool.computed_blocks(hs, 9, 4) == []
+
+
+def test_null_block_never_freed_and_usage_golden():  # `test_null_block_never_freed`, `test_usage`
+    pool = kv_index.BlockPool(4, False, 16)
+    null = pool.null_block_id()
+    pool.touch([null])                                          # ref 1 without going through the free list
+    pool.free_blocks([null])
+    assert pool.block_ref_cnt(null) == 0 and pool.num_free_blocks() == 3
+    assert pool.usage() < 0.01
+    pool.get_new_blocks(3)
+    assert abs(pool.usage() - 1.0) < 0.01
+    cached = kv_index.BlockPool(4, True, 4)
+    cached.cache_full_blocks([cached.null_block_id()], [123], 0, 1, 0)   # the null block is never published
+    assert cached.num_cached_blocks() == 0
+
+
+def test_get_cached_block_multiple_groups_golden():  # `test_get_cached_block_multiple_groups`
+    pool = kv_index.BlockPool(8, True, 4)
+    g0, g1 = pool.get_new_blocks(1), pool.get_new_blocks(1)
+    h0 = kv_index.hash_block_tokens(None, [1, 2, 3, 4])
+    pool.cache_full_blocks(g0, [h0], 0, 1, 0)
+    pool.cache_full_blocks(g1, [h0], 0, 1, 1)
+    assert pool.get_cached_block(h0, [0, 1]) == [g0[0], g1[0]]
+    assert pool.get_cached_block(h0, [0, 2]) is None
+
+
+def test_same_block_can_cache_multiple_groups_golden():  # `test_same_block_can_cache_multiple_groups`
+    pool = kv_index.BlockPool(8, True, 4)
+    ids = pool.get_new_blocks(1)
+    h0 = kv_index.hash_block_tokens(None, [1, 2, 3, 4])
+    pool.cache_full_blocks(ids, [h0], 0, 1, 0)
+    pool.cache_full_blocks(ids, [h0], 0, 1, 1)
+    pool.cache_full_blocks(ids, [h0], 0, 1, 1)                  # a repeat is not recorded twice
+    assert pool.get_cached_block(h0, [0, 1]) == [ids[0], ids[0]]
+    assert pool.num_block_hashes(ids[0]) == 2
+    pool.free_blocks(ids)
+    pool.get_new_blocks(pool.num_free_blocks())
+    assert pool.get_cached_block(h0, [0]) is None and pool.get_cached_block(h0, [1]) is None
+
+
+def test_reset_prefix_cache_golden():  # `test_reset_prefix_cache`
+    pool = kv_index.BlockPool(4, True, 4)
+    ids = pool.get_new_blocks(2)
+    h0 = kv_index.hash_block_tokens(None, [1, 2, 3, 4])
+    pool.cache_full_blocks(ids, [h0, h0], 0, 1, 0)
+    assert not pool.reset_prefix_cache()
+    pool.free_blocks(ids)
+    assert pool.reset_prefix_cache()
+    assert pool.num_cached_blocks() == 0 and pool.num_block_hashes(ids[0]) == 0
+
+
+def test_computed_blocks_longest_prefix():  # kv_cache_manager.rs get_computed_blocks: never covers the last token
+    bs = 4
+    pool = kv_index.BlockPool(16, True, bs)
+    a = list(range(100, 112))                                   # 3 full blocks
+    ids = pool.get_new_blocks(3)
+    ha = kv_index.compute_block_hashes(a, bs)
+    pool.cache_full_blocks(ids, ha, 0, 3, 0)
+    b = a[:8] + [7, 7, 7, 7, 9]                                 # shares two blocks, then diverges
+    hb = kv_index.compute_block_hashes(b, bs)
+    assert pool.computed_blocks(hb, len(b), bs) == ids[:2]
+    assert pool.computed_blocks(ha, 12, bs) == ids[:2]          # the same 12 tokens again: the last block is recomputed
+    assert pool.computed_blocks(ha, 13, bs) == ids[:3]
+    assert pool.computed_blocks(kv_index.compute_block_hashes([1] * 8, bs), 8, bs) == []
+    # a hit is reused by touching it; the slot mapping of the suffix starts after the cached tokens
+    hit = pool.computed_blocks(hb, len(b), bs)
+    pool.touch(hit)
+    assert [pool.block_ref_cnt(i) for i in hit] == [2, 2]
+    table = hit + pool.get_new_blocks(2)
+    slots = kv_index.slot_mapping(table, bs, len(hit) * bs, len(b))
+    assert list(slots) == [table[2] * bs + i for i in range(4)] + [table[3] * bs]
+
+
+def test_prefix_cache_random_trace_vs_oracle():
+    rng = np.random.default_rng(11)
+    bs = 4
+    pool, ref = kv_index.BlockPool(48, True, bs), okv.BlockPool(48, True, bs)
+    prefixes = [list(rng.integers(0, 50, 12)) for _ in range(6)]
+    live = []
+    for step in range(1500):
+        op = rng.integers(0, 4)
+        if op <= 1 or not live:
+            toks = prefixes[int(rng.integers(0, 6))][: int(rng.integers(1, 4)) * bs] + list(rng.integers(0, 50, int(rng.integers(1, 9))))
+            hs = kv_index.compute_block_hashes(toks, bs)
+            grp = [0] if step % 3 else [0, 1]
+            hit, rhit = pool.computed_blocks(hs, len(toks), bs, grp), ref.computed_blocks(hs, len(toks), bs, grp)
+            assert hit == rhit
+            need = -(-len(toks) // bs) - len(hit)
+            new, rnew = pool.get_new_blocks(need), ref.get_new_blocks(need)
+            assert new == rnew
+            if new is None:
+                continue
+            pool.touch(hit); ref.touch(hit)
+            table = hit + new
+            for g in grp:
+                pool.cache_full_blocks(table, hs, len(hit), len(toks) // bs, g)
+                ref.cache_full_blocks(table, hs, len(hit), len(toks) // bs, g)
+            live.append(table)
+        elif op == 2:
+            t = live.pop(int(rng.integers(0, len(live))))
+            order = list(reversed(t))                            # tail blocks are evicted first
+            pool.free_blocks(order); ref.free_blocks(order)
+        else:
+            if not live:
+                continue
+        assert pool.num_free_blocks() == ref.num_free_blocks()
+        assert pool.num_cached_blocks() == ref.num_cached_blocks()
+    for t in live:
+        pool.free_blocks(t); ref.free_blocks(t)
+    assert pool.reset_prefix_cache() and ref.reset_prefix_cache()
