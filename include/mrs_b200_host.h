@@ -45,6 +45,35 @@ int64_t mrs_block_hashes(const uint32_t *tokens, int64_t n, int64_t block_size, 
 int64_t mrs_block_pool_computed_blocks(void *pool, const uint64_t *hashes, int64_t n_hashes, int64_t num_tokens,
                                        int64_t block_size, const uint32_t *groups, int64_t n_groups, int64_t *out);
 
+/* ---- per-request block tables over a pool: admission with prefix-cache hits, growth, trim, release, publishing,
+ *      slot mapping and padded block tables.  REF mistralrs-core/src/paged_attention/kv_cache_manager.rs:62-435.
+ *      Request ids are the caller's sequence ids. ---- */
+void *mrs_kv_manager_new(int64_t num_gpu_blocks, int64_t block_size, int32_t enable_caching, const uint32_t *groups,
+                         int64_t n_groups);
+void mrs_kv_manager_free(void *mgr);
+void *mrs_kv_manager_pool(void *mgr); /* borrowed mrs_block_pool handle; do not free */
+int64_t mrs_kv_manager_num_free_blocks(void *mgr);
+int64_t mrs_kv_manager_num_usable_blocks(void *mgr);
+double mrs_kv_manager_usage(void *mgr);
+int64_t mrs_kv_manager_get_computed_blocks(void *mgr, const uint64_t *hashes, int64_t n_hashes, int64_t num_tokens,
+                                           int64_t *out);
+int64_t mrs_kv_manager_allocate_slots(void *mgr, uint64_t request_id, int64_t num_tokens, const int64_t *computed,
+                                      int64_t n_computed, int64_t *out); /* fresh ids written, or -1: pool exhausted */
+void mrs_kv_manager_release(void *mgr, uint64_t request_id);
+void mrs_kv_manager_trim(void *mgr, uint64_t request_id, int64_t num_tokens);
+int mrs_kv_manager_cache_blocks(void *mgr, uint64_t request_id, const uint64_t *hashes, int64_t n_hashes,
+                                int64_t num_computed_tokens);
+int mrs_kv_manager_has_request(void *mgr, uint64_t request_id);
+int64_t mrs_kv_manager_num_blocks(void *mgr, uint64_t request_id);
+int64_t mrs_kv_manager_num_cached_blocks(void *mgr, uint64_t request_id);
+int mrs_kv_manager_reset_prefix_cache(void *mgr);
+int mrs_kv_manager_slot_mapping(void *mgr, uint64_t request_id, int64_t start_token, int64_t num_tokens, int64_t *out);
+int mrs_kv_manager_block_table(void *mgr, uint64_t request_id, int64_t max_blocks, int32_t *out);
+/* one decode step of a batch into staging arrays: tables [batch, max_blocks] i32, slots [batch] i64 (slot of the last
+ * token); returns -1, or the index of the first request that is unknown or could not grow */
+int64_t mrs_kv_manager_decode_step(void *mgr, const uint64_t *request_ids, const int64_t *context_lens, int64_t batch,
+                                   int64_t max_blocks, int32_t *tables, int64_t *slots);
+
 /* ---- slots / CSR / tile plans ---- */
 int mrs_slot_mapping(const int64_t *table, int64_t table_len, int64_t block_size, int64_t start, int64_t end,
                      int64_t *out);

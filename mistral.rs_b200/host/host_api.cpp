@@ -1,5 +1,6 @@
 // host_api.cpp — C API over the C++ host layer (kv_index.hpp) for the Python test/bench harness.
 #include "gguf_reader.hpp"
+#include "kv_cache_manager.hpp"
 #include "kv_index.hpp"
 #include "safetensors_reader.hpp"
 
@@ -88,6 +89,55 @@ int64_t mrs_block_pool_computed_blocks(void *p, const uint64_t *hashes, int64_t 
     out[k] = (int64_t)v[0];
   }
   return k;
+}
+
+// ---- per-request block tables over a pool (kv_cache_manager.hpp) ----
+void *mrs_kv_manager_new(int64_t num_gpu_blocks, int64_t block_size, int32_t enable_caching, const uint32_t *groups, int64_t n_groups) {
+  try {
+    return new KvCacheManager((size_t)num_gpu_blocks, (size_t)block_size, enable_caching != 0, std::vector<uint32_t>(groups, groups + n_groups));
+  } catch (...) { return nullptr; }
+}
+void mrs_kv_manager_free(void *m) { delete (KvCacheManager *)m; }
+void *mrs_kv_manager_pool(void *m) { return &((KvCacheManager *)m)->pool(); }   // borrowed: valid while the manager lives
+int64_t mrs_kv_manager_num_free_blocks(void *m) { return (int64_t)((KvCacheManager *)m)->pool().num_free_blocks(); }
+int64_t mrs_kv_manager_num_usable_blocks(void *m) { return (int64_t)((KvCacheManager *)m)->num_usable_blocks(); }
+double mrs_kv_manager_usage(void *m) { return ((KvCacheManager *)m)->pool().usage(); }
+// number of cached leading blocks written to out (room for n_hashes)
+int64_t mrs_kv_manager_get_computed_blocks(void *m, const uint64_t *hashes, int64_t n_hashes, int64_t num_tokens, int64_t *out) {
+  std::vector<size_t> v;
+  ((KvCacheManager *)m)->computed_blocks(hashes, (size_t)n_hashes, (size_t)num_tokens, v);
+  for (size_t i = 0; i < v.size(); i++) out[i] = (int64_t)v[i];
+  return (int64_t)v.size();
+}
+// >= 0: number of fresh block ids written to out (room for ceil(num_tokens / block_size)); -1: not enough free blocks
+int64_t mrs_kv_manager_allocate_slots(void *m, uint64_t req, int64_t num_tokens, const int64_t *computed, int64_t n_computed, int64_t *out) {
+  std::vector<size_t> c(computed, computed + n_computed), fresh;
+  if (!((KvCacheManager *)m)->allocate_slots(req, (size_t)num_tokens, c, fresh)) return -1;
+  for (size_t i = 0; i < fresh.size(); i++) out[i] = (int64_t)fresh[i];
+  return (int64_t)fresh.size();
+}
+void mrs_kv_manager_release(void *m, uint64_t req) { ((KvCacheManager *)m)->free(req); }
+void mrs_kv_manager_trim(void *m, uint64_t req, int64_t num_tokens) { ((KvCacheManager *)m)->trim(req, (size_t)num_tokens); }
+int mrs_kv_manager_cache_blocks(void *m, uint64_t req, const uint64_t *hashes, int64_t n_hashes, int64_t num_computed_tokens) {
+  try { ((KvCacheManager *)m)->cache_blocks(req, hashes, (size_t)n_hashes, (size_t)num_computed_tokens); return 0; } catch (...) { return -1; }
+}
+int mrs_kv_manager_has_request(void *m, uint64_t req) { return ((KvCacheManager *)m)->has(req) ? 1 : 0; }
+int64_t mrs_kv_manager_num_blocks(void *m, uint64_t req) {
+  const std::vector<size_t> *v = ((KvCacheManager *)m)->block_ids(req);
+  return v ? (int64_t)v->size() : 0;
+}
+int64_t mrs_kv_manager_num_cached_blocks(void *m, uint64_t req) { return (int64_t)((KvCacheManager *)m)->num_cached_blocks(req); }
+int mrs_kv_manager_reset_prefix_cache(void *m) { return ((KvCacheManager *)m)->pool().reset_prefix_cache() ? 1 : 0; }
+// 0 ok, -1 unknown request
+int mrs_kv_manager_slot_mapping(void *m, uint64_t req, int64_t start_token, int64_t num_tokens, int64_t *out) {
+  return ((KvCacheManager *)m)->slot_mapping(req, (size_t)start_token, (size_t)num_tokens, out) ? 0 : -1;
+}
+int mrs_kv_manager_block_table(void *m, uint64_t req, int64_t max_blocks, int32_t *out) {
+  return ((KvCacheManager *)m)->block_table(req, (size_t)max_blocks, out) ? 0 : -1;
+}
+int64_t mrs_kv_manager_decode_step(void *m, const uint64_t *req_ids, const int64_t *context_lens, int64_t batch, int64_t max_blocks,
+                                   int32_t *tables, int64_t *slots) {
+  return ((KvCacheManager *)m)->decode_step(req_ids, context_lens, (size_t)batch, (size_t)max_blocks, tables, slots);
 }
 
 // slot mapping for tokens [start, end) of one sequence; returns 0 ok, -1 table too small

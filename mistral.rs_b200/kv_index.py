@@ -25,6 +25,12 @@ def host_lib():
         for f in ("null_block_id", "num_free_blocks", "ref_cnt", "num_cached_blocks", "num_block_hashes", "computed_blocks"):
             getattr(L, f"mrs_block_pool_{f}").restype = ctypes.c_int64
         L.mrs_block_hashes.restype = ctypes.c_int64
+        L.mrs_kv_manager_new.restype = ctypes.c_void_p
+        L.mrs_kv_manager_pool.restype = ctypes.c_void_p
+        L.mrs_kv_manager_usage.restype = ctypes.c_double
+        for f in ("num_free_blocks", "num_usable_blocks", "get_computed_blocks", "allocate_slots", "num_blocks", "num_cached_blocks",
+                  "decode_step"):
+            getattr(L, f"mrs_kv_manager_{f}").restype = ctypes.c_int64
         L.mrs_decode_split_pages.restype = ctypes.c_int64
         L.mrs_make_decode_tiles.restype = ctypes.c_int64
         _lib = L
@@ -140,6 +146,121 @@ class BlockPool:
     def touch(self, block_ids):
         a = _i64(block_ids)
         host_lib().mrs_block_pool_touch(self._h, ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(a.size))
+
+
+class ComputedBlocks:
+    def __init__(self, block_ids, num_computed_tokens):
+        self.block_ids, self.num_computed_tokens = block_ids, num_computed_tokens
+
+
+class KVCacheManager:
+    """Per-request block tables over a BlockPool (C++ host/kv_cache_manager.hpp; REF kv_cache_manager.rs:62-435):
+    same method names and results as the reference's manager."""
+
+    def __init__(self, num_gpu_blocks, block_size, enable_caching, kv_cache_group_ids=(0,)):
+        g = _u32(list(kv_cache_group_ids))
+        self._h = ctypes.c_void_p(host_lib().mrs_kv_manager_new(ctypes.c_int64(num_gpu_blocks), ctypes.c_int64(block_size),
+                                                                ctypes.c_int32(int(enable_caching)), ctypes.c_void_p(g.ctypes.data),
+                                                                ctypes.c_int64(g.size)))
+        if not self._h:
+            raise ValueError("Must have at least 1 GPU block and a positive block size")
+        self.block_size, self.enable_caching = block_size, bool(enable_caching)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            try:
+                _lib.mrs_kv_manager_free(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _rid(self, request_id):
+        return ctypes.c_uint64(request_id)
+
+    def num_free_blocks(self):
+        return host_lib().mrs_kv_manager_num_free_blocks(self._h)
+
+    def num_usable_blocks(self):
+        return host_lib().mrs_kv_manager_num_usable_blocks(self._h)
+
+    def usage(self):
+        return host_lib().mrs_kv_manager_usage(self._h)
+
+    def caching_enabled(self):
+        return self.enable_caching
+
+    def get_computed_blocks(self, block_hashes, num_tokens):
+        h = _u64(block_hashes)
+        out = np.empty(max(h.size, 1), dtype=np.int64)
+        n = host_lib().mrs_kv_manager_get_computed_blocks(self._h, ctypes.c_void_p(h.ctypes.data), ctypes.c_int64(h.size),
+                                                          ctypes.c_int64(num_tokens), ctypes.c_void_p(out.ctypes.data))
+        return ComputedBlocks([int(v) for v in out[:n]], n * self.block_size)
+
+    def allocate_slots(self, request_id, num_tokens, computed_blocks=()):
+        c = _i64(list(computed_blocks))
+        out = np.empty(-(-num_tokens // self.block_size) + 1, dtype=np.int64)
+        n = host_lib().mrs_kv_manager_allocate_slots(self._h, self._rid(request_id), ctypes.c_int64(num_tokens),
+                                                     ctypes.c_void_p(c.ctypes.data), ctypes.c_int64(c.size), ctypes.c_void_p(out.ctypes.data))
+        return None if n < 0 else [int(v) for v in out[:n]]
+
+    def free(self, request_id):
+        host_lib().mrs_kv_manager_release(self._h, self._rid(request_id))
+
+    def trim_request_to_num_tokens(self, request_id, num_tokens):
+        host_lib().mrs_kv_manager_trim(self._h, self._rid(request_id), ctypes.c_int64(num_tokens))
+
+    def cache_blocks(self, request_id, block_hashes, num_computed_tokens):
+        h = _u64(block_hashes)
+        if host_lib().mrs_kv_manager_cache_blocks(self._h, self._rid(request_id), ctypes.c_void_p(h.ctypes.data), ctypes.c_int64(h.size),
+                                                  ctypes.c_int64(num_computed_tokens)) != 0:
+            raise ValueError("Not enough block hashes for the full blocks")
+
+    def has_request(self, request_id):
+        return bool(host_lib().mrs_kv_manager_has_request(self._h, self._rid(request_id)))
+
+    def num_blocks_for_request(self, request_id):
+        return host_lib().mrs_kv_manager_num_blocks(self._h, self._rid(request_id))
+
+    def num_cached_blocks(self, request_id):
+        return host_lib().mrs_kv_manager_num_cached_blocks(self._h, self._rid(request_id))
+
+    def reset_prefix_cache(self):
+        return bool(host_lib().mrs_kv_manager_reset_prefix_cache(self._h))
+
+    def get_block_ids(self, request_id):
+        n = self.num_blocks_for_request(request_id)
+        if not self.has_request(request_id):
+            return None
+        t = self.get_block_table(request_id, n)
+        return [int(v) for v in t]
+
+    def get_slot_mapping(self, request_id, start_token, num_tokens):
+        out = np.empty(max(num_tokens, 1), dtype=np.int64)
+        rc = host_lib().mrs_kv_manager_slot_mapping(self._h, self._rid(request_id), ctypes.c_int64(start_token), ctypes.c_int64(num_tokens),
+                                                    ctypes.c_void_p(out.ctypes.data))
+        return None if rc != 0 else out[:num_tokens]
+
+    def get_block_table(self, request_id, max_blocks):
+        out = np.empty(max(max_blocks, 1), dtype=np.int32)
+        rc = host_lib().mrs_kv_manager_block_table(self._h, self._rid(request_id), ctypes.c_int64(max_blocks), ctypes.c_void_p(out.ctypes.data))
+        return None if rc != 0 else out[:max_blocks]
+
+    def decode_step(self, request_ids, context_lens, max_blocks, tables=None, slots=None):
+        """Grow every request to context_lens[b] tokens and write its table row + last-token slot into `tables`
+        ([batch, max_blocks] int32) / `slots` ([batch] int64) — numpy arrays, e.g. views of pinned staging tensors."""
+        r, c = _u64(list(request_ids)), _i64(list(context_lens))
+        if tables is None:
+            tables = np.zeros((r.size, max_blocks), dtype=np.int32)
+        if slots is None:
+            slots = np.zeros(r.size, dtype=np.int64)
+        assert tables.dtype == np.int32 and tables.flags.c_contiguous and tables.shape == (r.size, max_blocks)
+        assert slots.dtype == np.int64 and slots.flags.c_contiguous and slots.shape == (r.size,)
+        bad = host_lib().mrs_kv_manager_decode_step(self._h, ctypes.c_void_p(r.ctypes.data), ctypes.c_void_p(c.ctypes.data),
+                                                    ctypes.c_int64(r.size), ctypes.c_int64(max_blocks),
+                                                    ctypes.c_void_p(tables.ctypes.data), ctypes.c_void_p(slots.ctypes.data))
+        if bad >= 0:
+            raise MemoryError(f"request {int(r[bad])} (batch index {bad}) is unknown or the pool cannot grow it")
+        return tables, slots
 
 
 def slot_mapping(table, block_size, start, end):

@@ -132,3 +132,63 @@ def make_decode_tiles(tables, context_lens, block_size, split_pages, padded):
     valid = len(req)
     mask = [1] * valid + [0] * (padded - valid)
     return req + [0] * (padded - valid), tile + [0] * (padded - valid), o_indptr, (split_pages or 1) * block_size, mask
+
+
+class KVCacheManager:
+    """Pure-Python restatement of the reference's per-request manager (REF kv_cache_manager.rs:188-350)."""
+
+    def __init__(self, num_gpu_blocks, block_size, enable_caching, groups=(0,)):
+        self.pool = BlockPool(num_gpu_blocks, enable_caching, block_size)
+        self.bs, self.caching, self.groups = block_size, enable_caching, list(groups)
+        self.reqs = {}   # id -> [block ids, cached count]
+
+    def get_computed_blocks(self, hashes, num_tokens):
+        return self.pool.computed_blocks(hashes, num_tokens, self.bs, self.groups) if hashes else []
+
+    def allocate_slots(self, rid, num_tokens, computed=()):
+        need = -(-num_tokens // self.bs)
+        if rid in self.reqs:
+            ids = self.reqs[rid][0]
+            if need <= len(ids):
+                return []
+            new = self.pool.get_new_blocks(need - len(ids))
+            if new is None:
+                return None
+            ids += new
+            return new
+        computed = list(computed)
+        n_new = max(need - len(computed), 0)
+        evictable = sum(self.pool.ref[b] == 0 for b in computed) if self.caching else 0
+        if n_new + evictable > self.pool.num_free_blocks():
+            return None
+        if computed and self.caching:
+            self.pool.touch(computed)
+        new = self.pool.get_new_blocks(n_new) if n_new else []
+        self.reqs[rid] = [computed + new, len(computed)]
+        return new
+
+    def free(self, rid):
+        if rid in self.reqs:
+            self.pool.free_blocks(list(reversed(self.reqs.pop(rid)[0])))
+
+    def trim(self, rid, num_tokens):
+        if rid not in self.reqs:
+            return
+        r = self.reqs[rid]
+        need = -(-num_tokens // self.bs)
+        if need < len(r[0]):
+            gone = r[0][need:]
+            del r[0][need:]
+            self.pool.free_blocks(list(reversed(gone)))
+        r[1] = min(r[1], len(r[0]))
+
+    def cache_blocks(self, rid, hashes, num_computed_tokens):
+        if not self.caching or rid not in self.reqs:
+            return
+        r = self.reqs[rid]
+        full = min(num_computed_tokens // self.bs, len(r[0]))
+        if r[1] >= full:
+            return
+        for g in self.groups:
+            self.pool.cache_full_blocks(r[0], hashes, r[1], full, g)
+        r[1] = full
