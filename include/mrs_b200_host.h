@@ -74,6 +74,19 @@ int mrs_kv_manager_block_table(void *mgr, uint64_t request_id, int64_t max_block
 int64_t mrs_kv_manager_decode_step(void *mgr, const uint64_t *request_ids, const int64_t *context_lens, int64_t batch,
                                    int64_t max_blocks, int32_t *tables, int64_t *slots);
 
+/* ---- host tail of the on-device sampler: packed rows of topk_large_f32_packed[_batched] / top1_large_f32_packed
+ *      (mrs_b200_ops.h) -> token + logprob.  REF mistralrs-core/src/sampler.rs:1172-1273,666-742,1284-1297.
+ *      u is the caller's uniform variate in [0,1) (the random stream stays with the caller).
+ *      0 ok, -1 bad row length / k, -2 bad softmax normaliser, -3 nothing survives the filters, -4 negative or
+ *      non-finite probability, -5 invalid top-1 row ---- */
+int mrs_sample_topk_packed_row(const float *packed, int64_t packed_len, int64_t packed_k, int64_t row_k,
+                               float inv_temperature, float top_p, float min_p, double u, uint32_t *token,
+                               float *logprob);
+int64_t mrs_sample_topk_packed_batch(const float *packed, int64_t batch, int64_t packed_k, const int64_t *row_k,
+                                     const float *inv_temperature, const float *top_p, const float *min_p,
+                                     const double *u, uint32_t *tokens, float *logprobs, int32_t *status);
+int mrs_sample_top1_row(const float *packed, uint32_t *token);
+
 /* ---- slots / CSR / tile plans ---- */
 int mrs_slot_mapping(const int64_t *table, int64_t table_len, int64_t block_size, int64_t start, int64_t end,
                      int64_t *out);

@@ -3,6 +3,7 @@
 #include "kv_cache_manager.hpp"
 #include "kv_index.hpp"
 #include "safetensors_reader.hpp"
+#include "sampler_tail.hpp"
 
 #include <cstring>
 
@@ -90,6 +91,28 @@ int64_t mrs_block_pool_computed_blocks(void *p, const uint64_t *hashes, int64_t 
   }
   return k;
 }
+
+// ---- host tail of the on-device sampler (sampler_tail.hpp) ----
+int mrs_sample_topk_packed_row(const float *packed, int64_t packed_len, int64_t packed_k, int64_t row_k, float inv_temperature, float top_p,
+                               float min_p, double u, uint32_t *token, float *logprob) {
+  return sample_topk_packed_row(packed, packed_len, packed_k, row_k, inv_temperature, top_p, min_p, u, token, logprob);
+}
+// rows [batch, 2*packed_k+2]; per-row k / temperature / filters / variate; status[batch] gets each row's code.
+// Returns the number of rows that failed.
+int64_t mrs_sample_topk_packed_batch(const float *packed, int64_t batch, int64_t packed_k, const int64_t *row_k, const float *inv_temperature,
+                                     const float *top_p, const float *min_p, const double *u, uint32_t *tokens, float *logprobs,
+                                     int32_t *status) {
+  int64_t bad = 0;
+  const int64_t w = 2 * packed_k + 2;
+  for (int64_t b = 0; b < batch; b++) {
+    const int rc = sample_topk_packed_row(packed + b * w, w, packed_k, row_k[b], inv_temperature[b], top_p[b], min_p[b], u[b], tokens + b,
+                                          logprobs + b);
+    if (status) status[b] = rc;
+    bad += (rc != 0);
+  }
+  return bad;
+}
+int mrs_sample_top1_row(const float *packed, uint32_t *token) { return sample_top1_row(packed, token); }
 
 // ---- per-request block tables over a pool (kv_cache_manager.hpp) ----
 void *mrs_kv_manager_new(int64_t num_gpu_blocks, int64_t block_size, int32_t enable_caching, const uint32_t *groups, int64_t n_groups) {
