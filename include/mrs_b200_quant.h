@@ -120,6 +120,29 @@ int32_t mrs_w4a16_gemm(const void *x, const void *w_tiles, const void *scales, c
                        int32_t K, int32_t N, int32_t group, int32_t dtype, int32_t scale_perm, void *stream);
 int32_t mrs_dense_linear(const void *x, const void *w, void *y, int32_t M, int32_t K, int32_t N, int32_t dtype, void *stream);
 
+/* ---- packed-affine GGUF (the reference's opt-in `PackedAffine` path for batched GGUF linears) — same names, argument
+ * order and return convention as REF mistralrs-quant/src/gguf/packed_affine.rs:1436-1509 (0 ok, -1 shape / format
+ * outside the plan, else a cudaError).
+ * repack: `format` = ggml type code (2,3,6,7,8,9,10..15: Q4_0 Q4_1 Q5_0 Q5_1 Q8_0 Q8_1 Q2_K..Q6_K Q8_K, :44-69);
+ * `source` = ggml blocks [n, k/block]; writes payload (padded_n*k*bits/8 bytes: 4-bit for Q4_0/Q4_1/Q2_K/Q3_K/Q4_K,
+ * else 8-bit), scales and offsets (k/group*padded_n 16-bit values each, group 16 for Q2_K/Q3_K/Q6_K else 32) such that
+ * w = scale * q - offset; rows n..padded_n-1 are zero.  The layout inside the three buffers is this library's
+ * (csrc/affine.cuh) and only its own marlin_affine_* reads it.
+ * matmul: output [m, n] with n the PADDED width the buffers were packed for; `workspace` unused.  Kernel: the
+ * tcgen05 dequant GEMM of csrc/mmq_tc.cu with csrc/affine.cuh's dequantiser; any m >= 1, k % 64 == 0. */
+int32_t mrs_gguf_affine_repack_f16(int32_t format, const void *source, void *payload, void *scales, void *offsets,
+                                   int32_t k, int32_t n, int32_t padded_n, uintptr_t stream);
+int32_t mrs_gguf_affine_repack_bf16(int32_t format, const void *source, void *payload, void *scales, void *offsets,
+                                    int32_t k, int32_t n, int32_t padded_n, uintptr_t stream);
+int32_t marlin_affine_u4_f16(const void *input, const void *weight, void *scales, void *offsets, void *output, int32_t m,
+                             int32_t k, int32_t n, int32_t group_size, void *workspace, int64_t stream);
+int32_t marlin_affine_u4_bf16(const void *input, const void *weight, void *scales, void *offsets, void *output, int32_t m,
+                              int32_t k, int32_t n, int32_t group_size, void *workspace, int64_t stream);
+int32_t marlin_affine_u8_f16(const void *input, const void *weight, void *scales, void *offsets, void *output, int32_t m,
+                             int32_t k, int32_t n, int32_t group_size, void *workspace, int64_t stream);
+int32_t marlin_affine_u8_bf16(const void *input, const void *weight, void *scales, void *offsets, void *output, int32_t m,
+                              int32_t k, int32_t n, int32_t group_size, void *workspace, int64_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@
 // reference's int8-activation MMQ.
 // (Round 2: mrs_mmq_gguf sends Q8_0 / Q4_K / Q6_K launches with K % 256 == 0 to csrc/mmq_ts.cu; this kernel keeps the
 // other seven types, odd shapes and the GPTQ/AWQ checkpoint-layout GEMM, and is required to agree with it bit for bit.)
+#include "affine.cuh"
 #include "dequant.cuh"
 #include "tc_common.cuh"
 
@@ -222,7 +223,8 @@ __device__ __forceinline__ void expand32(const Raw32<TYPE> &r, const uint8_t *ro
 }
 
 struct TcParams;
-template <int TYPE> struct IsInt4Ckpt { static constexpr bool value = (TYPE == 100 || TYPE == 101); };
+// "checkpoint" types: weights are not ggml blocks addressed by row_bytes but separate arrays read through dequant32_ckpt
+template <int TYPE> struct IsInt4Ckpt { static constexpr bool value = (TYPE >= 100 && TYPE <= 103); };
 
 struct TcParams {
   const uint8_t *w;
@@ -235,8 +237,12 @@ struct TcParams {
   const int32_t *qzeros;    // AWQ [K/group, N/8]; GPTQ: ignored (symmetric, w = (q-8)*s — REF marlin kU4B8)
   const int32_t *g_idx;     // GPTQ act-order group of each k, or nullptr (k / group)
   int group;
+  // packed-affine ggml weights (TYPE_AFF4 / TYPE_AFF8; layout in affine.cuh): w = scale * q - offset, group 16 or 32
+  const uint8_t *aff_payload;
+  const uint16_t *aff_scales, *aff_offsets;
+  int aff_bf16;             // 16-bit format of scales / offsets
 };
-constexpr int TYPE_GPTQ4 = 100, TYPE_AWQ4 = 101;
+constexpr int TYPE_GPTQ4 = 100, TYPE_AWQ4 = 101, TYPE_AFF4 = 102, TYPE_AFF8 = 103;
 
 // 64 weights k0..k0+63 of output channel n from a GPTQ / AWQ int4 checkpoint, as the Marlin
 // path of the reference computes them: w = f16((q - 8) * s) (GPTQ, REF marlin_matmul_f16.cu /
@@ -269,7 +275,9 @@ __device__ __forceinline__ void dequant64_ckpt(const TcParams &p, int n, int k0,
 
 template <int TYPE>
 __device__ __forceinline__ void dequant32_ckpt(const TcParams &p, int n, int k0, float *out) {
-  if constexpr (TYPE == TYPE_GPTQ4) {
+  if constexpr (TYPE == TYPE_AFF4 || TYPE == TYPE_AFF8) {
+    affine::dequant32(p.aff_payload, p.aff_scales, p.aff_offsets, TYPE == TYPE_AFF4 ? 4 : 8, p.group, p.aff_bf16 != 0, p.K, n, k0, out);
+  } else if constexpr (TYPE == TYPE_GPTQ4) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const uint32_t w = (uint32_t)p.qweight[(size_t)(k0 / 8 + i) * p.N + n];
@@ -548,3 +556,44 @@ extern "C" int32_t mrs_gptq_gemm(const void *x, const int32_t *qweight, const vo
   p.qweight = qweight; p.scales = (const __half *)scales; p.qzeros = qzeros; p.g_idx = g_idx; p.group = group_size;
   return (int32_t)(is_awq ? launch_tc<TYPE_AWQ4>(p, tmap, (cudaStream_t)stream) : launch_tc<TYPE_GPTQ4>(p, tmap, (cudaStream_t)stream));
 }
+
+// Packed-affine ggml linear (a5): Y[m, n] = X[m, k] . W^T with W held as unsigned 4- / 8-bit payload + per-group 16-bit
+// scale and offset, as mrs_gguf_affine_repack_* (affine.cu) wrote them.  Behind the reference's symbols
+// `marlin_affine_{u4,u8}_{f16,bf16}` (REF mistralrs-quant/src/gguf/packed_affine.rs:1458-1509 declarations, :697-752 call
+// site: n is the PADDED width, the output is [m, padded_n]; `workspace` is the reference kernel's lock array — unused here).
+// Same tcgen05 kernel as the checkpoint-layout int4 GEMM: each weight is fma(q, scale, -offset) in f32, rounded once to the
+// activations' 16-bit format, f32 accumulation in tensor memory.  0 ok, -1 bad shape, else a cudaError.
+static int32_t affine_gemm(const void *x, const void *payload, const void *scales, const void *offsets, void *y, int m, int k, int n, int group,
+                           int bits, int dtype, cudaStream_t st) {
+  if (m <= 0 || n <= 0) return 0;
+  if (k <= 0 || k % 64 != 0 || (group != 16 && group != 32) || n % 8 != 0) return -1;
+  if (x == nullptr || payload == nullptr || scales == nullptr || offsets == nullptr || y == nullptr) return -1;
+  if (((uintptr_t)x & 15) || ((uintptr_t)payload & 15) || ((uintptr_t)y & 15) || ((uintptr_t)scales & 1) || ((uintptr_t)offsets & 1))
+    return (int32_t)cudaErrorMisalignedAddress;
+  PFN_encodeTiled enc = tc_get_encode();
+  if (enc == nullptr) return (int32_t)cudaErrorNotSupported;
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)m};
+  const cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tmap, dtype == MRS_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(x), dims, strides,
+          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return (int32_t)cudaErrorInvalidValue;
+  TcParams p = {};
+  p.y = y; p.M = m; p.N = n; p.K = k; p.out_dtype = dtype; p.b_fmt = dtype; p.group = group;
+  p.aff_payload = (const uint8_t *)payload; p.aff_scales = (const uint16_t *)scales; p.aff_offsets = (const uint16_t *)offsets;
+  p.aff_bf16 = dtype == MRS_BF16;
+  return (int32_t)(bits == 4 ? launch_tc<TYPE_AFF4>(p, tmap, st) : launch_tc<TYPE_AFF8>(p, tmap, st));
+}
+#define MRS_AFFINE_ENTRY(NAME, BITS, DT)                                                                                                      \
+  extern "C" int32_t NAME(const void *input, const void *weight, void *scales, void *offsets, void *output, int32_t m, int32_t k, int32_t n,   \
+                          int32_t group_size, void *workspace, int64_t stream) {                                                              \
+    (void)workspace;                                                                                                                          \
+    return affine_gemm(input, weight, scales, offsets, output, m, k, n, group_size, BITS, DT, (cudaStream_t)stream);                          \
+  }
+MRS_AFFINE_ENTRY(marlin_affine_u4_f16, 4, MRS_F16)
+MRS_AFFINE_ENTRY(marlin_affine_u4_bf16, 4, MRS_BF16)
+MRS_AFFINE_ENTRY(marlin_affine_u8_f16, 8, MRS_F16)
+MRS_AFFINE_ENTRY(marlin_affine_u8_bf16, 8, MRS_BF16)

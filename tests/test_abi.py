@@ -47,7 +47,10 @@ def test_host_library_exports_its_header():
 
 
 FFI_FILES = ("mistralrs-quant/src/gguf/ffi.rs", "mistralrs-quant/src/rotary/ffi.rs", "mistralrs-quant/src/utils/ffi.rs",
-             "mistralrs-quant/src/gptq/marlin_ffi.rs", "mistralrs-paged-attn/src/cuda/ffi.rs", "mistralrs-core/src/cuda/ffi.rs")
+             "mistralrs-quant/src/gptq/marlin_ffi.rs", "mistralrs-paged-attn/src/cuda/ffi.rs", "mistralrs-core/src/cuda/ffi.rs",
+             "mistralrs-quant/src/gguf/packed_affine.rs")
+# reference symbols that happen to carry the mrs_ prefix themselves (declared in packed_affine.rs:1436-1457)
+REF_MRS_NAMES = ("mrs_gguf_affine_repack_f16", "mrs_gguf_affine_repack_bf16")
 
 
 def _rust_class(t):
@@ -66,7 +69,7 @@ def _c_class(t):
     if "*" in t or t in ("cudaStream_t", "mrs_ops_stream_t", "mrs_stream_t", "CUstream"):
         return "ptr"
     return {"int": "i32", "int32_t": "i32", "unsigned int": "u32", "unsigned": "u32", "uint32_t": "u32", "long": "i64",
-            "int64_t": "i64", "long long": "i64", "uint64_t": "u64", "size_t": "u64", "float": "f32", "double": "f64",
+            "int64_t": "i64", "long long": "i64", "uint64_t": "u64", "size_t": "u64", "uintptr_t": "u64", "float": "f32", "double": "f64",
             "bool": "bool", "_Bool": "bool", "uint8_t": "u8"}.get(t, "?" + t)
 
 
@@ -133,8 +136,11 @@ def test_reference_signatures_match_ffi_rs():
         pytest.skip("reference tree not present (GPU box)")
     rust = {}
     for f in FFI_FILES:
-        rust.update(_rust_signatures(open(os.path.join(ref, f)).read()))
-    ours = {n: v for n, v in _c_signatures().items() if not n.startswith("mrs_")}
+        text = open(os.path.join(ref, f)).read()
+        if not f.endswith("ffi.rs"):                       # a full source file: only its trailing `mod ffi { extern "C" { .. } }`
+            text = text[text.rindex("mod ffi"):]
+        rust.update(_rust_signatures(text))
+    ours = {n: v for n, v in _c_signatures().items() if not n.startswith("mrs_") or n in REF_MRS_NAMES}
     missing = sorted(n for n in ours if n not in rust)
     assert not missing, missing
     assert sum(n.startswith("launch_mmvq_gguf_") for n in ours) == 93
