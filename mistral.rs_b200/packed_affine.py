@@ -3,6 +3,7 @@
 `PackedAffine::{new, forward}` (:456-602, :604-770).  The repack and the GEMM are calls through the C ABI of
 libmrs_b200.so under the reference's own symbol names (`mrs_gguf_affine_repack_*`, `marlin_affine_{u4,u8}_*`)."""
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -83,6 +84,26 @@ class PackedAffinePlan:
         values = k // fmt.group_size * padded_n
         ws = padded_n // MARLIN_N_TILE * MARLIN_MAX_PARALLEL
         return PackedAffinePlan(fmt, n, padded_n, k, payload, values, values * 2, ws, payload + 2 * values * 2 + ws * 4)
+
+
+BACKEND_ENV = "MISTRALRS_GGUF_AFFINE_BACKEND"
+
+
+def enabled():
+    """Off unless MISTRALRS_GGUF_AFFINE_BACKEND is "on" / "auto": the repacked copy is a second full set of weights
+    (REF packed_affine.rs:295-310).  Read on every call (the reference latches it once per process)."""
+    return os.environ.get(BACKEND_ENV, "off") in ("on", "auto")
+
+
+def should_dispatch(source_dtype, shape, flat_batch, act_dtype, device_type):
+    """The dispatcher's decision, host logic only (REF gguf/mod.rs:326-366 `packed_affine_for`): backend enabled, a
+    format with an affine form, batch at or above that format's minimum, 16-bit activations on CUDA, tile-compatible shape."""
+    if not enabled():
+        return False
+    min_batch = minimum_batch(source_dtype)
+    if min_batch is None or flat_batch < min_batch:
+        return False
+    return act_dtype in _DT and device_type == "cuda" and len(shape) == 2 and PackedAffinePlan.new(source_dtype, shape[0], shape[1]) is not None
 
 
 class PackedAffine:

@@ -245,8 +245,21 @@ class GgufMatMul:
     def quantized_act_type(self):
         return None  # gguf/mod.rs: GGUF keeps the caller's activation dtype
 
+    def _packed_affine_for(self, flat_batch, x):
+        """Opt-in packed path (REF gguf/mod.rs:326-366): the pack is built on first use and kept."""
+        from . import packed_affine as PA
+        if not PA.should_dispatch(self.w.dtype, self.w.shape, flat_batch, x.dtype, x.device.type) or x.device != self.w.device:
+            return None
+        if getattr(self, "_packed", None) is None or self._packed.dtype != x.dtype:
+            self._packed = PA.PackedAffine(self.w.data, self.w.dtype, self.w.shape, x.dtype)
+        return self._packed
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         b_size = x.numel() // x.shape[-1]
+        packed = self._packed_affine_for(b_size, x)
+        if packed is not None:
+            y = packed.forward(x)
+            return y if self.b is None else y + self.b
         if 1 <= b_size <= MMVQ_MAX_BATCH:
             y = plain(self.w, x)
         else:

@@ -138,3 +138,26 @@ def test_plan_sizes():   # packed_affine.rs:94-135
     assert PA.PackedAffinePlan.new("q4_k", 64, 128) is None            # K must hold whole source blocks
     assert PA.PackedAffinePlan.new("q6_k", 64, 256).metadata_values == 256 // 16 * 64
     assert PA.PackedAffinePlan.new("f16", 64, 256) is None and PA.PackedAffinePlan.new("q4_0", 0, 256) is None
+
+
+def test_dispatch_rule(monkeypatch):   # packed_affine.rs `dispatch_switches_to_packed_at_minimum_batch`, `format_specific_minimum_batches_are_enforced`
+    import torch
+    from mistralrs_b200 import packed_affine as PA
+    monkeypatch.delenv(PA.BACKEND_ENV, raising=False)
+    assert not PA.enabled() and not PA.should_dispatch("q4_k", (128, 256), 64, torch.bfloat16, "cuda")     # off by default
+    monkeypatch.setenv(PA.BACKEND_ENV, "off")
+    assert not PA.enabled()
+    for v in ("on", "auto"):
+        monkeypatch.setenv(PA.BACKEND_ENV, v)
+        assert PA.enabled()
+    M = PA.GGUF_AFFINE_MIN_BATCH
+    assert not PA.should_dispatch("q4_k", (128, 256), M - 1, torch.bfloat16, "cuda")
+    assert PA.should_dispatch("q4_k", (128, 256), M, torch.bfloat16, "cuda")
+    for t, mb in (("q5_0", 16), ("q5_1", 128), ("q6_k", 128)):
+        assert not PA.should_dispatch(t, (128, 256), mb - 1, torch.bfloat16, "cuda")
+        assert PA.should_dispatch(t, (128, 256), mb, torch.float16, "cuda")
+    assert PA.should_dispatch("q8_k", (128, 256), 1, torch.bfloat16, "cuda")                   # affine-only formats from batch 1
+    assert not PA.should_dispatch("q4_k", (128, 256), 64, torch.float32, "cuda")               # 16-bit activations only
+    assert not PA.should_dispatch("q4_k", (128, 256), 64, torch.bfloat16, "cpu")
+    assert not PA.should_dispatch("q4_k", (128, 96), 64, torch.bfloat16, "cuda")               # `unsupported_k_tile_uses_canonical_dispatch`
+    assert PA.should_dispatch("q4_0", (96, 256), 64, torch.bfloat16, "cuda")                   # `unaligned_width_uses_padded_packed_dispatch`

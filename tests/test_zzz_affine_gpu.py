@@ -108,3 +108,22 @@ def test_rejects_what_the_plan_rejects(cuda):
     import ctypes
     assert lib().mrs_gguf_affine_repack_f16(ctypes.c_int32(1), ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(z.data_ptr()),
                                             ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(z.data_ptr()), 256, 64, 64, ctypes.c_size_t(0)) == -1
+
+
+def test_dispatch_switches_to_packed_at_minimum_batch(cuda, monkeypatch):   # packed_affine.rs:1181-1201, and the bias is kept (:1018)
+    from mistralrs_b200 import quant
+    monkeypatch.setenv(PA.BACKEND_ENV, "on")
+    n, k = 128, 256
+    rng = np.random.default_rng(7)
+    blocks = _blocks("q4_k", n * k // 256, rng)
+    bias = torch.from_numpy(_patterned(1, n, 3, 0.05)[0]).to(cuda).to(torch.bfloat16)
+    layer = quant.GgufMatMul(quant.QTensor(torch.from_numpy(blocks.reshape(-1)).to(cuda), "q4_k", (n, k)), bias)
+    small = torch.from_numpy(_patterned(PA.GGUF_AFFINE_MIN_BATCH - 1, k, 81, 0.1)).to(cuda).to(torch.bfloat16)
+    layer.forward(small)
+    assert getattr(layer, "_packed", None) is None
+    x = torch.from_numpy(_patterned(PA.GGUF_AFFINE_MIN_BATCH, k, 83, 0.1)).to(cuda).to(torch.bfloat16)
+    y = layer.forward(x)
+    assert layer._packed is not None
+    monkeypatch.setenv(PA.BACKEND_ENV, "off")
+    y_canonical = layer.forward(x)                       # same layer through MMVQ (batch 8): the two paths agree to activation-quantisation noise
+    assert torch.allclose(y.float(), y_canonical.float(), atol=0.08, rtol=0.05)
