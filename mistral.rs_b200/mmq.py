@@ -41,3 +41,28 @@ def set_path(path: str):
 def set_weight_format(fmt: str):
     """'same' (default: the activations' 16-bit format), 'f16' or 'bf16' for the dequantised weights."""
     lib().mrs_mmq_set_weight_format(ctypes.c_int({"same": -1, "f16": 0, "bf16": 1}[fmt]))
+
+
+# ---- the reference's entry points over this kernel (REF mistralrs-quant/src/gguf/fast_mmq.rs:760-826).  In the reference the
+# point of the fused forms is ONE activation-quantisation pass shared by the projections; this design never quantises
+# activations, so they are the same projections over the same bf16/f16 input — kept under the reference's names so a
+# caller written against fast_mmq finds them. ----
+def plain(w, xs: torch.Tensor) -> torch.Tensor:
+    return forward(w, xs)
+
+
+def fused_qkv(q_w, k_w, v_w, xs: torch.Tensor):
+    return forward(q_w, xs), forward(k_w, xs), forward(v_w, xs)
+
+
+def fused_glu(gate_w, up_w, xs: torch.Tensor, activation) -> torch.Tensor:
+    if tuple(gate_w.shape) != tuple(up_w.shape):
+        raise ValueError(f"fast_mmq fused_glu: gate/up shape mismatch {tuple(gate_w.shape)} vs {tuple(up_w.shape)}")
+    from . import ops
+    return ops.fused_glu(forward(gate_w, xs), forward(up_w, xs), activation)
+
+
+def fused_ffn(gate_w, up_w, down_w, xs: torch.Tensor, activation) -> torch.Tensor:
+    if tuple(gate_w.shape) != tuple(up_w.shape):
+        raise ValueError(f"fast_mmq fused_ffn: gate/up shape mismatch {tuple(gate_w.shape)} vs {tuple(up_w.shape)}")
+    return forward(down_w, fused_glu(gate_w, up_w, xs, activation))

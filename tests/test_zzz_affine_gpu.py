@@ -127,3 +127,17 @@ def test_dispatch_switches_to_packed_at_minimum_batch(cuda, monkeypatch):   # pa
     monkeypatch.setenv(PA.BACKEND_ENV, "off")
     y_canonical = layer.forward(x)                       # same layer through MMVQ (batch 8): the two paths agree to activation-quantisation noise
     assert torch.allclose(y.float(), y_canonical.float(), atol=0.08, rtol=0.05)
+
+
+def test_fast_mmq_named_entry_points(cuda):   # fast_mmq.rs:760-826 over the (already covered) prefill GEMM + GLU kernels
+    from mistralrs_b200 import mmq, ops, quant
+    rng = np.random.default_rng(21)
+    K, I, M = 512, 768, 40
+    mk = lambda n, k: quant.QTensor(torch.from_numpy(oracle.random_blocks("q4_k", n * k // 256, rng).reshape(-1)).to(cuda), "q4_k", (n, k))
+    g, u, d = mk(I, K), mk(I, K), mk(K, I)
+    x = torch.from_numpy(_patterned(M, K, 5, 0.5)).to(cuda).to(torch.bfloat16)
+    q, k, v = mmq.fused_qkv(g, u, u, x)
+    assert torch.equal(q, mmq.plain(g, x)) and torch.equal(k, v)
+    glu = mmq.fused_glu(g, u, x, quant.GluActivationType.Silu)
+    assert torch.equal(glu, ops.fused_glu(mmq.forward(g, x), mmq.forward(u, x), quant.GluActivationType.Silu))
+    assert torch.equal(mmq.fused_ffn(g, u, d, x, quant.GluActivationType.Silu), mmq.forward(d, glu))
