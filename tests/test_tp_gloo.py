@@ -116,3 +116,71 @@ def test_kv_heads_replicated_when_ranks_outnumber_them():
     q_rows = [sh.layers[0]["attn_q"][2] for sh in shards]
     assert q_rows == [cfg.n_heads * cfg.head_dim // 2] * 2
     assert np.array_equal(np.concatenate([sh.host[(0, "attn_q")] for sh in shards]), full.host[(0, "attn_q")])
+
+
+# ---- the layer classes (distributed.py) with biases, under gloo: the CUDA linear replaced by an oracle stand-in ----
+def _layer_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.load_package()
+    import oracle
+    from mistralrs_b200 import distributed as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class CpuLinear:                       # stand-in for quant.GgufMatMul: exact product with the dequantised shard
+        def __init__(self, data, dtype, shape):
+            self.w = torch.from_numpy(oracle.dequantize(dtype, data.numpy()).reshape(shape).astype(np.float64))
+
+        def forward(self, xs):
+            return xs @ self.w.T
+
+    ok = True
+    for dtype, n, k in (("q4_k", 96, 512), ("q6_k", 64, 1024), ("q8_0", 48, 192)):
+        rng = np.random.default_rng(11)                                   # same bytes on every rank
+        blocks = torch.from_numpy(oracle.random_blocks(dtype, n * k // oracle.BLOCK_ELEMS[dtype], rng).reshape(-1))
+        bias = torch.from_numpy(rng.standard_normal(n))
+        x = torch.from_numpy(rng.standard_normal((3, k)))
+        full = D.ReplicatedLayer(blocks, dtype, (n, k), bias, CpuLinear).forward(x)
+        col = D.ColumnParallelLayer(blocks, dtype, (n, k), rank, world, bias, CpuLinear)
+        parts = [torch.zeros(3, n // world, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, col.forward(x))
+        ok &= bool(torch.equal(torch.cat(parts, dim=1), full))            # rows are disjoint: bit-identical
+        row = D.RowParallelLayer(blocks, dtype, (n, k), rank, world, D.SumAllReduce(), bias, CpuLinear)
+        y = row.forward(row.input_slice(x).contiguous())
+        ok &= bool(torch.allclose(y, full, rtol=1e-12, atol=1e-12))       # bias once, after the reduce
+        ok &= row.shape == (n, k // world) and col.shape == (n // world, k)
+    single = D.SumAllReduce(world_size=1)
+    t = torch.ones(2)
+    ok &= single.is_noop() and single.sum_all_reduce(t) is t and not D.SumAllReduce().is_noop()
+    custom = D.SumAllReduce(world_size=world, reduce_fn=lambda v: v * world)   # a plugged-in exchange is what gets called
+    ok &= bool(torch.equal(custom.sum_all_reduce(torch.ones(2)), torch.full((2,), float(world))))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_parallel_layers_with_bias_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() * 7 + 3) % 2000
+    procs = [ctx.Process(target=_layer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def test_shard_rules_reject_what_the_reference_rejects():
+    import oracle
+    from mistralrs_b200 import distributed as D
+    blocks = torch.from_numpy(oracle.random_blocks("q4_k", 6 * 3, np.random.default_rng(0)).reshape(-1))   # [6, 768]
+    with pytest.raises(ValueError, match="block boundaries"):
+        D.shard_k_blocks(blocks, "q4_k", (6, 768), 0, 2)          # 3 blocks of 256 do not split in two
+    with pytest.raises(ValueError, match="do not divide"):
+        D.shard_rows(blocks, "q4_k", (6, 768), 0, 4)
+    s, shape = D.shard_k_blocks(blocks, "q4_k", (6, 768), 1, 3)
+    assert shape == (6, 256) and s.numel() == 6 * 144
+    assert torch.equal(s.reshape(6, 144), blocks.reshape(6, 3, 144)[:, 1])
