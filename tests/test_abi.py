@@ -98,7 +98,7 @@ def _rust_signatures(text):
         f = re.search(r"fn\s+\$" + m.group(2) + r"\s*\((.*?)\)\s*(->\s*[\w:]+)?\s*;", body, flags=re.S)
         if f:
             macros[m.group(1)] = (f.group(1), f.group(2))
-    for m in re.finditer(r"\bfn\s+([A-Za-z_][A-Za-z0-9_]*)\s*\((.*?)\)\s*(->\s*[\w:]+)?\s*;", text, flags=re.S):
+    for m in re.finditer(r"\bfn\s+([A-Za-z_][A-Za-z0-9_]*)\s*\((.*?)\)\s*(->\s*(?:\*(?:mut|const)\s+)?[\w:]+)?\s*;", text, flags=re.S):
         args = [_rust_class(a.split(":", 1)[1]) for a in _split_args(m.group(2))]
         sigs[m.group(1)] = (args, m.group(3) is not None)
     for m in re.finditer(r"\b(\w+)!\s*\(\s*([A-Za-z_][A-Za-z0-9_]*)\s*\)\s*;", text):
@@ -108,10 +108,10 @@ def _rust_signatures(text):
     return sigs
 
 
-def _c_signatures():
+def _c_signatures(host=False):
     sigs = {}
     for h in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
-        if h.endswith("_host.h"):
+        if h.endswith("_host.h") != host:
             continue
         src = subprocess.run(["gcc", "-E", "-P", h], capture_output=True, text=True, check=True).stdout
         src = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
@@ -183,3 +183,16 @@ def test_product_never_imports_oracle():
         if path.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
             src = open(path).read()
             assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, path
+
+
+def test_rust_host_ffi_source_matches_header():
+    """rust/mrs_b200_host_ffi.rs — generated declarations for libmrs_b200_host (block pool / prefix cache / KV manager,
+    slot + CSR builders, sampler tail, file readers) — re-parsed and compared with include/mrs_b200_host.h."""
+    rust = _rust_signatures(open(os.path.join(ROOT, "rust", "mrs_b200_host_ffi.rs")).read())
+    ours = _c_signatures(host=True)
+    assert set(rust) == set(ours), sorted(set(rust) ^ set(ours))
+    assert len(ours) >= 60
+    for n, (cargs, cret) in ours.items():
+        rargs, rret = rust[n]
+        cargs = ["ptr" if c.startswith("?") else c for c in cargs]
+        assert cargs == rargs and cret == rret, (n, cargs, rargs)
