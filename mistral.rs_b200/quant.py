@@ -271,3 +271,24 @@ class GgufMatMul:
 
     def dtype_and_device(self):
         return (self.w.dtype, self.w.device)
+
+    # ---- UQFF (REF gguf/mod.rs:755-806 `serialize_uqff` / `deserialize_uqff`; entry names docs uqff-format.md) ----
+    QUANTIZED_SERDE_TYPE_GGUF = 0       # REF lib.rs `QuantizedSerdeType::Gguf`
+
+    def serialize_uqff(self, prefix: str):
+        """name -> array entries of this layer: `<prefix>.weight.format` (u8 scalar), `<prefix>.weight` (raw ggml blocks),
+        `<prefix>.weight.dtype` (u32 scalar, ggml code), `<prefix>.weight.shape` (u32 vector), `<prefix>.bias` if any."""
+        import numpy as np
+        out = {f"{prefix}.weight.format": np.array(self.QUANTIZED_SERDE_TYPE_GGUF, dtype=np.uint8),
+               f"{prefix}.weight": self.w.data.detach().cpu().numpy().reshape(-1),
+               f"{prefix}.weight.dtype": np.array(_ggml_code(self.w.dtype), dtype=np.uint32),
+               f"{prefix}.weight.shape": np.array(list(self.w.shape), dtype=np.uint32)}
+        if self.b is not None:
+            out[f"{prefix}.bias"] = self.b.detach().cpu()
+        return out
+
+    @classmethod
+    def deserialize_uqff(cls, archive, prefix: str, device):
+        """archive: uqff_file.UqffArchive.  Blocks are uploaded as stored."""
+        bias = archive.load_tensor(f"{prefix}.bias", device) if archive.contains(f"{prefix}.bias") else None
+        return cls(archive.load_qtensor(prefix, device), bias)

@@ -242,3 +242,48 @@ class UqffArchive:
         t = torch.from_numpy(a.view(np.int16)).view(torch.bfloat16) if dt == "BF16" else torch.from_numpy(a)
         t = t.to(device)
         return t.to(dtype) if dtype is not None else t
+
+
+# ---- writing -------------------------------------------------------------------------------------
+_ST = {np.dtype(v): k for k, v in _NP.items()}
+
+
+def version_entries(version=UQFF_VERSION):
+    """the three scalar U32 version tensors every shard carries (REF uqff/mod.rs:27-29, reader.rs version check)"""
+    return {k: np.array(v, dtype=np.uint32) for k, v in zip(_VERSION_KEYS, version)}
+
+
+def save_uqff(path, entries, version=UQFF_VERSION, metadata=None):
+    """Write one `.uqff` shard: a safetensors container (8-byte little-endian header length, JSON header
+    name -> {dtype, shape, data_offsets}, then the tensor bytes in header order, each 8-byte aligned through header
+    padding only — tensors are packed back to back) holding `entries` (name -> numpy array; torch bf16 tensors are
+    stored as BF16) plus the version tag.  The counterpart of `UqffArchive`; what `GgufMatMul.serialize_uqff` feeds."""
+    entries = dict(entries)
+    entries.update(version_entries(version))
+    header, blobs, off = {}, [], 0
+    if metadata:
+        header["__metadata__"] = {str(k): str(v) for k, v in metadata.items()}
+    for name in sorted(entries):
+        a = entries[name]
+        if isinstance(a, torch.Tensor):
+            if a.dtype == torch.bfloat16:
+                raw, st, shape = a.detach().cpu().contiguous().view(torch.int16).numpy().tobytes(), "BF16", tuple(a.shape)
+            else:
+                a = a.detach().cpu().numpy()
+        if not isinstance(a, torch.Tensor):
+            a = np.asarray(a)                       # (ascontiguousarray would turn a scalar into shape (1,))
+            if not a.flags.c_contiguous:
+                a = a.copy(order="C")
+            if a.dtype not in _ST:
+                raise ValueError(f"UQFF tensor `{name}`: unsupported dtype {a.dtype}")
+            raw, st, shape = a.tobytes(), _ST[a.dtype], tuple(a.shape)
+        header[name] = {"dtype": st, "shape": list(shape), "data_offsets": [off, off + len(raw)]}
+        blobs.append(raw)
+        off += len(raw)
+    h = json.dumps(header, separators=(",", ":")).encode()
+    h += b" " * (-len(h) % 8)
+    with open(path, "wb") as f:
+        f.write(len(h).to_bytes(8, "little"))
+        f.write(h)
+        for b in blobs:
+            f.write(b)

@@ -191,3 +191,40 @@ def test_tied_and_llama3_rope_scaling(tmp_path, cfg):
         assert w.cfg.rope_scaling["factor"] == 8.0
         plain = M.rope_tables(M.LlamaWeights.config_from_hf({**cj, "rope_scaling": None}))[0]
         assert not np.array_equal(M.rope_tables(w.cfg)[0], plain)      # scaled frequencies differ
+
+
+def test_layer_serialize_roundtrip_and_layout(tmp_path):   # gguf/mod.rs:755-806 serialize_uqff / deserialize_uqff
+    import oracle
+    from safetensors.numpy import load_file
+    from mistralrs_b200 import quant, uqff_file
+    rng = np.random.default_rng(4)
+    n, k = 24, 512
+    blocks = oracle.random_blocks("q6_k", n * k // 256, rng)
+    bias = torch.from_numpy(rng.standard_normal(n).astype(np.float32)).to(torch.bfloat16)
+    layer = quant.GgufMatMul(quant.QTensor(torch.from_numpy(blocks.reshape(-1)), "q6_k", (n, k)), bias)
+    key = "model.layers.3.mlp.down_proj"
+    entries = layer.serialize_uqff(key)
+    want = uqff_layer_entries(key, "q6_k", n, k, blocks)          # the documented four entries
+    assert set(entries) == set(want) | {f"{key}.bias"}
+    for name, a in want.items():
+        assert entries[name].dtype == a.dtype and entries[name].shape == a.shape and np.array_equal(entries[name], a), name
+    plain = quant.GgufMatMul(quant.QTensor(torch.from_numpy(blocks.reshape(-1)), "q6_k", (n, k)))
+    other = plain.serialize_uqff("lm_head")
+    assert "lm_head.bias" not in other
+    path = tmp_path / "q-0.uqff"
+    uqff_file.save_uqff(path, {**entries, **other}, metadata={"writer": "test"})
+    # an independent reader agrees on every tensor (bf16 bias aside, which numpy cannot represent)
+    try:
+        ref = load_file(str(path))
+    except (TypeError, ValueError):
+        ref = None
+    if ref is not None:
+        assert np.array_equal(ref[f"{key}.weight"], blocks.reshape(-1)) and int(ref["uqff.version.minor"]) == uqff_file.UQFF_VERSION[1]
+    with uqff_file.UqffArchive([path]) as ar:
+        assert ar.version == uqff_file.UQFF_VERSION and ar.layer_keys() == ["lm_head", key]
+        back = quant.GgufMatMul.deserialize_uqff(ar, key, "cpu")
+        assert back.w.dtype == "q6_k" and tuple(back.w.shape) == (n, k) and torch.equal(back.w.data, layer.w.data)
+        assert back.b.dtype == torch.bfloat16 and torch.equal(back.b, bias)
+        assert quant.GgufMatMul.deserialize_uqff(ar, "lm_head", "cpu").b is None
+    with pytest.raises(ValueError):
+        uqff_file.save_uqff(tmp_path / "bad.uqff", {"x": np.zeros(2, dtype=np.complex64)})
