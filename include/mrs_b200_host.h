@@ -74,6 +74,12 @@ int mrs_kv_manager_block_table(void *mgr, uint64_t request_id, int64_t max_block
 int64_t mrs_kv_manager_decode_step(void *mgr, const uint64_t *request_ids, const int64_t *context_lens, int64_t batch,
                                    int64_t max_blocks, int32_t *tables, int64_t *slots);
 
+/* ---- f32 -> ggml blocks on the host, for in-situ re-quantisation of a GGUF layer (REF gguf/mod.rs:633-708 apply_isq;
+ *      arithmetic = candle k_quants `from_float` / ggml `quantize_row_*_ref`).  Types 2,3,6,7,8 (Q4_0 Q4_1 Q5_0 Q5_1 Q8_0);
+ *      K-quants have no quantiser here.  n % 32 == 0.  Returns bytes written or -1. ---- */
+int64_t mrs_ggml_quantize(int32_t ggml_type, const float *x, int64_t n, uint8_t *out);
+int32_t mrs_ggml_quantize_block_bytes(int32_t ggml_type); /* 0: no quantiser for this type */
+
 /* ---- host tail of the on-device sampler: packed rows of topk_large_f32_packed[_batched] / top1_large_f32_packed
  *      (mrs_b200_ops.h) -> token + logprob.  REF mistralrs-core/src/sampler.rs:1172-1273,666-742,1284-1297.
  *      u is the caller's uniform variate in [0,1) (the random stream stays with the caller).

@@ -1,4 +1,5 @@
 // host_api.cpp — C API over the C++ host layer (kv_index.hpp) for the Python test/bench harness.
+#include "ggml_quantize.hpp"
 #include "gguf_reader.hpp"
 #include "kv_cache_manager.hpp"
 #include "kv_index.hpp"
@@ -91,6 +92,10 @@ int64_t mrs_block_pool_computed_blocks(void *p, const uint64_t *hashes, int64_t 
   }
   return k;
 }
+
+// ---- f32 -> ggml blocks (ggml_quantize.hpp): Q4_0 / Q4_1 / Q5_0 / Q5_1 / Q8_0 ----
+int64_t mrs_ggml_quantize(int32_t ggml_type, const float *x, int64_t n, uint8_t *out) { return quantize_row(ggml_type, x, n, out); }
+int32_t mrs_ggml_quantize_block_bytes(int32_t ggml_type) { return quantize_block_bytes(ggml_type); }
 
 // ---- host tail of the on-device sampler (sampler_tail.hpp) ----
 int mrs_sample_topk_packed_row(const float *packed, int64_t packed_len, int64_t packed_k, int64_t row_k, float inv_temperature, float top_p,

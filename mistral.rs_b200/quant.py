@@ -61,6 +61,29 @@ class QTensor:
     def nbytes(self):
         return self.data.numel()
 
+    QUANTIZABLE = ("q4_0", "q4_1", "q5_0", "q5_1", "q8_0")
+
+    @classmethod
+    def quantize(cls, src: torch.Tensor, dtype: str, device=None):
+        """f32 [rows, cols] -> ggml blocks of `dtype` (candle `QTensor::quantize`, REF gguf/mod.rs:601-604): on the host
+        (C++ host/ggml_quantize.hpp), uploaded to `device` (default: src's).  The 32-wide block types only."""
+        import ctypes as C
+        import numpy as np
+        from . import GGML
+        from .kv_index import host_lib
+        if dtype not in cls.QUANTIZABLE:
+            raise NotImplementedError(f"no host quantiser for {dtype} (only {', '.join(cls.QUANTIZABLE)}); K-quant quantisation is not provided")
+        if src.dim() != 2 or src.shape[1] % BLOCK_ELEMS[dtype]:
+            raise ValueError(f"quantize: expected [rows, cols] with cols a multiple of {BLOCK_ELEMS[dtype]}, got {tuple(src.shape)}")
+        x = np.ascontiguousarray(src.detach().to(torch.float32).cpu().numpy())
+        out = np.empty(x.size // BLOCK_ELEMS[dtype] * BLOCK_BYTES[dtype], dtype=np.uint8)
+        L = host_lib()
+        L.mrs_ggml_quantize.restype = C.c_int64
+        n = L.mrs_ggml_quantize(C.c_int32(GGML[dtype]), C.c_void_p(x.ctypes.data), C.c_int64(x.size), C.c_void_p(out.ctypes.data))
+        if n != out.size:
+            raise RuntimeError(f"mrs_ggml_quantize({dtype}) returned {n}, expected {out.size}")
+        return cls(torch.from_numpy(out).to(device if device is not None else src.device), dtype, tuple(src.shape))
+
 
 def supports(dtype: str) -> bool:
     return dtype in MMVQ_TYPES
@@ -271,6 +294,24 @@ class GgufMatMul:
 
     def dtype_and_device(self):
         return (self.w.dtype, self.w.device)
+
+    def dequantize_w(self) -> torch.Tensor:
+        """f32 [N, K] of the weight, on its device (REF gguf/mod.rs `dequantize_w`): every row through the block decoder
+        of the embedding gather kernel.  CUDA only — there is no host dequantiser in the product."""
+        from . import ops
+        if self.w.device.type != "cuda":
+            raise RuntimeError("dequantize_w runs on the CUDA block decoders; the weight is on " + str(self.w.device))
+        ids = torch.arange(self.w.shape[0], dtype=torch.int32, device=self.w.device)
+        return ops.embedding_gather(self.w, ids, dtype=torch.float32)
+
+    def apply_isq(self, dtype, device=None):
+        """In-situ re-quantisation (REF gguf/mod.rs:633-708): None or the layer's own type -> the same blocks moved to
+        `device`; another type -> dequantise, quantise on the host, upload.  Bias follows."""
+        device = torch.device(device) if device is not None else self.w.device
+        bias = None if self.b is None else self.b.to(device)
+        if dtype is None or dtype == self.w.dtype:
+            return GgufMatMul(QTensor(self.w.data.to(device), self.w.dtype, self.w.shape), bias)
+        return GgufMatMul(QTensor.quantize(self.dequantize_w(), dtype, device), bias)
 
     # ---- UQFF (REF gguf/mod.rs:755-806 `serialize_uqff` / `deserialize_uqff`; entry names docs uqff-format.md) ----
     QUANTIZED_SERDE_TYPE_GGUF = 0       # REF lib.rs `QuantizedSerdeType::Gguf`

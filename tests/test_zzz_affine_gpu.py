@@ -141,3 +141,19 @@ def test_fast_mmq_named_entry_points(cuda):   # fast_mmq.rs:760-826 over the (al
     glu = mmq.fused_glu(g, u, x, quant.GluActivationType.Silu)
     assert torch.equal(glu, ops.fused_glu(mmq.forward(g, x), mmq.forward(u, x), quant.GluActivationType.Silu))
     assert torch.equal(mmq.fused_ffn(g, u, d, x, quant.GluActivationType.Silu), mmq.forward(d, glu))
+
+
+def test_apply_isq_requantises_through_the_device_decoders(cuda):   # gguf/mod.rs:633-708
+    from mistralrs_b200 import quant
+    rng = np.random.default_rng(9)
+    n, k = 32, 512
+    blocks = oracle.random_blocks("q4_k", n * k // 256, rng)
+    layer = quant.GgufMatMul(quant.QTensor(torch.from_numpy(blocks.reshape(-1)).to(cuda), "q4_k", (n, k)))
+    w = layer.dequantize_w()
+    assert w.dtype == torch.float32 and np.array_equal(w.cpu().numpy(), oracle.dequantize("q4_k", blocks).reshape(n, k))
+    out = layer.apply_isq("q8_0", cuda)
+    assert out.w.dtype == "q8_0" and out.w.data.device.type == "cuda"
+    import gguf
+    from gguf import quants
+    want = quants.quantize(oracle.dequantize("q4_k", blocks).reshape(n, k), gguf.GGMLQuantizationType.Q8_0).reshape(-1)
+    assert np.array_equal(out.w.data.cpu().numpy(), want)
