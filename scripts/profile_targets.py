@@ -52,3 +52,13 @@ elif what == "prefill_attn":      # optional second argument "mma": keep the cal
     for _ in range(3):
         paged_attn.prefill_attention(q, k, v, D ** -0.5)
     torch.cuda.synchronize()
+elif what == "affine":            # packed-affine GGUF GEMM (a5): optional source type, default q4_k
+    from mistralrs_b200 import packed_affine as PA
+    dtype = sys.argv[2] if len(sys.argv) > 2 else "q4_k"
+    Mm, N, K = 4096, 4096, 4096
+    wb = oracle.random_blocks(dtype, N * K // oracle.BLOCK_ELEMS[dtype], rng)
+    packed = PA.PackedAffine(torch.from_numpy(wb.reshape(-1)).to(dev), dtype, (N, K), torch.bfloat16)
+    x = torch.randn(Mm, K, device=dev).to(torch.bfloat16)
+    for _ in range(4):
+        packed.forward(x)
+    torch.cuda.synchronize()
