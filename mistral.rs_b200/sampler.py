@@ -50,3 +50,33 @@ def sample_top1_row(packed):
     if p.size != 2 or host_lib().mrs_sample_top1_row(ctypes.c_void_p(p.ctypes.data), ctypes.byref(tok)) != 0:
         raise ValueError(_ERR[-5])
     return tok.value
+
+
+CUDA_TOPK_MAX_K = 128      # REF mistralrs-core/src/ops.rs:18
+
+
+def cuda_batch_sampling_plan(temperature, top_k, top_p, min_p, *, return_logprobs=False, frequency_penalty=None, presence_penalty=None,
+                             repetition_penalty=None, dry_multiplier=None, has_logits_bias=False, has_logits_processors=False):
+    """Which device kernel a request's row goes through, or None when the row must take the host path
+    (REF sampler.rs:613-660 `cuda_batch_sampling_plan`): ("greedy", 1.0) — no temperature;
+    ("topk", k, inv_temperature) — top_k in 1..=128; ("categorical", inv_temperature) — no top-k and neither nucleus nor
+    min-p filtering.  Anything that edits the logits on the host (penalties, DRY, bias, processors) or asks for logprobs
+    rules the batched device path out."""
+    import math
+    has_penalties = ((frequency_penalty or 0.0) != 0.0 or (presence_penalty or 0.0) != 0.0
+                     or (1.0 if repetition_penalty is None else repetition_penalty) != 1.0)
+    if return_logprobs or has_penalties or (dry_multiplier or 0.0) != 0.0 or has_logits_bias or has_logits_processors:
+        return None
+    if temperature is None:
+        return ("greedy", 1.0)
+    if not (math.isfinite(temperature) and temperature > 0.0):
+        return None
+    with np.errstate(over="ignore"):
+        inv_t = float(np.float32(1.0 / temperature))      # the reference keeps it as f32: a tiny temperature overflows to inf -> no plan
+    if not (math.isfinite(inv_t) and inv_t > 0.0):
+        return None
+    if top_k > 0:
+        return ("topk", int(top_k), inv_t) if top_k <= CUDA_TOPK_MAX_K else None
+    if not (0.0 < top_p < 1.0) and not (0.0 < min_p < 1.0):
+        return ("categorical", inv_t)
+    return None

@@ -101,3 +101,19 @@ def test_top1_row():   # sampler.rs:1284-1297
     for bad in ([np.nan, 1.0], [1.0, np.inf], [1.0, -1.0], [1.0, 2.5]):
         with pytest.raises(ValueError):
             sampler.sample_top1_row(bad)
+
+
+def test_cuda_batch_sampling_plan():   # sampler.rs:613-660
+    plan = sampler.cuda_batch_sampling_plan
+    assert plan(None, 40, 0.9, 0.0) == ("greedy", 1.0)
+    assert plan(0.5, 40, 0.9, 0.05) == ("topk", 40, 2.0)
+    assert plan(0.5, 128, 1.0, 0.0) == ("topk", 128, 2.0) and plan(0.5, 129, 1.0, 0.0) is None
+    assert plan(2.0, -1, 1.0, 0.0) == ("categorical", 0.5) and plan(2.0, 0, 0.0, 1.0) == ("categorical", 0.5)
+    assert plan(2.0, -1, 0.9, 0.0) is None and plan(2.0, -1, 1.0, 0.1) is None       # nucleus / min-p need the sorted head
+    for bad_t in (0.0, -1.0, float("inf"), float("nan"), 1e-45):
+        assert plan(bad_t, 40, 1.0, 0.0) is None
+    assert plan(0.7, 40, 1.0, 0.0, return_logprobs=True) is None
+    assert plan(0.7, 40, 1.0, 0.0, frequency_penalty=0.1) is None and plan(0.7, 40, 1.0, 0.0, presence_penalty=-0.2) is None
+    assert plan(0.7, 40, 1.0, 0.0, repetition_penalty=1.1) is None and plan(0.7, 40, 1.0, 0.0, repetition_penalty=1.0) is not None
+    assert plan(0.7, 40, 1.0, 0.0, dry_multiplier=0.8) is None and plan(0.7, 40, 1.0, 0.0, dry_multiplier=0.0) is not None
+    assert plan(0.7, 40, 1.0, 0.0, has_logits_bias=True) is None and plan(None, 1, 1.0, 0.0, has_logits_processors=True) is None
