@@ -17,6 +17,35 @@ _DT_CODE = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}
 _TAG = {torch.float16: "f16", torch.bfloat16: "bf16", torch.float32: "f32"}
 _SUPPORTED_HEAD_SIZES = (64, 80, 96, 112, 128, 192, 256)      # backend/paged_attention.rs:251-261
 PARTITION_SIZE = 512  # backend/paged_attention.rs:302
+FLASHINFER_DECODE_ENV = "MISTRALRS_FLASHINFER_DECODE"
+
+
+def _env_flag(name, default):
+    """REF mistralrs-core/src/perf_flags.rs:9-22"""
+    import os
+    v = os.environ.get(name)
+    if v in ("1", "true", "TRUE", "yes", "on"):
+        return True
+    if v in ("0", "false", "FALSE", "no", "off"):
+        return False
+    return default
+
+
+def flashinfer_decode_enabled():
+    return _env_flag(FLASHINFER_DECODE_ENV, True)
+
+
+def supports_flashinfer_group_size(q_heads, kv_heads):
+    """REF mistralrs-core/src/flashinfer/mod.rs:266-273 (the GQA group sizes the decode kernel is instantiated for)"""
+    return kv_heads != 0 and q_heads % kv_heads == 0 and q_heads // kv_heads in (1, 2, 3, 4, 6, 8, 16)
+
+
+def flashinfer_supports_layer(q_heads, kv_heads, k_head_dim, v_head_dim):
+    """Which decode backend a layer gets (REF flashinfer/mod.rs:257-264 `supports_layer`): the HND / CSR path
+    (`flashinfer_decode`) when this holds, the vLLM-layout `paged_attention` otherwise or when
+    MISTRALRS_FLASHINFER_DECODE=0."""
+    return (flashinfer_decode_enabled() and k_head_dim == v_head_dim and k_head_dim in (64, 128, 256, 512)
+            and supports_flashinfer_group_size(q_heads, kv_heads))
 
 
 def _p(t):
