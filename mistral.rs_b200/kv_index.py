@@ -25,6 +25,8 @@ def host_lib():
         for f in ("null_block_id", "num_free_blocks", "ref_cnt", "num_cached_blocks", "num_block_hashes", "computed_blocks"):
             getattr(L, f"mrs_block_pool_{f}").restype = ctypes.c_int64
         L.mrs_block_hashes.restype = ctypes.c_int64
+        L.mrs_sample_topk_packed_batch.restype = ctypes.c_int64
+        L.mrs_ggml_quantize.restype = ctypes.c_int64
         L.mrs_kv_manager_new.restype = ctypes.c_void_p
         L.mrs_kv_manager_pool.restype = ctypes.c_void_p
         L.mrs_kv_manager_usage.restype = ctypes.c_double

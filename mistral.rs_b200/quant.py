@@ -78,7 +78,6 @@ class QTensor:
         x = np.ascontiguousarray(src.detach().to(torch.float32).cpu().numpy())
         out = np.empty(x.size // BLOCK_ELEMS[dtype] * BLOCK_BYTES[dtype], dtype=np.uint8)
         L = host_lib()
-        L.mrs_ggml_quantize.restype = C.c_int64
         n = L.mrs_ggml_quantize(C.c_int32(GGML[dtype]), C.c_void_p(x.ctypes.data), C.c_int64(x.size), C.c_void_p(out.ctypes.data))
         if n != out.size:
             raise RuntimeError(f"mrs_ggml_quantize({dtype}) returned {n}, expected {out.size}")

@@ -38,7 +38,6 @@ def sample_topk_packed_batch(packed, packed_k, row_k, inv_temperature, top_p, mi
     uu = np.ascontiguousarray(np.broadcast_to(u, (batch,)), dtype=np.float64)
     tokens, logprobs, status = np.zeros(batch, np.uint32), np.zeros(batch, np.float32), np.zeros(batch, np.int32)
     P = lambda a: ctypes.c_void_p(a.ctypes.data)
-    host_lib().mrs_sample_topk_packed_batch.restype = ctypes.c_int64
     host_lib().mrs_sample_topk_packed_batch(P(p), ctypes.c_int64(batch), ctypes.c_int64(packed_k), P(rk), P(it), P(tp), P(mp), P(uu),
                                             P(tokens), P(logprobs), P(status))
     return tokens, logprobs, status
